@@ -1,0 +1,129 @@
+"""TEST INFRASTRUCTURE ONLY -- import shims that let the reference's OWN in-repo code execute here.
+
+/root/reference (andreeaiana/manner) imports lightning, torch_geometric, torchmetrics,
+pytorch_metric_learning, MulticoreTSNE, seaborn, colorcet and matplotlib at module top
+(manner/models/cr_module.py:5-10, ensemble_module.py:4-7, a_module.py:3-12); none of them is
+installed in this image and there is no network.  ``install()`` registers placeholder modules for
+them in ``sys.modules``:
+
+* the arithmetic the hot path needs from them (``to_dense_batch``, the torchmetrics metric classes
+  and helpers) comes from the restatement in oracle/thirdparty.py;
+* everything off the path (losses, tSNE, plotting) is an inert placeholder.
+
+With the shims in place tests/golden/make_golden.py runs the reference's unmodified
+``CRModule.forward/model_step/test_step/on_test_epoch_end``, ``EnsembleModule.*``, ``DotProduct``,
+``manner.metrics.functional.*`` and ``Diversity``/``Personalization`` on table-lookup "news
+encoders" and stores the outputs as golden vectors.  It is only ever used in this container (the
+GPU box has no /root/reference); nothing under manner_b200/ imports it.
+"""
+from __future__ import annotations
+
+import inspect
+import sys
+import types
+from typing import Any, Dict
+
+import torch
+
+from . import thirdparty as tp
+
+
+class _AttrDict(dict):
+    __getattr__ = dict.__getitem__
+    __setattr__ = dict.__setitem__
+
+
+class LightningModule(torch.nn.Module):
+    """Inert stand-in for lightning.LightningModule: hparams capture, CPU device, log capture."""
+
+    def __init__(self, *args: Any, **kwargs: Any) -> None:
+        super().__init__()
+        self.logged: Dict[str, Any] = {}
+
+    @property
+    def device(self) -> torch.device:
+        return torch.device("cpu")
+
+    @property
+    def hparams(self) -> _AttrDict:
+        if "_hparams" not in self.__dict__:
+            self.__dict__["_hparams"] = _AttrDict()
+        return self.__dict__["_hparams"]
+
+    def save_hyperparameters(self, *args: Any, logger: bool = True, **kwargs: Any) -> None:
+        frame = inspect.currentframe().f_back
+        local = frame.f_locals
+        names = [n for n in inspect.signature(type(self).__init__).parameters if n != "self"]
+        self.hparams.update({n: local[n] for n in names if n in local})
+
+    def log(self, name: str, value: Any, *args: Any, **kwargs: Any) -> None:
+        self.__dict__.setdefault("logged", {})[name] = value
+
+    def log_dict(self, dictionary: Any, *args: Any, **kwargs: Any) -> None:
+        values = dictionary.compute() if hasattr(dictionary, "compute") else dictionary
+        for k, v in values.items():
+            self.log(k, v)
+
+    @classmethod
+    def load_from_checkpoint(cls, checkpoint_path: str, **kwargs: Any):  # pragma: no cover
+        raise RuntimeError("checkpoints are not available here; make_golden.py patches this")
+
+
+def _module(name: str, **attrs: Any) -> types.ModuleType:
+    mod = types.ModuleType(name)
+    mod.__dict__.update(attrs)
+    sys.modules[name] = mod
+    return mod
+
+
+class _Inert:
+    def __init__(self, *args: Any, **kwargs: Any) -> None:
+        pass
+
+    def add_to_recordable_attributes(self, *args: Any, **kwargs: Any) -> None:
+        pass
+
+
+def install(reference_root: str = "/root/reference") -> None:
+    """Register the shims and put the reference on sys.path (idempotent)."""
+    if reference_root not in sys.path:
+        sys.path.insert(0, reference_root)
+    if "lightning" in sys.modules and getattr(sys.modules["lightning"], "_mb200_stub", False):
+        return
+    _module("lightning", LightningModule=LightningModule, _mb200_stub=True)
+    pyg = _module("torch_geometric")
+    pyg.utils = _module("torch_geometric.utils", to_dense_batch=tp.to_dense_batch)
+
+    tm = _module(
+        "torchmetrics",
+        Metric=tp.Metric,
+        MetricCollection=tp.MetricCollection,
+        MeanMetric=tp.MeanMetric,
+        MinMetric=tp.MinMetric,
+    )
+    tm.classification = _module("torchmetrics.classification", AUROC=tp.AUROC)
+    tm.retrieval = _module(
+        "torchmetrics.retrieval", RetrievalMRR=tp.RetrievalMRR, RetrievalNormalizedDCG=tp.RetrievalNormalizedDCG
+    )
+    tm.retrieval.base = _module("torchmetrics.retrieval.base", RetrievalMetric=tp.RetrievalMetric)
+    tm.utilities = _module("torchmetrics.utilities")
+    tm.utilities.checks = _module(
+        "torchmetrics.utilities.checks",
+        _check_retrieval_inputs=tp._check_retrieval_inputs,
+        _check_retrieval_functional_inputs=tp._check_retrieval_functional_inputs,
+    )
+    tm.utilities.data = _module(
+        "torchmetrics.utilities.data", _flexible_bincount=tp._flexible_bincount, dim_zero_cat=tp.dim_zero_cat
+    )
+
+    pml = _module("pytorch_metric_learning")
+    pml.losses = _module("pytorch_metric_learning.losses", SupConLoss=_Inert)
+    pml.distances = _module("pytorch_metric_learning.distances", DotProductSimilarity=_Inert)
+    pml.utils = _module("pytorch_metric_learning.utils")
+    pml.utils.common_functions = _module("pytorch_metric_learning.utils.common_functions")
+    pml.utils.loss_and_miner_utils = _module("pytorch_metric_learning.utils.loss_and_miner_utils")
+    _module("MulticoreTSNE", MulticoreTSNE=_Inert)
+    _module("seaborn")
+    _module("colorcet")
+    mpl = _module("matplotlib")
+    mpl.pyplot = _module("matplotlib.pyplot")
