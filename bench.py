@@ -1,0 +1,331 @@
+#!/usr/bin/env python
+"""Benchmark of the MANNeR scoring / ensemble / metrics hot path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload ...]
+
+Metric (BASELINE.json): impressions/sec for pool + score + ensemble + metrics.  A *step* is one pass
+of the hot path over one MIND-small-shaped set of impressions (73 152 impressions, 65 238 news,
+768-d fp32): CR-Module + category A-Module ensemble (z-score, aspect weight), nDCG@5/10 + MRR +
+gAUC per impression and the pooled AUROC -- BASELINE.json configs[1].
+
+Prints ONE JSON line.  ``value`` is device-timed (CUDA events, max over ranks) with the inputs resident
+in HBM; ``e2e`` is the same pass through ScoreEvaluator.upload + evaluate from pinned host buffers,
+copies inside the timed region.  ``--impl reference`` times the oracle port of the reference's own CPU
+path (steps of 8 impressions, per-row Python loops, torchmetrics-style group loop run twice) on the
+host cores and prints the same line with "impl": "reference".
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np
+import torch
+
+METRIC = "impressions/sec (pool+score+ensemble+metrics)"
+UNIT = "impressions/s"
+CATEG_WEIGHT = 0.4  # model.categ_weight (the YAMLs ship 0 and are swept by CLI override; 0 would not load the A-Module)
+FALLBACK_HBM_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md
+
+
+def workload_config(args) -> dict:
+    return {
+        "workload": f"MIND-{args.workload}-shaped synthetic impressions, CR + category A-Module z-score ensemble, fp32 768-d tables",
+        "shape": args.workload,
+        "n_modules": args.modules,
+        "categ_weight": CATEG_WEIGHT,
+        "metrics": "ndcg@5 ndcg@10 mrr gauc + pooled auroc",
+        "ids": "uniform" if args.uniform_ids else "zipf(1.05)",
+        "l2": "flushed between timed steps (256 MiB write); table 200 MB/module > 126 MB L2",
+    }
+
+
+def peaks() -> tuple:
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured"
+    return FALLBACK_HBM_GBS, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (profiling recipe's clocks line)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int) -> None:
+        self.lines = []
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(gpu_index)],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True,
+            )
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self) -> None:
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.lines:
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) < 9:
+                continue
+            try:
+                sm.append(float(parts[1])), mx.append(float(parts[2]))
+            except ValueError:
+                continue
+            for name, val in zip(names, parts[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {
+            "sm_mhz": statistics.median(sm) if sm else None,
+            "sm_max_mhz": max(mx) if mx else None,
+            "samples": len(sm),
+            "reasons": sorted(reasons),
+        }
+
+
+def cpu_reference_pass(tables, bhv, n_sample: int, threads: int) -> tuple:
+    """Times the oracle port of the reference's CPU path on the first ``n_sample`` impressions."""
+    from oracle import manner_oracle as mo
+
+    torch.set_num_threads(threads)
+    head = bhv.slice(0, min(n_sample, bhv.n_impressions))
+    ob = mo.Behaviours(head.hist_offsets, head.hist_ids, head.cand_offsets, head.cand_ids, head.labels)
+    weights = [1.0, CATEG_WEIGHT] + [0.0] * (len(tables) - 2)
+    t0 = time.perf_counter()
+    mo.ensemble_eval_epoch(tables, weights[: len(tables)], ob, double_compute=True, reference_only=True)
+    dt = time.perf_counter() - t0
+    return head.n_impressions / dt, dt, head.n_impressions
+
+
+def run_reference_arm(args) -> None:
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return  # rank 0 alone runs the CPU arm
+    from manner_b200 import data as mdata
+
+    threads = os.cpu_count() or 1
+    tables, bhv = mdata.synth_workload(args.workload, n_modules=args.modules, uniform_ids=args.uniform_ids)
+    # bound the whole run to a few minutes whatever K and W the driver passes (~550 impressions/s on 8 cores)
+    budget_s = 150.0 / (args.steps + 0.25 * args.warmup)
+    n_sample = int(min(args.cpu_sample, max(256, budget_s * 500))) // 8 * 8
+    for _ in range(args.warmup):
+        cpu_reference_pass(tables, bhv, max(64, n_sample // 16), threads)
+    rates, times = [], []
+    for _ in range(args.steps):
+        r, dt, n = cpu_reference_pass(tables, bhv, n_sample, threads)
+        rates.append(r), times.append(dt)
+    value = n_sample * len(times) / sum(times)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * sum(times) / len(times), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic", "config": workload_config(args),
+        "cpu_baseline": {
+            "value": value, "unit": UNIT, "cores": threads, "kind": "port",
+            "sample": f"first {n_sample} impressions of the workload per step; oracle port of EnsembleModule.test_step (batches of 8, "
+                      "per-row loops) + torchmetrics-style nDCG@5/10 group loop run twice, torch.set_num_threads(cores)",
+        },
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def run_gpu_arm(args) -> None:
+    import torch.distributed as dist
+
+    from manner_b200 import data as mdata
+    from manner_b200 import dist as mdist
+    from manner_b200 import ops
+    from manner_b200.evaluator import ScoreEvaluator
+
+    rank, local_rank, world = mdist.init_from_env("nccl")
+    if world != args.gpus and world > 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    dev = torch.device(f"cuda:{local_rank}")
+    distributed = world > 1
+
+    # weak scaling: every rank scores its own MIND-small-shaped shard (different behaviour seed), tables replicated
+    tables, bhv = mdata.synth_workload(args.workload, n_modules=args.modules, seed_offset=rank, uniform_ids=args.uniform_ids)
+    ev = ScoreEvaluator(tables, dev)
+    pinned = ev.pin(bhv)
+    dev_bhv = ev.upload(bhv, pinned)
+    weights = [[1.0, CATEG_WEIGHT] + [0.0] * (args.modules - 2)][0][: args.modules]
+    w_dev = torch.tensor([weights], dtype=torch.float32, device=dev)
+    kw = dict(weights=w_dev, zscore=True, pooled_auc=True, distributed=distributed)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    ops.set_tuning(time_kernel=1)
+    if args.variant is not None:
+        ops.set_tuning(variant=args.variant)
+    if args.chunks_per_warp is not None:
+        ops.set_tuning(chunks_per_warp=args.chunks_per_warp)
+    if args.ctas_per_sm is not None:
+        ops.set_tuning(ctas_per_sm=args.ctas_per_sm)
+
+    def barrier() -> None:
+        if distributed:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def device_step(timed: bool):
+        flush.fill_(rank + 1)  # evict L2 between steps
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        pending = ev.launch(dev_bhv, **kw)
+        e1.record()
+        return e0, e1, pending
+
+    for _ in range(max(args.warmup, 3)):
+        _, _, pending = device_step(False)
+    res = ev.finish(pending)
+    barrier()
+
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    launches0 = ops.launch_counts()
+    barrier()
+    wall0 = time.perf_counter()
+    events, kernel_ms = [], []
+    for _ in range(args.steps):
+        e0, e1, pending = device_step(True)
+        events.append((e0, e1))
+        kernel_ms.append(ops.last_score_kernel_ms())  # waits for the fused kernel of this step only
+    barrier()
+    wall = time.perf_counter() - wall0
+    launches1 = ops.launch_counts()
+    step_ms = [a.elapsed_time(b) for a, b in events]
+    total_ms = torch.tensor([sum(step_ms)], dtype=torch.float64, device=dev)
+    if distributed:
+        dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
+    total_ms = float(total_ms.item())
+    res = ev.finish(pending)
+
+    # end to end: pinned host CSR -> device, pass, metric sums back to the host, every step
+    barrier()
+    e2e_events = []
+    for i in range(max(2, min(args.steps, 5)) + 1):
+        flush.fill_(rank + 1)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        step_bhv = ev.upload(bhv, pinned)
+        r = ev.evaluate(step_bhv, **kw)  # includes the device -> host read of sums / AUC statistics
+        e1.record()
+        torch.cuda.synchronize(dev)
+        if i > 0:
+            e2e_events.append(e0.elapsed_time(e1))
+    e2e_ms = torch.tensor([sum(e2e_events) / len(e2e_events)], dtype=torch.float64, device=dev)
+    if distributed:
+        dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
+    e2e_ms = float(e2e_ms.item())
+    clocks = sampler.stop() if sampler is not None else None
+
+    n_impr_rank = bhv.n_impressions
+    n_impr_total = torch.tensor([n_impr_rank], dtype=torch.float64, device=dev)
+    if distributed:
+        dist.all_reduce(n_impr_total, op=dist.ReduceOp.SUM)
+    n_impr_total = float(n_impr_total.item())
+
+    if rank != 0:
+        if distributed:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
+
+    hbm_peak, peak_kind = peaks()
+    algo_bytes = bhv.algorithmic_bytes(args.modules, tables[0].shape[1], 4, scores_written=True)
+    k_ms = sum(kernel_ms) / len(kernel_ms)
+    achieved = algo_bytes / (k_ms * 1e-3) / 1e9
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath):
+        with open(tpath) as f:
+            t = json.load(f)
+        if t.get("shape") == args.workload and t.get("n_modules") == args.modules and bool(t.get("uniform_ids")) == args.uniform_ids:
+            traffic = t.get("dram_bytes_per_launch")
+
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        rate, dt, n = cpu_reference_pass(tables, bhv, args.cpu_sample, threads)
+        cpu = {
+            "value": rate, "unit": UNIT, "cores": threads, "kind": "port",
+            "sample": f"first {n} impressions of the workload ({dt:.1f} s); oracle port of EnsembleModule.test_step (batches of 8, per-row loops) "
+                      "+ torchmetrics-style nDCG@5/10 group loop run twice",
+        }
+
+    line = {
+        "metric": METRIC, "value": n_impr_total * args.steps / (total_ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(args),
+        "e2e": {
+            "value": n_impr_total / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": dev_bhv.h2d_bytes,
+            "d2h_bytes_per_step": r.d2h_bytes, "ms_per_step": e2e_ms,
+        },
+        "gpu_launches": launches1[0] - launches0[0],
+        "library_launches": launches1[1] - launches0[1],
+        "roofline": {
+            "bound": "hbm", "kernel": "score_eval_kernel", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
+            "peak_kind": peak_kind, "traffic": traffic, "algorithmic_bytes_per_launch": algo_bytes, "kernel_ms": k_ms,
+            "kernel_share_of_step": k_ms * args.steps / total_ms if total_ms > 0 else None,
+        },
+        "cpu_baseline": cpu,
+        "clocks": clocks,
+        "wall_s_timed_region": wall,
+        "impressions_per_rank": n_impr_rank,
+        "check": {k: round(v, 6) for k, v in res.metrics().items()},
+    }
+    print(json.dumps(line))
+    if distributed:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main() -> None:
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="small", choices=["tiny", "mini", "small", "large"])
+    ap.add_argument("--modules", type=int, default=2)
+    ap.add_argument("--uniform-ids", action="store_true", help="draw ids uniformly over the catalogue (no L2-friendly head)")
+    ap.add_argument("--cpu-sample", type=int, default=8192)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--variant", type=int, default=None)
+    ap.add_argument("--chunks-per-warp", type=int, default=None)
+    ap.add_argument("--ctas-per-sm", type=int, default=None)
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_gpu_arm(args)
+
+
+if __name__ == "__main__":
+    main()

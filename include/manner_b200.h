@@ -1,0 +1,196 @@
+/*
+ * manner_b200.h -- C ABI of libmanner_b200.so: the B200 (sm_100a) scoring / ensemble / metrics hot
+ * path of MANNeR (andreeaiana/manner) as a drop-in for the reference's evaluation path.
+ *
+ * The reference is pure Python and has NO native operator interface; its plugin seam
+ * is Hydra's `_target_` (configs/model/*.yaml:1).  This header is therefore the interface a
+ * maintainer binds with ctypes (INTEGRATION.md shows the stub); each entry point cites the
+ * reference lines whose arithmetic it replaces.
+ *
+ * Conventions
+ *  - plain C: pointers and sizes only.  Every buffer is CALLER-OWNED DEVICE memory unless marked
+ *    HOST; the library never allocates, frees or retains caller memory.
+ *  - every call is asynchronous on `stream` (a cudaStream_t / CUstream passed as void*, NULL = the
+ *    legacy default stream) and runs on the device that owns `tables[0]` / `preds`.
+ *  - return value: MB200_OK or an MB200_ERR_* code; never throws, never exits.  Data-dependent
+ *    problems found by a kernel (bad row id, impression longer than max_cand) are OR-ed into the
+ *    caller's device `flags` word (MB200_FLAG_*), to be read after the stream is synchronised.
+ *  - re-entrant; one call per (device, stream) at a time.  NCCL stays outside this ABI: the sums
+ *    and rank statistics it returns are plain additive integers / fp64 that the host layer
+ *    all-reduces (manner_b200/dist.py).
+ */
+#ifndef MANNER_B200_H
+#define MANNER_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define MB200_API __attribute__((visibility("default")))
+#else
+#define MB200_API
+#endif
+
+#define MB200_ABI_VERSION 1
+#define MB200_MAX_MODULES 4 /* CR-Module + up to 3 A-Modules (reference: CR, category, sentiment) */
+#define MB200_MAX_K 31      /* largest ranking cut-off k for nDCG / diversity / personalization */
+#define MB200_MAX_CLASSES 64
+
+/* ---- status codes ------------------------------------------------------------------------------ */
+#define MB200_OK 0
+#define MB200_ERR_INVALID_ARG 1 /* NULL / negative / inconsistent argument                      */
+#define MB200_ERR_UNSUPPORTED 2 /* shape outside what the kernels cover (dim, max_cand, ...)     */
+#define MB200_ERR_CUDA 3        /* a CUDA runtime call failed (mb200_last_cuda_error() has text) */
+#define MB200_ERR_WORKSPACE 4   /* workspace NULL or smaller than mb200_*_workspace_bytes()      */
+
+/* ---- bits of the device `flags` word -------------------------------------------------------------- */
+#define MB200_FLAG_BAD_ID 1          /* a hist/cand id was outside [0, n_news): the row was read as 0 */
+#define MB200_FLAG_CAND_OVERFLOW 2   /* an impression had more than max_cand candidates: skipped      */
+#define MB200_FLAG_OUTSIDE_UNIT 4    /* some materialised score was not in [0,1] (AUROC sigmoid rule) */
+#define MB200_FLAG_BAD_ASPECT 8      /* an aspect label was outside [0, num_classes)                  */
+
+/* ---- embedding table element types ----------------------------------------------------------------- */
+#define MB200_F32 0
+#define MB200_BF16 1 /* rows stored as bf16, all arithmetic in fp32 */
+
+/* ---- metric slots: layout of `sums` [n_weightings][MB200_NUM_METRICS] (fp64) and of
+ *      `per_impression` [n_weightings][n_impressions][MB200_NUM_METRICS] (fp32) ------------------------ */
+#define MB200_M_MRR 0        /* RetrievalMRR: first-hit reciprocal rank      (cr_module.py:82)          */
+#define MB200_M_NDCG_K0 1    /* RetrievalNormalizedDCG(k=k0)                 (cr_module.py:83)          */
+#define MB200_M_NDCG_K1 2    /* RetrievalNormalizedDCG(k=k1)                 (cr_module.py:84)          */
+#define MB200_M_GAUC 3       /* per-impression AUC, 0 where undefined        (new)           */
+#define MB200_M_GAUC_VALID 4 /* 1 where 0 < positives < candidates                                      */
+#define MB200_M_CATEG_DIV_K0 5  /* Diversity(num_categ_classes, k0)          (ensemble_module.py:56-61) */
+#define MB200_M_CATEG_DIV_K1 6
+#define MB200_M_SENT_DIV_K0 7   /* Diversity(num_sent_classes, k)            (ensemble_module.py:62-67) */
+#define MB200_M_SENT_DIV_K1 8
+#define MB200_M_CATEG_PERS_K0 9 /* Personalization(num_categ_classes, k)     (ensemble_module.py:68-73) */
+#define MB200_M_CATEG_PERS_K1 10
+#define MB200_M_SENT_PERS_K0 11 /* Personalization(num_sent_classes, k)      (ensemble_module.py:74-79) */
+#define MB200_M_SENT_PERS_K1 12
+#define MB200_NUM_METRICS 13
+
+/*
+ * One evaluation call = one pass over a set of impressions: what the reference spreads over
+ * CRModule.forward (cr_module.py:105-131), model_step's flattening (:173-182), test_step (:253-264)
+ * and on_test_epoch_end (:266-274); with zscore != 0 and weights, EnsembleModule.forward /
+ * _submodel_forward (ensemble_module.py:95-151) and its epoch end (:214-238).
+ *
+ *   for every impression i and every active module m:
+ *       u     = (sum of table_m[hist_ids[h]] over the impression's history) / H_i   cr_module.py:116-123
+ *       s^m_j = dot(u, table_m[cand_ids[j]])                                          click_predictors.py:12
+ *       zscore: s^m = (s^m - sum(s^m)/C_i) / std_unbiased(s^m)                        ensemble_module.py:137-149
+ *   for every weighting w:  s = w[0]*s^0 (+ w[m]*s^m for m >= 1 when w[m] != 0)       ensemble_module.py:97-107
+ *       rank by s descending, lower position first on ties; per-impression metrics; fp64 sums.
+ */
+typedef struct mb200_eval_desc {
+  uint32_t struct_size; /* = sizeof(mb200_eval_desc), checked */
+
+  /* embedding tables: n_modules row-major [n_news, dim] arrays of `dtype`, rows `row_stride` elements apart
+     (row_stride * element size must be a multiple of 16 bytes; table base 16-byte aligned) */
+  int32_t n_modules; /* 1..MB200_MAX_MODULES; module 0 is the CR-Module */
+  int32_t dtype;     /* MB200_F32 | MB200_BF16 */
+  int32_t dim;       /* embedding width D (text_embedding_dim, configs/model/cr_module.yaml:23) */
+  int32_t active_modules_mask; /* bit m set = module m is gathered; bit 0 must be set.  A module whose
+                                  weight is 0 in every weighting need not be active
+                                  (ensemble_module.py:37-46 does not even load it) */
+  int64_t n_news;
+  int64_t row_stride;
+  const void* tables[MB200_MAX_MODULES];
+
+  /* behaviours in CSR form (the reference's sorted segment-id vectors, mind_rec_dataset.py:114-132,171-174) */
+  int64_t n_impressions;
+  const int32_t* hist_offsets; /* [n_impressions + 1] */
+  const int32_t* hist_ids;     /* [hist_offsets[n_impressions]] table rows, already cut to the first 50 clicks */
+  const int32_t* cand_offsets; /* [n_impressions + 1] */
+  const int32_t* cand_ids;     /* [cand_offsets[n_impressions]] */
+  const uint8_t* labels;       /* [same] 0 / 1 */
+  int32_t max_cand;            /* upper bound on candidates per impression (sizes shared memory) */
+
+  /* ensemble */
+  int32_t zscore;         /* 0: raw dot products (CRModule); 1: per-impression z-score per module (EnsembleModule) */
+  int32_t n_weightings;   /* W >= 1 */
+  const float* weights;   /* [W, n_modules] fp32 DEVICE; NULL = a single weighting of all ones */
+
+  /* metric cut-offs (reference: 5 and 10), 1..MB200_MAX_K */
+  int32_t k0, k1;
+
+  /* optional aspect labels per news row for Diversity / Personalization; NULL skips slots 5..12 */
+  const int32_t* news_category;  /* [n_news] in [0, num_categ_classes) */
+  const int32_t* news_sentiment; /* [n_news] in [0, num_sent_classes)  */
+  int32_t num_categ_classes;     /* <= MB200_MAX_CLASSES (configs/model/ensemble_module.yaml:8 -> 19) */
+  int32_t num_sent_classes;      /* (ensemble_module.yaml:9 -> 4) */
+
+  /* outputs (any may be NULL except sums) */
+  float* scores;            /* [sum C] combined scores of weighting `scores_weighting` == the reference's flat `preds` */
+  int32_t scores_weighting;
+  int32_t reserved0;
+  float* per_impression;    /* [W, n_impressions, MB200_NUM_METRICS] */
+  double* sums;             /* [W, MB200_NUM_METRICS] sums over impressions (means = sums / n_impressions) */
+  int32_t* flags;           /* one int32, OR-ed with MB200_FLAG_*; the caller zeroes it */
+
+  void* workspace; /* >= mb200_eval_workspace_bytes(desc) bytes, 256-byte aligned */
+  size_t workspace_bytes;
+} mb200_eval_desc;
+
+MB200_API int mb200_abi_version(void);
+MB200_API const char* mb200_status_str(int status);
+MB200_API const char* mb200_last_cuda_error(void); /* HOST string, thread-local, "" if none */
+
+MB200_API size_t mb200_eval_workspace_bytes(const mb200_eval_desc* desc);
+MB200_API int mb200_score_eval(const mb200_eval_desc* desc, void* stream);
+
+/*
+ * Pooled AUROC exactly as torchmetrics 0.11.4 `AUROC(task="binary")` defines it (cr_module.py:81,273;
+ * SURVEY a12/A6): all candidate rows of the epoch in one pool, fp32 sigmoid applied iff some pred is
+ * outside [0,1], ties get half credit.  Evaluated as the exact rank statistic
+ *     auc = sum over positives (#neg below + #neg not above) / (2 * P * N)
+ * in integer arithmetic, in three stages so that a multi-GPU caller can exchange the (few) positive
+ * keys between stages 2 and 3:
+ *   1. build_keys : order-preserving uint32 key per row; negatives stay in place (positives become
+ *                   0xFFFFFFFF), positives are appended to `pos_keys`; counts[0] = P
+ *   2. sort_keys  : ascending radix sort of the n keys (the negatives end up in [0, n - P))
+ *   3. rank_sum   : for every positive key, lower_bound + upper_bound in the sorted negatives, added
+ *                   into *sum2 (uint64)
+ * sigmoid_mode: 0 never, 1 always, 2 = iff (*flags & MB200_FLAG_OUTSIDE_UNIT).
+ */
+MB200_API int mb200_auc_build_keys(const float* preds, const uint8_t* labels, int64_t n, int sigmoid_mode,
+                         const int32_t* flags, uint32_t* neg_keys, uint32_t* pos_keys,
+                         int64_t* n_pos /* device, zeroed by this call */, void* stream);
+MB200_API size_t mb200_auc_sort_workspace_bytes(int64_t n);
+MB200_API int mb200_auc_sort_keys(const uint32_t* keys_in, uint32_t* keys_out, int64_t n, void* workspace,
+                        size_t workspace_bytes, void* stream);
+MB200_API int mb200_auc_rank_sum(const uint32_t* sorted_keys, int64_t n_sorted, const int64_t* n_pos_local /* device: sorted negatives = n_sorted - *n_pos_local */,
+                       const uint32_t* pos_keys, int64_t pos_capacity, const int64_t* n_pos /* device: entries of pos_keys to use */,
+                       uint64_t* sum2 /* device, accumulated (caller zeroes) */, void* stream);
+
+/* Single-GPU convenience: the three stages + the division.  out (device, 4 doubles) = {auc, P, N, sum2}.
+ * auc = 0 when P == 0 or N == 0 (torchmetrics returns 0 with a warning). */
+MB200_API size_t mb200_pooled_auc_workspace_bytes(int64_t n);
+MB200_API int mb200_pooled_auc(const float* preds, const uint8_t* labels, int64_t n, int sigmoid_mode,
+                     const int32_t* flags, void* workspace, size_t workspace_bytes, double* out, void* stream);
+
+/* ---- introspection ------------------------------------------------------------------------------- */
+/* 1 / log2(rank + 1) as fp32, rank = 1..MB200_MAX_K: the discount table the kernels use for
+ * torchmetrics' `_dcg` (HOST function; lets CPU tests pin it against torch.log2). */
+MB200_API float mb200_dcg_discount(int rank);
+/* number of kernels this library has launched in this process (own kernels; CUB sort passes counted
+ * separately by mb200_library_launch_count). */
+MB200_API int64_t mb200_launch_count(void);
+MB200_API int64_t mb200_library_launch_count(void);
+/* tuning knobs (key: 0 = chunks per warp, 1 = row-load cache policy, 2 = CTAs per SM, 3 = time the fused
+ * kernel with CUDA events); returns the previous value */
+MB200_API int mb200_set_tuning(int key, int value);
+
+/* duration in ms of the most recent fused score/eval kernel launched while tuning key 3 was on
+ * (synchronises on its end event; -1 if none).  This is the kernel bench.py reports a roofline for. */
+MB200_API float mb200_last_score_kernel_ms(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MANNER_B200_H */

@@ -1,0 +1,128 @@
+"""ctypes binding of libmanner_b200.so (include/manner_b200.h).  No torch types cross this boundary:
+raw device pointers, sizes and the stream handle only.
+
+There is NO CPU fallback: if the shared library is missing, every compute entry point raises.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import POINTER, Structure, c_char_p, c_double, c_float, c_int, c_int32, c_int64, c_size_t, c_uint32, c_uint64, c_void_p
+from typing import Optional
+
+LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libmanner_b200.so")
+
+ABI_VERSION = 1
+MAX_MODULES = 4
+MAX_K = 31
+MAX_CLASSES = 64
+NUM_METRICS = 13
+
+OK, ERR_INVALID_ARG, ERR_UNSUPPORTED, ERR_CUDA, ERR_WORKSPACE = 0, 1, 2, 3, 4
+FLAG_BAD_ID, FLAG_CAND_OVERFLOW, FLAG_OUTSIDE_UNIT, FLAG_BAD_ASPECT = 1, 2, 4, 8
+F32, BF16 = 0, 1
+
+# metric slots
+M_MRR, M_NDCG_K0, M_NDCG_K1, M_GAUC, M_GAUC_VALID = 0, 1, 2, 3, 4
+M_CATEG_DIV_K0, M_CATEG_DIV_K1, M_SENT_DIV_K0, M_SENT_DIV_K1 = 5, 6, 7, 8
+M_CATEG_PERS_K0, M_CATEG_PERS_K1, M_SENT_PERS_K0, M_SENT_PERS_K1 = 9, 10, 11, 12
+
+
+class EvalDesc(Structure):
+    """mb200_eval_desc, field for field."""
+
+    _fields_ = [
+        ("struct_size", c_uint32),
+        ("n_modules", c_int32),
+        ("dtype", c_int32),
+        ("dim", c_int32),
+        ("active_modules_mask", c_int32),
+        ("n_news", c_int64),
+        ("row_stride", c_int64),
+        ("tables", c_void_p * MAX_MODULES),
+        ("n_impressions", c_int64),
+        ("hist_offsets", c_void_p),
+        ("hist_ids", c_void_p),
+        ("cand_offsets", c_void_p),
+        ("cand_ids", c_void_p),
+        ("labels", c_void_p),
+        ("max_cand", c_int32),
+        ("zscore", c_int32),
+        ("n_weightings", c_int32),
+        ("weights", c_void_p),
+        ("k0", c_int32),
+        ("k1", c_int32),
+        ("news_category", c_void_p),
+        ("news_sentiment", c_void_p),
+        ("num_categ_classes", c_int32),
+        ("num_sent_classes", c_int32),
+        ("scores", c_void_p),
+        ("scores_weighting", c_int32),
+        ("reserved0", c_int32),
+        ("per_impression", c_void_p),
+        ("sums", c_void_p),
+        ("flags", c_void_p),
+        ("workspace", c_void_p),
+        ("workspace_bytes", c_size_t),
+    ]
+
+
+# every symbol include/manner_b200.h declares: (restype, argtypes)
+SIGNATURES = {
+    "mb200_abi_version": (c_int, []),
+    "mb200_status_str": (c_char_p, [c_int]),
+    "mb200_last_cuda_error": (c_char_p, []),
+    "mb200_eval_workspace_bytes": (c_size_t, [POINTER(EvalDesc)]),
+    "mb200_score_eval": (c_int, [POINTER(EvalDesc), c_void_p]),
+    "mb200_auc_build_keys": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "mb200_auc_sort_workspace_bytes": (c_size_t, [c_int64]),
+    "mb200_auc_sort_keys": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_size_t, c_void_p]),
+    "mb200_auc_rank_sum": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
+    "mb200_pooled_auc_workspace_bytes": (c_size_t, [c_int64]),
+    "mb200_pooled_auc": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p, c_size_t, c_void_p, c_void_p]),
+    "mb200_dcg_discount": (c_float, [c_int]),
+    "mb200_launch_count": (c_int64, []),
+    "mb200_library_launch_count": (c_int64, []),
+    "mb200_set_tuning": (c_int, [c_int, c_int]),
+    "mb200_last_score_kernel_ms": (c_float, []),
+}
+
+_lib: Optional[ctypes.CDLL] = None
+
+
+class NativeLibraryMissing(RuntimeError):
+    pass
+
+
+def lib() -> ctypes.CDLL:
+    """The loaded shared library.  Raises (loudly) when it has not been built -- there is no fallback."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise NativeLibraryMissing(
+                f"{LIB_PATH} not found: build it with `python -m manner_b200.build` (needs nvcc). "
+                "manner_b200 has no CPU or PyTorch fallback for its CUDA path."
+            )
+        handle = ctypes.CDLL(LIB_PATH)
+        for name, (restype, argtypes) in SIGNATURES.items():
+            if not hasattr(handle, name):
+                raise NativeLibraryMissing(f"{LIB_PATH} does not export {name}; rebuild it")
+            fn = getattr(handle, name)
+            fn.restype, fn.argtypes = restype, argtypes
+        if handle.mb200_abi_version() != ABI_VERSION:
+            raise NativeLibraryMissing(f"{LIB_PATH} has ABI {handle.mb200_abi_version()}, python side expects {ABI_VERSION}; rebuild")
+        _lib = handle
+    return _lib
+
+
+class NativeError(RuntimeError):
+    pass
+
+
+def check(status: int, what: str) -> None:
+    if status != OK:
+        l = lib()
+        detail = l.mb200_status_str(status).decode()
+        if status == ERR_CUDA:
+            detail += ": " + l.mb200_last_cuda_error().decode()
+        raise NativeError(f"{what} failed: {detail} (status {status})")

@@ -1,0 +1,142 @@
+// extern "C" surface of libmanner_b200.so (include/manner_b200.h).  Thin: argument checks, device
+// selection, launch bookkeeping.  No torch types, no allocation of caller-visible memory.
+
+#include <atomic>
+#include <cstdio>
+#include <cstring>
+
+#include "common.cuh"
+
+namespace mb200 {
+
+static thread_local char g_cuda_err[256] = "";
+static std::atomic<long long> g_launches{0};
+static std::atomic<long long> g_library_launches{0};
+
+Tuning& tuning() {
+  static Tuning t;
+  return t;
+}
+
+int cuda_status(cudaError_t e, const char* what) {
+  if (e == cudaSuccess) return MB200_OK;
+  snprintf(g_cuda_err, sizeof(g_cuda_err), "%s: %s", what, cudaGetErrorString(e));
+  (void)cudaGetLastError();  // clear the sticky-free error so the next call starts clean
+  return MB200_ERR_CUDA;
+}
+
+void note_launch(int n) { g_launches += n; }
+void note_library_launch(int n) { g_library_launches += n; }
+
+int use_device_of(const void* ptr, int* device_out) {
+  cudaPointerAttributes attr;
+  int st = cuda_status(cudaPointerGetAttributes(&attr, ptr), "cudaPointerGetAttributes");
+  if (st != MB200_OK) return st;
+  if (attr.type != cudaMemoryTypeDevice && attr.type != cudaMemoryTypeManaged) {
+    snprintf(g_cuda_err, sizeof(g_cuda_err), "pointer %p is not device memory", ptr);
+    return MB200_ERR_INVALID_ARG;
+  }
+  st = cuda_status(cudaSetDevice(attr.device), "cudaSetDevice");
+  if (st != MB200_OK) return st;
+  if (device_out) *device_out = attr.device;
+  return MB200_OK;
+}
+
+// implemented in score_eval.cu / pooled_auc.cu
+float host_dcg_discount(int rank);
+float last_score_kernel_ms();
+size_t eval_workspace_bytes(const mb200_eval_desc* d);
+int score_eval(const mb200_eval_desc* d, cudaStream_t stream);
+int auc_build_keys(const float*, const uint8_t*, long long, int, const int32_t*, uint32_t*, uint32_t*, long long*, cudaStream_t);
+size_t auc_sort_workspace_bytes(long long n);
+int auc_sort_keys(const uint32_t*, uint32_t*, long long, void*, size_t, cudaStream_t);
+int auc_rank_sum(const uint32_t*, long long, const long long*, const uint32_t*, long long, const long long*, unsigned long long*, cudaStream_t);
+size_t pooled_auc_workspace_bytes(long long n);
+int pooled_auc(const float*, const uint8_t*, long long, int, const int32_t*, void*, size_t, double*, cudaStream_t);
+
+}  // namespace mb200
+
+using namespace mb200;
+
+extern "C" {
+
+int mb200_abi_version(void) { return MB200_ABI_VERSION; }
+
+const char* mb200_status_str(int status) {
+  switch (status) {
+    case MB200_OK: return "ok";
+    case MB200_ERR_INVALID_ARG: return "invalid argument";
+    case MB200_ERR_UNSUPPORTED: return "unsupported shape (dim / row stride / max_cand outside what the kernels cover)";
+    case MB200_ERR_CUDA: return "CUDA runtime error";
+    case MB200_ERR_WORKSPACE: return "workspace missing, misaligned or too small";
+  }
+  return "unknown status";
+}
+
+const char* mb200_last_cuda_error(void) { return g_cuda_err; }
+
+size_t mb200_eval_workspace_bytes(const mb200_eval_desc* desc) { return eval_workspace_bytes(desc); }
+
+int mb200_score_eval(const mb200_eval_desc* desc, void* stream) { return score_eval(desc, static_cast<cudaStream_t>(stream)); }
+
+int mb200_auc_build_keys(const float* preds, const uint8_t* labels, int64_t n, int sigmoid_mode, const int32_t* flags, uint32_t* neg_keys,
+                         uint32_t* pos_keys, int64_t* n_pos, void* stream) {
+  if (n < 0 || n_pos == nullptr || (n > 0 && (!preds || !labels || !neg_keys || !pos_keys))) return MB200_ERR_INVALID_ARG;
+  if (sigmoid_mode < 0 || sigmoid_mode > 2 || (sigmoid_mode == 2 && flags == nullptr)) return MB200_ERR_INVALID_ARG;
+  int st = use_device_of(n_pos, nullptr);
+  if (st != MB200_OK) return st;
+  return auc_build_keys(preds, labels, n, sigmoid_mode, flags, neg_keys, pos_keys, reinterpret_cast<long long*>(n_pos),
+                        static_cast<cudaStream_t>(stream));
+}
+
+size_t mb200_auc_sort_workspace_bytes(int64_t n) { return n < 0 ? 0 : auc_sort_workspace_bytes(n); }
+
+int mb200_auc_sort_keys(const uint32_t* keys_in, uint32_t* keys_out, int64_t n, void* workspace, size_t workspace_bytes, void* stream) {
+  if (n < 0 || (n > 0 && (!keys_in || !keys_out))) return MB200_ERR_INVALID_ARG;
+  if (n == 0) return MB200_OK;
+  int st = use_device_of(keys_in, nullptr);
+  if (st != MB200_OK) return st;
+  return auc_sort_keys(keys_in, keys_out, n, workspace, workspace_bytes, static_cast<cudaStream_t>(stream));
+}
+
+int mb200_auc_rank_sum(const uint32_t* sorted_keys, int64_t n_sorted, const int64_t* n_pos_local, const uint32_t* pos_keys,
+                       int64_t pos_capacity, const int64_t* n_pos, uint64_t* sum2, void* stream) {
+  if (n_sorted < 0 || pos_capacity < 0 || !n_pos_local || !n_pos || !sum2) return MB200_ERR_INVALID_ARG;
+  if (pos_capacity > 0 && !pos_keys) return MB200_ERR_INVALID_ARG;
+  if (n_sorted > 0 && !sorted_keys) return MB200_ERR_INVALID_ARG;
+  int st = use_device_of(sum2, nullptr);
+  if (st != MB200_OK) return st;
+  return auc_rank_sum(sorted_keys, n_sorted, reinterpret_cast<const long long*>(n_pos_local), pos_keys, pos_capacity,
+                      reinterpret_cast<const long long*>(n_pos), reinterpret_cast<unsigned long long*>(sum2),
+                      static_cast<cudaStream_t>(stream));
+}
+
+size_t mb200_pooled_auc_workspace_bytes(int64_t n) { return n < 0 ? 0 : pooled_auc_workspace_bytes(n); }
+
+int mb200_pooled_auc(const float* preds, const uint8_t* labels, int64_t n, int sigmoid_mode, const int32_t* flags, void* workspace,
+                     size_t workspace_bytes, double* out, void* stream) {
+  if (n < 0 || out == nullptr || (n > 0 && (!preds || !labels))) return MB200_ERR_INVALID_ARG;
+  if (sigmoid_mode < 0 || sigmoid_mode > 2 || (sigmoid_mode == 2 && flags == nullptr)) return MB200_ERR_INVALID_ARG;
+  int st = use_device_of(out, nullptr);
+  if (st != MB200_OK) return st;
+  return pooled_auc(preds, labels, n, sigmoid_mode, flags, workspace, workspace_bytes, out, static_cast<cudaStream_t>(stream));
+}
+
+float mb200_dcg_discount(int rank) { return host_dcg_discount(rank); }
+int64_t mb200_launch_count(void) { return g_launches.load(); }
+int64_t mb200_library_launch_count(void) { return g_library_launches.load(); }
+
+float mb200_last_score_kernel_ms(void) { return last_score_kernel_ms(); }
+
+int mb200_set_tuning(int key, int value) {
+  int prev = -1;
+  switch (key) {
+    case 0: prev = tuning().chunks_per_warp, tuning().chunks_per_warp = value; break;
+    case 1: prev = tuning().variant, tuning().variant = value; break;
+    case 2: prev = tuning().ctas_per_sm, tuning().ctas_per_sm = value; break;
+    case 3: prev = tuning().time_kernel, tuning().time_kernel = value; break;
+  }
+  return prev;
+}
+
+}  // extern "C"

@@ -1,0 +1,806 @@
+// Fused gather -> late-fusion mean pool -> dot-product scores -> z-score -> aspect-weighted ensemble ->
+// per-impression ranking metrics, one warp per impression, for sm_100a.
+//
+// Replaces (reference = andreeaiana/manner, file:line under /root/reference/manner):
+//   news_encoder(x_hist / x_cand) on cached embeddings ........ models/cr_module.py:107,113 (row gather)
+//   to_dense_batch x2, hist_size loop, sum(dim=1) / hist_size .. models/cr_module.py:108-123
+//   DotProduct.forward (bmm) ................................... models/components/click_predictors.py:9-12
+//   z-score + `scores += w * z` ................................ models/ensemble_module.py:95-109,137-149
+//   mask-flatten loops, epoch-end cat / indexes ................ models/cr_module.py:173-182,266-271
+//   RetrievalMRR / RetrievalNormalizedDCG(k) per impression ..... models/cr_module.py:82-84 (torchmetrics 0.11.4)
+//   Diversity / Personalization per impression .................. metrics/functional.py:8-70, metrics/base.py:92-129
+//
+// Data layout: tables row-major [n_news, dim] (fp32 or bf16) resident in HBM; behaviours as CSR
+// (int32 offsets / ids, uint8 labels).  Nothing is padded.  A warp owns one impression at a time:
+// each lane keeps dim/32 elements of the user vector in registers, rows are fetched as coalesced
+// 16-byte vectors (lane l reads vectors l, l+32, ...), R rows in flight per warp, dot products are
+// finished with warp shuffles, scores of the impression live in shared memory for ranking.
+// HBM-bound: 0.5 flop per byte -- tensor cores are deliberately not used here.
+
+#include <float.h>
+#include <math.h>
+
+#include "common.cuh"
+
+namespace mb200 {
+
+__constant__ float c_inv_disc[32] = {MB200_INV_DISC_TABLE};
+static const float h_inv_disc[32] = {MB200_INV_DISC_TABLE};
+float host_dcg_discount(int rank) { return (rank >= 1 && rank <= MB200_MAX_K) ? h_inv_disc[rank - 1] : 0.0f; }
+
+struct EvalParams {
+  const void* tables[MB200_MAX_MODULES];
+  const int32_t* hist_offsets;
+  const int32_t* hist_ids;
+  const int32_t* cand_offsets;
+  const int32_t* cand_ids;
+  const uint8_t* labels;
+  const float* weights;
+  const int32_t* news_category;
+  const int32_t* news_sentiment;
+  float* scores;
+  float* per_impr;
+  double* partials;  // [total_warps][W][MB200_NUM_METRICS]
+  const int32_t* bounds;  // [n_chunks + 1] impression boundaries of the work-balanced chunks
+  int32_t* flags;
+  long long n_news;
+  long long row_stride;  // elements
+  int n_impr;
+  int n_modules;
+  int active_mask;
+  int vec_per_row;  // 16-byte vectors per row
+  int zscore;
+  int n_weightings;
+  int scores_weighting;
+  int k0, k1;
+  int cpad;           // max_cand rounded up to 32
+  int max_cand;
+  int n_chunks;
+  int num_categ, num_sent;
+  int smem_per_warp;  // bytes
+  int acc_bytes;      // bytes of the per-warp fp64 accumulators (16-byte multiple)
+};
+
+template <typename T>
+struct Elem;
+template <>
+struct Elem<float> {
+  static constexpr int E = 4;
+  static __device__ __forceinline__ void unpack(const uint4& r, float (&f)[4]) {
+    f[0] = __uint_as_float(r.x), f[1] = __uint_as_float(r.y), f[2] = __uint_as_float(r.z), f[3] = __uint_as_float(r.w);
+  }
+};
+template <>
+struct Elem<__nv_bfloat16> {
+  static constexpr int E = 8;
+  static __device__ __forceinline__ void unpack(const uint4& r, float (&f)[8]) {
+    f[0] = __uint_as_float(r.x << 16), f[1] = __uint_as_float(r.x & 0xffff0000u);
+    f[2] = __uint_as_float(r.y << 16), f[3] = __uint_as_float(r.y & 0xffff0000u);
+    f[4] = __uint_as_float(r.z << 16), f[5] = __uint_as_float(r.z & 0xffff0000u);
+    f[6] = __uint_as_float(r.w << 16), f[7] = __uint_as_float(r.w & 0xffff0000u);
+  }
+};
+
+template <int POLICY>
+__device__ __forceinline__ uint4 load_row_vec(const uint4* p) {
+  if constexpr (POLICY == 1) {
+    uint4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+                 : "l"(p));
+    return r;
+  } else {
+    return __ldg(p);
+  }
+}
+
+// torch sort semantics: NaN is the largest value; equal NaNs tie.
+__device__ __forceinline__ bool ranks_before(float a, float b) { return (a > b) || (a != a && b == b); }
+__device__ __forceinline__ bool ranks_equal(float a, float b) { return (a == b) || (a != a && b != b); }
+
+// Sum of x_j = (bit j of mask) ? 1/log2(j+2) : 0 over j < L in the fp32 summation order of ATen's
+// CPU `sum` over a contiguous vector (SumKernel.cpp: 8-lane vectors, scalar tail first, then the
+// lanes in order; L < 8 takes the 4-way ILP scalar path) -- what torchmetrics' `_dcg` evaluates.
+__device__ __forceinline__ float dcg_term(unsigned mask, int j) { return ((mask >> j) & 1u) ? c_inv_disc[j] : 0.0f; }
+__device__ float dcg_sum_aten_order(unsigned mask, int L) {
+  if (L < 8) {
+    float p0 = 0.f, p1 = 0.f, p2 = 0.f, p3 = 0.f;
+    const int r = L >> 2;
+    if (r) p0 = dcg_term(mask, 0), p1 = dcg_term(mask, 1), p2 = dcg_term(mask, 2), p3 = dcg_term(mask, 3);
+    for (int j = 4 * r; j < L; ++j) p0 = __fadd_rn(p0, dcg_term(mask, j));
+    p0 = __fadd_rn(p0, p1), p0 = __fadd_rn(p0, p2), p0 = __fadd_rn(p0, p3);
+    return p0;
+  }
+  const int vs = L >> 3;  // 1..3 because L <= MB200_MAX_K
+  float fin = 0.f;
+  for (int j = 8 * vs; j < L; ++j) fin = __fadd_rn(fin, dcg_term(mask, j));
+  for (int l8 = 0; l8 < 8; ++l8) {
+    float a = dcg_term(mask, l8);
+    for (int v = 1; v < vs; ++v) a = __fadd_rn(a, dcg_term(mask, 8 * v + l8));
+    fin = __fadd_rn(fin, a);
+  }
+  return fin;
+}
+
+__device__ __forceinline__ float ndcg_at(unsigned hit_mask, int n_pos, int n_cand, int k) {
+  const int L = min(k, n_cand);
+  const int ideal_hits = min(n_pos, L);
+  if (ideal_hits == 0) return 0.f;
+  const float idcg = dcg_sum_aten_order((ideal_hits >= 32) ? 0xffffffffu : ((1u << ideal_hits) - 1u), L);
+  const unsigned keep = (L >= 32) ? 0xffffffffu : ((1u << L) - 1u);
+  const float dcg = dcg_sum_aten_order(hit_mask & keep, L);
+  return __fdiv_rn(dcg, idcg);
+}
+
+// ensemble_module.py:137-149.  mean = fp32 row sum / C; std = unbiased, accumulated in fp64 and
+// rounded to fp32 (ATen's CPU std of a float tensor accumulates in double).  C == 1 gives NaN.
+__device__ void zscore_inplace(float* s, int C, int lane) {
+  float part = 0.f;
+  double dpart = 0.0;
+  for (int j = lane; j < C; j += 32) {
+    const float v = s[j];
+    part += v;
+    dpart += (double)v;
+  }
+  const float mean = __fdiv_rn(warp_sum(part), (float)C);
+  const double dmean = warp_sum(dpart) / (double)C;
+  double q = 0.0;
+  for (int j = lane; j < C; j += 32) {
+    const double d = (double)s[j] - dmean;
+    q += d * d;
+  }
+  const float sd = (float)sqrt(warp_sum(q) / (double)(C - 1));
+  for (int j = lane; j < C; j += 32) s[j] = __fdiv_rn(__fsub_rn(s[j], mean), sd);
+}
+
+// Entropy-based Diversity@k of one aspect (metrics/functional.py:8-28): lanes own classes.
+__device__ float diversity_value(const uint8_t* top, int kk, int num_classes, int lane) {
+  float prob[2];
+  float total = 0.f;
+#pragma unroll
+  for (int t = 0; t < 2; ++t) {
+    const int c = lane + 32 * t;
+    int cnt = 0;
+    if (c < num_classes)
+      for (int r = 0; r < kk; ++r) cnt += (top[r] == c);
+    prob[t] = __fdiv_rn((float)cnt, (float)num_classes);
+    total += prob[t];
+  }
+  total = warp_sum(total);
+  float ent = 0.f;
+#pragma unroll
+  for (int t = 0; t < 2; ++t) {
+    const int c = lane + 32 * t;
+    if (c < num_classes) {
+      const float p = __fdiv_rn(prob[t], total);
+      const float pc = fminf(fmaxf(p, FLT_EPSILON), 1.0f - FLT_EPSILON);
+      ent += __fmul_rn(logf(pc), p);
+    }
+  }
+  ent = -warp_sum(ent);
+  return __fdiv_rn(ent, logf((float)num_classes));
+}
+
+// Generalised Jaccard of top-k candidate aspect counts vs history aspect counts (functional.py:31-70).
+__device__ float personalization_value(const uint8_t* top, int kk, const int* hist_count, int num_classes, int lane) {
+  int mn = 0, mx = 0;
+#pragma unroll
+  for (int t = 0; t < 2; ++t) {
+    const int c = lane + 32 * t;
+    if (c < num_classes) {
+      int cnt = 0;
+      for (int r = 0; r < kk; ++r) cnt += (top[r] == c);
+      const int hc = hist_count[c];
+      mn += min(cnt, hc);
+      mx += max(cnt, hc);
+    }
+  }
+  mn = __reduce_add_sync(kFull, mn);
+  mx = __reduce_add_sync(kFull, mx);
+  return __fdiv_rn((float)mn, (float)mx);
+}
+
+// One module of one impression: gather the history rows and mean-pool them (cr_module.py:107-123),
+// then gather the candidate rows and dot them with the pooled user vector (click_predictors.py:12).
+// The loops are branch-free on purpose: a batch always loads R rows (slots past the end re-read the
+// batch's first row and are masked out), so the R*NV 16-byte loads stay in registers and are all in
+// flight before the first use.  Returns MB200_FLAG_* bits.
+template <typename T, int NV, int R, bool EXACT, int POLICY>
+__device__ __forceinline__ int gather_pool_score(const T* __restrict__ table, long long row_stride, int vec_per_row, long long n_news,
+                                                 const int32_t* __restrict__ hist_ids, int H, const int32_t* __restrict__ cand_ids, int C,
+                                                 float* __restrict__ s_out) {
+  constexpr int E = Elem<T>::E;
+  const int lane = threadIdx.x & 31;
+  int flags = 0;
+  // per-lane vector slots: slot v covers 16-byte vector lane + 32 v of the row; for widths that do not
+  // fill the last slot the address is clamped and the slot's contribution multiplied by 0
+  int voff[NV];
+  float vmask[NV];
+#pragma unroll
+  for (int v = 0; v < NV; ++v) {
+    const bool ok = EXACT || (lane + 32 * v < vec_per_row);
+    voff[v] = ok ? lane + 32 * v : 0;
+    vmask[v] = ok ? 1.0f : 0.0f;
+  }
+
+  float u[NV * E];
+#pragma unroll
+  for (int t = 0; t < NV * E; ++t) u[t] = 0.f;
+
+#pragma unroll 1
+  for (int b0 = 0; b0 < H; b0 += 32) {
+    const int cnt = min(32, H - b0);
+    int my_id = hist_ids[b0 + ((lane < cnt) ? lane : 0)];
+    if ((unsigned long long)(long long)my_id >= (unsigned long long)n_news) my_id = 0, flags |= MB200_FLAG_BAD_ID;
+#pragma unroll 1
+    for (int r0 = 0; r0 < cnt; r0 += R) {
+      uint4 buf[R][NV];
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        const int src = (r0 + r < cnt) ? (r0 + r) : 0;
+        const int id = __shfl_sync(kFull, my_id, src);
+        const uint4* row = reinterpret_cast<const uint4*>(table + (long long)id * row_stride);
+#pragma unroll
+        for (int v = 0; v < NV; ++v) buf[r][v] = load_row_vec<POLICY>(row + (EXACT ? lane + 32 * v : voff[v]));
+      }
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        const float keep = (r0 + r < cnt) ? 1.0f : 0.0f;
+#pragma unroll
+        for (int v = 0; v < NV; ++v) {
+          float f[E];
+          Elem<T>::unpack(buf[r][v], f);
+          const float k = EXACT ? keep : keep * vmask[v];
+#pragma unroll
+          for (int e = 0; e < E; ++e) u[v * E + e] = fmaf(f[e], k, u[v * E + e]);  // k is 1 or 0: exact add or no-op
+        }
+      }
+    }
+  }
+  // true division by the history length, as torch.div(sum, hist_size) (cr_module.py:121-123)
+  const float hf = (float)H;
+#pragma unroll
+  for (int t = 0; t < NV * E; ++t) u[t] = __fdiv_rn(u[t], hf);
+  if (!EXACT) {
+#pragma unroll
+    for (int v = 0; v < NV; ++v)
+#pragma unroll
+      for (int e = 0; e < E; ++e) u[v * E + e] = (vmask[v] != 0.0f) ? u[v * E + e] : 0.0f;
+  }
+
+#pragma unroll 1
+  for (int b0 = 0; b0 < C; b0 += 32) {
+    const int cnt = min(32, C - b0);
+    int my_id = cand_ids[b0 + ((lane < cnt) ? lane : 0)];
+    if ((unsigned long long)(long long)my_id >= (unsigned long long)n_news) my_id = 0, flags |= MB200_FLAG_BAD_ID;
+#pragma unroll 1
+    for (int r0 = 0; r0 < cnt; r0 += R) {
+      uint4 buf[R][NV];
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        const int src = (r0 + r < cnt) ? (r0 + r) : 0;
+        const int id = __shfl_sync(kFull, my_id, src);
+        const uint4* row = reinterpret_cast<const uint4*>(table + (long long)id * row_stride);
+#pragma unroll
+        for (int v = 0; v < NV; ++v) buf[r][v] = load_row_vec<POLICY>(row + (EXACT ? lane + 32 * v : voff[v]));
+      }
+      float mine = 0.f;
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        float part = 0.f;
+#pragma unroll
+        for (int v = 0; v < NV; ++v) {
+          float f[E];
+          Elem<T>::unpack(buf[r][v], f);
+#pragma unroll
+          for (int e = 0; e < E; ++e) part = fmaf(u[v * E + e], f[e], part);  // u is 0 in masked slots
+        }
+        part = warp_sum(part);
+        mine = (lane == r) ? part : mine;
+      }
+      if (lane < R && r0 + lane < cnt) s_out[b0 + r0 + lane] = mine;
+    }
+  }
+  return flags;
+}
+
+struct WarpSmem {
+  double* acc;        // [W][NUM_METRICS] fp64 sums of this warp
+  float* sc;          // [n_active][cpad] per-module scores of the current impression
+  float* comb;        // [cpad] combined scores of one weighting
+  uint8_t* lab;       // [cpad] labels
+  uint8_t* ccat;      // [cpad] candidate category labels
+  uint8_t* csent;     // [cpad] candidate sentiment labels
+  int* hist_cat;      // [MB200_MAX_CLASSES] history category histogram
+  int* hist_sent;     // [MB200_MAX_CLASSES]
+  uint8_t* top_cat;   // [32] category of the candidate at rank r
+  uint8_t* top_sent;  // [32]
+};
+
+// Everything after the per-module scores of impression i sit in shared memory: z-scores are already
+// applied; combine per weighting, rank, metrics, accumulate.  Not inlined (see gather_pool_score).
+__device__ __noinline__ int rank_and_metrics(const EvalParams& p, const WarpSmem& sm, int i, int h0, int H, int c0, int C) {
+  const int lane = threadIdx.x & 31;
+  const int W = p.n_weightings;
+  const int n_active = __popc(p.active_mask);
+  const int kmax = max(p.k0, p.k1);
+  const bool aspects = p.news_category != nullptr;
+  float* sc = sm.sc;
+  float* comb = sm.comb;
+  const uint8_t* lab = sm.lab;
+  int warp_flags = 0;
+
+  // ---- aspects of this impression (once, independent of the weighting) -----------------------------
+  bool categ_group_ok = false, sent_group_ok = false;
+  if (aspects) {
+    for (int t = lane; t < MB200_MAX_CLASSES; t += 32) sm.hist_cat[t] = 0, sm.hist_sent[t] = 0;
+    __syncwarp();
+    int cat_sum = 0, sent_sum = 0;
+    for (int j = lane; j < C; j += 32) {
+      int id = p.cand_ids[c0 + j];
+      if ((unsigned long long)(long long)id >= (unsigned long long)p.n_news) id = 0;
+      int a = p.news_category[id], b = p.news_sentiment[id];
+      if ((unsigned)a >= (unsigned)p.num_categ) a = 0, warp_flags |= MB200_FLAG_BAD_ASPECT;
+      if ((unsigned)b >= (unsigned)p.num_sent) b = 0, warp_flags |= MB200_FLAG_BAD_ASPECT;
+      sm.ccat[j] = (uint8_t)a, sm.csent[j] = (uint8_t)b;
+      cat_sum += a, sent_sum += b;
+    }
+    for (int h = lane; h < H; h += 32) {
+      int id = p.hist_ids[h0 + h];
+      if ((unsigned long long)(long long)id >= (unsigned long long)p.n_news) id = 0;
+      int a = p.news_category[id], b = p.news_sentiment[id];
+      if ((unsigned)a >= (unsigned)p.num_categ) a = 0, warp_flags |= MB200_FLAG_BAD_ASPECT;
+      if ((unsigned)b >= (unsigned)p.num_sent) b = 0, warp_flags |= MB200_FLAG_BAD_ASPECT;
+      atomicAdd(&sm.hist_cat[a], 1);
+      atomicAdd(&sm.hist_sent[b], 1);
+    }
+    // `if not mini_target.sum()` -> 0.0 (metrics/base.py:114-122 and torchmetrics RetrievalMetric.compute)
+    categ_group_ok = __reduce_add_sync(kFull, cat_sum) != 0;
+    sent_group_ok = __reduce_add_sync(kFull, sent_sum) != 0;
+    __syncwarp();
+  }
+
+  for (int w = 0; w < W; ++w) {
+    const float* scores_w = sc;
+    if (p.weights != nullptr || n_active > 1) {
+      // s = w0 * z0 ; s += w_m * z_m for m >= 1 when w_m != 0  (ensemble_module.py:97-107; separate
+      // multiply and add in fp32, no fused multiply-add, like the reference's two torch ops)
+      float wt[MB200_MAX_MODULES];
+#pragma unroll
+      for (int m = 0; m < MB200_MAX_MODULES; ++m)
+        wt[m] = (m < p.n_modules) ? (p.weights ? p.weights[(size_t)w * p.n_modules + m] : 1.0f) : 0.0f;
+      for (int j = lane; j < C; j += 32) {
+        float s = (wt[0] == 1.0f) ? sc[j] : __fmul_rn(wt[0], sc[j]);
+        int sl = 1;
+#pragma unroll
+        for (int m = 1; m < MB200_MAX_MODULES; ++m) {
+          if (m < p.n_modules && ((p.active_mask >> m) & 1)) {
+            if (wt[m] != 0.0f) s = __fadd_rn(s, __fmul_rn(wt[m], sc[(size_t)sl * p.cpad + j]));
+            ++sl;
+          }
+        }
+        comb[j] = s;
+      }
+      __syncwarp();
+      scores_w = comb;
+    }
+
+    if (p.scores != nullptr && w == p.scores_weighting) {
+      bool outside = false;
+      for (int j = lane; j < C; j += 32) {
+        const float s = scores_w[j];
+        p.scores[c0 + j] = s;
+        outside |= !(s >= 0.0f && s <= 1.0f);
+      }
+      if (outside) warp_flags |= MB200_FLAG_OUTSIDE_UNIT;
+    }
+
+    int n_pos = 0, min_rank = 0x7fffffff;
+    unsigned hit_mask = 0;
+    long long gauc2 = 0;  // sum over positives of 2 * (#neg below) + (#neg equal)
+
+    if (!aspects) {
+      // positives only: lanes split the comparison partners
+      for (int b0 = 0; b0 < C; b0 += 32) {
+        const int j = b0 + lane;
+        unsigned pm = __ballot_sync(kFull, j < C && lab[j] != 0);
+        n_pos += __popc(pm);
+        while (pm) {
+          const int pj = b0 + __ffs(pm) - 1;
+          pm &= pm - 1;
+          const float sp = scores_w[pj];
+          int before = 0, nlt = 0, neq = 0;
+          for (int k = lane; k < C; k += 32) {
+            const float sk = scores_w[k];
+            before += (ranks_before(sk, sp) || (k < pj && ranks_equal(sk, sp))) ? 1 : 0;
+            if (lab[k] == 0) nlt += (sk < sp) ? 1 : 0, neq += (sk == sp) ? 1 : 0;
+          }
+          const int rank = 1 + __reduce_add_sync(kFull, before);
+          gauc2 += 2ll * __reduce_add_sync(kFull, nlt) + __reduce_add_sync(kFull, neq);
+          min_rank = min(min_rank, rank);
+          if (rank <= 32) hit_mask |= 1u << (rank - 1);
+        }
+      }
+    } else {
+      // full ranking: lanes own candidates (needed for the identity of the top-k)
+      int my_min = 0x7fffffff, my_pos = 0;
+      unsigned my_hits = 0;
+      long long my_g2 = 0;
+      for (int j = lane; j < C; j += 32) {
+        const float sj = scores_w[j];
+        const bool pos = lab[j] != 0;
+        int before = 0, nlt = 0, neq = 0;
+        for (int k = 0; k < C; ++k) {
+          const float sk = scores_w[k];
+          before += (ranks_before(sk, sj) || (k < j && ranks_equal(sk, sj))) ? 1 : 0;
+          if (pos && lab[k] == 0) nlt += (sk < sj) ? 1 : 0, neq += (sk == sj) ? 1 : 0;
+        }
+        const int rank = 1 + before;
+        if (rank <= kmax) sm.top_cat[rank - 1] = sm.ccat[j], sm.top_sent[rank - 1] = sm.csent[j];
+        if (pos) {
+          ++my_pos;
+          my_min = min(my_min, rank);
+          if (rank <= 32) my_hits |= 1u << (rank - 1);
+          my_g2 += 2ll * nlt + neq;
+        }
+      }
+      n_pos = __reduce_add_sync(kFull, my_pos);
+      min_rank = __reduce_min_sync(kFull, my_min);
+      hit_mask = __reduce_or_sync(kFull, my_hits);
+      gauc2 = (long long)warp_sum((double)my_g2);
+      __syncwarp();
+    }
+
+    // lane t computes metric slot t (uniform inputs), so there is no per-lane register array
+    float mine = 0.f;
+    // RetrievalMRR: 1 / (first hit position + 1); impressions without a positive count as 0
+    if (lane == MB200_M_MRR) mine = n_pos ? __fdiv_rn(1.0f, (float)min_rank) : 0.f;
+    if (lane == MB200_M_NDCG_K0) mine = ndcg_at(hit_mask, n_pos, C, p.k0);
+    if (lane == MB200_M_NDCG_K1) mine = ndcg_at(hit_mask, n_pos, C, p.k1);
+    if (n_pos > 0 && n_pos < C) {
+      if (lane == MB200_M_GAUC) mine = (float)((double)gauc2 / (2.0 * (double)n_pos * (double)(C - n_pos)));
+      if (lane == MB200_M_GAUC_VALID) mine = 1.f;
+    }
+    if (aspects) {
+      const int kk0 = min(p.k0, C), kk1 = min(p.k1, C);
+      if (categ_group_ok) {
+        float v;
+        v = diversity_value(sm.top_cat, kk0, p.num_categ, lane); if (lane == MB200_M_CATEG_DIV_K0) mine = v;
+        v = diversity_value(sm.top_cat, kk1, p.num_categ, lane); if (lane == MB200_M_CATEG_DIV_K1) mine = v;
+        v = personalization_value(sm.top_cat, kk0, sm.hist_cat, p.num_categ, lane); if (lane == MB200_M_CATEG_PERS_K0) mine = v;
+        v = personalization_value(sm.top_cat, kk1, sm.hist_cat, p.num_categ, lane); if (lane == MB200_M_CATEG_PERS_K1) mine = v;
+      }
+      if (sent_group_ok) {
+        float v;
+        v = diversity_value(sm.top_sent, kk0, p.num_sent, lane); if (lane == MB200_M_SENT_DIV_K0) mine = v;
+        v = diversity_value(sm.top_sent, kk1, p.num_sent, lane); if (lane == MB200_M_SENT_DIV_K1) mine = v;
+        v = personalization_value(sm.top_sent, kk0, sm.hist_sent, p.num_sent, lane); if (lane == MB200_M_SENT_PERS_K0) mine = v;
+        v = personalization_value(sm.top_sent, kk1, sm.hist_sent, p.num_sent, lane); if (lane == MB200_M_SENT_PERS_K1) mine = v;
+      }
+      __syncwarp();
+    }
+    if (lane < MB200_NUM_METRICS) {
+      sm.acc[w * MB200_NUM_METRICS + lane] += (double)mine;
+      if (p.per_impr) p.per_impr[((size_t)w * p.n_impr + i) * MB200_NUM_METRICS + lane] = mine;
+    }
+    __syncwarp();
+  }
+  return warp_flags;
+}
+
+template <typename T, int NV, int R, bool EXACT, int POLICY>
+__global__ void __launch_bounds__(kThreads, 3) score_eval_kernel(const __grid_constant__ EvalParams p) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const int gw = blockIdx.x * kWarpsPerCta + warp;
+  const int total_warps = gridDim.x * kWarpsPerCta;
+  const int W = p.n_weightings;
+  const int n_active = __popc(p.active_mask);
+
+  unsigned char* base = smem + (size_t)warp * p.smem_per_warp;
+  WarpSmem sm;
+  sm.acc = reinterpret_cast<double*>(base);
+  sm.sc = reinterpret_cast<float*>(base + p.acc_bytes);
+  sm.comb = sm.sc + (size_t)n_active * p.cpad;
+  sm.lab = reinterpret_cast<uint8_t*>(sm.comb + p.cpad);
+  sm.ccat = sm.lab + p.cpad;
+  sm.csent = sm.ccat + p.cpad;
+  sm.hist_cat = reinterpret_cast<int*>(sm.csent + p.cpad);
+  sm.hist_sent = sm.hist_cat + MB200_MAX_CLASSES;
+  sm.top_cat = reinterpret_cast<uint8_t*>(sm.hist_sent + MB200_MAX_CLASSES);
+  sm.top_sent = sm.top_cat + 32;
+
+  for (int t = lane; t < W * MB200_NUM_METRICS; t += 32) sm.acc[t] = 0.0;
+  __syncwarp();
+
+  int warp_flags = 0;
+  for (int chunk = gw; chunk < p.n_chunks; chunk += total_warps) {
+    const int i_begin = p.bounds[chunk], i_end = p.bounds[chunk + 1];
+    for (int i = i_begin; i < i_end; ++i) {
+      const int h0 = p.hist_offsets[i], h1 = p.hist_offsets[i + 1];
+      const int c0 = p.cand_offsets[i], c1 = p.cand_offsets[i + 1];
+      const int H = h1 - h0, C = c1 - c0;
+      if (C > p.max_cand || C <= 0 || H < 0) {
+        warp_flags |= MB200_FLAG_CAND_OVERFLOW;
+        if (p.per_impr)
+          for (int t = lane; t < W * MB200_NUM_METRICS; t += 32)
+            p.per_impr[((size_t)(t / MB200_NUM_METRICS) * p.n_impr + i) * MB200_NUM_METRICS + t % MB200_NUM_METRICS] = 0.f;
+        continue;
+      }
+      __syncwarp();
+      for (int j = lane; j < C; j += 32) sm.lab[j] = p.labels[c0 + j];
+
+      int slot = 0;
+      for (int m = 0; m < p.n_modules; ++m) {
+        if (!((p.active_mask >> m) & 1)) continue;
+        float* s_m = sm.sc + (size_t)slot * p.cpad;
+        warp_flags |= gather_pool_score<T, NV, R, EXACT, POLICY>(reinterpret_cast<const T*>(p.tables[m]), p.row_stride, p.vec_per_row,
+                                                                 p.n_news, p.hist_ids + h0, H, p.cand_ids + c0, C, s_m);
+        __syncwarp();
+        if (p.zscore) {
+          zscore_inplace(s_m, C, lane);
+          __syncwarp();
+        }
+        ++slot;
+      }
+      warp_flags |= rank_and_metrics(p, sm, i, h0, H, c0, C);
+    }
+  }
+
+  __syncwarp();
+  for (int t = lane; t < W * MB200_NUM_METRICS; t += 32) p.partials[(size_t)gw * W * MB200_NUM_METRICS + t] = sm.acc[t];
+  warp_flags = __reduce_or_sync(kFull, warp_flags);
+  if (lane == 0 && warp_flags && p.flags) atomicOr(p.flags, warp_flags);
+}
+
+// bounds[c] = first impression whose work prefix reaches c/n_chunks of the total; work = rows gathered
+// (+ a per-impression constant), so chunks are balanced by sum(H_i + C_i), not by count.
+__global__ void partition_kernel(const int32_t* __restrict__ hist_offsets, const int32_t* __restrict__ cand_offsets, int n_impr,
+                                 int n_chunks, int32_t* __restrict__ bounds) {
+  constexpr long long kPerImpression = 4;
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c > n_chunks) return;
+  if (c == n_chunks) {
+    bounds[c] = n_impr;
+    return;
+  }
+  const long long total = (long long)hist_offsets[n_impr] + cand_offsets[n_impr] + kPerImpression * n_impr;
+  const long long target = total * c / n_chunks;  // total < 2^35, c < 2^16: no overflow
+  int lo = 0, hi = n_impr;  // smallest i with work(i) >= target
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    const long long wk = (long long)hist_offsets[mid] + cand_offsets[mid] + kPerImpression * mid;
+    if (wk >= target) hi = mid; else lo = mid + 1;
+  }
+  bounds[c] = lo;
+}
+
+// Deterministic second stage: sums[w][k] = sum over warps of partials, fixed order (strided per thread,
+// then a fixed shared-memory tree).  One block per weighting.
+__global__ void __launch_bounds__(256) reduce_partials_kernel(const double* __restrict__ partials, int total_warps, int W,
+                                                              double* __restrict__ sums) {
+  __shared__ double sh[256][MB200_NUM_METRICS];
+  const int w = blockIdx.x, t = threadIdx.x;
+  double a[MB200_NUM_METRICS];
+#pragma unroll
+  for (int k = 0; k < MB200_NUM_METRICS; ++k) a[k] = 0.0;
+  for (int g = t; g < total_warps; g += 256) {
+    const double* src = partials + ((size_t)g * W + w) * MB200_NUM_METRICS;
+#pragma unroll
+    for (int k = 0; k < MB200_NUM_METRICS; ++k) a[k] += src[k];
+  }
+#pragma unroll
+  for (int k = 0; k < MB200_NUM_METRICS; ++k) sh[t][k] = a[k];
+  __syncthreads();
+  for (int s = 128; s > 0; s >>= 1) {
+    if (t < s)
+#pragma unroll
+      for (int k = 0; k < MB200_NUM_METRICS; ++k) sh[t][k] += sh[t + s][k];
+    __syncthreads();
+  }
+  if (t < MB200_NUM_METRICS) sums[(size_t)w * MB200_NUM_METRICS + t] = sh[0][t];
+}
+
+// ------------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------------
+
+struct LaunchPlan {
+  int grid = 0;
+  int total_warps = 0;
+  int n_chunks = 0;
+  int cpad = 0;
+  int acc_bytes = 0;
+  int smem_per_warp = 0;
+  size_t smem_per_cta = 0;
+  size_t bounds_bytes = 0, partials_bytes = 0;
+};
+
+static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+static int make_plan(const mb200_eval_desc* d, int sm_count, LaunchPlan* plan) {
+  const int n_active = __builtin_popcount((unsigned)d->active_modules_mask);
+  plan->cpad = (int)align_up((size_t)(d->max_cand > 0 ? d->max_cand : 1), 32);
+  plan->acc_bytes = (int)align_up((size_t)d->n_weightings * MB200_NUM_METRICS * sizeof(double), 16);
+  size_t per_warp = (size_t)plan->acc_bytes + (size_t)(n_active + 1) * plan->cpad * sizeof(float) + 3 * (size_t)plan->cpad +
+                    2 * MB200_MAX_CLASSES * sizeof(int) + 64;
+  per_warp = align_up(per_warp, 16);
+  plan->smem_per_warp = (int)per_warp;
+  plan->smem_per_cta = per_warp * kWarpsPerCta;
+  if (plan->smem_per_cta > 227 * 1024) return MB200_ERR_UNSUPPORTED;
+  int ctas = tuning().ctas_per_sm;
+  if (ctas < 1) ctas = 1;
+  while (ctas > 1 && (plan->smem_per_cta + 1024) * ctas > 227 * 1024) --ctas;
+  plan->grid = sm_count * ctas;
+  plan->total_warps = plan->grid * kWarpsPerCta;
+  long long chunks = (long long)plan->total_warps * (tuning().chunks_per_warp > 0 ? tuning().chunks_per_warp : 1);
+  if (chunks > d->n_impressions) chunks = d->n_impressions;
+  if (chunks < 1) chunks = 1;
+  plan->n_chunks = (int)chunks;
+  plan->bounds_bytes = align_up((size_t)(plan->n_chunks + 1) * sizeof(int32_t), 256);
+  plan->partials_bytes = align_up((size_t)plan->total_warps * d->n_weightings * MB200_NUM_METRICS * sizeof(double), 256);
+  return MB200_OK;
+}
+
+static int validate(const mb200_eval_desc* d) {
+  if (d == nullptr || d->struct_size != sizeof(mb200_eval_desc)) return MB200_ERR_INVALID_ARG;
+  if (d->n_modules < 1 || d->n_modules > MB200_MAX_MODULES) return MB200_ERR_INVALID_ARG;
+  if (!(d->active_modules_mask & 1) || (d->active_modules_mask >> d->n_modules) != 0) return MB200_ERR_INVALID_ARG;
+  if (d->dtype != MB200_F32 && d->dtype != MB200_BF16) return MB200_ERR_INVALID_ARG;
+  if (d->n_news <= 0 || d->dim <= 0 || d->row_stride < d->dim) return MB200_ERR_INVALID_ARG;
+  if (d->n_impressions < 0 || d->n_impressions > 0x7ffffff0ll) return MB200_ERR_INVALID_ARG;
+  if (!d->hist_offsets || !d->cand_offsets || !d->sums) return MB200_ERR_INVALID_ARG;
+  if (d->n_impressions > 0 && (!d->hist_ids || !d->cand_ids || !d->labels)) return MB200_ERR_INVALID_ARG;
+  if (d->n_weightings < 1 || d->max_cand < 1) return MB200_ERR_INVALID_ARG;
+  if (d->k0 < 1 || d->k0 > MB200_MAX_K || d->k1 < 1 || d->k1 > MB200_MAX_K) return MB200_ERR_INVALID_ARG;
+  if (d->scores && (d->scores_weighting < 0 || d->scores_weighting >= d->n_weightings)) return MB200_ERR_INVALID_ARG;
+  if ((d->news_category == nullptr) != (d->news_sentiment == nullptr)) return MB200_ERR_INVALID_ARG;
+  if (d->news_category &&
+      (d->num_categ_classes < 1 || d->num_categ_classes > MB200_MAX_CLASSES || d->num_sent_classes < 1 || d->num_sent_classes > MB200_MAX_CLASSES))
+    return MB200_ERR_INVALID_ARG;
+  const int esz = d->dtype == MB200_F32 ? 4 : 2;
+  for (int m = 0; m < d->n_modules; ++m) {
+    if (((d->active_modules_mask >> m) & 1) && (d->tables[m] == nullptr || ((uintptr_t)d->tables[m] & 15))) return MB200_ERR_INVALID_ARG;
+  }
+  if ((d->row_stride * esz) % 16 != 0 || (d->dim * esz) % 16 != 0) return MB200_ERR_UNSUPPORTED;
+  const int vec_per_row = d->dim * esz / 16;
+  if (vec_per_row > 8 * 32) return MB200_ERR_UNSUPPORTED;  // dim <= 1024 (fp32) / 2048 (bf16)
+  return MB200_OK;
+}
+
+template <typename T, int NV, int R, bool EXACT, bool BOTH_POLICIES>
+static cudaError_t launch_variant(const EvalParams& p, const LaunchPlan& plan, cudaStream_t stream) {
+  auto go = [&](auto kernel) -> cudaError_t {
+    if (plan.smem_per_cta > 48 * 1024) {
+      cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem_per_cta);
+      if (e != cudaSuccess) return e;
+    }
+    kernel<<<plan.grid, kThreads, plan.smem_per_cta, stream>>>(p);
+    return cudaGetLastError();
+  };
+  if constexpr (BOTH_POLICIES) {
+    if (tuning().variant == 1) return go(score_eval_kernel<T, NV, R, EXACT, 1>);
+  }
+  return go(score_eval_kernel<T, NV, R, EXACT, 0>);
+}
+
+// Instantiations: the reference width (dim 768: 6 fp32 / 3 bf16 16-byte vectors per lane) gets an exact,
+// predicate-free kernel in both cache policies; every other width runs a predicated kernel whose
+// per-lane vector count is rounded up to 1, 2, 4 or 8.
+template <typename T, int NV>
+static cudaError_t launch_generic(const EvalParams& p, const LaunchPlan& plan, cudaStream_t stream) {
+  constexpr int R = (NV <= 2) ? 8 : (NV <= 4) ? 6 : 3;
+  return launch_variant<T, NV, R, false, false>(p, plan, stream);
+}
+
+template <typename T>
+static cudaError_t launch_dtype(const EvalParams& p, const LaunchPlan& plan, cudaStream_t stream) {
+  constexpr int kRefNV = 768 / Elem<T>::E / 32;  // 6 (fp32) or 3 (bf16)
+  constexpr int kRefR = (kRefNV == 6) ? 4 : 8;
+  if (p.vec_per_row == kRefNV * 32) return launch_variant<T, kRefNV, kRefR, true, true>(p, plan, stream);
+  const int nv = (p.vec_per_row + 31) / 32;
+  if (nv <= 1) return launch_generic<T, 1>(p, plan, stream);
+  if (nv <= 2) return launch_generic<T, 2>(p, plan, stream);
+  if (nv <= 4) return launch_generic<T, 4>(p, plan, stream);
+  return launch_generic<T, 8>(p, plan, stream);
+}
+
+static int sm_count_of(int device, int* out) {
+  static int cached[64] = {0};
+  if (device >= 0 && device < 64 && cached[device]) {
+    *out = cached[device];
+    return MB200_OK;
+  }
+  int n = 0;
+  int st = cuda_status(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, device), "cudaDeviceGetAttribute");
+  if (st != MB200_OK) return st;
+  if (device >= 0 && device < 64) cached[device] = n;
+  *out = n;
+  return MB200_OK;
+}
+
+// Optional CUDA-event bracket around the fused kernel alone (bench.py's roofline figure needs the
+// kernel's own duration, not the duration of the partition + kernel + reduction sequence).
+struct KernelTimer {
+  cudaEvent_t begin = nullptr, end = nullptr;
+  bool armed = false;
+};
+static KernelTimer g_timers[64];
+static KernelTimer* g_last_timer = nullptr;
+
+static KernelTimer* timer_for(int device) {
+  if (device < 0 || device >= 64) return nullptr;
+  KernelTimer* t = &g_timers[device];
+  if (t->begin == nullptr) {
+    if (cudaEventCreate(&t->begin) != cudaSuccess || cudaEventCreate(&t->end) != cudaSuccess) return nullptr;
+  }
+  return t;
+}
+
+float last_score_kernel_ms() {
+  KernelTimer* t = g_last_timer;
+  if (t == nullptr || !t->armed) return -1.0f;
+  float ms = -1.0f;
+  if (cudaEventSynchronize(t->end) != cudaSuccess || cudaEventElapsedTime(&ms, t->begin, t->end) != cudaSuccess) return -1.0f;
+  return ms;
+}
+
+size_t eval_workspace_bytes(const mb200_eval_desc* d) {
+  if (validate(d) != MB200_OK) return 0;
+  LaunchPlan plan;
+  // the SM count is not known without a device; size for the largest part this library targets (148 SMs, <= 160)
+  if (make_plan(d, 160, &plan) != MB200_OK) return 0;
+  return plan.bounds_bytes + plan.partials_bytes + 256;
+}
+
+int score_eval(const mb200_eval_desc* d, cudaStream_t stream) {
+  int st = validate(d);
+  if (st != MB200_OK) return st;
+  int device = 0;
+  st = use_device_of(d->tables[0], &device);
+  if (st != MB200_OK) return st;
+  int sms = 0;
+  st = sm_count_of(device, &sms);
+  if (st != MB200_OK) return st;
+  if (sms > 160) return MB200_ERR_UNSUPPORTED;
+  LaunchPlan plan;
+  st = make_plan(d, sms, &plan);
+  if (st != MB200_OK) return st;
+  const size_t need = plan.bounds_bytes + plan.partials_bytes;
+  if (d->workspace == nullptr || ((uintptr_t)d->workspace & 255) || d->workspace_bytes < need) return MB200_ERR_WORKSPACE;
+
+  EvalParams p{};
+  for (int m = 0; m < MB200_MAX_MODULES; ++m) p.tables[m] = d->tables[m];
+  p.hist_offsets = d->hist_offsets, p.hist_ids = d->hist_ids, p.cand_offsets = d->cand_offsets, p.cand_ids = d->cand_ids;
+  p.labels = d->labels, p.weights = d->weights;
+  p.news_category = d->news_category, p.news_sentiment = d->news_sentiment;
+  p.scores = d->scores, p.per_impr = d->per_impression, p.flags = d->flags;
+  p.bounds = reinterpret_cast<int32_t*>(d->workspace);
+  p.partials = reinterpret_cast<double*>(reinterpret_cast<unsigned char*>(d->workspace) + plan.bounds_bytes);
+  p.n_news = d->n_news, p.row_stride = d->row_stride;
+  p.n_impr = (int)d->n_impressions, p.n_modules = d->n_modules, p.active_mask = d->active_modules_mask;
+  p.vec_per_row = d->dim * (d->dtype == MB200_F32 ? 4 : 2) / 16;
+  p.zscore = d->zscore, p.n_weightings = d->n_weightings, p.scores_weighting = d->scores_weighting;
+  p.k0 = d->k0, p.k1 = d->k1, p.cpad = plan.cpad, p.max_cand = d->max_cand, p.n_chunks = plan.n_chunks;
+  p.num_categ = d->num_categ_classes, p.num_sent = d->num_sent_classes;
+  p.smem_per_warp = plan.smem_per_warp, p.acc_bytes = plan.acc_bytes;
+
+  partition_kernel<<<(plan.n_chunks + 1 + 255) / 256, 256, 0, stream>>>(d->hist_offsets, d->cand_offsets, p.n_impr, plan.n_chunks,
+                                                                       reinterpret_cast<int32_t*>(d->workspace));
+  st = cuda_status(cudaGetLastError(), "partition_kernel");
+  if (st != MB200_OK) return st;
+  KernelTimer* timer = tuning().time_kernel ? timer_for(device) : nullptr;
+  if (timer) cudaEventRecord(timer->begin, stream);
+  cudaError_t e = (d->dtype == MB200_F32) ? launch_dtype<float>(p, plan, stream) : launch_dtype<__nv_bfloat16>(p, plan, stream);
+  if (timer) cudaEventRecord(timer->end, stream), timer->armed = true, g_last_timer = timer;
+  st = cuda_status(e, "score_eval_kernel");
+  if (st != MB200_OK) return st;
+  reduce_partials_kernel<<<d->n_weightings, 256, 0, stream>>>(p.partials, plan.total_warps, d->n_weightings, d->sums);
+  st = cuda_status(cudaGetLastError(), "reduce_partials_kernel");
+  if (st != MB200_OK) return st;
+  note_launch(3);
+  return MB200_OK;
+}
+
+}  // namespace mb200

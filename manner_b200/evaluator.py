@@ -1,0 +1,237 @@
+"""ScoreEvaluator: the host side of the B200 scoring / ensemble / metrics path.
+
+It owns what the reference's LightningModules own between "news vectors" and "logged metrics":
+
+  reference (file:line under manner/)                         here
+  ---------------------------------------------------------  --------------------------------------
+  news_encoder(...) per batch      cr_module.py:107,113       cached embedding tables on the device
+  MINDRecBatch segment ids         mind_rec_dataset.py:114    CSR behaviours (data.Behaviours)
+  CRModule.forward / model_step    cr_module.py:105-184       torch.ops.manner_b200.score_eval
+  EnsembleModule.forward           ensemble_module.py:95-151  same op, zscore=True + weights
+  on_test_epoch_end + log_dict     cr_module.py:266-274       EvalResult.metrics() (same log keys)
+  AUROC(task="binary")             cr_module.py:81            torch.ops.manner_b200.pooled_auc
+
+One ``evaluate`` call is one pass over all impressions handed to it (an epoch, or a rank's shard of
+it) -- the reference also computes its metrics once per epoch.  With a process group the additive
+results are all-reduced over NCCL (dist.py); nothing else crosses GPUs.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional, Sequence, Tuple, Union
+
+import numpy as np
+import torch
+from torch import Tensor
+
+from . import _native as nat
+from . import dist as mdist
+from . import ops
+from .data import NUM_CATEG_CLASSES, NUM_SENT_CLASSES, Behaviours
+
+# log keys of the reference (cr_module.py:79-89 prefix "test/"; ensemble_module.py:50-84) by metric slot
+SLOT_KEYS = {
+    nat.M_MRR: "mrr",
+    nat.M_NDCG_K0: "ndcg@{k0}",
+    nat.M_NDCG_K1: "ndcg@{k1}",
+    nat.M_CATEG_DIV_K0: "categ_div@{k0}",
+    nat.M_CATEG_DIV_K1: "categ_div@{k1}",
+    nat.M_SENT_DIV_K0: "sent_div@{k0}",
+    nat.M_SENT_DIV_K1: "sent_div@{k1}",
+    nat.M_CATEG_PERS_K0: "categ_pers@{k0}",
+    nat.M_CATEG_PERS_K1: "categ_pers@{k1}",
+    nat.M_SENT_PERS_K0: "sent_pers@{k0}",
+    nat.M_SENT_PERS_K1: "sent_pers@{k1}",
+}
+
+
+@dataclass
+class DeviceBehaviours:
+    """CSR behaviours resident on the device (+ the two host-side facts the launch needs)."""
+
+    hist_offsets: Tensor
+    hist_ids: Tensor
+    cand_offsets: Tensor
+    cand_ids: Tensor
+    labels: Tensor
+    n_impressions: int
+    max_cand: int
+    h2d_bytes: int = 0
+
+
+@dataclass
+class EvalResult:
+    sums: np.ndarray  # fp64 [W, NUM_METRICS], summed over all ranks
+    n_impressions: int  # over all ranks
+    flags: int
+    ks: Tuple[int, int]
+    has_aspects: bool
+    auc: Optional[float] = None  # pooled AUROC (reference "auc"), weighting `scores_weighting`
+    auc_counts: Optional[Tuple[int, int]] = None  # (positives, negatives)
+    scores: Optional[Tensor] = None  # device fp32 [sum C] of this rank
+    per_impression: Optional[Tensor] = None  # device fp32 [W, B, NUM_METRICS] of this rank
+    d2h_bytes: int = 0
+
+    def metrics(self, weighting: int = 0, prefix: str = "test/") -> Dict[str, float]:
+        """Means under the reference's log keys (+ ``gauc``, which the reference does not have)."""
+        s = self.sums[weighting]
+        n = max(self.n_impressions, 1)
+        out: Dict[str, float] = {}
+        for slot, key in SLOT_KEYS.items():
+            if slot >= nat.M_CATEG_DIV_K0 and not self.has_aspects:
+                continue
+            out[prefix + key.format(k0=self.ks[0], k1=self.ks[1])] = float(s[slot] / n)
+        out[prefix + "gauc"] = float(s[nat.M_GAUC] / s[nat.M_GAUC_VALID]) if s[nat.M_GAUC_VALID] > 0 else 0.0
+        if self.auc is not None:
+            out[prefix + "auc"] = self.auc
+        return out
+
+
+@dataclass
+class PendingEval:
+    """Device-side results of an enqueued pass (no host synchronisation yet)."""
+
+    sums: Tensor
+    flags: Tensor
+    n_total: Union[int, Tensor]
+    auc_stats: Optional[Tensor]
+    scores: Optional[Tensor]
+    per_impression: Optional[Tensor]
+
+
+class ScoreEvaluator:
+    """Cached embedding tables + aspect labels on one device; ``evaluate`` runs the fused path.
+
+    tables[0] is the CR-Module's table, tables[1:] the A-Modules' (category, sentiment, ...), all
+    [n_news, dim] fp32 or bf16 with the same shape (the table is the new boundary, filled
+    once by the PyTorch news encoders)."""
+
+    def __init__(
+        self,
+        tables: Sequence[Tensor],
+        device: Union[str, torch.device, None] = None,
+        news_category: Optional[Union[Tensor, np.ndarray]] = None,
+        news_sentiment: Optional[Union[Tensor, np.ndarray]] = None,
+        num_categ_classes: int = NUM_CATEG_CLASSES,
+        num_sent_classes: int = NUM_SENT_CLASSES,
+        ks: Tuple[int, int] = (5, 10),
+    ) -> None:
+        nat.lib()  # fail now, loudly, if the CUDA library is not built
+        if not torch.cuda.is_available():
+            raise RuntimeError("manner_b200.ScoreEvaluator needs a CUDA device; there is no CPU path")
+        self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+        if not 1 <= len(tables) <= nat.MAX_MODULES:
+            raise ValueError(f"1..{nat.MAX_MODULES} tables expected")
+        self.tables: List[Tensor] = [t.to(self.device, non_blocking=True).contiguous() for t in tables]
+        self.n_news, self.dim = self.tables[0].shape
+        self.ks = (int(ks[0]), int(ks[1]))
+        self.num_categ_classes, self.num_sent_classes = int(num_categ_classes), int(num_sent_classes)
+        self.news_category = self._aspect(news_category)
+        self.news_sentiment = self._aspect(news_sentiment)
+        if (self.news_category is None) != (self.news_sentiment is None):
+            raise ValueError("give both aspect label arrays or neither")
+
+    def _aspect(self, a: Optional[Union[Tensor, np.ndarray]]) -> Optional[Tensor]:
+        if a is None:
+            return None
+        t = torch.as_tensor(np.asarray(a) if not isinstance(a, Tensor) else a).to(torch.int32)
+        if t.numel() != self.n_news:
+            raise ValueError("aspect labels must have one entry per news row")
+        return t.to(self.device).contiguous()
+
+    # -- inputs ----------------------------------------------------------------------------------------------
+    def upload(self, bhv: Behaviours, pinned: Optional[Dict[str, Tensor]] = None) -> DeviceBehaviours:
+        """Host CSR -> device (asynchronous on the current stream).  ``pinned`` lets a caller reuse
+        page-locked staging tensors (see ``pin``)."""
+        src = pinned if pinned is not None else self.pin(bhv)
+        dev = {k: v.to(self.device, non_blocking=True) for k, v in src.items()}
+        nbytes = sum(v.numel() * v.element_size() for v in src.values())
+        return DeviceBehaviours(
+            dev["hist_offsets"], dev["hist_ids"], dev["cand_offsets"], dev["cand_ids"], dev["labels"],
+            bhv.n_impressions, max(bhv.max_cand, 1), nbytes,
+        )
+
+    @staticmethod
+    def pin(bhv: Behaviours) -> Dict[str, Tensor]:
+        arrays = dict(hist_offsets=bhv.hist_offsets, hist_ids=bhv.hist_ids, cand_offsets=bhv.cand_offsets, cand_ids=bhv.cand_ids, labels=bhv.labels)
+        return {k: torch.from_numpy(np.ascontiguousarray(v)).pin_memory() for k, v in arrays.items()}
+
+    # -- the hot path ----------------------------------------------------------------------------------------
+    def launch(
+        self,
+        bhv: DeviceBehaviours,
+        weights: Optional[Union[Sequence[Sequence[float]], Tensor]] = None,
+        zscore: bool = False,
+        pooled_auc: bool = False,
+        want_scores: bool = False,
+        want_per_impression: bool = False,
+        scores_weighting: int = 0,
+        group: Optional["torch.distributed.ProcessGroup"] = None,
+        distributed: bool = False,
+    ) -> "PendingEval":
+        """Enqueue one pass on the current stream and return device-side results without waiting for
+        them.  ``weights`` may be a device fp32 tensor [W, n_modules] (then every module is gathered)."""
+        n_mod = len(self.tables)
+        w_dev: Optional[Tensor] = None
+        active = (1 << n_mod) - 1
+        if isinstance(weights, Tensor) and weights.is_cuda:
+            w_dev = weights.float().reshape(-1, n_mod).contiguous()
+        elif weights is not None:
+            w_host = torch.as_tensor(weights, dtype=torch.float32).reshape(-1, n_mod)
+            # a module whose weight is 0 everywhere is never gathered (ensemble_module.py:37-46,100-107)
+            active = 1
+            for m in range(1, n_mod):
+                if bool((w_host[:, m] != 0).any()):
+                    active |= 1 << m
+            w_dev = w_host.to(self.device, non_blocking=True).contiguous()
+        need_scores = want_scores or pooled_auc
+        scores, per_impr, sums, flags = torch.ops.manner_b200.score_eval(
+            self.tables, bhv.hist_offsets, bhv.hist_ids, bhv.cand_offsets, bhv.cand_ids, bhv.labels, w_dev, zscore,
+            bhv.max_cand, active, self.ks[0], self.ks[1], need_scores, scores_weighting, want_per_impression,
+            self.news_category, self.news_sentiment, self.num_categ_classes, self.num_sent_classes,
+        )
+        n_total: Union[int, Tensor] = bhv.n_impressions
+        auc_stats: Optional[Tensor] = None
+        if distributed:
+            payload = mdist.pack_metric_payload(sums, flags, bhv.n_impressions)
+            torch.distributed.all_reduce(payload, op=torch.distributed.ReduceOp.SUM, group=group)
+            n_total = payload  # unpacked in finish(): the count sits behind the sums
+            if pooled_auc:
+                _, gflags, _ = mdist.unpack_metric_payload_device(payload, sums.shape)
+                auc_stats = mdist.pooled_auc_distributed(scores, bhv.labels, gflags, group)
+        elif pooled_auc:
+            auc_stats = torch.ops.manner_b200.pooled_auc(scores, bhv.labels, 2, flags)
+        return PendingEval(sums, flags, n_total, auc_stats, scores if want_scores else None, per_impr if want_per_impression else None)
+
+    def finish(self, pending: "PendingEval") -> EvalResult:
+        """The one device -> host read of a pass: metric sums, flag word, AUC statistics."""
+        if isinstance(pending.n_total, Tensor):
+            sums_t, flags_t, n_total = mdist.unpack_metric_payload(pending.n_total.cpu(), pending.sums.shape)
+            sums_h, flags_h = sums_t.numpy(), int(flags_t.item())
+            d2h = pending.n_total.numel() * 8
+        else:
+            packed = torch.cat([pending.sums.reshape(-1), pending.flags.to(torch.float64)]).cpu().numpy()
+            sums_h, flags_h, n_total = packed[:-1].reshape(tuple(pending.sums.shape)), int(packed[-1]), pending.n_total
+            d2h = packed.size * 8
+        auc = counts = None
+        if pending.auc_stats is not None:
+            a = pending.auc_stats.cpu().numpy()
+            d2h += a.size * 8
+            auc, counts = float(a[0]), (int(a[1]), int(a[2]))
+        if flags_h & (nat.FLAG_BAD_ID | nat.FLAG_CAND_OVERFLOW | nat.FLAG_BAD_ASPECT):
+            raise nat.NativeError(
+                f"manner_b200 kernels flagged bad input (flags={flags_h}): "
+                "1=row id outside the table, 2=impression longer than max_cand, 8=aspect label outside [0, num_classes)"
+            )
+        return EvalResult(
+            sums=sums_h, n_impressions=int(n_total), flags=flags_h, ks=self.ks, has_aspects=self.news_category is not None,
+            auc=auc, auc_counts=counts, scores=pending.scores, per_impression=pending.per_impression, d2h_bytes=d2h,
+        )
+
+    def evaluate(self, bhv: DeviceBehaviours, **kwargs) -> EvalResult:
+        """One pass: scores (+ z-score ensemble for every row of ``weights`` [W, n_modules]) and metric
+        means.  ``zscore=False, weights=None`` is the CRModule evaluation (cr_module.py:105-131,266-274);
+        ``zscore=True`` with ``weights=[[1, categ_weight, sent_weight]]`` is the EnsembleModule
+        (ensemble_module.py:95-151,214-238).  With ``distributed=True`` the sums (and the pooled-AUC rank
+        statistic) are reduced over ``group`` with NCCL.  See ``launch`` for the arguments."""
+        return self.finish(self.launch(bhv, **kwargs))

@@ -1,0 +1,243 @@
+"""torch custom ops over the C ABI: ``torch.ops.manner_b200.score_eval`` and
+``torch.ops.manner_b200.pooled_auc``.
+
+torch is plumbing here -- device memory, the current stream, output allocation.  The arithmetic is
+in libmanner_b200.so (manner_b200/csrc/*.cu), reached through ctypes with raw pointers.  There is no
+fallback: a CPU tensor or a missing library raises.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+from torch import Tensor
+
+from . import _native as nat
+
+_workspaces: Dict[Tuple[int, int, str], Tensor] = {}
+
+
+def _workspace(device: torch.device, stream: int, kind: str, nbytes: int) -> Tensor:
+    """Per-(device, stream) scratch cache, grown on demand; 256-byte aligned by the caching allocator."""
+    key = (device.index if device.index is not None else torch.cuda.current_device(), stream, kind)
+    ws = _workspaces.get(key)
+    if ws is None or ws.numel() < nbytes:
+        ws = torch.empty(max(nbytes, 256), dtype=torch.uint8, device=device)
+        _workspaces[key] = ws
+    return ws
+
+
+def _ptr(t: Optional[Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _require_cuda(name: str, t: Tensor, dtype: torch.dtype) -> None:
+    if not t.is_cuda:
+        raise RuntimeError(f"manner_b200: `{name}` must be a CUDA tensor (there is no CPU path)")
+    if t.dtype != dtype:
+        raise TypeError(f"manner_b200: `{name}` must be {dtype}, got {t.dtype}")
+    if not t.is_contiguous():
+        raise ValueError(f"manner_b200: `{name}` must be contiguous")
+
+
+@torch.library.custom_op("manner_b200::score_eval", mutates_args=())
+def score_eval(
+    tables: Sequence[Tensor],
+    hist_offsets: Tensor,
+    hist_ids: Tensor,
+    cand_offsets: Tensor,
+    cand_ids: Tensor,
+    labels: Tensor,
+    weights: Optional[Tensor],
+    zscore: bool,
+    max_cand: int,
+    active_mask: int,
+    k0: int,
+    k1: int,
+    want_scores: bool,
+    scores_weighting: int,
+    want_per_impression: bool,
+    news_category: Optional[Tensor],
+    news_sentiment: Optional[Tensor],
+    num_categ_classes: int,
+    num_sent_classes: int,
+) -> Tuple[Tensor, Tensor, Tensor, Tensor]:
+    """Fused gather / pool / score / z-score / ensemble / per-impression metrics (include/manner_b200.h,
+    mb200_score_eval).  Returns (scores fp32 [sum C] or empty, per_impression fp32 [W, B, 13] or empty,
+    sums fp64 [W, 13], flags int32 [1])."""
+    lib = nat.lib()
+    if len(tables) < 1 or len(tables) > nat.MAX_MODULES:
+        raise ValueError(f"1..{nat.MAX_MODULES} embedding tables expected")
+    t0 = tables[0]
+    if t0.dtype not in (torch.float32, torch.bfloat16):
+        raise TypeError("embedding tables must be float32 or bfloat16")
+    for m, t in enumerate(tables):
+        if not t.is_cuda:
+            raise RuntimeError("manner_b200: embedding tables must be CUDA tensors (there is no CPU path)")
+        if t.dtype != t0.dtype or t.shape != t0.shape or t.dim() != 2 or t.stride(1) != 1 or t.stride(0) != t0.stride(0):
+            raise ValueError(f"table {m}: all tables must share dtype, shape [n_news, dim] and row stride")
+    dev = t0.device
+    for name, t, dt in (
+        ("hist_offsets", hist_offsets, torch.int32), ("hist_ids", hist_ids, torch.int32),
+        ("cand_offsets", cand_offsets, torch.int32), ("cand_ids", cand_ids, torch.int32), ("labels", labels, torch.uint8),
+    ):
+        _require_cuda(name, t, dt)
+    n_impr = hist_offsets.numel() - 1
+    if cand_offsets.numel() != n_impr + 1 or labels.numel() != cand_ids.numel():
+        raise ValueError("inconsistent CSR arrays")
+    n_w = 1
+    if weights is not None:
+        _require_cuda("weights", weights, torch.float32)
+        if weights.dim() != 2 or weights.shape[1] != len(tables):
+            raise ValueError("weights must be [n_weightings, n_modules]")
+        n_w = weights.shape[0]
+    if (news_category is None) != (news_sentiment is None):
+        raise ValueError("news_category and news_sentiment must be given together")
+    if news_category is not None:
+        _require_cuda("news_category", news_category, torch.int32)
+        _require_cuda("news_sentiment", news_sentiment, torch.int32)
+
+    with torch.cuda.device(dev):
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        scores = torch.empty(cand_ids.numel() if want_scores else 0, dtype=torch.float32, device=dev)
+        per_impr = torch.empty((n_w, n_impr, nat.NUM_METRICS) if want_per_impression else (0,), dtype=torch.float32, device=dev)
+        sums = torch.empty((n_w, nat.NUM_METRICS), dtype=torch.float64, device=dev)
+        flags = torch.zeros(1, dtype=torch.int32, device=dev)
+
+        d = nat.EvalDesc()
+        d.struct_size = ctypes.sizeof(nat.EvalDesc)
+        d.n_modules = len(tables)
+        d.dtype = nat.F32 if t0.dtype == torch.float32 else nat.BF16
+        d.dim = t0.shape[1]
+        d.active_modules_mask = active_mask
+        d.n_news = t0.shape[0]
+        d.row_stride = t0.stride(0)
+        for m, t in enumerate(tables):
+            d.tables[m] = t.data_ptr()
+        d.n_impressions = n_impr
+        d.hist_offsets, d.hist_ids = hist_offsets.data_ptr(), hist_ids.data_ptr()
+        d.cand_offsets, d.cand_ids, d.labels = cand_offsets.data_ptr(), cand_ids.data_ptr(), labels.data_ptr()
+        d.max_cand = max_cand
+        d.zscore = int(zscore)
+        d.n_weightings = n_w
+        d.weights = _ptr(weights)
+        d.k0, d.k1 = k0, k1
+        d.news_category, d.news_sentiment = _ptr(news_category), _ptr(news_sentiment)
+        d.num_categ_classes, d.num_sent_classes = num_categ_classes, num_sent_classes
+        d.scores = scores.data_ptr() if want_scores else None
+        d.scores_weighting = scores_weighting
+        d.per_impression = per_impr.data_ptr() if want_per_impression else None
+        d.sums = sums.data_ptr()
+        d.flags = flags.data_ptr()
+        need = lib.mb200_eval_workspace_bytes(ctypes.byref(d))
+        if need == 0:
+            # the size query runs the same validation as the call: report the precise status
+            d.workspace, d.workspace_bytes = None, 0
+            nat.check(lib.mb200_score_eval(ctypes.byref(d), stream), "mb200_score_eval")
+            raise nat.NativeError("mb200_eval_workspace_bytes returned 0")
+        ws = _workspace(dev, stream, "eval", need)
+        d.workspace, d.workspace_bytes = ws.data_ptr(), ws.numel()
+        nat.check(lib.mb200_score_eval(ctypes.byref(d), stream), "mb200_score_eval")
+    return scores, per_impr, sums, flags
+
+
+@score_eval.register_fake
+def _(tables, hist_offsets, hist_ids, cand_offsets, cand_ids, labels, weights, zscore, max_cand, active_mask, k0, k1,
+      want_scores, scores_weighting, want_per_impression, news_category, news_sentiment, num_categ_classes, num_sent_classes):
+    dev = tables[0].device
+    n_w = 1 if weights is None else weights.shape[0]
+    n_impr = hist_offsets.numel() - 1
+    return (
+        torch.empty(cand_ids.numel() if want_scores else 0, dtype=torch.float32, device=dev),
+        torch.empty((n_w, n_impr, nat.NUM_METRICS) if want_per_impression else (0,), dtype=torch.float32, device=dev),
+        torch.empty((n_w, nat.NUM_METRICS), dtype=torch.float64, device=dev),
+        torch.empty(1, dtype=torch.int32, device=dev),
+    )
+
+
+@torch.library.custom_op("manner_b200::pooled_auc", mutates_args=())
+def pooled_auc(preds: Tensor, labels: Tensor, sigmoid_mode: int, flags: Optional[Tensor]) -> Tensor:
+    """Pooled AUROC of torchmetrics' ``AUROC(task="binary")`` (cr_module.py:81,273) on one device.
+    Returns fp64 [4] = (auc, P, N, sum2).  sigmoid_mode 0 never / 1 always / 2 from ``flags``."""
+    lib = nat.lib()
+    _require_cuda("preds", preds, torch.float32)
+    _require_cuda("labels", labels, torch.uint8)
+    if flags is not None:
+        _require_cuda("flags", flags, torch.int32)
+    dev = preds.device
+    n = preds.numel()
+    with torch.cuda.device(dev):
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        out = torch.empty(4, dtype=torch.float64, device=dev)
+        ws = _workspace(dev, stream, "auc", lib.mb200_pooled_auc_workspace_bytes(n))
+        nat.check(
+            lib.mb200_pooled_auc(preds.data_ptr(), labels.data_ptr(), n, sigmoid_mode, _ptr(flags), ws.data_ptr(), ws.numel(),
+                                 out.data_ptr(), stream),
+            "mb200_pooled_auc",
+        )
+    return out
+
+
+@pooled_auc.register_fake
+def _(preds, labels, sigmoid_mode, flags):
+    return torch.empty(4, dtype=torch.float64, device=preds.device)
+
+
+# ---- staged pooled AUC (multi-GPU: positives are exchanged between stage 2 and 3; see dist.py) ----------
+
+
+def auc_build_and_sort(preds: Tensor, labels: Tensor, sigmoid_mode: int, flags: Optional[Tensor]) -> Tuple[Tensor, Tensor, Tensor]:
+    """Stages 1+2 on this rank's rows: returns (sorted keys uint32-as-int32 [n], positive keys [n] with the
+    first n_pos entries valid, n_pos int64 [1])."""
+    lib = nat.lib()
+    _require_cuda("preds", preds, torch.float32)
+    _require_cuda("labels", labels, torch.uint8)
+    dev, n = preds.device, preds.numel()
+    with torch.cuda.device(dev):
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        keys = torch.empty(n, dtype=torch.int32, device=dev)
+        sorted_keys = torch.empty(n, dtype=torch.int32, device=dev)
+        pos_keys = torch.empty(n, dtype=torch.int32, device=dev)
+        n_pos = torch.zeros(1, dtype=torch.int64, device=dev)
+        nat.check(
+            lib.mb200_auc_build_keys(preds.data_ptr(), labels.data_ptr(), n, sigmoid_mode, _ptr(flags), keys.data_ptr(), pos_keys.data_ptr(),
+                                     n_pos.data_ptr(), stream),
+            "mb200_auc_build_keys",
+        )
+        ws = _workspace(dev, stream, "sort", lib.mb200_auc_sort_workspace_bytes(n))
+        nat.check(lib.mb200_auc_sort_keys(keys.data_ptr(), sorted_keys.data_ptr(), n, ws.data_ptr(), ws.numel(), stream), "mb200_auc_sort_keys")
+    return sorted_keys, pos_keys, n_pos
+
+
+def auc_rank_sum(sorted_keys: Tensor, n_pos_local: Tensor, pos_keys: Tensor, n_pos: Tensor, sum2: Tensor) -> None:
+    """Stage 3: adds sum over ``pos_keys[:n_pos]`` of (lower_bound + upper_bound) in this rank's sorted
+    negatives into ``sum2`` (int64 [1], holds a uint64)."""
+    lib = nat.lib()
+    dev = sorted_keys.device
+    with torch.cuda.device(dev):
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        nat.check(
+            lib.mb200_auc_rank_sum(sorted_keys.data_ptr(), sorted_keys.numel(), n_pos_local.data_ptr(), pos_keys.data_ptr(), pos_keys.numel(),
+                                   n_pos.data_ptr(), sum2.data_ptr(), stream),
+            "mb200_auc_rank_sum",
+        )
+
+
+def launch_counts() -> Tuple[int, int]:
+    """(kernels of this library launched so far, CUB sort invocations so far) in this process."""
+    lib = nat.lib()
+    return int(lib.mb200_launch_count()), int(lib.mb200_library_launch_count())
+
+
+def last_score_kernel_ms() -> float:
+    """Duration of the most recent fused kernel launched with ``set_tuning(time_kernel=1)`` (synchronises)."""
+    return float(nat.lib().mb200_last_score_kernel_ms())
+
+
+def set_tuning(chunks_per_warp: Optional[int] = None, variant: Optional[int] = None, ctas_per_sm: Optional[int] = None,
+               time_kernel: Optional[int] = None) -> None:
+    lib = nat.lib()
+    for key, val in ((0, chunks_per_warp), (1, variant), (2, ctas_per_sm), (3, time_kernel)):
+        if val is not None:
+            lib.mb200_set_tuning(key, int(val))

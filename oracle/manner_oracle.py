@@ -250,8 +250,10 @@ def ensemble_eval_epoch(
     num_classes: Optional[Dict[str, int]] = None,
     step: int = STEP_BATCH,
     double_compute: bool = False,
+    reference_only: bool = False,
 ) -> Dict:
-    """EnsembleModule test epoch (ensemble_module.py:202-256).  ``aspects`` maps "category" /
+    """EnsembleModule test epoch (ensemble_module.py:202-256).  ``reference_only`` skips the two extras
+    the reference does not compute (mrr, gauc) -- used when this function is the timed CPU baseline.  ``aspects`` maps "category" /
     "sentiment" to per-news int labels; when given, the diversity / personalization keys of
     ensemble_module.py:231-238 are produced as well."""
     acc: Dict[str, List[Tensor]] = {k: [] for k in ("preds", "targets", "cs", "hs", "tc", "ts", "hc", "hsent")}
@@ -282,6 +284,8 @@ def ensemble_eval_epoch(
             out[f"test/sent_div@{k}"] = float(diversity_epoch(preds, ts, cs.tolist(), nc["sentiment"], k))
             out[f"test/categ_pers@{k}"] = float(personalization_epoch(preds, tc, hc, cs.tolist(), hs.tolist(), nc["category"], k))
             out[f"test/sent_pers@{k}"] = float(personalization_epoch(preds, ts, hsent, cs.tolist(), hs.tolist(), nc["sentiment"], k))
+    if reference_only:
+        return {"scores": preds.numpy(), "targets": targets.numpy(), "cand_news_size": cs.numpy(), "metrics": out}
     # extras the reference's EnsembleModule does not log but the B200 path reports for every call
     extra = tp.MetricCollection({"mrr": tp.RetrievalMRR()}).clone(prefix="test/")
     out.update({k: float(v) for k, v in extra(preds, targets, **{"indexes": indexes}).items()})

@@ -1,0 +1,100 @@
+"""CPU: the C-ABI shared library loads without a GPU and exports exactly what include/manner_b200.h
+declares; host-only entry points behave; the product refuses to compute without CUDA."""
+import ctypes
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+import torch
+
+from manner_b200 import _native as nat
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "manner_b200.h")
+
+
+def _declared_symbols():
+    text = open(HEADER).read()
+    return sorted(set(re.findall(r"MB200_API[^;(]*?\b(mb200_\w+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = nat.lib()
+    declared = _declared_symbols()
+    assert len(declared) >= 15
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in the header but not exported"
+    assert sorted(nat.SIGNATURES) == declared, "python binding and header disagree on the symbol list"
+    exported = subprocess.run(["nm", "-D", "--defined-only", nat.LIB_PATH], capture_output=True, text=True).stdout
+    public = sorted(set(re.findall(r" T (mb200_\w+)", exported)))
+    assert public == declared, "the library exports symbols the header does not declare (or the reverse)"
+
+
+def test_struct_layout_matches_c(tmp_path):
+    src = tmp_path / "sz.c"
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "manner_b200.h"\nint main(){printf("%zu %zu %zu %zu %zu",'
+                   "sizeof(mb200_eval_desc),offsetof(mb200_eval_desc,tables),offsetof(mb200_eval_desc,weights),"
+                   "offsetof(mb200_eval_desc,scores),offsetof(mb200_eval_desc,workspace_bytes));return 0;}\n")
+    exe = tmp_path / "sz"
+    subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)  # the header is plain C
+    got = [int(x) for x in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()]
+    E = nat.EvalDesc
+    assert got == [ctypes.sizeof(E), E.tables.offset, E.weights.offset, E.scores.offset, E.workspace_bytes.offset]
+
+
+def test_host_only_entry_points():
+    lib = nat.lib()
+    assert lib.mb200_abi_version() == nat.ABI_VERSION
+    assert lib.mb200_status_str(nat.OK) == b"ok" and b"workspace" in lib.mb200_status_str(nat.ERR_WORKSPACE)
+    assert lib.mb200_pooled_auc_workspace_bytes(1000) >= 3 * 4000
+    assert lib.mb200_launch_count() == 0  # nothing has been launched in a CPU-only process
+    # the DCG discount table the kernels use == what torchmetrics' _dcg computes on the reference's CPU path
+    want = (torch.ones(nat.MAX_K) / torch.log2(torch.arange(nat.MAX_K) + 2.0)).numpy()
+    got = np.array([lib.mb200_dcg_discount(r) for r in range(1, nat.MAX_K + 1)], dtype=np.float32)
+    np.testing.assert_array_equal(got, want)
+    assert lib.mb200_dcg_discount(0) == 0.0 and lib.mb200_dcg_discount(nat.MAX_K + 1) == 0.0
+
+
+def test_descriptor_validation_without_a_gpu():
+    lib = nat.lib()
+    d = nat.EvalDesc()
+    assert lib.mb200_eval_workspace_bytes(ctypes.byref(d)) == 0  # struct_size unset -> invalid
+    assert lib.mb200_score_eval(ctypes.byref(d), None) == nat.ERR_INVALID_ARG
+    assert lib.mb200_score_eval(None, None) == nat.ERR_INVALID_ARG
+    assert lib.mb200_pooled_auc(None, None, -1, 0, None, None, 0, None, None) == nat.ERR_INVALID_ARG
+
+
+def test_product_refuses_to_run_without_cuda():
+    """No CPU fallback anywhere: CPU tensors raise, and the evaluator needs a device."""
+    import manner_b200.ops  # noqa: F401  registers the custom ops
+
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        torch.ops.manner_b200.pooled_auc(torch.rand(4), torch.zeros(4, dtype=torch.uint8), 0, None)
+    t = torch.zeros(8, 128)
+    i32 = torch.zeros(2, dtype=torch.int32)
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        torch.ops.manner_b200.score_eval([t], i32, i32, i32, i32, torch.zeros(2, dtype=torch.uint8), None, False, 4, 1, 5, 10,
+                                         False, 0, False, None, None, 19, 4)
+    if not torch.cuda.is_available():
+        from manner_b200.evaluator import ScoreEvaluator
+
+        with pytest.raises(RuntimeError, match="CUDA"):
+            ScoreEvaluator([t])
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "manner_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", text, re.M), f"{f} imports the oracle"
+
+
+def test_missing_library_fails_loudly(monkeypatch, tmp_path):
+    monkeypatch.setattr(nat, "_lib", None)
+    monkeypatch.setattr(nat, "LIB_PATH", str(tmp_path / "nope.so"))
+    with pytest.raises(nat.NativeLibraryMissing, match="no CPU or PyTorch fallback"):
+        nat.lib()

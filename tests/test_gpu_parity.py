@@ -1,0 +1,201 @@
+"""GPU parity tests proper: the CUDA path (through the C ABI) against the oracle / the golden vectors the
+reference's own code produced.  Run with ``pytest -m gpu`` on a B200."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from oracle import manner_oracle as mo  # noqa: E402  (checker only)
+from oracle import thirdparty as tp  # noqa: E402
+
+import manner_b200  # noqa: E402
+from manner_b200 import _native as nat  # noqa: E402
+from manner_b200 import data as mdata  # noqa: E402
+
+SCORE_RTOL = 1e-5  # BASELINE.json: scores within 1e-5 relative in fp32
+METRIC_ATOL = 1e-6  # AUC / MRR / nDCG within 1e-6 absolute
+
+
+@pytest.fixture(scope="module")
+def evaluator_cls():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from manner_b200.evaluator import ScoreEvaluator
+
+    return ScoreEvaluator
+
+
+def _bhv(z):
+    return mdata.Behaviours(z["hist_offsets"].astype(np.int32), z["hist_ids"].astype(np.int32), z["cand_offsets"].astype(np.int32),
+                            z["cand_ids"].astype(np.int32), z["labels"].astype(np.uint8))
+
+
+def _score_tol(table: torch.Tensor, bhv, scores_ref: np.ndarray) -> np.ndarray:
+    """Condition-aware tolerance: |ds| <= rtol * sum_i |u_i c_i| per candidate -- a dot product
+    can cancel to ~0, so the error scales with the magnitude of its terms, not of its value."""
+    tol = np.empty_like(scores_ref, dtype=np.float64)
+    t = table.double().abs()
+    for i in range(bhv.n_impressions):
+        h = bhv.hist_ids[bhv.hist_offsets[i]:bhv.hist_offsets[i + 1]]
+        c = bhv.cand_ids[bhv.cand_offsets[i]:bhv.cand_offsets[i + 1]]
+        u = t[torch.from_numpy(h.astype(np.int64))].mean(0)
+        tol[bhv.cand_offsets[i]:bhv.cand_offsets[i + 1]] = (t[torch.from_numpy(c.astype(np.int64))] @ u).numpy()
+    return SCORE_RTOL * tol + 1e-30
+
+
+@pytest.mark.parametrize("name", ["cr_d128", "cr_d768", "cr_ties"])
+def test_cr_eval_matches_reference_golden(golden_dir, evaluator_cls, name):
+    z = np.load(os.path.join(golden_dir, name + ".npz"))
+    table, bhv = torch.from_numpy(z["table"]), _bhv(z)
+    ev = evaluator_cls([table])
+    res = ev.evaluate(ev.upload(bhv), pooled_auc=True, want_scores=True, want_per_impression=True)
+    scores = res.scores.cpu().numpy()
+    # scores: within 1e-5 relative (condition-aware) of what the reference's CRModule produced
+    assert np.all(np.abs(scores.astype(np.float64) - z["preds"].astype(np.float64)) <= _score_tol(table, bhv, z["preds"]))
+    # rankings + per-impression metrics: bit-exact on identical scores (the device's own scores)
+    per_dev = res.per_impression.cpu().numpy()[0]
+    per_ref = mo.per_impression_metrics(scores, bhv.labels, bhv.cand_offsets)
+    np.testing.assert_array_equal(per_dev[:, :3], per_ref[:, :3])
+    np.testing.assert_allclose(per_dev[:, 3:5], per_ref[:, 3:5], atol=1e-7)
+    # epoch metrics vs the reference's logged values
+    m = res.metrics()
+    for k in ("auc", "mrr", "ndcg@5", "ndcg@10"):
+        assert abs(m["test/" + k] - float(z["test_" + k])) <= METRIC_ATOL, (k, m["test/" + k], float(z["test_" + k]))
+    assert res.n_impressions == bhv.n_impressions
+
+
+def test_ensemble_matches_reference_golden(golden_dir, evaluator_cls):
+    z = np.load(os.path.join(golden_dir, "ensemble_d128.npz"))
+    tabs = [torch.from_numpy(z[f"table{m}"]) for m in range(3)]
+    bhv = _bhv(z)
+    ev = evaluator_cls(tabs, news_category=z["category"], news_sentiment=z["sentiment"])
+    dev_bhv = ev.upload(bhv)
+    weightings = [[1.0, wc, ws] for wc, ws in z["weightings"].tolist()]
+    # (a) one call per weighting, like one EnsembleModule run each
+    for w, wt in enumerate(weightings):
+        res = ev.evaluate(dev_bhv, weights=[wt], zscore=True, want_scores=True)
+        got = res.scores.cpu().numpy().astype(np.float64)
+        ref = z[f"w{w}_preds"].astype(np.float64)
+        assert np.all(np.abs(got - ref) <= 2e-5 * np.maximum(1.0, np.abs(ref))), w  # z-scores are O(1)
+        m = res.metrics()
+        for k in ("ndcg@5", "ndcg@10", "categ_div@5", "categ_div@10", "sent_div@5", "sent_div@10",
+                  "categ_pers@5", "categ_pers@10", "sent_pers@5", "sent_pers@10"):
+            assert abs(m["test/" + k] - float(z[f"w{w}_test_{k}"])) <= METRIC_ATOL, (w, k, m["test/" + k], float(z[f"w{w}_test_{k}"]))
+    # (b) the sweep: all weightings from ONE gather give the same sums as the separate calls
+    sweep = ev.evaluate(dev_bhv, weights=weightings, zscore=True)
+    for w, wt in enumerate(weightings):
+        single = ev.evaluate(dev_bhv, weights=[wt], zscore=True)
+        np.testing.assert_allclose(sweep.sums[w], single.sums[0], rtol=0, atol=1e-9)
+
+
+def test_bf16_table_matches_oracle_on_rounded_table(golden_dir, evaluator_cls):
+    z = np.load(os.path.join(golden_dir, "cr_d768.npz"))
+    table, bhv = torch.from_numpy(z["table"]).bfloat16(), _bhv(z)
+    ev = evaluator_cls([table])
+    res = ev.evaluate(ev.upload(bhv), want_scores=True)
+    ref = mo.cr_eval_epoch(table.float(), mo.Behaviours(bhv.hist_offsets, bhv.hist_ids, bhv.cand_offsets, bhv.cand_ids, bhv.labels))
+    got = res.scores.cpu().numpy().astype(np.float64)
+    # stated bf16 tolerance: the table is rounded to bf16 on both sides, arithmetic is fp32 on both sides
+    assert np.all(np.abs(got - ref["scores"]) <= _score_tol(table.float(), bhv, ref["scores"]))
+
+
+@pytest.mark.parametrize("dim", [64, 100, 256, 400, 1024])
+def test_other_widths_against_oracle(evaluator_cls, dim):
+    n_news = 300
+    bhv = mdata.synth_behaviours(n_news, 48, seed=dim, cand_window=200)
+    table = mdata.synth_table(n_news, dim, 77)
+    ev = evaluator_cls([table])
+    res = ev.evaluate(ev.upload(bhv), pooled_auc=True, want_scores=True)
+    ref = mo.cr_eval_epoch(table, mo.Behaviours(bhv.hist_offsets, bhv.hist_ids, bhv.cand_offsets, bhv.cand_ids, bhv.labels))
+    got = res.scores.cpu().numpy()
+    assert np.all(np.abs(got.astype(np.float64) - ref["scores"]) <= _score_tol(table, bhv, ref["scores"]))
+    per = mo.per_impression_metrics(got, bhv.labels, bhv.cand_offsets)
+    n = bhv.n_impressions
+    assert abs(res.sums[0, nat.M_MRR] / n - per[:, 0].astype(np.float64).mean()) < 1e-9
+    assert abs(res.sums[0, nat.M_NDCG_K1] / n - per[:, 2].astype(np.float64).mean()) < 1e-9
+    assert abs(res.auc - mo.pooled_auc_exact(got, bhv.labels)) < METRIC_ATOL
+    assert abs(res.auc - float(tp.binary_auroc(torch.from_numpy(got), torch.from_numpy(bhv.labels.astype(np.int64))))) < METRIC_ATOL
+
+
+def test_pooled_auc_kernels_known_answers(evaluator_cls):
+    dev = torch.device("cuda:0")
+    rng = np.random.default_rng(5)
+    # heavy ties + saturating scores + in-unit-interval scores (no sigmoid) + one-class edge cases
+    cases = []
+    s = (rng.standard_normal(50_000) * 3).astype(np.float32)
+    s[::5] = s[7]
+    cases.append((s, (rng.random(50_000) < 0.04).astype(np.uint8), 1))
+    cases.append(((rng.standard_normal(20_000) * 40).astype(np.float32), (rng.random(20_000) < 0.3).astype(np.uint8), 1))
+    cases.append((rng.random(30_000).astype(np.float32), (rng.random(30_000) < 0.1).astype(np.uint8), 0))
+    cases.append((np.array([0.5, 0.5], np.float32), np.array([0, 1], np.uint8), 0))
+    for preds, labels, mode in cases:
+        out = torch.ops.manner_b200.pooled_auc(torch.from_numpy(preds).to(dev), torch.from_numpy(labels).to(dev), mode, None).cpu().numpy()
+        want = float(tp.binary_auroc(torch.from_numpy(preds), torch.from_numpy(labels.astype(np.int64))))
+        assert abs(out[0] - want) < METRIC_ATOL
+        assert out[1] == labels.sum() and out[2] == labels.size - labels.sum()
+    for labels in (np.zeros(100, np.uint8), np.ones(100, np.uint8)):
+        out = torch.ops.manner_b200.pooled_auc(torch.rand(100, device=dev), torch.from_numpy(labels).to(dev), 0, None).cpu().numpy()
+        assert out[0] == 0.0  # torchmetrics: no positive or no negative -> 0 (with a warning)
+
+
+def test_edge_cases_and_error_reporting(evaluator_cls):
+    table = mdata.synth_table(64, 128, 3)
+    ev = evaluator_cls([table])
+    # C = 1 with z-score -> NaN scores like torch.std of one element; rank is still 1
+    bhv = mdata.Behaviours(np.array([0, 2, 3], np.int32), np.array([1, 2, 3], np.int32), np.array([0, 1, 4], np.int32),
+                           np.array([5, 6, 7, 8], np.int32), np.array([1, 0, 1, 0], np.uint8))
+    res = ev.evaluate(ev.upload(bhv), weights=[[1.0]], zscore=True, want_scores=True, want_per_impression=True)
+    sc = res.scores.cpu().numpy()
+    assert np.isnan(sc[0]) and not np.isnan(sc[1:]).any()
+    per = res.per_impression.cpu().numpy()[0]
+    assert per[0, nat.M_MRR] == 1.0 and per[0, nat.M_NDCG_K0] == 1.0
+    # a row id outside the table is flagged, not read
+    bad = mdata.Behaviours(bhv.hist_offsets, bhv.hist_ids, bhv.cand_offsets, np.array([5, 6, 7, 64], np.int32), bhv.labels)
+    with pytest.raises(nat.NativeError):
+        ev.evaluate(ev.upload(bad))
+    # CPU tensors are refused: there is no fallback path
+    with pytest.raises(RuntimeError):
+        torch.ops.manner_b200.pooled_auc(torch.rand(4), torch.zeros(4, dtype=torch.uint8), 0, None)
+
+
+def test_small_shape_properties_full_size(evaluator_cls):
+    """BASELINE.json's MIND-small shape (73 152 impressions, 768-d): size-independent properties."""
+    tables, bhv = mdata.synth_workload("small", n_modules=1)
+    ev = evaluator_cls(tables)
+    dev_bhv = ev.upload(bhv)
+    full = ev.evaluate(dev_bhv, pooled_auc=True, want_scores=True, want_per_impression=True)
+    scores = full.scores.cpu().numpy()
+    # per-impression metrics bit-exact against the oracle on the device's scores, at full size
+    per_ref = mo.per_impression_metrics(scores, bhv.labels, bhv.cand_offsets)
+    per_dev = full.per_impression.cpu().numpy()[0]
+    np.testing.assert_array_equal(per_dev[:, :3], per_ref[:, :3])
+    np.testing.assert_allclose(per_dev[:, 3:5], per_ref[:, 3:5], atol=1e-7)
+    assert abs(full.auc - mo.pooled_auc_exact(scores, bhv.labels)) < 1e-9
+    # run-to-run determinism (fixed-order reduction): bit-identical sums
+    again = ev.evaluate(dev_bhv, pooled_auc=True)
+    np.testing.assert_array_equal(full.sums, again.sums)
+    assert full.auc == again.auc
+    # sharding invariance: metric sums over any partition equal the whole (<= 1e-12 relative)
+    bounds = mdata.balanced_shard_bounds(bhv, 3)
+    acc = np.zeros_like(full.sums)
+    for r in range(3):
+        part = ev.evaluate(ev.upload(bhv.slice(int(bounds[r]), int(bounds[r + 1]))))
+        acc += part.sums
+    np.testing.assert_allclose(acc, full.sums, rtol=1e-12, atol=1e-9)
+    # a 2 000-impression prefix against the reference-faithful oracle loop (steps of 8, padding, metric objects)
+    head = bhv.slice(0, 2000)
+    ref = mo.cr_eval_epoch(tables[0], mo.Behaviours(head.hist_offsets, head.hist_ids, head.cand_offsets, head.cand_ids, head.labels))
+    n = head.n_cand
+    assert np.all(np.abs(scores[:n].astype(np.float64) - ref["scores"]) <= _score_tol(tables[0], head, ref["scores"]))
+    flips = int((mo.stable_ranks(scores[:n], head.cand_offsets) != mo.stable_ranks(ref["scores"], head.cand_offsets)).sum())
+    head_res = ev.evaluate(ev.upload(head), pooled_auc=True)
+    m = head_res.metrics()
+    if flips == 0:  # near-tie flips (|ds| below tolerance) are reported, not hidden: they may move a metric by 1/B
+        for k in ("auc", "mrr", "ndcg@5", "ndcg@10"):
+            assert abs(m["test/" + k] - ref["metrics"]["test/" + k]) <= METRIC_ATOL, k
+    else:
+        print(f"near-tie rank flips between device and oracle scores: {flips}")
+        assert flips <= 4
