@@ -142,7 +142,17 @@ def _dedupe_within_segments(seg: np.ndarray, ids: np.ndarray, draw, rounds: int 
             return ids
         ids[dup] = draw(dup.size, uniform=it >= rounds // 2)
         live = live[np.isin(seg[live], np.unique(seg[dup]))]
-    raise RuntimeError("could not draw duplicate-free candidate lists")
+    # a few segments nearly as long as the pool they draw from: finish them exactly
+    pool = np.unique(draw(max(4096, 64 * ids.shape[0] // max(1, np.unique(seg).size)), uniform=True))
+    for sgm in np.unique(seg[live]):
+        where = np.nonzero(seg == sgm)[0]
+        _, first = np.unique(ids[where], return_index=True)
+        dup_pos = np.setdiff1d(np.arange(where.size), first)
+        free = np.setdiff1d(pool, ids[where])
+        if free.size < dup_pos.size:
+            raise RuntimeError("could not draw duplicate-free candidate lists")
+        ids[where[dup_pos]] = free[: dup_pos.size]
+    return ids
 
 
 def synth_behaviours(
