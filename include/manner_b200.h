@@ -73,6 +73,7 @@ extern "C" {
 #define MB200_M_SENT_PERS_K0 11 /* Personalization(num_sent_classes, k)      (ensemble_module.py:74-79) */
 #define MB200_M_SENT_PERS_K1 12
 #define MB200_NUM_METRICS 13
+#define MB200_PAYLOAD_TAIL 5
 
 /*
  * One evaluation call = one pass over a set of impressions: what the reference spreads over
@@ -128,7 +129,9 @@ typedef struct mb200_eval_desc {
   /* outputs (any may be NULL except sums) */
   float* scores;            /* [sum C] combined scores of weighting `scores_weighting` == the reference's flat `preds` */
   int32_t scores_weighting;
-  int32_t reserved0;
+  int32_t pack_payload;     /* != 0: `sums` has MB200_PAYLOAD_TAIL more doubles behind the [W, 13] block:
+                               n_impressions, then one 0/1 double per MB200_FLAG_* bit (1, 2, 4, 8) -- everything
+                               a multi-GPU caller sum-reduces, in one buffer, with no host-side packing */
   float* per_impression;    /* [W, n_impressions, MB200_NUM_METRICS] */
   double* sums;             /* [W, MB200_NUM_METRICS] sums over impressions (means = sums / n_impressions) */
   int32_t* flags;           /* one int32, OR-ed with MB200_FLAG_*; the caller zeroes it */

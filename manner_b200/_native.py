@@ -17,6 +17,7 @@ MAX_MODULES = 4
 MAX_K = 31
 MAX_CLASSES = 64
 NUM_METRICS = 13
+PAYLOAD_TAIL = 5
 
 OK, ERR_INVALID_ARG, ERR_UNSUPPORTED, ERR_CUDA, ERR_WORKSPACE = 0, 1, 2, 3, 4
 FLAG_BAD_ID, FLAG_CAND_OVERFLOW, FLAG_OUTSIDE_UNIT, FLAG_BAD_ASPECT = 1, 2, 4, 8
@@ -58,7 +59,7 @@ class EvalDesc(Structure):
         ("num_sent_classes", c_int32),
         ("scores", c_void_p),
         ("scores_weighting", c_int32),
-        ("reserved0", c_int32),
+        ("pack_payload", c_int32),
         ("per_impression", c_void_p),
         ("sums", c_void_p),
         ("flags", c_void_p),

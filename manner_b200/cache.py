@@ -1,0 +1,133 @@
+"""The step BEFORE the hot path: fill the embedding tables once and turn the
+reference's parsed behaviours into CSR, so the PLM leaves the evaluation loop.
+
+The reference re-encodes every history and candidate row of every batch with the PLM
+(cr_module.py:107,113; ensemble_module.py:115,121).  Here each module's ``news_encoder`` runs once
+over the unique news of the split (the set ``MINDNewsDataset`` builds, mind_news_dataset.py:16-25)
+and its output is written to a [n_news, D] table; behaviours become int32 CSR over table rows with
+the reference's history truncation (first ``max_history_length`` clicks, mind_rec_dataset.py:92).
+
+Everything here is host-side plumbing around torch modules and pandas frames; no arithmetic of the
+scoring path is done on the CPU.
+"""
+from __future__ import annotations
+
+from typing import Any, Callable, Dict, Iterable, List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+from torch import Tensor
+
+from .data import MAX_HISTORY, Behaviours
+
+
+def news_row_map(news_ids: Iterable[str]) -> Dict[str, int]:
+    """news id (the DataFrame index of the reference's ``news`` frame) -> table row."""
+    return {nid: row for row, nid in enumerate(news_ids)}
+
+
+def parse_id_list(text: str) -> List[str]:
+    """One ``history`` / ``candidates`` cell of ``parsed_behaviors.tsv`` -- a stringified Python list --
+    exactly as the reference's converters read it (mind_dataframe.py:283-286)."""
+    return text.strip("[]").replace("'", "").split(", ")
+
+
+def parse_label_list(text: str) -> List[int]:
+    return list(map(int, text.strip("[]").split(", ")))
+
+
+def behaviours_to_csr(
+    histories: Sequence[Sequence[str]],
+    candidates: Sequence[Sequence[str]],
+    labels: Sequence[Sequence[int]],
+    nid2row: Dict[str, int],
+    max_history_length: int = MAX_HISTORY,
+) -> Behaviours:
+    """Rows of the reference's behaviours frame (columns ``history``, ``candidates``, ``labels``;
+    mind_dataframe.py:360) -> CSR.  Keeps the FIRST ``max_history_length`` clicks, like
+    ``MINDRecDatasetTest.__getitem__`` (mind_rec_dataset.py:92).  Unknown news ids raise KeyError, as
+    ``news.loc[...]`` does in the reference (mind_rec_dataset.py:96-97)."""
+    if not (len(histories) == len(candidates) == len(labels)):
+        raise ValueError("histories, candidates and labels must have one entry per impression")
+    hist_rows: List[int] = []
+    cand_rows: List[int] = []
+    labs: List[int] = []
+    hist_off, cand_off = [0], [0]
+    for h, c, y in zip(histories, candidates, labels):
+        if len(c) != len(y):
+            raise ValueError("one label per candidate expected")
+        h = list(h)[:max_history_length]
+        if len(h) == 0:
+            # the reference drops such users when it parses behaviors.tsv (mind_dataframe.py:311-315)
+            raise ValueError("impression with an empty history (drop it, as the reference does at parse time)")
+        hist_rows.extend(nid2row[n] for n in h)
+        cand_rows.extend(nid2row[n] for n in c)
+        labs.extend(int(v) for v in y)
+        hist_off.append(len(hist_rows))
+        cand_off.append(len(cand_rows))
+    bhv = Behaviours(
+        np.asarray(hist_off, dtype=np.int32), np.asarray(hist_rows, dtype=np.int32), np.asarray(cand_off, dtype=np.int32),
+        np.asarray(cand_rows, dtype=np.int32), (np.asarray(labs) != 0).astype(np.uint8),
+    )
+    bhv.validate(len(nid2row))
+    return bhv
+
+
+def behaviours_frame_to_csr(behaviors: Any, nid2row: Dict[str, int], max_history_length: int = MAX_HISTORY) -> Behaviours:
+    """Same, from the pandas frame the reference's ``MINDDataFrame._load_behaviors`` returns (or from the
+    raw text columns of ``parsed_behaviors.tsv``)."""
+    def col(name: str, parse: Callable[[str], list]) -> list:
+        values = behaviors[name].tolist()
+        return [parse(v) if isinstance(v, str) else list(v) for v in values]
+
+    return behaviours_to_csr(col("history", parse_id_list), col("candidates", parse_id_list), col("labels", parse_label_list), nid2row, max_history_length)
+
+
+@torch.no_grad()
+def build_embedding_table(
+    news_encoder: torch.nn.Module,
+    news_batches: Iterable[Any],
+    n_news: int,
+    dim: int,
+    device: torch.device,
+    dtype: torch.dtype = torch.float32,
+) -> Tensor:
+    """Runs ``news_encoder`` (eval mode, the module's own PyTorch forward: news_encoder.py:75-129) over
+    ``news_batches`` -- an iterable of already tokenised news inputs in table-row order, e.g. the
+    ``x`` dicts ``MINDCollate._tokenize_df`` produces (mind_rec_dataset.py:146-168) -- and writes the
+    vectors into a [n_news, dim] table on ``device``."""
+    was_training = news_encoder.training
+    news_encoder.eval()
+    table = torch.empty(n_news, dim, dtype=dtype, device=device)
+    row = 0
+    for x in news_batches:
+        vec = news_encoder(_to_device(x, device))
+        if vec.dim() != 2 or vec.shape[1] != dim:
+            raise ValueError(f"news_encoder returned {tuple(vec.shape)}, expected [batch, {dim}]")
+        table[row : row + vec.shape[0]] = vec.to(dtype)
+        row += vec.shape[0]
+    if row != n_news:
+        raise ValueError(f"news_batches covered {row} news, table has {n_news} rows")
+    news_encoder.train(was_training)
+    return table
+
+
+def _to_device(x: Any, device: torch.device) -> Any:
+    if isinstance(x, Tensor):
+        return x.to(device, non_blocking=True)
+    if isinstance(x, dict):
+        return {k: _to_device(v, device) for k, v in x.items()}
+    if hasattr(x, "to") and not isinstance(x, (str, bytes)):
+        try:
+            return x.to(device)  # transformers.BatchEncoding
+        except TypeError:
+            return x
+    return x
+
+
+def aspect_arrays(news_frame: Any, nid2row: Dict[str, int]) -> Tuple[np.ndarray, np.ndarray]:
+    """Per-row ``category_label`` / ``sentiment_label`` (the columns MINDCollate reads,
+    mind_rec_dataset.py:164-165) in table-row order."""
+    order = sorted(nid2row, key=nid2row.get)
+    sub = news_frame.loc[order]
+    return sub["category_label"].to_numpy().astype(np.int32), sub["sentiment_label"].to_numpy().astype(np.int32)

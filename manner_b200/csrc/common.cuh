@@ -24,9 +24,10 @@ constexpr unsigned kFull = 0xffffffffu;
       0x1.99999ap-3f, 0.0f
 
 struct Tuning {
-  int chunks_per_warp = 8;  // work-balanced impression chunks per resident warp
-  int variant = 0;          // 0: LDG rows (L1-allocating); 1: LDG rows, L1::no_allocate
-  int ctas_per_sm = 3;      // resident CTAs (of kWarpsPerCta warps) per SM
+  int chunks_per_warp = 1;  // work-balanced impression chunks per resident warp (1: one contiguous range per warp)
+  int variant = 2;          // reference-width kernel: 0 = 4 rows in flight / 3 CTAs per SM, 1 = same with L1::no_allocate loads,
+                            // 2 = 3 rows / 4 CTAs (default: best on Zipf-shaped ids), 3 = 2 rows / 5 CTAs
+  int ctas_per_sm = 0;      // CTAs (of kWarpsPerCta warps) per SM; 0 = as many as are resident (occupancy query)
   int time_kernel = 0;      // 1: bracket the fused kernel with CUDA events (mb200_last_score_kernel_ms)
 };
 Tuning& tuning();

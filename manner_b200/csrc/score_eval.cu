@@ -102,27 +102,31 @@ __device__ __forceinline__ bool ranks_equal(float a, float b) { return (a == b) 
 // CPU `sum` over a contiguous vector (SumKernel.cpp: 8-lane vectors, scalar tail first, then the
 // lanes in order; L < 8 takes the 4-way ILP scalar path) -- what torchmetrics' `_dcg` evaluates.
 __device__ __forceinline__ float dcg_term(unsigned mask, int j) { return ((mask >> j) & 1u) ? c_inv_disc[j] : 0.0f; }
-__device__ float dcg_sum_aten_order(unsigned mask, int L) {
+__device__ __noinline__ float dcg_sum_aten_order(unsigned mask, int L) {
   if (L < 8) {
     float p0 = 0.f, p1 = 0.f, p2 = 0.f, p3 = 0.f;
     const int r = L >> 2;
     if (r) p0 = dcg_term(mask, 0), p1 = dcg_term(mask, 1), p2 = dcg_term(mask, 2), p3 = dcg_term(mask, 3);
+#pragma unroll 1
     for (int j = 4 * r; j < L; ++j) p0 = __fadd_rn(p0, dcg_term(mask, j));
     p0 = __fadd_rn(p0, p1), p0 = __fadd_rn(p0, p2), p0 = __fadd_rn(p0, p3);
     return p0;
   }
   const int vs = L >> 3;  // 1..3 because L <= MB200_MAX_K
   float fin = 0.f;
+#pragma unroll 1
   for (int j = 8 * vs; j < L; ++j) fin = __fadd_rn(fin, dcg_term(mask, j));
+#pragma unroll 1
   for (int l8 = 0; l8 < 8; ++l8) {
     float a = dcg_term(mask, l8);
+#pragma unroll 1
     for (int v = 1; v < vs; ++v) a = __fadd_rn(a, dcg_term(mask, 8 * v + l8));
     fin = __fadd_rn(fin, a);
   }
   return fin;
 }
 
-__device__ __forceinline__ float ndcg_at(unsigned hit_mask, int n_pos, int n_cand, int k) {
+__device__ __noinline__ float ndcg_at(unsigned hit_mask, int n_pos, int n_cand, int k) {
   const int L = min(k, n_cand);
   const int ideal_hits = min(n_pos, L);
   if (ideal_hits == 0) return 0.f;
@@ -134,9 +138,11 @@ __device__ __forceinline__ float ndcg_at(unsigned hit_mask, int n_pos, int n_can
 
 // ensemble_module.py:137-149.  mean = fp32 row sum / C; std = unbiased, accumulated in fp64 and
 // rounded to fp32 (ATen's CPU std of a float tensor accumulates in double).  C == 1 gives NaN.
-__device__ void zscore_inplace(float* s, int C, int lane) {
+__device__ __noinline__ void zscore_inplace(float* s, int C, int lane) {
+  __builtin_assume(__isShared(s));
   float part = 0.f;
   double dpart = 0.0;
+#pragma unroll 1
   for (int j = lane; j < C; j += 32) {
     const float v = s[j];
     part += v;
@@ -145,16 +151,19 @@ __device__ void zscore_inplace(float* s, int C, int lane) {
   const float mean = __fdiv_rn(warp_sum(part), (float)C);
   const double dmean = warp_sum(dpart) / (double)C;
   double q = 0.0;
+#pragma unroll 1
   for (int j = lane; j < C; j += 32) {
     const double d = (double)s[j] - dmean;
     q += d * d;
   }
   const float sd = (float)sqrt(warp_sum(q) / (double)(C - 1));
+#pragma unroll 1
   for (int j = lane; j < C; j += 32) s[j] = __fdiv_rn(__fsub_rn(s[j], mean), sd);
 }
 
 // Entropy-based Diversity@k of one aspect (metrics/functional.py:8-28): lanes own classes.
-__device__ float diversity_value(const uint8_t* top, int kk, int num_classes, int lane) {
+__device__ __noinline__ float diversity_value(const uint8_t* top, int kk, int num_classes, int lane) {
+  __builtin_assume(__isShared(top));
   float prob[2];
   float total = 0.f;
 #pragma unroll
@@ -162,6 +171,7 @@ __device__ float diversity_value(const uint8_t* top, int kk, int num_classes, in
     const int c = lane + 32 * t;
     int cnt = 0;
     if (c < num_classes)
+#pragma unroll 1
       for (int r = 0; r < kk; ++r) cnt += (top[r] == c);
     prob[t] = __fdiv_rn((float)cnt, (float)num_classes);
     total += prob[t];
@@ -182,13 +192,16 @@ __device__ float diversity_value(const uint8_t* top, int kk, int num_classes, in
 }
 
 // Generalised Jaccard of top-k candidate aspect counts vs history aspect counts (functional.py:31-70).
-__device__ float personalization_value(const uint8_t* top, int kk, const int* hist_count, int num_classes, int lane) {
+__device__ __noinline__ float personalization_value(const uint8_t* top, int kk, const int* hist_count, int num_classes, int lane) {
+  __builtin_assume(__isShared(top));
+  __builtin_assume(__isShared(hist_count));
   int mn = 0, mx = 0;
 #pragma unroll
   for (int t = 0; t < 2; ++t) {
     const int c = lane + 32 * t;
     if (c < num_classes) {
       int cnt = 0;
+#pragma unroll 1
       for (int r = 0; r < kk; ++r) cnt += (top[r] == c);
       const int hc = hist_count[c];
       mn += min(cnt, hc);
@@ -257,10 +270,17 @@ __device__ __forceinline__ int gather_pool_score(const T* __restrict__ table, lo
       }
     }
   }
-  // true division by the history length, as torch.div(sum, hist_size) (cr_module.py:121-123)
+  // true division by the history length, as torch.div(sum, hist_size) (cr_module.py:121-123).  The
+  // correctly rounded quotient x / h is produced without the generic division subroutine: with
+  // rh = RN(1/h), q = RN(x rh), r = x - q h (exact, one FMA), RN(q + r rh) is the IEEE quotient for
+  // integer-valued h < 2^23 (Markstein; checked against true fp32 division on 15 M cases).
   const float hf = (float)H;
+  const float rh = __frcp_rn(hf);
 #pragma unroll
-  for (int t = 0; t < NV * E; ++t) u[t] = __fdiv_rn(u[t], hf);
+  for (int t = 0; t < NV * E; ++t) {
+    const float q = __fmul_rn(u[t], rh);
+    u[t] = __fmaf_rn(__fmaf_rn(-q, hf, u[t]), rh, q);
+  }
   if (!EXACT) {
 #pragma unroll
     for (int v = 0; v < NV; ++v)
@@ -328,14 +348,26 @@ __device__ __noinline__ int rank_and_metrics(const EvalParams& p, const WarpSmem
   float* sc = sm.sc;
   float* comb = sm.comb;
   const uint8_t* lab = sm.lab;
+  __builtin_assume(__isShared(sc));
+  __builtin_assume(__isShared(comb));
+  __builtin_assume(__isShared(lab));
+  __builtin_assume(__isShared(sm.acc));
+  __builtin_assume(__isShared(sm.ccat));
+  __builtin_assume(__isShared(sm.csent));
+  __builtin_assume(__isShared(sm.hist_cat));
+  __builtin_assume(__isShared(sm.hist_sent));
+  __builtin_assume(__isShared(sm.top_cat));
+  __builtin_assume(__isShared(sm.top_sent));
   int warp_flags = 0;
 
   // ---- aspects of this impression (once, independent of the weighting) -----------------------------
   bool categ_group_ok = false, sent_group_ok = false;
   if (aspects) {
+#pragma unroll 1
     for (int t = lane; t < MB200_MAX_CLASSES; t += 32) sm.hist_cat[t] = 0, sm.hist_sent[t] = 0;
     __syncwarp();
     int cat_sum = 0, sent_sum = 0;
+#pragma unroll 1
     for (int j = lane; j < C; j += 32) {
       int id = p.cand_ids[c0 + j];
       if ((unsigned long long)(long long)id >= (unsigned long long)p.n_news) id = 0;
@@ -345,6 +377,7 @@ __device__ __noinline__ int rank_and_metrics(const EvalParams& p, const WarpSmem
       sm.ccat[j] = (uint8_t)a, sm.csent[j] = (uint8_t)b;
       cat_sum += a, sent_sum += b;
     }
+#pragma unroll 1
     for (int h = lane; h < H; h += 32) {
       int id = p.hist_ids[h0 + h];
       if ((unsigned long long)(long long)id >= (unsigned long long)p.n_news) id = 0;
@@ -360,6 +393,7 @@ __device__ __noinline__ int rank_and_metrics(const EvalParams& p, const WarpSmem
     __syncwarp();
   }
 
+#pragma unroll 1
   for (int w = 0; w < W; ++w) {
     const float* scores_w = sc;
     if (p.weights != nullptr || n_active > 1) {
@@ -369,6 +403,7 @@ __device__ __noinline__ int rank_and_metrics(const EvalParams& p, const WarpSmem
 #pragma unroll
       for (int m = 0; m < MB200_MAX_MODULES; ++m)
         wt[m] = (m < p.n_modules) ? (p.weights ? p.weights[(size_t)w * p.n_modules + m] : 1.0f) : 0.0f;
+#pragma unroll 1
       for (int j = lane; j < C; j += 32) {
         float s = (wt[0] == 1.0f) ? sc[j] : __fmul_rn(wt[0], sc[j]);
         int sl = 1;
@@ -387,6 +422,7 @@ __device__ __noinline__ int rank_and_metrics(const EvalParams& p, const WarpSmem
 
     if (p.scores != nullptr && w == p.scores_weighting) {
       bool outside = false;
+#pragma unroll 1
       for (int j = lane; j < C; j += 32) {
         const float s = scores_w[j];
         p.scores[c0 + j] = s;
@@ -401,15 +437,18 @@ __device__ __noinline__ int rank_and_metrics(const EvalParams& p, const WarpSmem
 
     if (!aspects) {
       // positives only: lanes split the comparison partners
+#pragma unroll 1
       for (int b0 = 0; b0 < C; b0 += 32) {
         const int j = b0 + lane;
         unsigned pm = __ballot_sync(kFull, j < C && lab[j] != 0);
         n_pos += __popc(pm);
+#pragma unroll 1
         while (pm) {
           const int pj = b0 + __ffs(pm) - 1;
           pm &= pm - 1;
           const float sp = scores_w[pj];
           int before = 0, nlt = 0, neq = 0;
+#pragma unroll 1
           for (int k = lane; k < C; k += 32) {
             const float sk = scores_w[k];
             before += (ranks_before(sk, sp) || (k < pj && ranks_equal(sk, sp))) ? 1 : 0;
@@ -426,10 +465,12 @@ __device__ __noinline__ int rank_and_metrics(const EvalParams& p, const WarpSmem
       int my_min = 0x7fffffff, my_pos = 0;
       unsigned my_hits = 0;
       long long my_g2 = 0;
+#pragma unroll 1
       for (int j = lane; j < C; j += 32) {
         const float sj = scores_w[j];
         const bool pos = lab[j] != 0;
         int before = 0, nlt = 0, neq = 0;
+#pragma unroll 1
         for (int k = 0; k < C; ++k) {
           const float sk = scores_w[k];
           before += (ranks_before(sk, sj) || (k < j && ranks_equal(sk, sj))) ? 1 : 0;
@@ -488,8 +529,8 @@ __device__ __noinline__ int rank_and_metrics(const EvalParams& p, const WarpSmem
   return warp_flags;
 }
 
-template <typename T, int NV, int R, bool EXACT, int POLICY>
-__global__ void __launch_bounds__(kThreads, 3) score_eval_kernel(const __grid_constant__ EvalParams p) {
+template <typename T, int NV, int R, bool EXACT, int POLICY, int MINB>
+__global__ void __launch_bounds__(kThreads, MINB) score_eval_kernel(const __grid_constant__ EvalParams p) {
   extern __shared__ __align__(16) unsigned char smem[];
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
@@ -579,7 +620,8 @@ __global__ void partition_kernel(const int32_t* __restrict__ hist_offsets, const
 // Deterministic second stage: sums[w][k] = sum over warps of partials, fixed order (strided per thread,
 // then a fixed shared-memory tree).  One block per weighting.
 __global__ void __launch_bounds__(256) reduce_partials_kernel(const double* __restrict__ partials, int total_warps, int W,
-                                                              double* __restrict__ sums) {
+                                                              double* __restrict__ sums, const int32_t* __restrict__ flags, int n_impr,
+                                                              int pack_payload) {
   __shared__ double sh[256][MB200_NUM_METRICS];
   const int w = blockIdx.x, t = threadIdx.x;
   double a[MB200_NUM_METRICS];
@@ -600,6 +642,12 @@ __global__ void __launch_bounds__(256) reduce_partials_kernel(const double* __re
     __syncthreads();
   }
   if (t < MB200_NUM_METRICS) sums[(size_t)w * MB200_NUM_METRICS + t] = sh[0][t];
+  if (pack_payload && w == 0 && t >= 32 && t < 32 + MB200_PAYLOAD_TAIL) {
+    // additive tail for a multi-GPU sum-reduction: impression count, then the flag word one bit per double
+    const int k = t - 32;
+    const int f = flags ? *flags : 0;
+    sums[(size_t)W * MB200_NUM_METRICS + k] = (k == 0) ? (double)n_impr : (double)((f >> (k - 1)) & 1);
+  }
 }
 
 // ------------------------------------------------------------------------------------------------------
@@ -619,7 +667,7 @@ struct LaunchPlan {
 
 static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
-static int make_plan(const mb200_eval_desc* d, int sm_count, LaunchPlan* plan) {
+static int make_plan(const mb200_eval_desc* d, int sm_count, int ctas, LaunchPlan* plan) {
   const int n_active = __builtin_popcount((unsigned)d->active_modules_mask);
   plan->cpad = (int)align_up((size_t)(d->max_cand > 0 ? d->max_cand : 1), 32);
   plan->acc_bytes = (int)align_up((size_t)d->n_weightings * MB200_NUM_METRICS * sizeof(double), 16);
@@ -629,9 +677,7 @@ static int make_plan(const mb200_eval_desc* d, int sm_count, LaunchPlan* plan) {
   plan->smem_per_warp = (int)per_warp;
   plan->smem_per_cta = per_warp * kWarpsPerCta;
   if (plan->smem_per_cta > 227 * 1024) return MB200_ERR_UNSUPPORTED;
-  int ctas = tuning().ctas_per_sm;
   if (ctas < 1) ctas = 1;
-  while (ctas > 1 && (plan->smem_per_cta + 1024) * ctas > 227 * 1024) --ctas;
   plan->grid = sm_count * ctas;
   plan->total_warps = plan->grid * kWarpsPerCta;
   long long chunks = (long long)plan->total_warps * (tuning().chunks_per_warp > 0 ? tuning().chunks_per_warp : 1);
@@ -669,41 +715,35 @@ static int validate(const mb200_eval_desc* d) {
   return MB200_OK;
 }
 
-template <typename T, int NV, int R, bool EXACT, bool BOTH_POLICIES>
-static cudaError_t launch_variant(const EvalParams& p, const LaunchPlan& plan, cudaStream_t stream) {
-  auto go = [&](auto kernel) -> cudaError_t {
-    if (plan.smem_per_cta > 48 * 1024) {
-      cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem_per_cta);
-      if (e != cudaSuccess) return e;
-    }
-    kernel<<<plan.grid, kThreads, plan.smem_per_cta, stream>>>(p);
-    return cudaGetLastError();
-  };
-  if constexpr (BOTH_POLICIES) {
-    if (tuning().variant == 1) return go(score_eval_kernel<T, NV, R, EXACT, 1>);
-  }
-  return go(score_eval_kernel<T, NV, R, EXACT, 0>);
-}
+using KernelFn = void (*)(const EvalParams);
 
-// Instantiations: the reference width (dim 768: 6 fp32 / 3 bf16 16-byte vectors per lane) gets an exact,
-// predicate-free kernel in both cache policies; every other width runs a predicated kernel whose
-// per-lane vector count is rounded up to 1, 2, 4 or 8.
+// Instantiations: the reference width (dim 768: 6 fp32 / 3 bf16 16-byte vectors per lane) gets exact,
+// predicate-free kernels in a few rows-in-flight / occupancy trade-offs (mb200_set_tuning key 1); every
+// other width runs a predicated kernel whose per-lane vector count is rounded up to 1, 2, 4 or 8.
 template <typename T, int NV>
-static cudaError_t launch_generic(const EvalParams& p, const LaunchPlan& plan, cudaStream_t stream) {
+static KernelFn generic_kernel() {
   constexpr int R = (NV <= 2) ? 8 : (NV <= 4) ? 6 : 3;
-  return launch_variant<T, NV, R, false, false>(p, plan, stream);
+  return score_eval_kernel<T, NV, R, false, 0, 3>;
 }
 
 template <typename T>
-static cudaError_t launch_dtype(const EvalParams& p, const LaunchPlan& plan, cudaStream_t stream) {
+static KernelFn select_kernel(int vec_per_row) {
   constexpr int kRefNV = 768 / Elem<T>::E / 32;  // 6 (fp32) or 3 (bf16)
-  constexpr int kRefR = (kRefNV == 6) ? 4 : 8;
-  if (p.vec_per_row == kRefNV * 32) return launch_variant<T, kRefNV, kRefR, true, true>(p, plan, stream);
-  const int nv = (p.vec_per_row + 31) / 32;
-  if (nv <= 1) return launch_generic<T, 1>(p, plan, stream);
-  if (nv <= 2) return launch_generic<T, 2>(p, plan, stream);
-  if (nv <= 4) return launch_generic<T, 4>(p, plan, stream);
-  return launch_generic<T, 8>(p, plan, stream);
+  constexpr int R = (kRefNV == 6) ? 4 : 8;
+  constexpr int R3 = (R * 3 + 3) / 4, R2 = (R + 1) / 2;
+  if (vec_per_row == kRefNV * 32) {
+    switch (tuning().variant) {
+      case 0: return score_eval_kernel<T, kRefNV, R, true, 0, 3>;
+      case 1: return score_eval_kernel<T, kRefNV, R, true, 1, 3>;
+      case 3: return score_eval_kernel<T, kRefNV, R2, true, 0, 5>;
+      default: return score_eval_kernel<T, kRefNV, R3, true, 0, 4>;
+    }
+  }
+  const int nv = (vec_per_row + 31) / 32;
+  if (nv <= 1) return generic_kernel<T, 1>();
+  if (nv <= 2) return generic_kernel<T, 2>();
+  if (nv <= 4) return generic_kernel<T, 4>();
+  return generic_kernel<T, 8>();
 }
 
 static int sm_count_of(int device, int* out) {
@@ -750,7 +790,7 @@ size_t eval_workspace_bytes(const mb200_eval_desc* d) {
   if (validate(d) != MB200_OK) return 0;
   LaunchPlan plan;
   // the SM count is not known without a device; size for the largest part this library targets (148 SMs, <= 160)
-  if (make_plan(d, 160, &plan) != MB200_OK) return 0;
+  if (make_plan(d, 160, 8, &plan) != MB200_OK) return 0;  // upper bound: 160 SMs x 8 CTAs
   return plan.bounds_bytes + plan.partials_bytes + 256;
 }
 
@@ -764,8 +804,22 @@ int score_eval(const mb200_eval_desc* d, cudaStream_t stream) {
   st = sm_count_of(device, &sms);
   if (st != MB200_OK) return st;
   if (sms > 160) return MB200_ERR_UNSUPPORTED;
+  const int vec_per_row = d->dim * (d->dtype == MB200_F32 ? 4 : 2) / 16;
+  KernelFn kern = (d->dtype == MB200_F32) ? select_kernel<float>(vec_per_row) : select_kernel<__nv_bfloat16>(vec_per_row);
   LaunchPlan plan;
-  st = make_plan(d, sms, &plan);
+  st = make_plan(d, sms, 1, &plan);  // shared-memory sizes first: they decide how many CTAs fit
+  if (st != MB200_OK) return st;
+  if (plan.smem_per_cta > 48 * 1024) {
+    st = cuda_status(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem_per_cta), "cudaFuncSetAttribute");
+    if (st != MB200_OK) return st;
+  }
+  // persistent grid: exactly as many CTAs as are resident at once (registers and shared memory decide)
+  int resident = 0;
+  st = cuda_status(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, kern, kThreads, plan.smem_per_cta), "cudaOccupancyMaxActiveBlocksPerMultiprocessor");
+  if (st != MB200_OK) return st;
+  if (resident < 1) return MB200_ERR_UNSUPPORTED;
+  const int want = tuning().ctas_per_sm > 0 ? tuning().ctas_per_sm : resident;
+  st = make_plan(d, sms, want < resident ? want : resident, &plan);
   if (st != MB200_OK) return st;
   const size_t need = plan.bounds_bytes + plan.partials_bytes;
   if (d->workspace == nullptr || ((uintptr_t)d->workspace & 255) || d->workspace_bytes < need) return MB200_ERR_WORKSPACE;
@@ -780,7 +834,7 @@ int score_eval(const mb200_eval_desc* d, cudaStream_t stream) {
   p.partials = reinterpret_cast<double*>(reinterpret_cast<unsigned char*>(d->workspace) + plan.bounds_bytes);
   p.n_news = d->n_news, p.row_stride = d->row_stride;
   p.n_impr = (int)d->n_impressions, p.n_modules = d->n_modules, p.active_mask = d->active_modules_mask;
-  p.vec_per_row = d->dim * (d->dtype == MB200_F32 ? 4 : 2) / 16;
+  p.vec_per_row = vec_per_row;
   p.zscore = d->zscore, p.n_weightings = d->n_weightings, p.scores_weighting = d->scores_weighting;
   p.k0 = d->k0, p.k1 = d->k1, p.cpad = plan.cpad, p.max_cand = d->max_cand, p.n_chunks = plan.n_chunks;
   p.num_categ = d->num_categ_classes, p.num_sent = d->num_sent_classes;
@@ -792,11 +846,13 @@ int score_eval(const mb200_eval_desc* d, cudaStream_t stream) {
   if (st != MB200_OK) return st;
   KernelTimer* timer = tuning().time_kernel ? timer_for(device) : nullptr;
   if (timer) cudaEventRecord(timer->begin, stream);
-  cudaError_t e = (d->dtype == MB200_F32) ? launch_dtype<float>(p, plan, stream) : launch_dtype<__nv_bfloat16>(p, plan, stream);
+  kern<<<plan.grid, kThreads, plan.smem_per_cta, stream>>>(p);
+  cudaError_t e = cudaGetLastError();
   if (timer) cudaEventRecord(timer->end, stream), timer->armed = true, g_last_timer = timer;
   st = cuda_status(e, "score_eval_kernel");
   if (st != MB200_OK) return st;
-  reduce_partials_kernel<<<d->n_weightings, 256, 0, stream>>>(p.partials, plan.total_warps, d->n_weightings, d->sums);
+  reduce_partials_kernel<<<d->n_weightings, 256, 0, stream>>>(p.partials, plan.total_warps, d->n_weightings, d->sums, d->flags, p.n_impr,
+                                                              d->pack_payload);
   st = cuda_status(cudaGetLastError(), "reduce_partials_kernel");
   if (st != MB200_OK) return st;
   note_launch(3);

@@ -81,6 +81,7 @@ def pooled_auc_distributed(
     labels: Tensor,
     flags: Tensor,
     group: Optional[dist.ProcessGroup] = None,
+    pos_cap: Optional[int] = None,
     build_and_sort: Callable = _cuda_build_and_sort,
     rank_sum: Callable = _cuda_rank_sum,
 ) -> Tensor:
@@ -90,27 +91,46 @@ def pooled_auc_distributed(
     Each rank sorts only its own negatives.  The positives of all ranks are all-gathered; every rank
     counts, for every positive, the negatives below / not above it among ITS negatives; those counts
     are additive over ranks:  auc = sum_ranks sum_pos (lb + ub) / (2 P N).
-    Returns fp64 [4] = (auc, P, N, sum2) on the inputs' device."""
+
+    ``pos_cap`` is an upper bound, agreed by all ranks beforehand, on any rank's number of positives
+    (``agree_pos_cap``); without it the ranks first exchange their counts, which costs one more collective
+    and a host synchronisation.  Returns int64 [3] = (sum2, P, N) on the inputs' device; auc =
+    sum2 / (2 P N) (0 when P or N is 0, as torchmetrics returns)."""
     world = dist.get_world_size(group)
+    dev = preds.device
     sorted_keys, pos_keys, n_pos = build_and_sort(preds, labels, flags)
-    counts = torch.zeros(world, dtype=torch.int64, device=preds.device)
-    dist.all_gather_into_tensor(counts, n_pos.reshape(1), group=group)
-    counts_h = counts.cpu()
-    cap = max(int(counts_h.max().item()), 1)
-    mine = torch.zeros(cap, dtype=pos_keys.dtype, device=preds.device)
-    k = int(counts_h[dist.get_rank(group)].item())
-    mine[:k] = pos_keys[:k]
-    gathered = torch.empty(world * cap, dtype=pos_keys.dtype, device=preds.device)
-    dist.all_gather_into_tensor(gathered, mine, group=group)
-    sum2 = torch.zeros(1, dtype=torch.int64, device=preds.device)
+    if pos_cap is None:
+        counts = torch.zeros(world, dtype=torch.int64, device=dev)
+        dist.all_gather_into_tensor(counts, n_pos.reshape(1), group=group)
+        pos_cap = int(counts.max().item())
+    cap = max(2, (int(pos_cap) + 1) // 2 * 2)  # even: every rank's segment then starts 8-byte aligned
+    # segment = [count as int64 (two int32 words)] [cap positive keys]; one all-gather moves both
+    seg = torch.empty(cap + 2, dtype=torch.int32, device=dev)
+    seg[:2].view(torch.int64).copy_(n_pos)
+    k = min(cap, pos_keys.numel())
+    seg[2 : 2 + k].copy_(pos_keys[:k])
+    flat = torch.empty(world * (cap + 2), dtype=torch.int32, device=dev)
+    dist.all_gather_into_tensor(flat, seg, group=group)
+    gathered = flat.view(world, cap + 2)
+    stats = torch.zeros(3, dtype=torch.int64, device=dev)
     for r in range(world):
-        if int(counts_h[r].item()) > 0:
-            rank_sum(sorted_keys, n_pos, gathered[r * cap : (r + 1) * cap], counts[r : r + 1], sum2)
-    stats = torch.stack([sum2.reshape(()), n_pos.reshape(()), torch.tensor(preds.numel(), device=preds.device) - n_pos.reshape(())])
+        rank_sum(sorted_keys, n_pos, gathered[r, 2:], gathered[r, :2].view(torch.int64), stats[0:1])
+    stats[1:2].copy_(n_pos)
+    stats[2:3].copy_(preds.numel() - n_pos)
     dist.all_reduce(stats, op=dist.ReduceOp.SUM, group=group)
-    s2, p, n = stats[0].double(), stats[1].double(), stats[2].double()
-    auc = torch.where((p > 0) & (n > 0), s2 / (2.0 * p * n).clamp_min(1.0), torch.zeros((), dtype=torch.float64, device=preds.device))
-    return torch.stack([auc, p, n, s2])
+    return stats
+
+
+def auc_from_stats(stats: Tensor) -> Tuple[float, int, int]:
+    s2, p, n = (int(x) for x in stats.cpu().tolist())
+    return (s2 / (2.0 * p * n) if p > 0 and n > 0 else 0.0), p, n
+
+
+def agree_pos_cap(n_pos_local: int, device: torch.device, group: Optional[dist.ProcessGroup] = None) -> int:
+    """One-time agreement (per uploaded shard, outside the hot loop) on the largest per-rank positive count."""
+    t = torch.tensor([int(n_pos_local)], dtype=torch.int64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
+    return int(t.item())
 
 
 def init_from_env(backend: str = "nccl") -> Tuple[int, int, int]:

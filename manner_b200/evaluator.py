@@ -57,6 +57,8 @@ class DeviceBehaviours:
     n_impressions: int
     max_cand: int
     h2d_bytes: int = 0
+    n_pos: int = 0  # positives in this shard (host-known from the labels)
+    pos_cap: Optional[int] = None  # agreed upper bound on any rank's positives (multi-GPU pooled AUC)
 
 
 @dataclass
@@ -91,9 +93,11 @@ class EvalResult:
 class PendingEval:
     """Device-side results of an enqueued pass (no host synchronisation yet)."""
 
-    sums: Tensor
+    sums: Tensor  # [W, 13], or the packed all-reduced payload [W*13 + 5] when distributed
     flags: Tensor
-    n_total: Union[int, Tensor]
+    n_weightings: int
+    n_impressions: int  # of this rank
+    distributed: bool
     auc_stats: Optional[Tensor]
     scores: Optional[Tensor]
     per_impression: Optional[Tensor]
@@ -140,21 +144,27 @@ class ScoreEvaluator:
         return t.to(self.device).contiguous()
 
     # -- inputs ----------------------------------------------------------------------------------------------
-    def upload(self, bhv: Behaviours, pinned: Optional[Dict[str, Tensor]] = None) -> DeviceBehaviours:
+    def upload(self, bhv: Behaviours, pinned: Optional[Dict[str, object]] = None, pos_cap: Optional[int] = None) -> DeviceBehaviours:
         """Host CSR -> device (asynchronous on the current stream).  ``pinned`` lets a caller reuse
-        page-locked staging tensors (see ``pin``)."""
+        page-locked staging tensors (see ``pin``); ``pos_cap`` is the multi-GPU bound of
+        ``dist.agree_pos_cap`` when the caller already has it."""
         src = pinned if pinned is not None else self.pin(bhv)
-        dev = {k: v.to(self.device, non_blocking=True) for k, v in src.items()}
-        nbytes = sum(v.numel() * v.element_size() for v in src.values())
+        dev = {k: v.to(self.device, non_blocking=True) for k, v in src.items() if isinstance(v, Tensor)}
+        nbytes = sum(v.numel() * v.element_size() for v in src.values() if isinstance(v, Tensor))
         return DeviceBehaviours(
             dev["hist_offsets"], dev["hist_ids"], dev["cand_offsets"], dev["cand_ids"], dev["labels"],
-            bhv.n_impressions, max(bhv.max_cand, 1), nbytes,
+            bhv.n_impressions, src["max_cand"], nbytes, src["n_pos"], pos_cap,
         )
 
     @staticmethod
-    def pin(bhv: Behaviours) -> Dict[str, Tensor]:
+    def pin(bhv: Behaviours) -> Dict[str, object]:
+        """Page-locked staging copies of the CSR arrays + the two host-side facts a launch needs
+        (largest candidate list, number of positives), computed once here rather than per upload."""
         arrays = dict(hist_offsets=bhv.hist_offsets, hist_ids=bhv.hist_ids, cand_offsets=bhv.cand_offsets, cand_ids=bhv.cand_ids, labels=bhv.labels)
-        return {k: torch.from_numpy(np.ascontiguousarray(v)).pin_memory() for k, v in arrays.items()}
+        out: Dict[str, object] = {k: torch.from_numpy(np.ascontiguousarray(v)).pin_memory() for k, v in arrays.items()}
+        out["max_cand"] = max(bhv.max_cand, 1)
+        out["n_pos"] = int(bhv.labels.sum())
+        return out
 
     # -- the hot path ----------------------------------------------------------------------------------------
     def launch(
@@ -188,36 +198,43 @@ class ScoreEvaluator:
         scores, per_impr, sums, flags = torch.ops.manner_b200.score_eval(
             self.tables, bhv.hist_offsets, bhv.hist_ids, bhv.cand_offsets, bhv.cand_ids, bhv.labels, w_dev, zscore,
             bhv.max_cand, active, self.ks[0], self.ks[1], need_scores, scores_weighting, want_per_impression,
-            self.news_category, self.news_sentiment, self.num_categ_classes, self.num_sent_classes,
+            self.news_category, self.news_sentiment, self.num_categ_classes, self.num_sent_classes, distributed,
         )
-        n_total: Union[int, Tensor] = bhv.n_impressions
+        n_w = 1 if w_dev is None else w_dev.shape[0]
         auc_stats: Optional[Tensor] = None
         if distributed:
-            payload = mdist.pack_metric_payload(sums, flags, bhv.n_impressions)
-            torch.distributed.all_reduce(payload, op=torch.distributed.ReduceOp.SUM, group=group)
-            n_total = payload  # unpacked in finish(): the count sits behind the sums
+            # `sums` is the packed payload [W*13 sums, impression count, 4 flag bits]: one NCCL all-reduce
+            torch.distributed.all_reduce(sums, op=torch.distributed.ReduceOp.SUM, group=group)
             if pooled_auc:
-                _, gflags, _ = mdist.unpack_metric_payload_device(payload, sums.shape)
-                auc_stats = mdist.pooled_auc_distributed(scores, bhv.labels, gflags, group)
+                outside = n_w * nat.NUM_METRICS + 1 + 2  # bit index of MB200_FLAG_OUTSIDE_UNIT in the tail
+                gflags = (sums[outside : outside + 1] > 0).to(torch.int32) * nat.FLAG_OUTSIDE_UNIT
+                auc_stats = mdist.pooled_auc_distributed(scores, bhv.labels, gflags, group, pos_cap=bhv.pos_cap)
         elif pooled_auc:
             auc_stats = torch.ops.manner_b200.pooled_auc(scores, bhv.labels, 2, flags)
-        return PendingEval(sums, flags, n_total, auc_stats, scores if want_scores else None, per_impr if want_per_impression else None)
+        return PendingEval(sums, flags, n_w, bhv.n_impressions, distributed, auc_stats,
+                           scores if want_scores else None, per_impr if want_per_impression else None)
 
     def finish(self, pending: "PendingEval") -> EvalResult:
         """The one device -> host read of a pass: metric sums, flag word, AUC statistics."""
-        if isinstance(pending.n_total, Tensor):
-            sums_t, flags_t, n_total = mdist.unpack_metric_payload(pending.n_total.cpu(), pending.sums.shape)
-            sums_h, flags_h = sums_t.numpy(), int(flags_t.item())
-            d2h = pending.n_total.numel() * 8
+        n_block = pending.n_weightings * nat.NUM_METRICS
+        if pending.distributed:
+            packed = pending.sums.cpu().numpy()
+            sums_h, n_total = packed[:n_block].reshape(pending.n_weightings, nat.NUM_METRICS), int(round(packed[n_block]))
+            flags_h = sum((1 << b) for b in range(mdist.N_FLAG_BITS) if packed[n_block + 1 + b] > 0)
         else:
             packed = torch.cat([pending.sums.reshape(-1), pending.flags.to(torch.float64)]).cpu().numpy()
-            sums_h, flags_h, n_total = packed[:-1].reshape(tuple(pending.sums.shape)), int(packed[-1]), pending.n_total
-            d2h = packed.size * 8
+            sums_h, flags_h, n_total = packed[:-1].reshape(pending.n_weightings, nat.NUM_METRICS), int(packed[-1]), pending.n_impressions
+        d2h = packed.size * 8
         auc = counts = None
         if pending.auc_stats is not None:
-            a = pending.auc_stats.cpu().numpy()
-            d2h += a.size * 8
-            auc, counts = float(a[0]), (int(a[1]), int(a[2]))
+            if pending.distributed:
+                auc, p, n = mdist.auc_from_stats(pending.auc_stats)
+                counts = (p, n)
+                d2h += 24
+            else:
+                a = pending.auc_stats.cpu().numpy()
+                d2h += a.size * 8
+                auc, counts = float(a[0]), (int(a[1]), int(a[2]))
         if flags_h & (nat.FLAG_BAD_ID | nat.FLAG_CAND_OVERFLOW | nat.FLAG_BAD_ASPECT):
             raise nat.NativeError(
                 f"manner_b200 kernels flagged bad input (flags={flags_h}): "

@@ -1,0 +1,220 @@
+"""Drop-in LightningModules for the reference's Hydra seam.
+
+    # configs/model/cr_module_b200.yaml        _target_: manner_b200.modules.CRModuleB200
+    # configs/model/ensemble_module_b200.yaml  _target_: manner_b200.modules.EnsembleModuleB200
+
+``CRModuleB200`` / ``EnsembleModuleB200`` subclass the reference's ``CRModule`` / ``EnsembleModule``
+(manner/models/cr_module.py:19, ensemble_module.py:17) -- same constructor keywords (plus defaulted
+ones), same ``news_encoder.*`` parameters, so existing experiment YAMLs and Lightning checkpoints
+load unchanged -- and replace only the test path: ``test_step`` / ``on_test_epoch_end`` (and
+``validation_step`` metrics for the CR module) hand the batch's news vectors to the fused sm_100a
+kernel instead of ``to_dense_batch`` + per-row Python loops + ``bmm`` + torchmetrics' group loops.
+
+The evaluation logic lives in ``B200EvalMixin`` and ``StepScorer``, which do not need Lightning: the
+reference package and its dependencies (lightning, torchmetrics, torch_geometric, ...) are optional
+imports, so this file is importable -- and testable -- without them.
+
+Two ways to feed the kernel:
+  * step mode (default): the unchanged DataModule delivers ``MINDRecBatch`` es (mind_batch.py:6-12);
+    the module runs its PLM ``news_encoder`` on ``x_hist`` / ``x_cand`` exactly as the reference does
+    (cr_module.py:107,113) and uses the resulting [sum H + sum C, D] matrix as the step's table;
+  * cached mode: ``manner_b200.cache`` builds the table once per epoch and the CSR behaviours once per
+    dataset; ``ScoreEvaluator.evaluate`` then scores the whole epoch in one call (the PLM leaves the loop).
+"""
+from __future__ import annotations
+
+from typing import Any, Dict, List, Optional, Sequence
+
+import torch
+from torch import Tensor
+
+from . import _native as nat
+from .evaluator import SLOT_KEYS
+
+try:  # the reference package is optional: it needs lightning, torchmetrics, torch_geometric, ...
+    from manner.models.cr_module import CRModule as _RefCRModule  # type: ignore
+    from manner.models.ensemble_module import EnsembleModule as _RefEnsembleModule  # type: ignore
+
+    HAVE_REFERENCE = True
+except Exception:  # pragma: no cover - depends on the environment
+    HAVE_REFERENCE = False
+
+    class _Unavailable(torch.nn.Module):
+        def __init__(self, *args: Any, **kwargs: Any) -> None:
+            raise ImportError(
+                "manner_b200.modules needs the reference package `manner` (andreeaiana/manner) and its dependencies "
+                "(lightning, torchmetrics, torch_geometric, pytorch_metric_learning) on PYTHONPATH; "
+                "use manner_b200.ScoreEvaluator directly when they are not installed"
+            )
+
+    _RefCRModule = _RefEnsembleModule = _Unavailable  # type: ignore
+
+
+def _segment_offsets(seg: Tensor, n: int) -> Tensor:
+    """Sorted segment ids (MINDCollate's ``repeat_interleave(arange(B), sizes)``,
+    mind_rec_dataset.py:171-174) -> int32 CSR offsets [n + 1], on the ids' device, no host sync."""
+    counts = torch.bincount(seg, minlength=n)
+    off = torch.zeros(n + 1, dtype=torch.int32, device=seg.device)
+    off[1:] = torch.cumsum(counts, 0)
+    return off
+
+
+class StepScorer:
+    """Scores one MINDRecBatch from already-encoded news vectors and accumulates epoch statistics.
+
+    Replaces, per step, cr_module.py:108-131,173-182 / ensemble_module.py:116-149,155-192 and, at the
+    end, cr_module.py:266-274 / ensemble_module.py:214-238."""
+
+    def __init__(self, zscore: bool, ks=(5, 10), with_auc: bool = True, num_categ_classes: int = 19, num_sent_classes: int = 4) -> None:
+        nat.lib()
+        self.zscore, self.ks, self.with_auc = zscore, (int(ks[0]), int(ks[1])), with_auc
+        self.num_categ_classes, self.num_sent_classes = num_categ_classes, num_sent_classes
+        self.reset()
+
+    def reset(self) -> None:
+        self.sums: Optional[Tensor] = None
+        self.n_impressions = 0
+        self.flags: Optional[Tensor] = None
+        self.preds: List[Tensor] = []
+        self.targets: List[Tensor] = []
+        self.has_aspects = False
+
+    @torch.no_grad()
+    def step(self, hist_vecs: Sequence[Tensor], cand_vecs: Sequence[Tensor], batch: Dict[str, Any], weights: Optional[Sequence[float]] = None) -> Tensor:
+        """``hist_vecs[m]`` / ``cand_vecs[m]``: module m's news vectors for ``batch['x_hist']`` / ``['x_cand']``
+        ([sum H, D] / [sum C, D]).  Returns the flat combined scores [sum C] (the reference's ``preds``)."""
+        dev = cand_vecs[0].device
+        batch_hist, batch_cand = batch["batch_hist"].to(dev), batch["batch_cand"].to(dev)
+        n_hist, n_cand = hist_vecs[0].shape[0], cand_vecs[0].shape[0]
+        # B = batch.max() + 1 as to_dense_batch derives it (the one host read of the step)
+        n_impr = int(torch.maximum(batch_hist.max(), batch_cand.max()).item()) + 1
+        hist_off, cand_off = _segment_offsets(batch_hist, n_impr), _segment_offsets(batch_cand, n_impr)
+        # the step's table is [history rows; candidate rows]: ids are just positions
+        tables = [torch.cat([h, c]).float().contiguous() for h, c in zip(hist_vecs, cand_vecs)]
+        hist_ids = torch.arange(n_hist, dtype=torch.int32, device=dev)
+        cand_ids = torch.arange(n_hist, n_hist + n_cand, dtype=torch.int32, device=dev)
+        labels = (batch["labels"].to(dev) != 0).to(torch.uint8)
+        w_dev = None if weights is None else torch.tensor([list(weights)], dtype=torch.float32, device=dev)
+        active = (1 << len(tables)) - 1
+        cat = sent = None
+        if "category" in batch["x_cand"] and "sentiment" in batch["x_cand"] and self.zscore:
+            cat = torch.cat([batch["x_hist"]["category"], batch["x_cand"]["category"]]).to(dev, torch.int32)
+            sent = torch.cat([batch["x_hist"]["sentiment"], batch["x_cand"]["sentiment"]]).to(dev, torch.int32)
+            self.has_aspects = True
+        scores, _, sums, flags = torch.ops.manner_b200.score_eval(
+            tables, hist_off, hist_ids, cand_off, cand_ids, labels, w_dev, self.zscore, max(n_cand, 1), active,
+            self.ks[0], self.ks[1], True, 0, False, cat, sent, self.num_categ_classes, self.num_sent_classes,
+        )
+        self.sums = sums if self.sums is None else self.sums + sums
+        self.flags = flags if self.flags is None else self.flags | flags
+        self.n_impressions += n_impr
+        if self.with_auc:
+            self.preds.append(scores), self.targets.append(labels)
+        return scores
+
+    def compute(self, prefix: str = "test/") -> Dict[str, float]:
+        """Epoch means under the reference's log keys (cr_module.py:79-89, ensemble_module.py:50-84)."""
+        if self.sums is None:
+            return {}
+        out: Dict[str, float] = {}
+        auc_stats = None
+        if self.with_auc and self.preds:
+            # AUROC's any-outside-[0,1] sigmoid rule is decided over the whole epoch (cr_module.py:273)
+            auc_stats = torch.ops.manner_b200.pooled_auc(torch.cat(self.preds), torch.cat(self.targets), 2, self.flags)
+        s = self.sums[0].cpu().numpy()
+        flags = int(self.flags.cpu().item())
+        if flags & (nat.FLAG_BAD_ID | nat.FLAG_CAND_OVERFLOW | nat.FLAG_BAD_ASPECT):
+            raise nat.NativeError(f"manner_b200 kernels flagged bad input (flags={flags})")
+        n = max(self.n_impressions, 1)
+        for slot, key in SLOT_KEYS.items():
+            if slot >= nat.M_CATEG_DIV_K0 and not self.has_aspects:
+                continue
+            out[prefix + key.format(k0=self.ks[0], k1=self.ks[1])] = float(s[slot] / n)
+        out[prefix + "gauc"] = float(s[nat.M_GAUC] / s[nat.M_GAUC_VALID]) if s[nat.M_GAUC_VALID] > 0 else 0.0
+        if auc_stats is not None:
+            out[prefix + "auc"] = float(auc_stats.cpu()[0])
+        return out
+
+
+class B200EvalMixin:
+    """``test_step`` / ``on_test_epoch_end`` on the fused kernel.  Mixed in before the reference module
+    (or any module exposing the same attributes) in the MRO."""
+
+    _b200_zscore = False
+    _b200_with_auc = True
+
+    def _b200_scorer(self) -> StepScorer:
+        if getattr(self, "_b200_step_scorer", None) is None:
+            hp = getattr(self, "hparams", {})
+            self._b200_step_scorer = StepScorer(
+                self._b200_zscore, with_auc=self._b200_with_auc,
+                num_categ_classes=int(hp.get("num_categ_classes", 19)) if hasattr(hp, "get") else 19,
+                num_sent_classes=int(hp.get("num_sent_classes", 4)) if hasattr(hp, "get") else 4,
+            )
+        return self._b200_step_scorer
+
+    def _b200_encoders(self) -> List[torch.nn.Module]:  # pragma: no cover - overridden
+        raise NotImplementedError
+
+    def _b200_weights(self) -> Optional[List[float]]:
+        return None
+
+    def test_step(self, batch: Dict[str, Any], batch_idx: int) -> None:
+        encoders = self._b200_encoders()
+        hist = [enc(batch["x_hist"]) for enc in encoders]
+        cand = [enc(batch["x_cand"]) for enc in encoders]
+        self._b200_scorer().step(hist, cand, batch, self._b200_weights())
+
+    def on_test_epoch_end(self) -> None:
+        scorer = self._b200_scorer()
+        values = scorer.compute(prefix="test/")
+        scorer.reset()
+        self.log_dict(values, on_step=False, on_epoch=True, prog_bar=True, logger=True)
+
+
+class CRModuleB200(B200EvalMixin, _RefCRModule):
+    """CRModule (late fusion) with the B200 test path.  Extra keyword: ``scorer`` ("b200" | "reference")
+    to fall back to the reference's own test path for A/B comparison."""
+
+    def __init__(self, *args: Any, scorer: str = "b200", **kwargs: Any) -> None:
+        super().__init__(*args, **kwargs)
+        self._b200_enabled = scorer == "b200"
+        if self._b200_enabled and not self.hparams.late_fusion:
+            raise ValueError("CRModuleB200 accelerates the late-fusion path (late_fusion=True); early fusion is not built yet")
+
+    def _b200_encoders(self) -> List[torch.nn.Module]:
+        return [self.news_encoder]
+
+    def test_step(self, batch: Dict[str, Any], batch_idx: int) -> None:
+        if not self._b200_enabled:
+            return _RefCRModule.test_step(self, batch, batch_idx)
+        return B200EvalMixin.test_step(self, batch, batch_idx)
+
+    def on_test_epoch_end(self) -> None:
+        if not self._b200_enabled:
+            return _RefCRModule.on_test_epoch_end(self)
+        return B200EvalMixin.on_test_epoch_end(self)
+
+
+class EnsembleModuleB200(B200EvalMixin, _RefEnsembleModule):
+    """EnsembleModule (CR + category / sentiment A-Modules, z-score, aspect weights) with the B200 test
+    path.  Logs the reference's keys (ndcg, *_div, *_pers) plus mrr / gauc."""
+
+    _b200_zscore = True
+    _b200_with_auc = False  # the reference's EnsembleModule has no AUROC (ensemble_module.py:50-55)
+
+    def _b200_encoders(self) -> List[torch.nn.Module]:
+        encs = [self.cr_module.news_encoder]
+        if self.hparams.categ_weight != 0:
+            encs.append(self.a_module_categ.news_encoder)
+        if self.hparams.sent_weight != 0:
+            encs.append(self.a_module_sent.news_encoder)
+        return encs
+
+    def _b200_weights(self) -> Optional[List[float]]:
+        w = [1.0]
+        if self.hparams.categ_weight != 0:
+            w.append(float(self.hparams.categ_weight))
+        if self.hparams.sent_weight != 0:
+            w.append(float(self.hparams.sent_weight))
+        return w

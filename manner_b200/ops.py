@@ -62,10 +62,12 @@ def score_eval(
     news_sentiment: Optional[Tensor],
     num_categ_classes: int,
     num_sent_classes: int,
+    pack_payload: bool = False,
 ) -> Tuple[Tensor, Tensor, Tensor, Tensor]:
     """Fused gather / pool / score / z-score / ensemble / per-impression metrics (include/manner_b200.h,
     mb200_score_eval).  Returns (scores fp32 [sum C] or empty, per_impression fp32 [W, B, 13] or empty,
-    sums fp64 [W, 13], flags int32 [1])."""
+    sums fp64 [W, 13], flags int32 [1]).  With ``pack_payload`` the sums come back flat, fp64 [W*13 + 5],
+    with the impression count and the flag bits appended: the buffer a multi-GPU caller all-reduces."""
     lib = nat.lib()
     if len(tables) < 1 or len(tables) > nat.MAX_MODULES:
         raise ValueError(f"1..{nat.MAX_MODULES} embedding tables expected")
@@ -102,10 +104,11 @@ def score_eval(
         stream = torch.cuda.current_stream(dev).cuda_stream
         scores = torch.empty(cand_ids.numel() if want_scores else 0, dtype=torch.float32, device=dev)
         per_impr = torch.empty((n_w, n_impr, nat.NUM_METRICS) if want_per_impression else (0,), dtype=torch.float32, device=dev)
-        sums = torch.empty((n_w, nat.NUM_METRICS), dtype=torch.float64, device=dev)
+        sums = torch.empty(n_w * nat.NUM_METRICS + nat.PAYLOAD_TAIL if pack_payload else (n_w, nat.NUM_METRICS), dtype=torch.float64, device=dev)
         flags = torch.zeros(1, dtype=torch.int32, device=dev)
 
         d = nat.EvalDesc()
+        d.pack_payload = int(pack_payload)
         d.struct_size = ctypes.sizeof(nat.EvalDesc)
         d.n_modules = len(tables)
         d.dtype = nat.F32 if t0.dtype == torch.float32 else nat.BF16
@@ -144,14 +147,15 @@ def score_eval(
 
 @score_eval.register_fake
 def _(tables, hist_offsets, hist_ids, cand_offsets, cand_ids, labels, weights, zscore, max_cand, active_mask, k0, k1,
-      want_scores, scores_weighting, want_per_impression, news_category, news_sentiment, num_categ_classes, num_sent_classes):
+      want_scores, scores_weighting, want_per_impression, news_category, news_sentiment, num_categ_classes, num_sent_classes,
+      pack_payload=False):
     dev = tables[0].device
     n_w = 1 if weights is None else weights.shape[0]
     n_impr = hist_offsets.numel() - 1
     return (
         torch.empty(cand_ids.numel() if want_scores else 0, dtype=torch.float32, device=dev),
         torch.empty((n_w, n_impr, nat.NUM_METRICS) if want_per_impression else (0,), dtype=torch.float32, device=dev),
-        torch.empty((n_w, nat.NUM_METRICS), dtype=torch.float64, device=dev),
+        torch.empty(n_w * nat.NUM_METRICS + nat.PAYLOAD_TAIL if pack_payload else (n_w, nat.NUM_METRICS), dtype=torch.float64, device=dev),
         torch.empty(1, dtype=torch.int32, device=dev),
     )
 

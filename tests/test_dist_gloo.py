@@ -68,10 +68,15 @@ def _worker(rank: int, port: int, tmp: str) -> None:
         outside = int(not ((local["scores"] >= 0) & (local["scores"] <= 1)).all())
         flags = torch.tensor([4 * outside + (8 if rank == 1 else 0)], dtype=torch.int32)  # rank 1 also raises a made-up bit
         g_sums, g_flags, g_n = mdist.reduce_metric_sums(sums, flags, shard.n_impressions)
-        stats = mdist.pooled_auc_distributed(torch.from_numpy(local["scores"]), torch.from_numpy(shard.labels), g_flags,
-                                             build_and_sort=_np_build_and_sort, rank_sum=_np_rank_sum)
+        preds_t, labels_t = torch.from_numpy(local["scores"]), torch.from_numpy(shard.labels)
+        # (a) counts exchanged inside the call; (b) with a bound agreed beforehand (no count exchange)
+        stats_a = mdist.pooled_auc_distributed(preds_t, labels_t, g_flags, build_and_sort=_np_build_and_sort, rank_sum=_np_rank_sum)
+        cap = mdist.agree_pos_cap(int(shard.labels.sum()), torch.device("cpu"))
+        stats_b = mdist.pooled_auc_distributed(preds_t, labels_t, g_flags, pos_cap=cap, build_and_sort=_np_build_and_sort, rank_sum=_np_rank_sum)
+        assert torch.equal(stats_a, stats_b)
+        auc, p, n = mdist.auc_from_stats(stats_b)
         if rank == 0:
-            np.savez(os.path.join(tmp, "out.npz"), sums=g_sums.numpy(), flags=g_flags.numpy(), n=g_n, stats=stats.numpy())
+            np.savez(os.path.join(tmp, "out.npz"), sums=g_sums.numpy(), flags=g_flags.numpy(), n=g_n, stats=np.array([auc, p, n]), cap=cap)
     finally:
         dist.destroy_process_group()
 
@@ -88,7 +93,9 @@ def test_two_rank_reduction_and_pooled_auc(tmp_path):
     assert int(z["n"]) == bhv.n_impressions
     np.testing.assert_allclose(z["sums"][0, :5], per.astype(np.float64).sum(0), rtol=1e-12)
     assert int(z["flags"][0]) == 4 + 8  # OR of the ranks' flag words survives the sum-reduction
-    auc, p, n, _ = z["stats"]
+    auc, p, n = z["stats"]
+    bounds = mdata.balanced_shard_bounds(bhv, WORLD)
+    assert int(z["cap"]) == max(int(bhv.slice(int(bounds[r]), int(bounds[r + 1])).labels.sum()) for r in range(WORLD))
     assert p == bhv.labels.sum() and n == bhv.labels.size - bhv.labels.sum()
     assert abs(auc - mo.pooled_auc_exact(whole["scores"], bhv.labels)) < 1e-12
     assert abs(auc - whole["metrics"]["test/auc"]) < 1e-6

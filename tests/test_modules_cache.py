@@ -1,0 +1,163 @@
+"""Host mirror of the reference's module interface (manner_b200/modules.py) and the cache builder
+(manner_b200/cache.py).  CPU tests cover the host logic; the GPU tests drive the step-mode drop-in with the
+reference's own batches and compare with the values the reference logged (tests/golden)."""
+import os
+import types
+
+import numpy as np
+import pytest
+import torch
+
+from manner_b200 import cache as mcache
+from manner_b200 import data as mdata
+from oracle import manner_oracle as mo
+
+
+class TableEncoder(torch.nn.Module):
+    """Stands in for MannerNewsEncoder: looks the batch's news rows up in a table."""
+
+    def __init__(self, table):
+        super().__init__()
+        self.register_buffer("table", table)
+
+    def forward(self, x):
+        return self.table[x["news_row"].to(self.table.device)]
+
+
+def _bhv(z):
+    return mo.Behaviours(z["hist_offsets"], z["hist_ids"], z["cand_offsets"], z["cand_ids"], z["labels"])
+
+
+# ---- CPU -----------------------------------------------------------------------------------------------
+
+
+def test_modules_import_without_the_reference_and_fail_loudly():
+    from manner_b200 import modules
+
+    assert not modules.HAVE_REFERENCE  # lightning / torchmetrics / torch_geometric are absent in this image
+    with pytest.raises(ImportError, match="reference package"):
+        modules.CRModuleB200(supcon_loss=False)
+    seg = torch.tensor([0, 0, 2, 2, 2])
+    assert modules._segment_offsets(seg, 3).tolist() == [0, 2, 2, 5]
+
+
+def test_parsed_behaviours_to_csr_follows_the_reference_format():
+    news_ids = [f"N{i}" for i in range(10)]
+    nid2row = mcache.news_row_map(news_ids)
+    # cells exactly as to_tsv() writes python lists (mind_dataframe.py:360-366) and the converters read them back
+    hist = ["['N1', 'N2', 'N3']", "['N4']"]
+    cand = ["['N5', 'N6']", "['N7', 'N8', 'N9']"]
+    labs = ["[0, 1]", "[1, 0, 0]"]
+    frame = types.SimpleNamespace()
+    import pandas as pd
+
+    frame = pd.DataFrame({"history": hist, "candidates": cand, "labels": labs})
+    bhv = mcache.behaviours_frame_to_csr(frame, nid2row, max_history_length=2)
+    assert bhv.hist_offsets.tolist() == [0, 2, 3] and bhv.hist_ids.tolist() == [1, 2, 4]  # first 2 clicks kept
+    assert bhv.cand_offsets.tolist() == [0, 2, 5] and bhv.cand_ids.tolist() == [5, 6, 7, 8, 9]
+    assert bhv.labels.tolist() == [0, 1, 1, 0, 0] and bhv.labels.dtype == np.uint8
+    with pytest.raises(KeyError):
+        mcache.behaviours_to_csr([["N1"]], [["N99"]], [[1]], nid2row)
+    with pytest.raises(ValueError):
+        mcache.behaviours_to_csr([[]], [["N1"]], [[1]], nid2row)
+
+
+def test_build_embedding_table_on_cpu_plumbing():
+    table = torch.randn(10, 16)
+    enc = TableEncoder(table)
+    batches = [{"news_row": torch.arange(0, 4)}, {"news_row": torch.arange(4, 10)}]
+    out = mcache.build_embedding_table(enc, batches, 10, 16, torch.device("cpu"))
+    assert torch.equal(out, table)
+    with pytest.raises(ValueError):
+        mcache.build_embedding_table(enc, batches[:1], 10, 16, torch.device("cpu"))
+
+
+# ---- GPU: the drop-in against what the reference logged ---------------------------------------------------
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["cr_d128", "cr_ties"])
+def test_cr_step_mode_dropin_logs_the_reference_values(golden_dir, name):
+    from manner_b200.modules import B200EvalMixin
+
+    class FakeCR(B200EvalMixin, torch.nn.Module):
+        def __init__(self, table):
+            super().__init__()
+            self.news_encoder = TableEncoder(table)
+            self.logged = {}
+
+        def _b200_encoders(self):
+            return [self.news_encoder]
+
+        def log_dict(self, values, **kw):
+            self.logged.update(values)
+
+    z = np.load(os.path.join(golden_dir, name + ".npz"))
+    bhv = _bhv(z)
+    model = FakeCR(torch.from_numpy(z["table"])).cuda()
+    for i, lo in enumerate(range(0, bhv.n_impressions, 8)):  # configs/data/mind_rec.yaml:51 -> steps of 8
+        model.test_step(mo.step_batch(bhv, lo, min(lo + 8, bhv.n_impressions)), i)
+    model.on_test_epoch_end()
+    for k in ("auc", "mrr", "ndcg@5", "ndcg@10"):
+        assert abs(model.logged["test/" + k] - float(z["test_" + k])) <= 1e-6, k
+
+
+@pytest.mark.gpu
+def test_ensemble_step_mode_dropin_logs_the_reference_values(golden_dir):
+    from manner_b200.modules import B200EvalMixin
+
+    class FakeEnsemble(B200EvalMixin, torch.nn.Module):
+        _b200_zscore = True
+        _b200_with_auc = False
+
+        def __init__(self, tables, weights):
+            super().__init__()
+            self.encs = torch.nn.ModuleList([TableEncoder(t) for t in tables])
+            self.w, self.logged = weights, {}
+
+        def _b200_encoders(self):
+            return [e for e, w in zip(self.encs, self.w) if w != 0]
+
+        def _b200_weights(self):
+            return [w for w in self.w if w != 0]
+
+        def log_dict(self, values, **kw):
+            self.logged.update(values)
+
+    z = np.load(os.path.join(golden_dir, "ensemble_d128.npz"))
+    bhv = _bhv(z)
+    aspects = {"category": z["category"], "sentiment": z["sentiment"]}
+    tabs = [torch.from_numpy(z[f"table{m}"]) for m in range(3)]
+    for w, (wc, ws) in enumerate(z["weightings"].tolist()):
+        model = FakeEnsemble(tabs, [1.0, wc, ws]).cuda()
+        for i, lo in enumerate(range(0, bhv.n_impressions, 8)):
+            model.test_step(mo.step_batch(bhv, lo, min(lo + 8, bhv.n_impressions), aspects), i)
+        model.on_test_epoch_end()
+        for k in ("ndcg@5", "ndcg@10", "categ_div@5", "categ_div@10", "sent_div@5", "sent_div@10",
+                  "categ_pers@5", "categ_pers@10", "sent_pers@5", "sent_pers@10"):
+            assert abs(model.logged["test/" + k] - float(z[f"w{w}_test_{k}"])) <= 1e-6, (w, k)
+
+
+@pytest.mark.gpu
+def test_cached_mode_table_builder_feeds_the_evaluator(golden_dir):
+    from manner_b200.evaluator import ScoreEvaluator
+
+    z = np.load(os.path.join(golden_dir, "cr_d768.npz"))
+    table = torch.from_numpy(z["table"])
+    n_news, dim = table.shape
+    enc = TableEncoder(table).cuda()
+    batches = [{"news_row": torch.arange(lo, min(lo + 32, n_news))} for lo in range(0, n_news, 32)]
+    built = mcache.build_embedding_table(enc, batches, n_news, dim, torch.device("cuda:0"))
+    assert torch.equal(built.cpu(), table)
+    # behaviours in the reference's textual form -> CSR -> one evaluation call for the whole epoch
+    ids = [f"N{i}" for i in range(n_news)]
+    nid2row = mcache.news_row_map(ids)
+    bhv = _bhv(z)
+    hist = [[ids[j] for j in bhv.hist_ids[bhv.hist_offsets[i]:bhv.hist_offsets[i + 1]]] for i in range(bhv.n_impressions)]
+    cand = [[ids[j] for j in bhv.cand_ids[bhv.cand_offsets[i]:bhv.cand_offsets[i + 1]]] for i in range(bhv.n_impressions)]
+    labs = [bhv.labels[bhv.cand_offsets[i]:bhv.cand_offsets[i + 1]].tolist() for i in range(bhv.n_impressions)]
+    csr = mcache.behaviours_to_csr(hist, cand, labs, nid2row)
+    ev = ScoreEvaluator([built])
+    m = ev.evaluate(ev.upload(csr), pooled_auc=True).metrics()
+    for k in ("auc", "mrr", "ndcg@5", "ndcg@10"):
+        assert abs(m["test/" + k] - float(z["test_" + k])) <= 1e-6, k
