@@ -46,6 +46,7 @@ def workload_config(args) -> dict:
         "categ_weight": CATEG_WEIGHT,
         "metrics": "ndcg@5 ndcg@10 mrr gauc + pooled auroc",
         "ids": "uniform" if args.uniform_ids else "zipf(1.05)",
+        "weightings": (max(2, int(round(args.sweep ** 0.5))) ** 2 if args.sweep else 1),
         "l2": "flushed between timed steps (256 MiB write); table 200 MB/module > 126 MB L2",
     }
 
@@ -166,14 +167,21 @@ def run_gpu_arm(args) -> None:
     from manner_b200 import ops
     from manner_b200.evaluator import ScoreEvaluator
 
+    os.environ["NCCL_DEBUG"] = os.environ.get("MB200_NCCL_DEBUG", "WARN")  # keep stdout to the one JSON line
     rank, local_rank, world = mdist.init_from_env("nccl")
     if world != args.gpus and world > 1:
         raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
     dev = torch.device(f"cuda:{local_rank}")
     distributed = world > 1
 
-    # weak scaling: every rank scores its own MIND-small-shaped shard (different behaviour seed), tables replicated
-    tables, bhv = mdata.synth_workload(args.workload, n_modules=args.modules, seed_offset=rank, uniform_ids=args.uniform_ids)
+    if args.shard:
+        # strong scaling (BASELINE.json configs[2]): ONE set of impressions, sharded over the ranks by rows gathered
+        tables, full = mdata.synth_workload(args.workload, n_modules=args.modules, uniform_ids=args.uniform_ids)
+        bhv = mdist.shard_for_rank(full, rank, world)
+        del full
+    else:
+        # weak scaling: every rank scores its own MIND-small-shaped shard (different behaviour seed), tables replicated
+        tables, bhv = mdata.synth_workload(args.workload, n_modules=args.modules, seed_offset=rank, uniform_ids=args.uniform_ids)
     ev = ScoreEvaluator(tables, dev)
     pinned = ev.pin(bhv)
     # multi-GPU pooled AUC: agree once (outside the timed loop) on the largest per-rank positive count
@@ -182,6 +190,13 @@ def run_gpu_arm(args) -> None:
     weights = [[1.0, CATEG_WEIGHT] + [0.0] * (args.modules - 2)][0][: args.modules]
     w_dev = torch.tensor([weights], dtype=torch.float32, device=dev)
     kw = dict(weights=w_dev, zscore=True, pooled_auc=True, distributed=distributed)
+    if args.sweep:
+        # BASELINE.json configs[3]: aspect-weight sweep, every weighting re-scored from the one gather
+        side = max(2, int(round(args.sweep ** 0.5)))
+        grid = [[1.0] + ([a / (side - 1)] if args.modules > 1 else []) + ([b / (side - 1)] if args.modules > 2 else []) + [0.0] * max(0, args.modules - 3)
+                for a in range(side) for b in range(side)]
+        w_dev = torch.tensor(grid, dtype=torch.float32, device=dev)
+        kw = dict(weights=w_dev, zscore=True, pooled_auc=False, distributed=distributed)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     ops.set_tuning(time_kernel=1)
     if args.variant is not None:
@@ -284,7 +299,7 @@ def run_gpu_arm(args) -> None:
 
     line = {
         "metric": METRIC, "value": n_impr_total * args.steps / (total_ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
-        "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "strong" if args.shard else "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(args),
         "e2e": {
             "value": n_impr_total / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": dev_bhv.h2d_bytes,
@@ -317,6 +332,8 @@ def main() -> None:
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="small", choices=["tiny", "mini", "small", "large"])
     ap.add_argument("--modules", type=int, default=2)
+    ap.add_argument("--shard", action="store_true", help="strong scaling: shard one workload over the ranks instead of one workload per rank")
+    ap.add_argument("--sweep", type=int, default=0, help="aspect-weight sweep with about this many weightings (configs[3]); no pooled AUC")
     ap.add_argument("--uniform-ids", action="store_true", help="draw ids uniformly over the catalogue (no L2-friendly head)")
     ap.add_argument("--cpu-sample", type=int, default=8192)
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -337,6 +337,124 @@ struct WarpSmem {
   uint8_t* top_sent;  // [32]
 };
 
+constexpr int kSweepMinWeightings = 16;  // from here on lanes own weightings instead of candidates
+constexpr int kSweepPos = 2;             // positives ranked per pass over the candidates (91 % of MIND impressions have <= 2)
+
+// s = w0 * z0 ; s += w_m * z_m for m >= 1 when w_m != 0  (ensemble_module.py:97-107): separate multiply
+// and add in fp32 -- no fused multiply-add -- like the reference's two torch ops.
+__device__ __forceinline__ float combine_at(const float* sc, int cpad, int j, const float (&wt)[MB200_MAX_MODULES], int n_modules,
+                                            int active_mask) {
+  float s = (wt[0] == 1.0f) ? sc[j] : __fmul_rn(wt[0], sc[j]);
+  int sl = 1;
+#pragma unroll
+  for (int m = 1; m < MB200_MAX_MODULES; ++m) {
+    if (m < n_modules && ((active_mask >> m) & 1)) {
+      if (wt[m] != 0.0f) s = __fadd_rn(s, __fmul_rn(wt[m], sc[(size_t)sl * cpad + j]));
+      ++sl;
+    }
+  }
+  return s;
+}
+
+// Aspect-weight sweep (BASELINE.json configs[3]): the z-scored per-module scores of the impression are
+// already in shared memory; every lane re-scores the impression under its own weightings (w = lane,
+// lane + 32, ...) and ranks only the positives, reading the module scores as warp-wide broadcasts.
+// W weightings cost one gather.
+__device__ __noinline__ int sweep_weightings(const EvalParams& p, const WarpSmem& sm, int i, int c0, int C) {
+  const int lane = threadIdx.x & 31;
+  const int W = p.n_weightings;
+  const float* sc = sm.sc;
+  const uint8_t* lab = sm.lab;
+  int* pos_list = reinterpret_cast<int*>(sm.comb);  // the combined-score buffer is not needed in this mode
+  __builtin_assume(__isShared(sc));
+  __builtin_assume(__isShared(lab));
+  __builtin_assume(__isShared(pos_list));
+  __builtin_assume(__isShared(sm.acc));
+  int flags = 0;
+
+  int n_pos = 0;
+#pragma unroll 1
+  for (int b0 = 0; b0 < C; b0 += 32) {
+    const int j = b0 + lane;
+    const bool is_pos = j < C && lab[j] != 0;
+    const unsigned m = __ballot_sync(kFull, is_pos);
+    if (is_pos) pos_list[n_pos + __popc(m & ((1u << lane) - 1u))] = j;
+    n_pos += __popc(m);
+  }
+  __syncwarp();
+
+  if (p.scores != nullptr) {
+    float wt[MB200_MAX_MODULES];
+#pragma unroll
+    for (int m = 0; m < MB200_MAX_MODULES; ++m) wt[m] = (m < p.n_modules) ? p.weights[(size_t)p.scores_weighting * p.n_modules + m] : 0.0f;
+    bool outside = false;
+#pragma unroll 1
+    for (int j = lane; j < C; j += 32) {
+      const float s = combine_at(sc, p.cpad, j, wt, p.n_modules, p.active_mask);
+      p.scores[c0 + j] = s;
+      outside |= !(s >= 0.0f && s <= 1.0f);
+    }
+    if (outside) flags |= MB200_FLAG_OUTSIDE_UNIT;
+  }
+
+#pragma unroll 1
+  for (int w = lane; w < W; w += 32) {
+    float wt[MB200_MAX_MODULES];
+#pragma unroll
+    for (int m = 0; m < MB200_MAX_MODULES; ++m) wt[m] = (m < p.n_modules) ? p.weights[(size_t)w * p.n_modules + m] : 0.0f;
+    int min_rank = 0x7fffffff;
+    unsigned hit_mask = 0;
+    long long gauc2 = 0;
+#pragma unroll 1
+    for (int p0 = 0; p0 < n_pos; p0 += kSweepPos) {
+      int pj[kSweepPos], before[kSweepPos], nlt[kSweepPos], neq[kSweepPos];
+      float sp[kSweepPos];
+#pragma unroll
+      for (int q = 0; q < kSweepPos; ++q) {
+        pj[q] = (p0 + q < n_pos) ? pos_list[p0 + q] : -1;
+        sp[q] = (pj[q] >= 0) ? combine_at(sc, p.cpad, pj[q], wt, p.n_modules, p.active_mask) : 0.0f;
+        before[q] = nlt[q] = neq[q] = 0;
+      }
+#pragma unroll 4
+      for (int k = 0; k < C; ++k) {
+        const float sk = combine_at(sc, p.cpad, k, wt, p.n_modules, p.active_mask);
+        const bool neg = lab[k] == 0;
+#pragma unroll
+        for (int q = 0; q < kSweepPos; ++q) {
+          before[q] += (ranks_before(sk, sp[q]) || (k < pj[q] && ranks_equal(sk, sp[q]))) ? 1 : 0;
+          nlt[q] += (neg && sk < sp[q]) ? 1 : 0;
+          neq[q] += (neg && sk == sp[q]) ? 1 : 0;
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < kSweepPos; ++q) {
+        if (pj[q] >= 0) {
+          const int rank = 1 + before[q];
+          min_rank = min(min_rank, rank);
+          if (rank <= 32) hit_mask |= 1u << (rank - 1);
+          gauc2 += 2ll * nlt[q] + neq[q];
+        }
+      }
+    }
+    const float mrr = n_pos ? __fdiv_rn(1.0f, (float)min_rank) : 0.f;
+    const float nd0 = ndcg_at(hit_mask, n_pos, C, p.k0);
+    const float nd1 = ndcg_at(hit_mask, n_pos, C, p.k1);
+    const bool gvalid = n_pos > 0 && n_pos < C;
+    const float g = gvalid ? (float)((double)gauc2 / (2.0 * (double)n_pos * (double)(C - n_pos))) : 0.f;
+    double* a = sm.acc + (size_t)w * MB200_NUM_METRICS;
+    a[MB200_M_MRR] += (double)mrr, a[MB200_M_NDCG_K0] += (double)nd0, a[MB200_M_NDCG_K1] += (double)nd1;
+    a[MB200_M_GAUC] += (double)g, a[MB200_M_GAUC_VALID] += gvalid ? 1.0 : 0.0;
+    if (p.per_impr) {
+      float* o = p.per_impr + ((size_t)w * p.n_impr + i) * MB200_NUM_METRICS;
+      o[MB200_M_MRR] = mrr, o[MB200_M_NDCG_K0] = nd0, o[MB200_M_NDCG_K1] = nd1, o[MB200_M_GAUC] = g, o[MB200_M_GAUC_VALID] = gvalid ? 1.f : 0.f;
+#pragma unroll 1
+      for (int t = MB200_M_GAUC_VALID + 1; t < MB200_NUM_METRICS; ++t) o[t] = 0.f;
+    }
+  }
+  __syncwarp();
+  return flags;
+}
+
 // Everything after the per-module scores of impression i sit in shared memory: z-scores are already
 // applied; combine per weighting, rank, metrics, accumulate.  Not inlined (see gather_pool_score).
 __device__ __noinline__ int rank_and_metrics(const EvalParams& p, const WarpSmem& sm, int i, int h0, int H, int c0, int C) {
@@ -392,6 +510,8 @@ __device__ __noinline__ int rank_and_metrics(const EvalParams& p, const WarpSmem
     sent_group_ok = __reduce_add_sync(kFull, sent_sum) != 0;
     __syncwarp();
   }
+
+  if (!aspects && p.weights != nullptr && W >= kSweepMinWeightings) return warp_flags | sweep_weightings(p, sm, i, c0, C);
 
 #pragma unroll 1
   for (int w = 0; w < W; ++w) {

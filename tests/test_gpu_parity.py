@@ -91,6 +91,31 @@ def test_ensemble_matches_reference_golden(golden_dir, evaluator_cls):
         np.testing.assert_allclose(sweep.sums[w], single.sums[0], rtol=0, atol=1e-9)
 
 
+def test_weight_sweep_path_equals_single_weighting_calls(golden_dir, evaluator_cls):
+    """BASELINE.json configs[3]: >= 16 weightings take the lane-per-weighting path; it must give exactly
+    what one call per weighting gives (and therefore what the reference logs per weighting)."""
+    z = np.load(os.path.join(golden_dir, "ensemble_d128.npz"))
+    tabs = [torch.from_numpy(z[f"table{m}"]) for m in range(3)]
+    bhv = _bhv(z)
+    ev = evaluator_cls(tabs)  # no aspects: nDCG / MRR / gAUC only
+    dev_bhv = ev.upload(bhv)
+    grid = [[1.0, wc, ws] for wc in (0.0, 0.1, 0.25, 0.5, 1.0) for ws in (0.0, 0.2, 0.7, 1.0)] + [[1.0, wc, ws] for wc, ws in z["weightings"].tolist()]
+    assert len(grid) >= 16
+    sweep = ev.evaluate(dev_bhv, weights=grid, zscore=True, want_per_impression=True, want_scores=True, scores_weighting=23)
+    per_sweep = sweep.per_impression.cpu().numpy()
+    for w, wt in enumerate(grid):
+        single = ev.evaluate(dev_bhv, weights=[wt], zscore=True, want_per_impression=True, want_scores=(w == 23))
+        np.testing.assert_array_equal(per_sweep[w], single.per_impression.cpu().numpy()[0])
+        np.testing.assert_allclose(sweep.sums[w], single.sums[0], rtol=0, atol=1e-9)
+        if w == 23:
+            np.testing.assert_array_equal(sweep.scores.cpu().numpy(), single.scores.cpu().numpy())
+    # the last four weightings are the ones the reference was run with
+    for w in range(4):
+        m = sweep.metrics(weighting=len(grid) - 4 + w)
+        for k in ("ndcg@5", "ndcg@10"):
+            assert abs(m["test/" + k] - float(z[f"w{w}_test_{k}"])) <= METRIC_ATOL, (w, k)
+
+
 def test_bf16_table_matches_oracle_on_rounded_table(golden_dir, evaluator_cls):
     z = np.load(os.path.join(golden_dir, "cr_d768.npz"))
     table, bhv = torch.from_numpy(z["table"]).bfloat16(), _bhv(z)
