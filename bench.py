@@ -36,6 +36,7 @@ METRIC = "impressions/sec (pool+score+ensemble+metrics)"
 UNIT = "impressions/s"
 CATEG_WEIGHT = 0.4  # model.categ_weight (the YAMLs ship 0 and are swept by CLI override; 0 would not load the A-Module)
 FALLBACK_HBM_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md
+FALLBACK_BF16_TFLOPS = 1590.0
 
 
 def workload_config(args) -> dict:
@@ -324,6 +325,119 @@ def run_gpu_arm(args) -> None:
         dist.destroy_process_group()
 
 
+def run_retrieval_arm(args) -> None:
+    """BASELINE.json configs[4] (SURVEY 8(d) mode R): users x catalogue bf16 contraction on tcgen05 with the fused
+    per-user top-100, catalogue row-sharded over the ranks (1.25 M rows per GPU = 10 M over 8), NCCL exchange of
+    the per-shard top-k + merge kernel.  A step = one block of ``--users`` users against the whole catalogue."""
+    import torch.distributed as dist
+
+    from manner_b200 import dist as mdist
+    from manner_b200 import ops
+    from manner_b200 import retrieval as rt
+
+    os.environ["NCCL_DEBUG"] = os.environ.get("MB200_NCCL_DEBUG", "WARN")
+    rank, local_rank, world = mdist.init_from_env("nccl")
+    dev = torch.device(f"cuda:{local_rank}")
+    distributed = world > 1
+    dim, k = 768, 100
+    n_shard, n_users = args.catalog_per_gpu, args.users
+    g = torch.Generator(device=dev).manual_seed(4321 + rank)
+    catalog = (torch.randn(n_shard, dim, generator=g, device=dev) * dim ** -0.5).to(torch.bfloat16)  # this rank's rows of the catalogue
+    gu = torch.Generator().manual_seed(99)
+    users_host = (torch.randn(n_users, dim, generator=gu) * dim ** -0.5).to(torch.bfloat16).pin_memory()  # same users on every rank
+    users = users_host.to(dev)
+    r = rt.CatalogRetriever(catalog, k=k, catalog_id_offset=rank * n_shard, distributed=distributed, exchange=args.exchange, user_block=n_users)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def barrier() -> None:
+        if distributed:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def step(e2e: bool):
+        flush.fill_(rank + 1)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        u = users_host.to(dev, non_blocking=True) if e2e else users
+        s, i = r.retrieve(u)
+        if e2e:
+            s, i = s.cpu(), i.cpu()
+        e1.record()
+        return e0, e1, s, i
+
+    for _ in range(max(args.warmup, 3)):
+        step(False)
+    barrier()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    launches0 = ops.launch_counts()
+    barrier()
+    events = [step(False)[:2] for _ in range(args.steps)]
+    barrier()
+    launches1 = ops.launch_counts()
+    # the GEMM + top-k kernel alone (no exchange), for the roofline
+    k_events = []
+    for _ in range(args.steps):
+        flush.fill_(rank + 1)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        r.local_topk(users)
+        e1.record()
+        k_events.append((e0, e1))
+    barrier()
+    e2e_events = [step(True)[:2] for _ in range(args.steps + 1)][1:]
+    barrier()
+    clocks = sampler.stop() if sampler is not None else None
+
+    def max_over_ranks(ms: float) -> float:
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        if distributed:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    total_ms = max_over_ranks(sum(a.elapsed_time(b) for a, b in events))
+    kern_ms = max_over_ranks(sum(a.elapsed_time(b) for a, b in k_events)) / args.steps
+    e2e_ms = max_over_ranks(sum(a.elapsed_time(b) for a, b in e2e_events) / len(e2e_events))
+    if rank == 0:
+        peak, peak_kind = FALLBACK_BF16_TFLOPS, "fallback"
+        path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        if os.path.exists(path):
+            with open(path) as f:
+                peak, peak_kind = float(json.load(f)["bf16_tflops"]), "measured (burst: kernel timed alone)"
+        flops = 2.0 * n_users * n_shard * dim  # per launch, per GPU
+        achieved = flops / (kern_ms * 1e-3) / 1e12
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            from oracle import manner_oracle as mo
+
+            threads = os.cpu_count() or 1
+            torch.set_num_threads(threads)
+            nu, nc = min(n_users, 2048), min(n_shard, 131072)
+            t0 = time.perf_counter()
+            sc = mo.retrieval_scores(users_host[:nu], catalog[:nc].cpu())
+            torch.topk(sc, k, dim=1)
+            dt = time.perf_counter() - t0
+            cpu = {"value": nu / dt * (nc / (n_shard * world)), "unit": "users/s", "cores": threads, "kind": "port",
+                   "sample": f"{nu} users x {nc} catalogue rows ({dt:.1f} s) fp32 matmul + topk on the host, scaled linearly to the full catalogue"}
+        line = {
+            "metric": "users/sec (full-catalog retrieval, top-100)", "value": n_users * args.steps / (total_ms * 1e-3), "unit": "users/s",
+            "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": f"full-catalog retrieval: {n_users} users x {n_shard * world} news ({n_shard} rows per GPU), 768-d bf16, top-100",
+                       "exchange": args.exchange if distributed else "none", "l2": "flushed between timed steps (256 MiB write); catalogue shard > L2"},
+            "e2e": {"value": n_users / (e2e_ms * 1e-3), "unit": "users/s", "h2d_bytes_per_step": n_users * dim * 2,
+                    "d2h_bytes_per_step": (n_users if (not distributed or args.exchange == "all_gather") else -(-n_users // world)) * k * 12, "ms_per_step": e2e_ms},
+            "gpu_launches": launches1[0] - launches0[0],
+            "roofline": {"bound": "tensor", "kernel": "retrieve_topk_kernel", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+                         "peak_kind": peak_kind, "traffic": None, "flops_per_launch": flops, "kernel_ms": kern_ms,
+                         "kernel_share_of_step": kern_ms * args.steps / total_ms if total_ms > 0 else None},
+            "cpu_baseline": cpu, "clocks": clocks,
+        }
+        print(json.dumps(line))
+    if distributed:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 def main() -> None:
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -337,12 +451,18 @@ def main() -> None:
     ap.add_argument("--uniform-ids", action="store_true", help="draw ids uniformly over the catalogue (no L2-friendly head)")
     ap.add_argument("--cpu-sample", type=int, default=8192)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--mode", default="eval", choices=["eval", "retrieval"], help="retrieval: BASELINE.json configs[4] (tcgen05 GEMM + fused top-100)")
+    ap.add_argument("--users", type=int, default=32768, help="retrieval mode: users per step")
+    ap.add_argument("--catalog-per-gpu", type=int, default=1_250_000, help="retrieval mode: catalogue rows per GPU (10 M over 8)")
+    ap.add_argument("--exchange", default="all_gather", choices=["all_gather", "all_to_all"])
     ap.add_argument("--variant", type=int, default=None)
     ap.add_argument("--chunks-per-warp", type=int, default=None)
     ap.add_argument("--ctas-per-sm", type=int, default=None)
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)
+    elif args.mode == "retrieval":
+        run_retrieval_arm(args)
     else:
         run_gpu_arm(args)
 

@@ -177,6 +177,40 @@ MB200_API size_t mb200_pooled_auc_workspace_bytes(int64_t n);
 MB200_API int mb200_pooled_auc(const float* preds, const uint8_t* labels, int64_t n, int sigmoid_mode,
                      const int32_t* flags, void* workspace, size_t workspace_bytes, double* out, void* stream);
 
+/*
+ * Full-catalog retrieval (BASELINE.json configs[4]; no reference counterpart -- the reference scores only an
+ * impression's candidates, cr_module.py:105-131): scores = users [n_users, dim] x catalog [n_catalog, dim]^T in
+ * bf16 on the tcgen05 tensor cores (fp32 accumulation in TMEM), per-user top-k fused into the epilogue.
+ * Output lists are sorted by score descending, catalogue id ascending on ties; ids are int64 =
+ * catalogue row + catalog_id_offset (row-sharded catalogues); unused slots hold -inf / -1.
+ */
+typedef struct mb200_retrieval_desc {
+  uint32_t struct_size;  /* = sizeof(mb200_retrieval_desc) */
+  int32_t dim;           /* multiple of 64 (768 in the reference's configs) */
+  int32_t k;             /* 1..128 */
+  int32_t reserved;
+  int64_t n_users;
+  int64_t n_catalog;
+  int64_t catalog_id_offset;
+  const void* users;    /* bf16 [n_users, dim] row-major, 16-byte aligned (mb200_pool_users makes it) */
+  const void* catalog;  /* bf16 [n_catalog, dim] row-major, 16-byte aligned */
+  float* out_scores;    /* [n_users, k] */
+  int64_t* out_ids;     /* [n_users, k] */
+  float* debug_scores;  /* optional [n_users, n_catalog] fp32: the full score matrix (tests only) */
+  void* workspace;      /* >= mb200_retrieval_workspace_bytes(desc), 256-byte aligned */
+  size_t workspace_bytes;
+} mb200_retrieval_desc;
+
+MB200_API size_t mb200_retrieval_workspace_bytes(const mb200_retrieval_desc* desc);
+MB200_API int mb200_retrieve_topk(const mb200_retrieval_desc* desc, void* stream);
+/* user matrix for retrieval: out[u] = bf16(mean of table[hist_ids[h]] over user u's history), the late-fusion
+ * user vector of cr_module.py:116-123.  dtype MB200_F32 | MB200_BF16, dim even and <= 1024. */
+MB200_API int mb200_pool_users(const void* table, int dtype, int dim, int64_t row_stride, int64_t n_news, const int32_t* hist_offsets,
+                               const int32_t* hist_ids, int64_t n_users, void* out_bf16, int32_t* flags, void* stream);
+/* merge of per-shard top-k lists [shards, n_users, k] (each sorted as above) into the global top-k (shards <= 32) */
+MB200_API int mb200_merge_topk(const float* scores, const int64_t* ids, int shards, int64_t n_users, int k, float* out_scores,
+                               int64_t* out_ids, void* stream);
+
 /* ---- introspection ------------------------------------------------------------------------------- */
 /* 1 / log2(rank + 1) as fp32, rank = 1..MB200_MAX_K: the discount table the kernels use for
  * torchmetrics' `_dcg` (HOST function; lets CPU tests pin it against torch.log2). */

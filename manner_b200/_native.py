@@ -68,6 +68,27 @@ class EvalDesc(Structure):
     ]
 
 
+class RetrievalDesc(Structure):
+    """mb200_retrieval_desc, field for field."""
+
+    _fields_ = [
+        ("struct_size", c_uint32),
+        ("dim", c_int32),
+        ("k", c_int32),
+        ("reserved", c_int32),
+        ("n_users", c_int64),
+        ("n_catalog", c_int64),
+        ("catalog_id_offset", c_int64),
+        ("users", c_void_p),
+        ("catalog", c_void_p),
+        ("out_scores", c_void_p),
+        ("out_ids", c_void_p),
+        ("debug_scores", c_void_p),
+        ("workspace", c_void_p),
+        ("workspace_bytes", c_size_t),
+    ]
+
+
 # every symbol include/manner_b200.h declares: (restype, argtypes)
 SIGNATURES = {
     "mb200_abi_version": (c_int, []),
@@ -81,6 +102,10 @@ SIGNATURES = {
     "mb200_auc_rank_sum": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
     "mb200_pooled_auc_workspace_bytes": (c_size_t, [c_int64]),
     "mb200_pooled_auc": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p, c_size_t, c_void_p, c_void_p]),
+    "mb200_retrieval_workspace_bytes": (c_size_t, [POINTER(RetrievalDesc)]),
+    "mb200_retrieve_topk": (c_int, [POINTER(RetrievalDesc), c_void_p]),
+    "mb200_pool_users": (c_int, [c_void_p, c_int, c_int, c_int64, c_int64, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
+    "mb200_merge_topk": (c_int, [c_void_p, c_void_p, c_int, c_int64, c_int, c_void_p, c_void_p, c_void_p]),
     "mb200_dcg_discount": (c_float, [c_int]),
     "mb200_launch_count": (c_int64, []),
     "mb200_library_launch_count": (c_int64, []),

@@ -53,6 +53,10 @@ int auc_sort_keys(const uint32_t*, uint32_t*, long long, void*, size_t, cudaStre
 int auc_rank_sum(const uint32_t*, long long, const long long*, const uint32_t*, long long, const long long*, unsigned long long*, cudaStream_t);
 size_t pooled_auc_workspace_bytes(long long n);
 int pooled_auc(const float*, const uint8_t*, long long, int, const int32_t*, void*, size_t, double*, cudaStream_t);
+size_t retrieval_workspace_bytes(const mb200_retrieval_desc* d);
+int retrieve_topk(const mb200_retrieval_desc* d, cudaStream_t stream);
+int pool_users(const void*, int, int, long long, long long, const int32_t*, const int32_t*, long long, void*, int32_t*, cudaStream_t);
+int merge_topk(const float*, const long long*, int, long long, int, float*, long long*, cudaStream_t);
 
 }  // namespace mb200
 
@@ -120,6 +124,21 @@ int mb200_pooled_auc(const float* preds, const uint8_t* labels, int64_t n, int s
   int st = use_device_of(out, nullptr);
   if (st != MB200_OK) return st;
   return pooled_auc(preds, labels, n, sigmoid_mode, flags, workspace, workspace_bytes, out, static_cast<cudaStream_t>(stream));
+}
+
+size_t mb200_retrieval_workspace_bytes(const mb200_retrieval_desc* desc) { return retrieval_workspace_bytes(desc); }
+
+int mb200_retrieve_topk(const mb200_retrieval_desc* desc, void* stream) { return retrieve_topk(desc, static_cast<cudaStream_t>(stream)); }
+
+int mb200_pool_users(const void* table, int dtype, int dim, int64_t row_stride, int64_t n_news, const int32_t* hist_offsets,
+                     const int32_t* hist_ids, int64_t n_users, void* out_bf16, int32_t* flags, void* stream) {
+  return pool_users(table, dtype, dim, row_stride, n_news, hist_offsets, hist_ids, n_users, out_bf16, flags, static_cast<cudaStream_t>(stream));
+}
+
+int mb200_merge_topk(const float* scores, const int64_t* ids, int shards, int64_t n_users, int k, float* out_scores, int64_t* out_ids,
+                     void* stream) {
+  return merge_topk(scores, reinterpret_cast<const long long*>(ids), shards, n_users, k, out_scores, reinterpret_cast<long long*>(out_ids),
+                    static_cast<cudaStream_t>(stream));
 }
 
 float mb200_dcg_discount(int rank) { return host_dcg_discount(rank); }

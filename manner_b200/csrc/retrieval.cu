@@ -1,0 +1,505 @@
+// Full-catalog retrieval (BASELINE.json configs[4], SURVEY 8(d) mode R): every user's late-fusion vector
+// against every news row of the catalogue, top-k per user.  No reference counterpart (the reference only
+// scores the ~37 candidates of an impression, models/cr_module.py:105-131); this is the one part of the
+// path that really is a dense users x catalogue x D contraction, so it runs on the 5th-generation tensor
+// cores:
+//
+//   TMA (cp.async.bulk.tensor.2d, 128B swizzle)  ->  4-stage shared-memory ring (A 128x64, B 256x64 bf16)
+//   tcgen05.mma.cta_group::1.kind::f16 (M128 N256 K16), one elected thread, accumulators in TMEM
+//   (2 x 256 columns, double buffered)  ->  tcgen05.ld in 4 epilogue warps  ->  per-row running top-k
+//
+// The U x N score matrix is never written: an epilogue thread owns one user row for the whole sweep over
+// the catalogue, keeps the row's current k-th best score in a register, appends the (few) scores above it
+// to a per-row candidate buffer and lets its warp compact the buffer to the best k when it fills up.
+// Final order: score descending, catalogue id ascending on ties.
+//
+// mb200_pool_users builds the user matrix: mean of the history rows (cr_module.py:116-123), rounded to bf16.
+
+#include <cuda.h>
+#include <math_constants.h>
+
+#include "common.cuh"
+
+namespace mb200 {
+
+namespace rt {
+constexpr int BLOCK_M = 128, BLOCK_N = 256, BLOCK_K = 64, UMMA_K = 16, STAGES = 4;
+constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2, B_BYTES = BLOCK_N * BLOCK_K * 2, STAGE_BYTES = A_BYTES + B_BYTES;
+constexpr int CAP = 256;          // per-row candidate buffer entries
+constexpr int MAX_K = 128;        // top-k limit (k <= CAP / 2)
+constexpr int THREADS = 192;      // warp 0: TMA producer, warp 1: MMA issuer + TMEM owner, warps 2-5: epilogue
+constexpr int TMEM_COLS = 512;    // two 128 x 256 fp32 accumulators
+constexpr int SCRATCH_BYTES = 4 * CAP * 8;  // per epilogue warp: CAP (score, id) pairs for a compaction
+constexpr int SMEM_BYTES = 1024 /*alignment slack*/ + STAGES * STAGE_BYTES + SCRATCH_BYTES + 256 /*barriers*/;
+constexpr unsigned long long WAIT_LIMIT_NS = 2000ull * 1000 * 1000;
+}  // namespace rt
+
+struct RetrievalParams {
+  float* out_scores;       // [n_users, k]
+  long long* out_ids;      // [n_users, k]
+  float* cand_scores;      // workspace [grid][128][CAP]
+  int* cand_ids;           // workspace [grid][128][CAP]
+  float* debug_scores;     // optional [n_users, n_catalog]
+  int* error_flag;
+  long long n_users, n_catalog, id_offset;
+  int dim, k, m_tiles, n_tiles;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// Bounded wait: a protocol bug must end in a trap (a reported CUDA error), never in a hung GPU.  No legitimate
+// wait in this kernel is longer than one tile's MMA time (microseconds); the bound is 2 s of %globaltimer.
+__device__ __forceinline__ unsigned long long global_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int* error_flag) {
+  const uint32_t addr = smem_u32(bar);
+  unsigned long long t0 = 0;
+  for (unsigned spin = 0;; ++spin) {
+    uint32_t done;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(addr), "r"(parity)
+        : "memory");
+    if (done) return;
+    if ((spin & 1023u) == 1023u) {
+      const unsigned long long now = global_ns();
+      if (t0 == 0) t0 = now;
+      if (now - t0 > rt::WAIT_LIMIT_NS) {
+        if (error_flag) atomicExch(error_flag, 1);
+        __trap();
+      }
+    }
+  }
+}
+
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+                   smem_u32(smem_dst)),
+               "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+               : "memory");
+}
+
+// K-major operand tile in shared memory with 128-byte swizzle: rows of 64 bf16 (128 B), 8-row groups 1024 B
+// apart.  Descriptor: start >> 4, LBO = 1 (unused for swizzled K-major), SBO = 1024 >> 4, version 1 (sm_100),
+// layout SWIZZLE_128B.  Advancing by one UMMA_K (16 bf16 = 32 B) adds 2 to the start field.
+__device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr) {
+  return (uint64_t)((smem_addr & 0x3ffffu) >> 4) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+
+// kind::f16 instruction descriptor: D fp32, A and B bf16, both K-major, N = 256, M = 128.
+constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((rt::BLOCK_N >> 3) << 17) | ((rt::BLOCK_M >> 4) << 24);
+
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(kIdesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+        "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+        "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// (score, id) ordering of the final list: higher score first, lower id first on ties.
+__device__ __forceinline__ bool beats(float sa, int ia, float sb, int ib) { return sa > sb || (sa == sb && ia < ib); }
+
+// Warp-cooperative compaction of one row's candidate buffer: keep the best `k` of `n` entries, sorted.
+// Ranks are computed by counting (n <= 256: each lane ranks 8 entries against all n through a shared copy).
+__device__ float compact_row(float* cs, int* ci, int n, int k, float* sc_s, int* sc_i, int lane) {
+  __syncwarp();  // the owning lane's appends to cs / ci become visible to the whole warp
+  for (int t = lane; t < n; t += 32) sc_s[t] = cs[t], sc_i[t] = ci[t];
+  __syncwarp();
+  float kth = -CUDART_INF_F;
+  for (int t = lane; t < n; t += 32) {
+    const float s = sc_s[t];
+    const int id = sc_i[t];
+    int rank = 0;
+    for (int o = 0; o < n; ++o) rank += beats(sc_s[o], sc_i[o], s, id) ? 1 : 0;
+    if (rank < k) cs[rank] = s, ci[rank] = id;
+    if (rank == k - 1) kth = s;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) kth = fmaxf(kth, __shfl_xor_sync(kFull, kth, o));
+  __syncwarp();
+  return kth;  // -inf while fewer than k entries exist
+}
+
+__global__ void __launch_bounds__(rt::THREADS, 1)
+retrieve_topk_kernel(const __grid_constant__ CUtensorMap tmap_users, const __grid_constant__ CUtensorMap tmap_catalog, const RetrievalParams p) {
+  using namespace rt;
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  unsigned char* stage_base = smem;                                   // STAGES x (A | B), 1024-aligned
+  unsigned char* scratch = smem + STAGES * STAGE_BYTES;               // 4 warps x CAP x (float + int)
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(scratch + SCRATCH_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full = empty_bar + STAGES;   // [2]
+  uint64_t* tmem_empty = tmem_full + 2;       // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int k_blocks = p.dim / BLOCK_K;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) mbar_init(&full_bar[s], 1), mbar_init(&empty_bar[s], 1);
+    for (int s = 0; s < 2; ++s) mbar_init(&tmem_full[s], 1), mbar_init(&tmem_empty[s], 4);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int mt = blockIdx.x; mt < p.m_tiles; mt += gridDim.x) {
+        for (int nt = 0; nt < p.n_tiles; ++nt) {
+          for (int kb = 0; kb < k_blocks; ++kb) {
+            mbar_wait(&empty_bar[stage], phase ^ 1, p.error_flag);
+            unsigned char* a = stage_base + stage * STAGE_BYTES;
+            mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
+            tma_load_2d(a, &tmap_users, &full_bar[stage], kb * BLOCK_K, mt * BLOCK_M);
+            tma_load_2d(a + A_BYTES, &tmap_catalog, &full_bar[stage], kb * BLOCK_K, nt * BLOCK_N);
+            if (++stage == STAGES) stage = 0, phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    if (lane == 0) {
+      int stage = 0, as = 0;
+      uint32_t phase = 0, aphase = 0;
+      for (int mt = blockIdx.x; mt < p.m_tiles; mt += gridDim.x) {
+        for (int nt = 0; nt < p.n_tiles; ++nt) {
+          mbar_wait(&tmem_empty[as], aphase ^ 1, p.error_flag);
+          tc_fence_after();
+          const uint32_t d_tmem = tmem_base + as * BLOCK_N;
+          for (int kb = 0; kb < k_blocks; ++kb) {
+            mbar_wait(&full_bar[stage], phase, p.error_flag);
+            tc_fence_after();
+            const uint32_t a_addr = smem_u32(stage_base + stage * STAGE_BYTES);
+            const uint64_t adesc = umma_desc(a_addr), bdesc = umma_desc(a_addr + A_BYTES);
+#pragma unroll
+            for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
+              umma_f16(d_tmem, adesc + (uint64_t)(k * (UMMA_K * 2 / 16)), bdesc + (uint64_t)(k * (UMMA_K * 2 / 16)), (kb | k) != 0);
+            umma_commit(&empty_bar[stage]);  // frees the stage once these MMAs have read it
+            if (++stage == STAGES) stage = 0, phase ^= 1;
+          }
+          umma_commit(&tmem_full[as]);  // accumulator complete
+          if (++as == 2) as = 0, aphase ^= 1;
+        }
+      }
+    }
+  } else {
+    // ===== epilogue: 4 warps x 32 lanes = the 128 accumulator rows; warp w may touch TMEM lanes 32 (w % 4) .. + 31 =====
+    const int quarter = warp & 3;
+    const int row_in_tile = quarter * 32 + lane;
+    float* sc_s = reinterpret_cast<float*>(scratch + (warp - 2) * CAP * 8);
+    int* sc_i = reinterpret_cast<int*>(sc_s + CAP);
+    float* my_cs = p.cand_scores + ((size_t)blockIdx.x * BLOCK_M + row_in_tile) * CAP;
+    int* my_ci = p.cand_ids + ((size_t)blockIdx.x * BLOCK_M + row_in_tile) * CAP;
+    int as = 0;
+    uint32_t aphase = 0;
+    for (int mt = blockIdx.x; mt < p.m_tiles; mt += gridDim.x) {
+      const long long user = (long long)mt * BLOCK_M + row_in_tile;
+      const bool row_valid = user < p.n_users;
+      float thr = -CUDART_INF_F;
+      int cnt = 0;
+      for (int nt = 0; nt < p.n_tiles; ++nt) {
+        mbar_wait(&tmem_full[as], aphase, p.error_flag);
+        tc_fence_after();
+#pragma unroll 1
+        for (int c = 0; c < BLOCK_N / 32; ++c) {
+          // make room for a whole 32-column chunk in every row of the warp before looking at it
+          unsigned need = __ballot_sync(kFull, cnt > CAP - 32);
+          while (need) {
+            const int src = __ffs(need) - 1;
+            need &= need - 1;
+            const int n_src = __shfl_sync(kFull, cnt, src);
+            float* cs = reinterpret_cast<float*>(__shfl_sync(kFull, reinterpret_cast<unsigned long long>(my_cs), src));
+            int* ci = reinterpret_cast<int*>(__shfl_sync(kFull, reinterpret_cast<unsigned long long>(my_ci), src));
+            const float kth = compact_row(cs, ci, n_src, p.k, sc_s, sc_i, lane);
+            if (lane == src) thr = kth, cnt = min(n_src, p.k);
+          }
+          uint32_t v[32];
+          tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * BLOCK_N + c * 32), v);
+          const long long col0 = (long long)nt * BLOCK_N + c * 32;
+          if (p.debug_scores != nullptr && row_valid) {
+#pragma unroll
+            for (int t = 0; t < 32; ++t)
+              if (col0 + t < p.n_catalog) p.debug_scores[user * p.n_catalog + col0 + t] = __uint_as_float(v[t]);
+          }
+          if (row_valid) {
+            float mx = -CUDART_INF_F;
+#pragma unroll
+            for (int t = 0; t < 32; ++t) mx = fmaxf(mx, (col0 + t < p.n_catalog) ? __uint_as_float(v[t]) : -CUDART_INF_F);
+            if (mx > thr) {
+#pragma unroll
+              for (int t = 0; t < 32; ++t) {
+                const float s = __uint_as_float(v[t]);
+                if (s > thr && col0 + t < p.n_catalog) my_cs[cnt] = s, my_ci[cnt] = (int)(col0 + t), ++cnt;
+              }
+            }
+          }
+        }
+        // accumulator drained: hand the TMEM buffer back to the MMA warp
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tmem_empty[as]);
+        if (++as == 2) as = 0, aphase ^= 1;
+      }
+      // end of the sweep for this user tile: final compaction of every row, then write the sorted top-k
+      __syncwarp();
+      for (int src = 0; src < 32; ++src) {
+        const int n_src = __shfl_sync(kFull, cnt, src);
+        float* cs = reinterpret_cast<float*>(__shfl_sync(kFull, reinterpret_cast<unsigned long long>(my_cs), src));
+        int* ci = reinterpret_cast<int*>(__shfl_sync(kFull, reinterpret_cast<unsigned long long>(my_ci), src));
+        const long long u_src = (long long)mt * BLOCK_M + quarter * 32 + src;
+        if (u_src >= p.n_users) continue;  // warp-uniform
+        compact_row(cs, ci, n_src, p.k, sc_s, sc_i, lane);
+        const int kept = min(n_src, p.k);
+        for (int t = lane; t < p.k; t += 32) {
+          p.out_scores[u_src * p.k + t] = (t < kept) ? cs[t] : -CUDART_INF_F;
+          p.out_ids[u_src * p.k + t] = (t < kept) ? (long long)ci[t] + p.id_offset : -1ll;
+        }
+        __syncwarp();
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS) : "memory");
+  }
+}
+
+// ---- user matrix: mean of the history rows, bf16 (cr_module.py:116-123) ---------------------------------
+__device__ __forceinline__ float2 load_pair(const float* p) { return *reinterpret_cast<const float2*>(p); }
+__device__ __forceinline__ float2 load_pair(const __nv_bfloat16* p) { return __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(p)); }
+
+template <typename T>
+__global__ void __launch_bounds__(256) pool_users_kernel(const T* __restrict__ table, long long row_stride, long long n_news, int dim,
+                                                         const int32_t* __restrict__ hist_offsets, const int32_t* __restrict__ hist_ids,
+                                                         long long n_users, __nv_bfloat16* __restrict__ out, int32_t* __restrict__ flags) {
+  constexpr int MAXP = 16;  // column pairs per lane: dim <= 2 * 32 * 16 = 1024
+  const int lane = threadIdx.x & 31;
+  const long long user = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (user >= n_users) return;
+  const int h0 = hist_offsets[user], h1 = hist_offsets[user + 1];
+  float2 acc[MAXP];
+#pragma unroll
+  for (int j = 0; j < MAXP; ++j) acc[j] = make_float2(0.f, 0.f);
+  for (int h = h0; h < h1; ++h) {
+    long long id = hist_ids[h];
+    if ((unsigned long long)id >= (unsigned long long)n_news) {
+      id = 0;
+      if (flags && lane == 0) atomicOr(flags, MB200_FLAG_BAD_ID);
+    }
+    const T* row = table + id * row_stride;
+#pragma unroll
+    for (int j = 0; j < MAXP; ++j) {
+      const int d0 = 2 * (lane + 32 * j);
+      if (d0 < dim) {
+        const float2 v = load_pair(row + d0);
+        acc[j].x += v.x, acc[j].y += v.y;
+      }
+    }
+  }
+  const float hf = (float)(h1 - h0);  // true division, like torch.div(sum, hist_size)
+#pragma unroll
+  for (int j = 0; j < MAXP; ++j) {
+    const int d0 = 2 * (lane + 32 * j);
+    if (d0 < dim)
+      *reinterpret_cast<__nv_bfloat162*>(out + user * dim + d0) = __floats2bfloat162_rn(__fdiv_rn(acc[j].x, hf), __fdiv_rn(acc[j].y, hf));
+  }
+}
+
+// ---- multi-GPU merge: per-shard sorted top-k lists [shards][n_users][k] -> global top-k ------------------
+__global__ void __launch_bounds__(256) merge_topk_kernel(const float* __restrict__ scores, const long long* __restrict__ ids, int shards,
+                                                         long long n_users, int k, float* __restrict__ out_scores,
+                                                         long long* __restrict__ out_ids) {
+  // one warp per user; `shards` sorted lists are merged by repeated selection of the best head (shards <= 32)
+  const int lane = threadIdx.x & 31;
+  const long long user = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (user >= n_users) return;
+  int head = 0;  // lane s < shards walks list s
+  for (int t = 0; t < k; ++t) {
+    float s = -CUDART_INF_F;
+    long long id = 0x7fffffffffffffffll;
+    if (lane < shards && head < k) {
+      const size_t at = ((size_t)lane * n_users + user) * k + head;
+      s = scores[at], id = ids[at];
+      if (id < 0) s = -CUDART_INF_F, id = 0x7fffffffffffffffll;
+    }
+    float bs = s;
+    long long bi = id;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float os = __shfl_xor_sync(kFull, bs, o);
+      const long long oi = __shfl_xor_sync(kFull, bi, o);
+      if (os > bs || (os == bs && oi < bi)) bs = os, bi = oi;
+    }
+    if (lane < shards && head < k && s == bs && id == bi) ++head;
+    if (lane == 0) {
+      out_scores[user * k + t] = bs;
+      out_ids[user * k + t] = (bi == 0x7fffffffffffffffll) ? -1ll : bi;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------------
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn == nullptr) {
+    void* sym = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres) == cudaSuccess && qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(sym);
+  }
+  return fn;
+}
+
+static int make_map(CUtensorMap* map, const void* base, long long rows, int dim, int box_rows) {
+  EncodeTiledFn fn = encode_fn();
+  if (fn == nullptr) return MB200_ERR_CUDA;
+  const cuuint64_t gdim[2] = {(cuuint64_t)dim, (cuuint64_t)rows};
+  const cuuint64_t gstride[1] = {(cuuint64_t)dim * 2};
+  const cuuint32_t box[2] = {(cuuint32_t)rt::BLOCK_K, (cuuint32_t)box_rows};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? MB200_OK : MB200_ERR_CUDA;
+}
+
+static int retrieval_grid(int device, long long n_users) {
+  int sms = 148;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+  const long long m_tiles = (n_users + rt::BLOCK_M - 1) / rt::BLOCK_M;
+  return (int)(m_tiles < sms ? m_tiles : sms);
+}
+
+size_t retrieval_workspace_bytes(const mb200_retrieval_desc* d) {
+  if (d == nullptr || d->struct_size != sizeof(mb200_retrieval_desc) || d->n_users <= 0) return 0;
+  const long long m_tiles = (d->n_users + rt::BLOCK_M - 1) / rt::BLOCK_M;
+  const long long grid = m_tiles < 160 ? m_tiles : 160;
+  return (size_t)grid * rt::BLOCK_M * rt::CAP * 8 + 256;
+}
+
+int retrieve_topk(const mb200_retrieval_desc* d, cudaStream_t stream) {
+  if (d == nullptr || d->struct_size != sizeof(mb200_retrieval_desc)) return MB200_ERR_INVALID_ARG;
+  if (!d->users || !d->catalog || !d->out_scores || !d->out_ids || d->n_users <= 0 || d->n_catalog <= 0) return MB200_ERR_INVALID_ARG;
+  if (d->k < 1 || d->k > rt::MAX_K) return MB200_ERR_UNSUPPORTED;
+  if (d->dim < rt::BLOCK_K || d->dim % rt::BLOCK_K != 0) return MB200_ERR_UNSUPPORTED;
+  if (d->n_catalog > 0x7fffff00ll || d->n_users > 0x7fffff00ll * (long long)rt::BLOCK_M) return MB200_ERR_UNSUPPORTED;
+  if (((uintptr_t)d->users & 15) || ((uintptr_t)d->catalog & 15)) return MB200_ERR_INVALID_ARG;
+  int device = 0;
+  int st = use_device_of(d->users, &device);
+  if (st != MB200_OK) return st;
+  const size_t need = retrieval_workspace_bytes(d);
+  if (d->workspace == nullptr || ((uintptr_t)d->workspace & 255) || d->workspace_bytes < need) return MB200_ERR_WORKSPACE;
+
+  CUtensorMap map_u, map_c;
+  if ((st = make_map(&map_u, d->users, d->n_users, d->dim, rt::BLOCK_M)) != MB200_OK) return st;
+  if ((st = make_map(&map_c, d->catalog, d->n_catalog, d->dim, rt::BLOCK_N)) != MB200_OK) return st;
+
+  RetrievalParams p{};
+  const int grid = retrieval_grid(device, d->n_users);
+  unsigned char* ws = reinterpret_cast<unsigned char*>(d->workspace);
+  p.error_flag = reinterpret_cast<int*>(ws);
+  p.cand_scores = reinterpret_cast<float*>(ws + 256);
+  p.cand_ids = reinterpret_cast<int*>(ws + 256 + (size_t)grid * rt::BLOCK_M * rt::CAP * 4);
+  p.out_scores = d->out_scores, p.out_ids = reinterpret_cast<long long*>(d->out_ids), p.debug_scores = d->debug_scores;
+  p.n_users = d->n_users, p.n_catalog = d->n_catalog, p.id_offset = d->catalog_id_offset;
+  p.dim = d->dim, p.k = d->k;
+  p.m_tiles = (int)((d->n_users + rt::BLOCK_M - 1) / rt::BLOCK_M);
+  p.n_tiles = (int)((d->n_catalog + rt::BLOCK_N - 1) / rt::BLOCK_N);
+  st = cuda_status(cudaMemsetAsync(p.error_flag, 0, 256, stream), "cudaMemsetAsync");
+  if (st != MB200_OK) return st;
+  st = cuda_status(cudaFuncSetAttribute(retrieve_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, rt::SMEM_BYTES), "cudaFuncSetAttribute");
+  if (st != MB200_OK) return st;
+  retrieve_topk_kernel<<<grid, rt::THREADS, rt::SMEM_BYTES, stream>>>(map_u, map_c, p);
+  note_launch(1);
+  return cuda_status(cudaGetLastError(), "retrieve_topk_kernel");
+}
+
+int pool_users(const void* table, int dtype, int dim, long long row_stride, long long n_news, const int32_t* hist_offsets,
+               const int32_t* hist_ids, long long n_users, void* out_bf16, int32_t* flags, cudaStream_t stream) {
+  if (!table || !hist_offsets || !hist_ids || !out_bf16 || n_users <= 0 || dim <= 0 || row_stride < dim) return MB200_ERR_INVALID_ARG;
+  if (dim % 2 != 0 || dim > 1024 || row_stride % 2 != 0) return MB200_ERR_UNSUPPORTED;
+  int st = use_device_of(table, nullptr);
+  if (st != MB200_OK) return st;
+  const int warps = 8;
+  const unsigned grid = (unsigned)((n_users + warps - 1) / warps);
+  if (dtype == MB200_F32)
+    pool_users_kernel<float><<<grid, warps * 32, 0, stream>>>(reinterpret_cast<const float*>(table), row_stride, n_news, dim, hist_offsets, hist_ids,
+                                                               n_users, reinterpret_cast<__nv_bfloat16*>(out_bf16), flags);
+  else if (dtype == MB200_BF16)
+    pool_users_kernel<__nv_bfloat16><<<grid, warps * 32, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(table), row_stride, n_news, dim,
+                                                                       hist_offsets, hist_ids, n_users, reinterpret_cast<__nv_bfloat16*>(out_bf16), flags);
+  else
+    return MB200_ERR_INVALID_ARG;
+  note_launch(1);
+  return cuda_status(cudaGetLastError(), "pool_users_kernel");
+}
+
+int merge_topk(const float* scores, const long long* ids, int shards, long long n_users, int k, float* out_scores, long long* out_ids,
+               cudaStream_t stream) {
+  if (!scores || !ids || !out_scores || !out_ids || shards < 1 || shards > 32 || n_users <= 0 || k < 1) return MB200_ERR_INVALID_ARG;
+  int st = use_device_of(scores, nullptr);
+  if (st != MB200_OK) return st;
+  const int warps = 8;
+  merge_topk_kernel<<<(unsigned)((n_users + warps - 1) / warps), warps * 32, 0, stream>>>(scores, ids, shards, n_users, k, out_scores, out_ids);
+  note_launch(1);
+  return cuda_status(cudaGetLastError(), "merge_topk_kernel");
+}
+
+}  // namespace mb200

@@ -417,3 +417,40 @@ def pooled_auc_exact(preds: np.ndarray, labels: np.ndarray, sigmoid: Optional[bo
     lo = np.searchsorted(neg, pos, side="left").astype(np.float64)
     hi = np.searchsorted(neg, pos, side="right").astype(np.float64)
     return float((lo + hi).sum() / (2.0 * pos.size * neg.size))
+
+
+# ---- full-catalogue retrieval (BASELINE.json configs[4]; no reference counterpart) -----------------------
+
+
+def pooled_users(table: Tensor, hist_offsets: np.ndarray, hist_ids: np.ndarray) -> Tensor:
+    """fp32 [U, D]: late-fusion user vectors, `sum(dim=1) / hist_size` of cr_module.py:116-123 (history rows
+    added in history order, true division)."""
+    t = table.float()
+    out = torch.zeros((len(hist_offsets) - 1, t.shape[1]), dtype=torch.float32)
+    for u in range(out.shape[0]):
+        rows = t[torch.from_numpy(np.asarray(hist_ids[hist_offsets[u] : hist_offsets[u + 1]], dtype=np.int64))]
+        acc = torch.zeros(t.shape[1], dtype=torch.float32)
+        for r in rows:
+            acc = acc + r
+        out[u] = acc / float(rows.shape[0])
+    return out
+
+
+def retrieval_scores(users_bf16: Tensor, catalog_bf16: Tensor) -> Tensor:
+    """fp32 [U, N] = bf16 x bf16 products (exact in fp32) accumulated in fp32 -- what a bf16 tensor-core
+    contraction with fp32 accumulation computes, up to summation order (DotProduct, click_predictors.py:9-12,
+    applied to every catalogue row instead of an impression's candidates)."""
+    return users_bf16.float() @ catalog_bf16.float().T
+
+
+def topk_select(scores: np.ndarray, k: int, id_offset: int = 0) -> Tuple[np.ndarray, np.ndarray]:
+    """Exact selection rule of the retrieval path on a given fp32 score matrix [U, N]: the k best per row,
+    score descending, id ascending on ties (the A3 ranking rule); unused slots (k > N) = (-inf, -1)."""
+    u, n = scores.shape
+    order = np.argsort(-scores.astype(np.float64), axis=1, kind="stable")[:, :k]  # stable: lower id first on ties
+    top_s = np.full((u, k), -np.inf, dtype=np.float32)
+    top_i = np.full((u, k), -1, dtype=np.int64)
+    kk = min(k, n)
+    top_s[:, :kk] = np.take_along_axis(scores, order, axis=1)[:, :kk]
+    top_i[:, :kk] = order[:, :kk] + id_offset
+    return top_s, top_i

@@ -98,3 +98,46 @@ def test_missing_library_fails_loudly(monkeypatch, tmp_path):
     monkeypatch.setattr(nat, "LIB_PATH", str(tmp_path / "nope.so"))
     with pytest.raises(nat.NativeLibraryMissing, match="no CPU or PyTorch fallback"):
         nat.lib()
+
+
+def test_retrieval_desc_layout_and_validation_without_a_gpu(tmp_path):
+    """mb200_retrieval_desc: the ctypes mirror matches the C struct, and the entry points reject bad
+    descriptors on the host (no GPU needed to get a status code back)."""
+    src = tmp_path / "rsz.c"
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "manner_b200.h"\nint main(){printf("%zu %zu %zu %zu %zu",'
+                   "sizeof(mb200_retrieval_desc),offsetof(mb200_retrieval_desc,n_users),offsetof(mb200_retrieval_desc,users),"
+                   "offsetof(mb200_retrieval_desc,debug_scores),offsetof(mb200_retrieval_desc,workspace_bytes));return 0;}\n")
+    exe = tmp_path / "rsz"
+    subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    got = [int(x) for x in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()]
+    R = nat.RetrievalDesc
+    assert got == [ctypes.sizeof(R), R.n_users.offset, R.users.offset, R.debug_scores.offset, R.workspace_bytes.offset]
+
+    lib = nat.lib()
+    d = R()
+    assert lib.mb200_retrieval_workspace_bytes(ctypes.byref(d)) == 0  # struct_size unset
+    assert lib.mb200_retrieve_topk(ctypes.byref(d), None) == nat.ERR_INVALID_ARG
+    assert lib.mb200_retrieve_topk(None, None) == nat.ERR_INVALID_ARG
+    d.struct_size, d.n_users, d.n_catalog, d.dim, d.k = ctypes.sizeof(R), 1000, 5000, 768, 100
+    ws = lib.mb200_retrieval_workspace_bytes(ctypes.byref(d))
+    assert ws >= 8 * 128 * 256 * 8  # 8 user tiles x 128 rows x 256 candidate slots x (score + id)
+    assert lib.mb200_retrieve_topk(ctypes.byref(d), None) == nat.ERR_INVALID_ARG  # null pointers
+    assert lib.mb200_merge_topk(None, None, 2, 4, 4, None, None, None) == nat.ERR_INVALID_ARG
+    assert lib.mb200_pool_users(None, nat.F32, 768, 768, 10, None, None, 4, None, None, None) == nat.ERR_INVALID_ARG
+
+
+def test_retrieval_refuses_cpu_tensors():
+    import manner_b200.retrieval as rt
+
+    u, c = torch.zeros(4, 64, dtype=torch.bfloat16), torch.zeros(9, 64, dtype=torch.bfloat16)
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        torch.ops.manner_b200.retrieve_topk(u, c, 4, 0, False)
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        rt.pool_users(torch.zeros(4, 64), torch.zeros(2, dtype=torch.int32), torch.zeros(1, dtype=torch.int32))
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        rt.merge_topk(torch.zeros(2, 3, 4), torch.zeros(2, 3, 4, dtype=torch.int64))
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        rt.CatalogRetriever(c, k=4)
+    assert rt.catalog_shard_bounds(1000, 3) == [(0, 512), (512, 768), (768, 1000)]
+    assert rt.catalog_shard_bounds(100, 4) == [(0, 100), (100, 100), (100, 100), (100, 100)]
+    assert rt.catalog_shard_bounds(10_000_000, 8)[-1][1] == 10_000_000

@@ -109,3 +109,65 @@ def test_payload_round_trip():
     assert torch.equal(s, sums) and int(f.item()) == 5 and n == 1234
     s2, f2, n2 = mdist.unpack_metric_payload_device(payload + payload, sums.shape)  # two identical ranks
     assert torch.equal(s2, 2 * sums) and int(f2.item()) == 5 and float(n2) == 2468
+
+
+# ---- retrieval mode: the top-k exchange (SURVEY 8(e) collective 3) ----------------------------------------
+
+
+def _np_merge(scores, ids):
+    """numpy stand-in for mb200_merge_topk: [R, U, k] sorted lists -> global top-k (score desc, id asc)."""
+    r, u, k = scores.shape
+    s = scores.numpy().transpose(1, 0, 2).reshape(u, r * k).astype(np.float64)
+    i = ids.numpy().transpose(1, 0, 2).reshape(u, r * k)
+    s = np.where(i < 0, -np.inf, s)
+    key_i = np.where(i < 0, np.iinfo(np.int64).max, i)
+    order = np.lexsort((key_i, -s), axis=1)[:, :k]
+    out_s, out_i = np.take_along_axis(s, order, 1).astype(np.float32), np.take_along_axis(i, order, 1)
+    out_i = np.where(np.isneginf(out_s), -1, out_i)
+    return torch.from_numpy(out_s), torch.from_numpy(out_i)
+
+
+def _retrieval_worker(rank: int, port: int, tmp: str) -> None:
+    from manner_b200 import retrieval as rt
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(WORLD), LOCAL_RANK=str(rank))
+    dist.init_process_group("gloo", rank=rank, world_size=WORLD)
+    try:
+        g = torch.Generator().manual_seed(3)
+        users = torch.randn(37, 64, generator=g).to(torch.bfloat16)
+        catalog = torch.randn(700, 64, generator=g).to(torch.bfloat16)
+        catalog[350:] = catalog[:350]  # cross-shard ties: the lower global id must win after the merge
+        k = 20
+        lo, hi = rt.catalog_shard_bounds(700, WORLD)[rank]
+        s, i = mo.topk_select(mo.retrieval_scores(users, catalog[lo:hi]).numpy(), k, lo)  # the checker plays the per-rank kernel
+        s, i = torch.from_numpy(s), torch.from_numpy(i)
+        ag = rt.exchange_topk(s, i, None, "all_gather", merge=_np_merge)
+        a2a = rt.exchange_topk(s, i, None, "all_to_all", merge=_np_merge)
+        np.savez(os.path.join(tmp, f"r{rank}.npz"), ag_s=ag[0].numpy(), ag_i=ag[1].numpy(), a2a_s=a2a[0].numpy(), a2a_i=a2a[1].numpy())
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_topk_exchange(tmp_path):
+    from manner_b200 import retrieval as rt
+
+    port = _free_port()
+    mp.spawn(_retrieval_worker, args=(port, str(tmp_path)), nprocs=WORLD, join=True)
+    g = torch.Generator().manual_seed(3)
+    users = torch.randn(37, 64, generator=g).to(torch.bfloat16)
+    catalog = torch.randn(700, 64, generator=g).to(torch.bfloat16)
+    catalog[350:] = catalog[:350]
+    # per-shard scores are computed on row slices: restate the global matrix the same way so ties are exact
+    bounds = rt.catalog_shard_bounds(700, WORLD)
+    full = np.concatenate([mo.retrieval_scores(users, catalog[lo:hi]).numpy() for lo, hi in bounds], axis=1)
+    want_s, want_i = mo.topk_select(full, 20)
+    outs = [np.load(tmp_path / f"r{r}.npz") for r in range(WORLD)]
+    for z in outs:  # all_gather: every rank holds the full merged result
+        np.testing.assert_array_equal(z["ag_i"], want_i)
+        np.testing.assert_array_equal(z["ag_s"], want_s)
+    # all_to_all: rank r holds its slice; concatenated in rank order they are the full result
+    for r, z in enumerate(outs):
+        idx = rt.CatalogRetriever.user_slice(37, 37, r, WORLD)
+        np.testing.assert_array_equal(z["a2a_i"], want_i[idx])
+        np.testing.assert_array_equal(z["a2a_s"], want_s[idx])
+    assert sorted(sum((rt.CatalogRetriever.user_slice(37, 16, r, WORLD) for r in range(WORLD)), [])) == list(range(37))
