@@ -348,6 +348,8 @@ def run_retrieval_arm(args) -> None:
     users = users_host.to(dev)
     r = rt.CatalogRetriever(catalog, k=k, catalog_id_offset=rank * n_shard, distributed=distributed, exchange=args.exchange, user_block=n_users)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    if args.retrieval_diag:
+        ops.set_tuning(retrieval_diag=args.retrieval_diag)
 
     def barrier() -> None:
         if distributed:
@@ -452,9 +454,10 @@ def main() -> None:
     ap.add_argument("--cpu-sample", type=int, default=8192)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--mode", default="eval", choices=["eval", "retrieval"], help="retrieval: BASELINE.json configs[4] (tcgen05 GEMM + fused top-100)")
-    ap.add_argument("--users", type=int, default=32768, help="retrieval mode: users per step")
+    ap.add_argument("--users", type=int, default=37888, help="retrieval mode: users per step (37 888 = 2 full waves of 148 CTAs x 128 rows)")
     ap.add_argument("--catalog-per-gpu", type=int, default=1_250_000, help="retrieval mode: catalogue rows per GPU (10 M over 8)")
     ap.add_argument("--exchange", default="all_gather", choices=["all_gather", "all_to_all"])
+    ap.add_argument("--retrieval-diag", type=int, default=0, help="DIAGNOSTIC: 1/2 disable parts of the retrieval epilogue (results invalid)")
     ap.add_argument("--variant", type=int, default=None)
     ap.add_argument("--chunks-per-warp", type=int, default=None)
     ap.add_argument("--ctas-per-sm", type=int, default=None)

@@ -154,6 +154,7 @@ int mb200_set_tuning(int key, int value) {
     case 1: prev = tuning().variant, tuning().variant = value; break;
     case 2: prev = tuning().ctas_per_sm, tuning().ctas_per_sm = value; break;
     case 3: prev = tuning().time_kernel, tuning().time_kernel = value; break;
+    case 4: prev = tuning().retrieval_diag, tuning().retrieval_diag = value; break;
   }
   return prev;
 }

@@ -29,7 +29,7 @@ constexpr int CAP = 256;          // per-row candidate buffer entries
 constexpr int MAX_K = 128;        // top-k limit (k <= CAP / 2)
 constexpr int THREADS = 192;      // warp 0: TMA producer, warp 1: MMA issuer + TMEM owner, warps 2-5: epilogue
 constexpr int TMEM_COLS = 512;    // two 128 x 256 fp32 accumulators
-constexpr int SCRATCH_BYTES = 4 * CAP * 8;  // per epilogue warp: CAP (score, id) pairs for a compaction
+constexpr int SCRATCH_BYTES = 0;
 constexpr int SMEM_BYTES = 1024 /*alignment slack*/ + STAGES * STAGE_BYTES + SCRATCH_BYTES + 256 /*barriers*/;
 constexpr unsigned long long WAIT_LIMIT_NS = 2000ull * 1000 * 1000;
 }  // namespace rt
@@ -43,6 +43,7 @@ struct RetrievalParams {
   int* error_flag;
   long long n_users, n_catalog, id_offset;
   int dim, k, m_tiles, n_tiles;
+  int diag;  // Tuning::retrieval_diag
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -63,6 +64,7 @@ __device__ __forceinline__ unsigned long long global_ns() {
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
   return t;
 }
+template <int SLEEP_NS = 0>
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int* error_flag) {
   const uint32_t addr = smem_u32(bar);
   unsigned long long t0 = 0;
@@ -76,6 +78,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int* e
         : "r"(addr), "r"(parity)
         : "memory");
     if (done) return;
+    if (SLEEP_NS > 0) __nanosleep(SLEEP_NS);  // waits that are off the critical path give their issue slots to the epilogue warps
     if ((spin & 1023u) == 1023u) {
       const unsigned long long now = global_ns();
       if (t0 == 0) t0 = now;
@@ -132,28 +135,112 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
-// (score, id) ordering of the final list: higher score first, lower id first on ties.
-__device__ __forceinline__ bool beats(float sa, int ia, float sb, int ib) { return sa > sb || (sa == sb && ia < ib); }
+// ---- per-row candidate lists -------------------------------------------------------------------------
+// (score, id) ordering of the final list: higher score first, lower id first on ties.  Scores are compared
+// through an order-preserving uint32 key (s + 0.0f folds -0.0 into +0.0 so the key order equals the float order).
+__device__ __forceinline__ uint32_t score_key(float s) {
+  const uint32_t b = __float_as_uint(s + 0.0f);
+  return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__device__ __forceinline__ float key_score(uint32_t k) { return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k); }
 
-// Warp-cooperative compaction of one row's candidate buffer: keep the best `k` of `n` entries, sorted.
-// Ranks are computed by counting (n <= 256: each lane ranks 8 entries against all n through a shared copy).
-__device__ float compact_row(float* cs, int* ci, int n, int k, float* sc_s, int* sc_i, int lane) {
+constexpr int kPerLane = rt::CAP / 32;  // candidate entries a lane holds during a compaction
+
+// Largest T with |{key >= T}| >= kk over the warp's 32 x kPerLane keys (kk >= 1; absent entries are 0 and never
+// count): the kk-th largest key, found bit by bit -- 32 rounds of kPerLane compares + one REDUX.
+__device__ __forceinline__ uint32_t kth_largest(const uint32_t (&key)[kPerLane], int kk) {
+  uint32_t t = 0;
+#pragma unroll 4
+  for (int b = 31; b >= 0; --b) {
+    const uint32_t trial = t | (1u << b);
+    int c = 0;
+#pragma unroll
+    for (int j = 0; j < kPerLane; ++j) c += key[j] >= trial ? 1 : 0;
+    if ((int)__reduce_add_sync(kFull, (unsigned)c) >= kk) t = trial;
+  }
+  return t;
+}
+
+// Warp-cooperative compaction of one row's candidate buffer (n <= CAP entries, unsorted, in global memory):
+// keeps exactly min(n, k) best entries, still unsorted, at the front.  Returns the k-th best score (the new
+// admission threshold), or -inf while fewer than k entries exist.
+__device__ float compact_row(float* cs, int* ci, int n, int k, int lane) {
   __syncwarp();  // the owning lane's appends to cs / ci become visible to the whole warp
-  for (int t = lane; t < n; t += 32) sc_s[t] = cs[t], sc_i[t] = ci[t];
+  float sc[kPerLane];
+  int id[kPerLane];
+  uint32_t key[kPerLane];
+#pragma unroll
+  for (int j = 0; j < kPerLane; ++j) {
+    const int t = lane + 32 * j;
+    sc[j] = t < n ? cs[t] : 0.f;
+    id[j] = t < n ? ci[t] : 0;
+    key[j] = t < n ? score_key(sc[j]) : 0u;
+  }
+  if (n <= k) return -CUDART_INF_F;  // nothing to drop (warp-uniform)
+  const uint32_t kth = kth_largest(key, k);
+  int c_gt = 0, c_eq = 0;
+#pragma unroll
+  for (int j = 0; j < kPerLane; ++j) c_gt += key[j] > kth ? 1 : 0, c_eq += key[j] == kth ? 1 : 0;
+  c_gt = (int)__reduce_add_sync(kFull, (unsigned)c_gt);
+  c_eq = (int)__reduce_add_sync(kFull, (unsigned)c_eq);
+  const int need = k - c_gt;  // 1 <= need <= c_eq entries of score == kth survive: the ones with the lowest ids
+  uint32_t id_floor = 0;      // on (0x80000000 - id): larger = lower id
+  if (c_eq > need) {
+    uint32_t rid[kPerLane];
+#pragma unroll
+    for (int j = 0; j < kPerLane; ++j) rid[j] = key[j] == kth ? 0x80000000u - (uint32_t)id[j] : 0u;
+    id_floor = kth_largest(rid, need);
+  }
   __syncwarp();
-  float kth = -CUDART_INF_F;
-  for (int t = lane; t < n; t += 32) {
-    const float s = sc_s[t];
-    const int id = sc_i[t];
-    int rank = 0;
-    for (int o = 0; o < n; ++o) rank += beats(sc_s[o], sc_i[o], s, id) ? 1 : 0;
-    if (rank < k) cs[rank] = s, ci[rank] = id;
-    if (rank == k - 1) kth = s;
+  int base = 0;
+  const unsigned lt = (1u << lane) - 1u;
+#pragma unroll
+  for (int j = 0; j < kPerLane; ++j) {
+    const bool keep = key[j] > kth || (key[j] == kth && 0x80000000u - (uint32_t)id[j] >= id_floor);
+    const unsigned m = __ballot_sync(kFull, keep);
+    if (keep) {
+      const int pos = base + __popc(m & lt);
+      cs[pos] = sc[j], ci[pos] = id[j];
+    }
+    base += __popc(m);
+  }
+  __syncwarp();
+  return key_score(kth);
+}
+
+// Final pass over one row: its (already compacted, n <= k <= 128) entries are ranked by counting -- (score desc,
+// id asc) -- and written in order; slots n .. k-1 get (-inf, -1).
+__device__ void write_sorted_row(const float* cs, const int* ci, int n, int k, float* out_s, long long* out_i, long long id_offset, int lane) {
+  constexpr int PER = rt::MAX_K / 32;
+  unsigned long long key[PER];
+#pragma unroll
+  for (int j = 0; j < PER; ++j) {
+    const int t = lane + 32 * j;
+    // composite key: larger = better; ids are unique, so keys are distinct and the ranks a permutation
+    key[j] = t < n ? ((unsigned long long)score_key(cs[t]) << 32) | (0xffffffffu - (uint32_t)ci[t]) : 0ull;
+  }
+  int rank[PER];
+#pragma unroll
+  for (int j = 0; j < PER; ++j) rank[j] = 0;
+  for (int src = 0; src < 32; ++src) {
+#pragma unroll
+    for (int jj = 0; jj < PER; ++jj) {
+      if (src + 32 * jj >= n) break;  // warp-uniform
+      const unsigned long long other = __shfl_sync(kFull, key[jj], src);
+#pragma unroll
+      for (int j = 0; j < PER; ++j) rank[j] += other > key[j] ? 1 : 0;
+    }
   }
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) kth = fmaxf(kth, __shfl_xor_sync(kFull, kth, o));
-  __syncwarp();
-  return kth;  // -inf while fewer than k entries exist
+  for (int j = 0; j < PER; ++j) {
+    const int t = lane + 32 * j;
+    if (t < n) {
+      out_s[rank[j]] = key_score((uint32_t)(key[j] >> 32));
+      out_i[rank[j]] = (long long)(0xffffffffu - (uint32_t)key[j]) + id_offset;
+    } else if (t < k) {
+      out_s[t] = -CUDART_INF_F, out_i[t] = -1ll;
+    }
+  }
 }
 
 __global__ void __launch_bounds__(rt::THREADS, 1)
@@ -162,8 +249,7 @@ retrieve_topk_kernel(const __grid_constant__ CUtensorMap tmap_users, const __gri
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   unsigned char* stage_base = smem;                                   // STAGES x (A | B), 1024-aligned
-  unsigned char* scratch = smem + STAGES * STAGE_BYTES;               // 4 warps x CAP x (float + int)
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(scratch + SCRATCH_BYTES);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tmem_full = empty_bar + STAGES;   // [2]
   uint64_t* tmem_empty = tmem_full + 2;       // [2]
@@ -194,7 +280,7 @@ retrieve_topk_kernel(const __grid_constant__ CUtensorMap tmap_users, const __gri
       for (int mt = blockIdx.x; mt < p.m_tiles; mt += gridDim.x) {
         for (int nt = 0; nt < p.n_tiles; ++nt) {
           for (int kb = 0; kb < k_blocks; ++kb) {
-            mbar_wait(&empty_bar[stage], phase ^ 1, p.error_flag);
+            mbar_wait<64>(&empty_bar[stage], phase ^ 1, p.error_flag);
             unsigned char* a = stage_base + stage * STAGE_BYTES;
             mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
             tma_load_2d(a, &tmap_users, &full_bar[stage], kb * BLOCK_K, mt * BLOCK_M);
@@ -234,8 +320,6 @@ retrieve_topk_kernel(const __grid_constant__ CUtensorMap tmap_users, const __gri
     // ===== epilogue: 4 warps x 32 lanes = the 128 accumulator rows; warp w may touch TMEM lanes 32 (w % 4) .. + 31 =====
     const int quarter = warp & 3;
     const int row_in_tile = quarter * 32 + lane;
-    float* sc_s = reinterpret_cast<float*>(scratch + (warp - 2) * CAP * 8);
-    int* sc_i = reinterpret_cast<int*>(sc_s + CAP);
     float* my_cs = p.cand_scores + ((size_t)blockIdx.x * BLOCK_M + row_in_tile) * CAP;
     int* my_ci = p.cand_ids + ((size_t)blockIdx.x * BLOCK_M + row_in_tile) * CAP;
     int as = 0;
@@ -243,11 +327,12 @@ retrieve_topk_kernel(const __grid_constant__ CUtensorMap tmap_users, const __gri
     for (int mt = blockIdx.x; mt < p.m_tiles; mt += gridDim.x) {
       const long long user = (long long)mt * BLOCK_M + row_in_tile;
       const bool row_valid = user < p.n_users;
-      float thr = -CUDART_INF_F;
+      float thr = -CUDART_INF_F;  // admission threshold: the row's k-th best score at its last compaction
       int cnt = 0;
       for (int nt = 0; nt < p.n_tiles; ++nt) {
-        mbar_wait(&tmem_full[as], aphase, p.error_flag);
+        mbar_wait<20>(&tmem_full[as], aphase, p.error_flag);
         tc_fence_after();
+        const bool last_tile = nt == p.n_tiles - 1;
 #pragma unroll 1
         for (int c = 0; c < BLOCK_N / 32; ++c) {
           // make room for a whole 32-column chunk in every row of the warp before looking at it
@@ -258,29 +343,46 @@ retrieve_topk_kernel(const __grid_constant__ CUtensorMap tmap_users, const __gri
             const int n_src = __shfl_sync(kFull, cnt, src);
             float* cs = reinterpret_cast<float*>(__shfl_sync(kFull, reinterpret_cast<unsigned long long>(my_cs), src));
             int* ci = reinterpret_cast<int*>(__shfl_sync(kFull, reinterpret_cast<unsigned long long>(my_ci), src));
-            const float kth = compact_row(cs, ci, n_src, p.k, sc_s, sc_i, lane);
+            const float kth = compact_row(cs, ci, n_src, p.k, lane);
             if (lane == src) thr = kth, cnt = min(n_src, p.k);
           }
+          if (p.diag == 2) continue;
           uint32_t v[32];
           tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * BLOCK_N + c * 32), v);
-          const long long col0 = (long long)nt * BLOCK_N + c * 32;
+          const int col0 = nt * BLOCK_N + c * 32;
           if (p.debug_scores != nullptr && row_valid) {
 #pragma unroll
             for (int t = 0; t < 32; ++t)
               if (col0 + t < p.n_catalog) p.debug_scores[user * p.n_catalog + col0 + t] = __uint_as_float(v[t]);
           }
-          if (row_valid) {
-            float mx = -CUDART_INF_F;
+          if (last_tile) {  // columns past the catalogue hold 0 (TMA zero fill): they must never be admitted
 #pragma unroll
-            for (int t = 0; t < 32; ++t) mx = fmaxf(mx, (col0 + t < p.n_catalog) ? __uint_as_float(v[t]) : -CUDART_INF_F);
-            if (mx > thr) {
+            for (int t = 0; t < 32; ++t)
+              if (col0 + t >= p.n_catalog) v[t] = 0xff800000u;  // -inf
+          }
+          // two-level filter: the maxima of the four 8-column groups, then only the groups that can hold an admission
+          float g[4];
 #pragma unroll
-              for (int t = 0; t < 32; ++t) {
-                const float s = __uint_as_float(v[t]);
-                if (s > thr && col0 + t < p.n_catalog) my_cs[cnt] = s, my_ci[cnt] = (int)(col0 + t), ++cnt;
+          for (int q = 0; q < 4; ++q) {
+            const float a0 = fmaxf(__uint_as_float(v[8 * q + 0]), __uint_as_float(v[8 * q + 1])), a1 = fmaxf(__uint_as_float(v[8 * q + 2]), __uint_as_float(v[8 * q + 3]));
+            const float a2 = fmaxf(__uint_as_float(v[8 * q + 4]), __uint_as_float(v[8 * q + 5])), a3 = fmaxf(__uint_as_float(v[8 * q + 6]), __uint_as_float(v[8 * q + 7]));
+            g[q] = fmaxf(fmaxf(a0, a1), fmaxf(a2, a3));
+          }
+          float mx = fmaxf(fmaxf(g[0], g[1]), fmaxf(g[2], g[3]));
+          if (p.diag == 1 || !row_valid) mx = -CUDART_INF_F;
+          if (mx > thr) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              if (g[q] > thr) {
+#pragma unroll
+                for (int t = 8 * q; t < 8 * q + 8; ++t) {
+                  const float s = __uint_as_float(v[t]);
+                  if (s > thr) my_cs[cnt] = s, my_ci[cnt] = col0 + t, ++cnt;
+                }
               }
             }
           }
+          __syncwarp();
         }
         // accumulator drained: hand the TMEM buffer back to the MMA warp
         tc_fence_before();
@@ -288,7 +390,7 @@ retrieve_topk_kernel(const __grid_constant__ CUtensorMap tmap_users, const __gri
         if (lane == 0) mbar_arrive(&tmem_empty[as]);
         if (++as == 2) as = 0, aphase ^= 1;
       }
-      // end of the sweep for this user tile: final compaction of every row, then write the sorted top-k
+      // end of the sweep for this user tile: every row is cut to its best k and written in order
       __syncwarp();
       for (int src = 0; src < 32; ++src) {
         const int n_src = __shfl_sync(kFull, cnt, src);
@@ -296,12 +398,8 @@ retrieve_topk_kernel(const __grid_constant__ CUtensorMap tmap_users, const __gri
         int* ci = reinterpret_cast<int*>(__shfl_sync(kFull, reinterpret_cast<unsigned long long>(my_ci), src));
         const long long u_src = (long long)mt * BLOCK_M + quarter * 32 + src;
         if (u_src >= p.n_users) continue;  // warp-uniform
-        compact_row(cs, ci, n_src, p.k, sc_s, sc_i, lane);
-        const int kept = min(n_src, p.k);
-        for (int t = lane; t < p.k; t += 32) {
-          p.out_scores[u_src * p.k + t] = (t < kept) ? cs[t] : -CUDART_INF_F;
-          p.out_ids[u_src * p.k + t] = (t < kept) ? (long long)ci[t] + p.id_offset : -1ll;
-        }
+        compact_row(cs, ci, n_src, p.k, lane);
+        write_sorted_row(cs, ci, min(n_src, p.k), p.k, p.out_scores + u_src * p.k, p.out_ids + u_src * p.k, p.id_offset, lane);
         __syncwarp();
       }
     }
@@ -460,6 +558,7 @@ int retrieve_topk(const mb200_retrieval_desc* d, cudaStream_t stream) {
   p.out_scores = d->out_scores, p.out_ids = reinterpret_cast<long long*>(d->out_ids), p.debug_scores = d->debug_scores;
   p.n_users = d->n_users, p.n_catalog = d->n_catalog, p.id_offset = d->catalog_id_offset;
   p.dim = d->dim, p.k = d->k;
+  p.diag = tuning().retrieval_diag;
   p.m_tiles = (int)((d->n_users + rt::BLOCK_M - 1) / rt::BLOCK_M);
   p.n_tiles = (int)((d->n_catalog + rt::BLOCK_N - 1) / rt::BLOCK_N);
   st = cuda_status(cudaMemsetAsync(p.error_flag, 0, 256, stream), "cudaMemsetAsync");
