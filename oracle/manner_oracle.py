@@ -98,6 +98,70 @@ def late_fusion_scores(table: Tensor, batch: Dict) -> Tuple[Tensor, Tensor]:
     return scores, mask_cand
 
 
+@dataclass
+class Attention:
+    """Parameters of the reference's early-fusion user encoder: NAMLUserEncoder -> AdditiveAttention
+    (user_encoder.py:9-21, attention.py:6-13): linear.weight [Q, D], linear.bias [Q], query [Q]."""
+
+    weight: Tensor
+    bias: Tensor
+    query: Tensor
+
+
+def additive_attention(att: Attention, x: Tensor) -> Tensor:
+    """attention.py:15-29 on a padded batch [B, Hmax, D].  NOTE the reference does not mask the padded
+    (all-zero) history rows: they enter the softmax with the logit query . tanh(bias)."""
+    a = torch.tanh(torch.nn.functional.linear(x, att.weight, att.bias))
+    w = torch.nn.functional.softmax(torch.matmul(a, att.query), dim=1)
+    return torch.bmm(w.unsqueeze(dim=1), x).squeeze(dim=1)
+
+
+def early_fusion_scores(table: Tensor, att: Attention, batch: Dict) -> Tuple[Tensor, Tensor]:
+    """cr_module.py:105-131 with late_fusion=False: user_vector = self.user_encoder(clicked_news_vector_agg)."""
+    hist = table[batch["x_hist"]["news_row"]]
+    hist_dense, _ = tp.to_dense_batch(hist, batch["batch_hist"])
+    cand = table[batch["x_cand"]["news_row"]]
+    cand_dense, mask_cand = tp.to_dense_batch(cand, batch["batch_cand"])
+    user = additive_attention(att, hist_dense)
+    scores = dot_product(user.unsqueeze(dim=1), cand_dense.permute(0, 2, 1))
+    return scores, mask_cand
+
+
+def attention_logits(att: Attention, table: Tensor) -> Tensor:
+    """Per-news additive-attention logit  query . tanh(W x_n + b)  -- the quantity the B200 path caches next
+    to the embedding table (it depends on the news row only, not on the user)."""
+    return torch.matmul(torch.tanh(torch.nn.functional.linear(table, att.weight, att.bias)), att.query)
+
+
+def ce_step_loss(scores: Tensor, batch: Dict) -> Tensor:
+    """cr_module.py:140-142,171: CrossEntropyLoss()(scores [B, Cmax], y_true [B, Cmax]) with the 0/1 label
+    matrix as class probabilities -- padded columns (score exactly 0) are part of the log-softmax -- mean over
+    the step's impressions."""
+    y_true, _ = tp.to_dense_batch(batch["labels"], batch["batch_cand"])
+    return torch.nn.functional.cross_entropy(scores, y_true)
+
+
+def supcon_step_loss(scores: Tensor, batch: Dict, temperature: float) -> Tensor:
+    """PARITY UNPINNED restatement of cr_module.py:144-169 + components/losses.py:6-40 on top of
+    pytorch_metric_learning 2.1.1's SupConLoss (absent here): per impression with >= 1 positive,
+    -mean over positives of (s_p / T - logsumexp over the impression's real candidates of s / T);
+    AvgNonZeroReducer (the SupConLoss default) averages the impressions whose loss is > 0; a step without any
+    positive or without any negative gives 0."""
+    y_true, mask_cand = tp.to_dense_batch(batch["labels"], batch["batch_cand"])
+    pos = (y_true > 0) & mask_cand
+    neg = (y_true == 0) & mask_cand
+    if not bool(pos.any()) or not bool(neg.any()):
+        return torch.zeros(())
+    mat = scores / temperature
+    mat = mat - mat.max(dim=1, keepdim=True)[0]
+    denom = torch.logsumexp(mat.masked_fill(~mask_cand, float("-inf")), dim=1, keepdim=True)
+    log_prob = mat - denom
+    mean_log_prob_pos = (pos * log_prob).sum(dim=1) / (pos.sum(dim=1) + torch.finfo(torch.float32).tiny)
+    losses = -mean_log_prob_pos
+    nz = losses > 0
+    return losses[nz].mean() if bool(nz.any()) else torch.zeros(())
+
+
 def zscore(scores: Tensor, mask_cand: Tensor) -> Tensor:
     """ensemble_module.py:137-149: unbiased std over the valid columns, mean = row sum over ALL
     (padded) columns / candidate count."""
@@ -221,14 +285,18 @@ def _recommendation_metrics(with_auc_mrr: bool) -> tp.MetricCollection:
     return tp.MetricCollection(metrics).clone(prefix="test/")
 
 
-def cr_eval_epoch(table: Tensor, bhv: Behaviours, step: int = STEP_BATCH, double_compute: bool = False) -> Dict:
+def cr_eval_epoch(table: Tensor, bhv: Behaviours, step: int = STEP_BATCH, double_compute: bool = False, attention: Optional[Attention] = None,
+                  supcon_temperature: Optional[float] = None) -> Dict:
     """CRModule test epoch: test_step per batch (cr_module.py:253-264) then on_test_epoch_end
     (:266-274).  ``double_compute`` repeats the metric pass the way Lightning does (forward +
-    compute at log time) -- timing only, the values are identical."""
-    preds_l, targets_l, sizes_l = [], [], []
+    compute at log time) -- timing only, the values are identical.  ``attention`` switches to early fusion
+    (late_fusion=False); ``test/loss`` is the MeanMetric over the steps' losses (cr_module.py:255-259): cross
+    entropy, or the SupCon restatement when ``supcon_temperature`` is given."""
+    preds_l, targets_l, sizes_l, losses = [], [], [], []
     for lo in range(0, bhv.n_impressions, step):
         batch = step_batch(bhv, lo, min(lo + step, bhv.n_impressions))
-        scores, _ = late_fusion_scores(table, batch)
+        scores, _ = late_fusion_scores(table, batch) if attention is None else early_fusion_scores(table, attention, batch)
+        losses.append(ce_step_loss(scores, batch) if supcon_temperature is None else supcon_step_loss(scores, batch, supcon_temperature))
         p, t, s = flatten_for_metrics(scores, batch)
         preds_l.append(p), targets_l.append(t), sizes_l.append(s)
     preds, targets, sizes = torch.cat(preds_l), torch.cat(targets_l), torch.cat(sizes_l)
@@ -239,7 +307,12 @@ def cr_eval_epoch(table: Tensor, bhv: Behaviours, step: int = STEP_BATCH, double
         values = coll.compute()
     out = {k: float(v) for k, v in values.items()}
     out.update(gauc_epoch(preds.numpy(), targets.numpy(), sizes.numpy()))
-    return {"scores": preds.numpy(), "targets": targets.numpy(), "cand_news_size": sizes.numpy(), "metrics": out}
+    mean_loss = tp.MeanMetric()
+    for l in losses:
+        mean_loss.update(l)
+    out["test/loss"] = float(mean_loss.compute())
+    return {"scores": preds.numpy(), "targets": targets.numpy(), "cand_news_size": sizes.numpy(), "metrics": out,
+            "step_losses": np.asarray([float(l) for l in losses], dtype=np.float32)}
 
 
 def ensemble_eval_epoch(

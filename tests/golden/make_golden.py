@@ -117,25 +117,33 @@ def table(n_news: int, dim: int, seed: int) -> torch.Tensor:
     return torch.randn(n_news, dim, generator=g) * (2.0 / dim**0.5)
 
 
-def run_reference_cr(tab: torch.Tensor, bhv: mo.Behaviours, step: int = 8) -> Dict[str, np.ndarray]:
+def run_reference_cr(tab: torch.Tensor, bhv: mo.Behaviours, step: int = 8, late_fusion: bool = True, query_vector_dim: int = 200) -> Dict[str, np.ndarray]:
     ref_cr.MannerNewsEncoder = TableEncoder  # the only substitution inside CRModule.__init__
     model = ref_cr.CRModule(
-        supcon_loss=False, late_fusion=True, temperature=0.1, plm_model="", frozen_layers=[], dropout_probability=0.2,
+        supcon_loss=False, late_fusion=late_fusion, temperature=0.1, plm_model="", frozen_layers=[], dropout_probability=0.2,
         use_entities=False, pretrained_entity_embeddings_path="", entity_embedding_dim=100, num_attention_heads=10,
-        query_vector_dim=200, text_embedding_dim=tab.shape[1], optimizer=None,
+        query_vector_dim=query_vector_dim, text_embedding_dim=tab.shape[1], optimizer=None,
     )
     model.news_encoder.table = tab
     model.eval()
+    step_losses = []
     with torch.no_grad():
         for i, lo in enumerate(range(0, bhv.n_impressions, step)):
-            model.test_step(mo.step_batch(bhv, lo, min(lo + step, bhv.n_impressions)), i)
+            batch = mo.step_batch(bhv, lo, min(lo + step, bhv.n_impressions))
+            step_losses.append(float(model.model_step(batch)[0]))  # CrossEntropyLoss()(scores, y_true) of cr_module.py:171
+            model.test_step(batch, i)
         preds = torch.cat(model.test_step_outputs["preds"]).numpy().copy()
         targets = torch.cat(model.test_step_outputs["targets"]).numpy().copy()
         sizes = torch.cat(model.test_step_outputs["cand_news_size"]).numpy().copy()
         model.on_test_epoch_end()
-    out = {"preds": preds, "targets": targets, "cand_news_size": sizes}
+    out = {"preds": preds, "targets": targets, "cand_news_size": sizes, "step_losses": np.asarray(step_losses, dtype=np.float32),
+           "test/loss": np.float32(float(model.test_loss.compute()))}  # MeanMetric over the steps (cr_module.py:255-259)
     for k in ("test/auc", "test/mrr", "test/ndcg@5", "test/ndcg@10"):
         out[k] = np.float32(float(model.logged[k]))
+    if not late_fusion:
+        att = model.user_encoder.additive_attention  # NAMLUserEncoder -> AdditiveAttention (user_encoder.py:9-21, attention.py:6-29)
+        out.update(att_weight=att.linear.weight.detach().numpy().copy(), att_bias=att.linear.bias.detach().numpy().copy(),
+                   att_query=att.query.detach().numpy().copy())
     return out
 
 
@@ -205,6 +213,17 @@ def main() -> None:
     with stable_argsort():
         ref = run_reference_cr(tab, bhv)
     save("cr_ties", table=tab.numpy(), **bhv_arrays(bhv), **{k.replace("/", "_"): v for k, v in ref.items()})
+
+    # ---- CR eval, EARLY fusion (late_fusion=False: NAMLUserEncoder additive attention over the PADDED history) + CE loss ----
+    for name, dim, qdim, n_news, b, seed in (("cr_ef_d128", 128, 200, 256, 40, 2028), ("cr_ef_d768", 768, 200, 96, 20, 2029)):
+        rng = np.random.default_rng(seed)
+        hs, cs, ps = ragged_sizes(rng, b, cmax=40)
+        bhv = make_behaviours(rng, n_news, hs, cs, ps)
+        tab = table(n_news, dim, 1234)
+        torch.manual_seed(seed)  # the attention parameters are random-initialised by the reference's own constructors
+        with stable_argsort():
+            ref = run_reference_cr(tab, bhv, late_fusion=False, query_vector_dim=qdim)
+        save(name, table=tab.numpy(), **bhv_arrays(bhv), **{k.replace("/", "_"): v for k, v in ref.items()})
 
     # ---- ensemble: CR + category + sentiment A-Modules, 4 weightings, with aspects ------------------
     rng = np.random.default_rng(2027)

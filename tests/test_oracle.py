@@ -26,6 +26,56 @@ def test_cr_epoch_matches_reference_golden(golden_dir, name):
     np.testing.assert_array_equal(out["cand_news_size"], z["cand_news_size"])
     for k in ("auc", "mrr", "ndcg@5", "ndcg@10"):
         assert abs(out["metrics"]["test/" + k] - float(z["test_" + k])) <= 1e-7, k
+    # CrossEntropyLoss per step (cr_module.py:171) and its MeanMetric over the steps (:255-259)
+    np.testing.assert_allclose(out["step_losses"], z["step_losses"], rtol=1e-6)
+    assert abs(out["metrics"]["test/loss"] - float(z["test_loss"])) <= 1e-6 * abs(float(z["test_loss"]))
+
+
+def _attention(z):
+    return mo.Attention(torch.from_numpy(z["att_weight"]), torch.from_numpy(z["att_bias"]), torch.from_numpy(z["att_query"]))
+
+
+@pytest.mark.parametrize("name", ["cr_ef_d128", "cr_ef_d768"])
+def test_early_fusion_epoch_matches_reference_golden(golden_dir, name):
+    """late_fusion=False (cr_module.py:124-125): NAMLUserEncoder's additive attention over the PADDED history."""
+    z = np.load(os.path.join(golden_dir, name + ".npz"))
+    table, bhv, att = torch.from_numpy(z["table"]), _bhv(z), _attention(z)
+    out = mo.cr_eval_epoch(table, bhv, attention=att)
+    np.testing.assert_allclose(out["scores"], z["preds"], rtol=1e-6, atol=1e-7)
+    for k in ("auc", "mrr", "ndcg@5", "ndcg@10"):
+        assert abs(out["metrics"]["test/" + k] - float(z["test_" + k])) <= 1e-7, k
+    np.testing.assert_allclose(out["step_losses"], z["step_losses"], rtol=1e-6)
+    # the cached-logit formulation the CUDA path uses (softmax over per-news logits + pad logits) is the same function
+    logits = mo.attention_logits(att, table)
+    pad_logit = float(torch.dot(torch.tanh(att.bias), att.query))
+    H = np.diff(bhv.hist_offsets)
+    for i in range(bhv.n_impressions):
+        lo = i // 8 * 8
+        n_pad = int(H[lo : lo + 8].max() - H[i])
+        ids = torch.from_numpy(bhv.hist_ids[bhv.hist_offsets[i] : bhv.hist_offsets[i + 1]].astype(np.int64))
+        l = torch.cat([logits[ids], torch.full((n_pad,), pad_logit)])
+        w = torch.softmax(l, dim=0)[: len(ids)]
+        user = (w.unsqueeze(1) * table[ids]).sum(0)
+        cids = torch.from_numpy(bhv.cand_ids[bhv.cand_offsets[i] : bhv.cand_offsets[i + 1]].astype(np.int64))
+        np.testing.assert_allclose((table[cids] @ user).numpy(), z["preds"][bhv.cand_offsets[i] : bhv.cand_offsets[i + 1]], rtol=2e-5, atol=2e-6)
+
+
+def test_supcon_restatement_known_answers():
+    """PARITY UNPINNED (pytorch_metric_learning absent): hand-computed values of the restated SupCon step loss."""
+    bhv = mo.Behaviours(np.array([0, 1, 2, 3], np.int32), np.zeros(3, np.int32), np.array([0, 3, 5, 7], np.int32), np.zeros(7, np.int32),
+                        np.array([1, 0, 0, 1, 1, 0, 0], np.uint8))
+    batch = mo.step_batch(bhv, 0, 3)
+    scores = torch.tensor([[1.0, 0.0, -1.0], [0.5, 0.5, 0.0], [2.0, 1.0, 0.0]])  # third column of rows 1, 2 is padding
+    T = 0.5
+    l0 = -(2.0 - math.log(math.exp(2.0) + 1.0 + math.exp(-2.0)))
+    l1 = -(1.0 - math.log(2 * math.exp(1.0)))  # two positives, no negative: -mean(log 1/2) = log 2
+    # row 2 has no positive: contributes 0 and is dropped by the AvgNonZero reduction
+    want = (l0 + math.log(2.0)) / 2
+    assert l1 == pytest.approx(math.log(2.0))
+    assert float(mo.supcon_step_loss(scores, batch, T)) == pytest.approx(want, rel=1e-6)
+    # a step without negatives (or without positives) gives 0
+    bhv2 = mo.Behaviours(np.array([0, 1], np.int32), np.zeros(1, np.int32), np.array([0, 2], np.int32), np.zeros(2, np.int32), np.array([1, 1], np.uint8))
+    assert float(mo.supcon_step_loss(torch.tensor([[0.3, 0.1]]), mo.step_batch(bhv2, 0, 1), T)) == 0.0
 
 
 def test_ensemble_epoch_matches_reference_golden(golden_dir):
