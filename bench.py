@@ -244,10 +244,14 @@ def run_gpu_arm(args) -> None:
     total_ms = float(total_ms.item())
     res = ev.finish(pending)
 
+    # the clocks are sampled during the device-timed region only: nvidia-smi polling takes driver locks that can stall
+    # the host-side calls of the end-to-end loop below for a whole polling period
+    clocks = sampler.stop() if sampler is not None else None
+
     # end to end: pinned host CSR -> device, pass, metric sums back to the host, every step
     barrier()
     e2e_events = []
-    for i in range(args.steps + 1):
+    for i in range(max(args.steps, 10) + 1):
         flush.fill_(rank + 1)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
@@ -262,7 +266,6 @@ def run_gpu_arm(args) -> None:
     if distributed:
         dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
     e2e_ms = float(e2e_ms.item())
-    clocks = sampler.stop() if sampler is not None else None
 
     n_impr_rank = bhv.n_impressions
     n_impr_total = torch.tensor([n_impr_rank], dtype=torch.float64, device=dev)

@@ -35,7 +35,7 @@ extern "C" {
 #define MB200_API
 #endif
 
-#define MB200_ABI_VERSION 1
+#define MB200_ABI_VERSION 2
 #define MB200_MAX_MODULES 4 /* CR-Module + up to 3 A-Modules (reference: CR, category, sentiment) */
 #define MB200_MAX_K 31      /* largest ranking cut-off k for nDCG / diversity / personalization */
 #define MB200_MAX_CLASSES 64
@@ -72,8 +72,17 @@ extern "C" {
 #define MB200_M_CATEG_PERS_K1 10
 #define MB200_M_SENT_PERS_K0 11 /* Personalization(num_sent_classes, k)      (ensemble_module.py:74-79) */
 #define MB200_M_SENT_PERS_K1 12
-#define MB200_NUM_METRICS 13
+#define MB200_M_LOSS 13         /* per-impression loss of `loss_kind` on the scores of `scores_weighting` (cr_module.py:140-171) */
+#define MB200_M_LOSS_NONZERO 14 /* 1 where that loss is > 0 (the AvgNonZero reduction of the SupCon loss)                       */
+#define MB200_NUM_METRICS 15
 #define MB200_PAYLOAD_TAIL 5
+
+/* ---- loss kinds (mb200_eval_desc.loss_kind) ---------------------------------------------------------- */
+#define MB200_LOSS_NONE 0
+#define MB200_LOSS_CE 1     /* torch CrossEntropyLoss()(scores [B, Cmax], y_true [B, Cmax]) with the 0/1 labels as class
+                               probabilities; padded columns (score 0) take part in the log-softmax  (cr_module.py:75-76,171) */
+#define MB200_LOSS_SUPCON 2 /* components/losses.py:6-40 on pytorch_metric_learning's SupConLoss, similarity = scores
+                               (cr_module.py:144-169): -mean over positives of log softmax(s / T) over the real candidates */
 
 /*
  * One evaluation call = one pass over a set of impressions: what the reference spreads over
@@ -138,6 +147,22 @@ typedef struct mb200_eval_desc {
 
   void* workspace; /* >= mb200_eval_workspace_bytes(desc) bytes, 256-byte aligned */
   size_t workspace_bytes;
+
+  /* early fusion (cr_module.py:124-125 with late_fusion=False: NAMLUserEncoder -> AdditiveAttention, user_encoder.py:9-21,
+     attention.py:15-29).  attn_logits[m] = [n_news + 1] fp32 from mb200_attention_logits: query . tanh(W x_n + b) per news
+     row, and in the last slot the logit of an all-zero row.  The user vector of module m becomes
+     sum_h softmax(logits of the history rows and of hist_pad[i] zero rows)_h * row_h -- the reference does NOT mask the
+     rows its dense batch pads with (attention.py:23), so they take softmax mass.  NULL = late fusion (mean). */
+  const float* attn_logits[MB200_MAX_MODULES];
+  const int32_t* hist_pad; /* optional [n_impressions]: zero rows the reference's step batch appends to impression i's
+                              history = (longest history of its step) - H_i; NULL = none */
+
+  /* loss on the scores of `scores_weighting` (slots MB200_M_LOSS / _NONZERO; 0 in the aspect-weight sweep mode) */
+  int32_t loss_kind;        /* MB200_LOSS_* */
+  float loss_temperature;   /* SupCon temperature (configs/model/cr_module.yaml:6) */
+  const int32_t* cand_pad;  /* optional [n_impressions]: zero columns the step batch appends to impression i's candidates
+                               (cross entropy only); NULL = none */
+  float* loss_per_impression; /* optional [n_impressions] */
 } mb200_eval_desc;
 
 MB200_API int mb200_abi_version(void);
@@ -146,6 +171,25 @@ MB200_API const char* mb200_last_cuda_error(void); /* HOST string, thread-local,
 
 MB200_API size_t mb200_eval_workspace_bytes(const mb200_eval_desc* desc);
 MB200_API int mb200_score_eval(const mb200_eval_desc* desc, void* stream);
+
+/*
+ * Per-news additive-attention logits for early fusion: out[n] = query . tanh(weight x_n + bias) for the n_rows rows of
+ * `table` (fp32 arithmetic), out[n_rows] = query . tanh(bias) (the logit of a padded, all-zero history row).  weight
+ * [q_dim, dim], bias [q_dim], query [q_dim] fp32 = NAMLUserEncoder.additive_attention.{linear.weight, linear.bias, query}
+ * (attention.py:9-13).  The logit depends on the news row only, so it is cached next to the embedding table instead of
+ * being recomputed per impression (attention.py:20-24 runs the linear layer on every padded history row of every step).
+ * dim % 4 == 0, dim <= 1024, q_dim <= 1024.
+ */
+MB200_API int mb200_attention_logits(const void* table, int dtype, int dim, int64_t row_stride, int64_t n_rows, const float* weight,
+                                     const float* bias, const float* query, int q_dim, float* out /* [n_rows + 1] */, void* stream);
+
+/*
+ * The reference logs `test/loss` / `val/loss` as a MeanMetric over its steps (cr_module.py:214-225,253-259): every step of
+ * `step` consecutive impressions contributes one value -- the mean of its impressions' losses (cross entropy), or the mean
+ * of the losses that are > 0 (SupCon, AvgNonZeroReducer).  out (device, 2 doubles) = {sum of the step values, number of
+ * steps}: both additive over ranks when every rank's shard starts on a step boundary.
+ */
+MB200_API int mb200_step_loss(const float* loss_per_impression, int64_t n_impressions, int step, int loss_kind, double* out, void* stream);
 
 /*
  * Pooled AUROC exactly as torchmetrics 0.11.4 `AUROC(task="binary")` defines it (cr_module.py:81,273;

@@ -12,11 +12,11 @@ from typing import Optional
 
 LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libmanner_b200.so")
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 MAX_MODULES = 4
 MAX_K = 31
 MAX_CLASSES = 64
-NUM_METRICS = 13
+NUM_METRICS = 15
 PAYLOAD_TAIL = 5
 
 OK, ERR_INVALID_ARG, ERR_UNSUPPORTED, ERR_CUDA, ERR_WORKSPACE = 0, 1, 2, 3, 4
@@ -27,6 +27,8 @@ F32, BF16 = 0, 1
 M_MRR, M_NDCG_K0, M_NDCG_K1, M_GAUC, M_GAUC_VALID = 0, 1, 2, 3, 4
 M_CATEG_DIV_K0, M_CATEG_DIV_K1, M_SENT_DIV_K0, M_SENT_DIV_K1 = 5, 6, 7, 8
 M_CATEG_PERS_K0, M_CATEG_PERS_K1, M_SENT_PERS_K0, M_SENT_PERS_K1 = 9, 10, 11, 12
+M_LOSS, M_LOSS_NONZERO = 13, 14
+LOSS_NONE, LOSS_CE, LOSS_SUPCON = 0, 1, 2
 
 
 class EvalDesc(Structure):
@@ -65,6 +67,12 @@ class EvalDesc(Structure):
         ("flags", c_void_p),
         ("workspace", c_void_p),
         ("workspace_bytes", c_size_t),
+        ("attn_logits", c_void_p * MAX_MODULES),
+        ("hist_pad", c_void_p),
+        ("loss_kind", c_int32),
+        ("loss_temperature", c_float),
+        ("cand_pad", c_void_p),
+        ("loss_per_impression", c_void_p),
     ]
 
 
@@ -106,6 +114,8 @@ SIGNATURES = {
     "mb200_retrieve_topk": (c_int, [POINTER(RetrievalDesc), c_void_p]),
     "mb200_pool_users": (c_int, [c_void_p, c_int, c_int, c_int64, c_int64, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
     "mb200_merge_topk": (c_int, [c_void_p, c_void_p, c_int, c_int64, c_int, c_void_p, c_void_p, c_void_p]),
+    "mb200_attention_logits": (c_int, [c_void_p, c_int, c_int, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
+    "mb200_step_loss": (c_int, [c_void_p, c_int64, c_int, c_int, c_void_p, c_void_p]),
     "mb200_dcg_discount": (c_float, [c_int]),
     "mb200_launch_count": (c_int64, []),
     "mb200_library_launch_count": (c_int64, []),

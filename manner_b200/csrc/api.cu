@@ -57,6 +57,8 @@ size_t retrieval_workspace_bytes(const mb200_retrieval_desc* d);
 int retrieve_topk(const mb200_retrieval_desc* d, cudaStream_t stream);
 int pool_users(const void*, int, int, long long, long long, const int32_t*, const int32_t*, long long, void*, int32_t*, cudaStream_t);
 int merge_topk(const float*, const long long*, int, long long, int, float*, long long*, cudaStream_t);
+int attention_logits(const void*, int, int, long long, long long, const float*, const float*, const float*, int, float*, cudaStream_t);
+int step_loss(const float*, long long, int, int, double*, cudaStream_t);
 
 }  // namespace mb200
 
@@ -139,6 +141,15 @@ int mb200_merge_topk(const float* scores, const int64_t* ids, int shards, int64_
                      void* stream) {
   return merge_topk(scores, reinterpret_cast<const long long*>(ids), shards, n_users, k, out_scores, reinterpret_cast<long long*>(out_ids),
                     static_cast<cudaStream_t>(stream));
+}
+
+int mb200_attention_logits(const void* table, int dtype, int dim, int64_t row_stride, int64_t n_rows, const float* weight, const float* bias,
+                           const float* query, int q_dim, float* out, void* stream) {
+  return attention_logits(table, dtype, dim, row_stride, n_rows, weight, bias, query, q_dim, out, static_cast<cudaStream_t>(stream));
+}
+
+int mb200_step_loss(const float* loss_per_impression, int64_t n_impressions, int step, int loss_kind, double* out, void* stream) {
+  return step_loss(loss_per_impression, n_impressions, step, loss_kind, out, static_cast<cudaStream_t>(stream));
 }
 
 float mb200_dcg_discount(int rank) { return host_dcg_discount(rank); }

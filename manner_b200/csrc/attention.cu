@@ -1,0 +1,176 @@
+// Early-fusion support kernels (cr_module.py:124-125 with late_fusion=False).
+//
+// The reference's NAMLUserEncoder (user_encoder.py:9-21) applies AdditiveAttention (attention.py:6-29) to the padded
+// history of every step: tanh(linear(x)) . query per history row, softmax over the rows, weighted sum.  The logit of a
+// row depends on the news row alone, so this library computes it ONCE per news row (attention_logits_kernel, below) and
+// keeps it next to the embedding table; the fused scoring kernel then only needs a softmax over <= 50 cached scalars
+// per impression (score_eval.cu, gather_pool_score<ATTN>).  That removes 2 * 200 * 768 flop per history row per step
+// from the hot path: the path stays a pure HBM gather.
+//
+// step_loss_kernel restates the MeanMetric-over-steps the reference logs as test/loss (cr_module.py:253-259).
+
+#include <math.h>
+
+#include "common.cuh"
+
+namespace mb200 {
+
+namespace att {
+constexpr int ROWS = 16;     // news rows per CTA, staged in shared memory as fp32
+constexpr int WARPS = 8;     // each warp owns query rows q = warp, warp + 8, ... in groups of QG
+constexpr int QG = 4;        // query rows per pass: QG x ROWS = 64 accumulators per lane
+constexpr int MAX_DIM = 1024;
+}  // namespace att
+
+// Transposed butterfly reduction: every lane holds v[0..31]; afterwards lane l holds sum over lanes of v[l]
+// (31 shuffles instead of 32 x 5).
+__device__ __forceinline__ float reduce_transpose32(float (&v)[32], int lane) {
+#pragma unroll
+  for (int half = 16; half >= 1; half >>= 1) {
+    const bool upper = (lane & half) != 0;
+#pragma unroll
+    for (int i = 0; i < half; ++i) {
+      const float send = upper ? v[i] : v[i + half];
+      const float keep = upper ? v[i + half] : v[i];
+      v[i] = keep + __shfl_xor_sync(kFull, send, half);
+    }
+  }
+  return v[0];
+}
+
+template <typename T>
+__global__ void __launch_bounds__(att::WARPS * 32) attention_logits_kernel(const T* __restrict__ table, long long row_stride, long long n_rows,
+                                                                          int dim, const float* __restrict__ weight,
+                                                                          const float* __restrict__ bias, const float* __restrict__ query,
+                                                                          int q_dim, float* __restrict__ out) {
+  using namespace att;
+  extern __shared__ __align__(16) float xs[];                 // [ROWS][dim]
+  float* part = xs + (size_t)ROWS * dim;                      // [WARPS][QG * ROWS] per-warp partial logits
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const long long row0 = (long long)blockIdx.x * ROWS;
+
+  for (int t = threadIdx.x; t < ROWS * dim; t += blockDim.x) {
+    const int r = t / dim, d = t - r * dim;
+    const long long row = row0 + r;
+    float x = 0.f;  // rows past the end (and the extra all-zero row at n_rows: the pad logit) are zeros
+    if (row < n_rows) {
+      if constexpr (sizeof(T) == 4) x = reinterpret_cast<const float*>(table)[row * row_stride + d];
+      else x = __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(table)[row * row_stride + d]);
+    }
+    xs[t] = x;
+  }
+  __syncthreads();
+
+  // lane l accumulates, over this warp's query rows, the contribution to logit (qi = l / 16 .. , row = l % 16)
+  float mine[2] = {0.f, 0.f};  // value index l (qi 0..1) and 32 + l (qi 2..3)
+  const int n4 = dim >> 2;
+  for (int q0 = warp * QG; q0 < q_dim; q0 += WARPS * QG) {
+    float acc[QG][ROWS];
+#pragma unroll
+    for (int a = 0; a < QG; ++a)
+#pragma unroll
+      for (int r = 0; r < ROWS; ++r) acc[a][r] = 0.f;
+    for (int c = lane; c < n4; c += 32) {
+      float4 w[QG];
+#pragma unroll
+      for (int a = 0; a < QG; ++a)
+        w[a] = (q0 + a < q_dim) ? __ldg(reinterpret_cast<const float4*>(weight + (size_t)(q0 + a) * dim) + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int r = 0; r < ROWS; ++r) {
+        const float4 x = reinterpret_cast<const float4*>(xs + (size_t)r * dim)[c];
+#pragma unroll
+        for (int a = 0; a < QG; ++a) {
+          acc[a][r] = fmaf(w[a].x, x.x, acc[a][r]);
+          acc[a][r] = fmaf(w[a].y, x.y, acc[a][r]);
+          acc[a][r] = fmaf(w[a].z, x.z, acc[a][r]);
+          acc[a][r] = fmaf(w[a].w, x.w, acc[a][r]);
+        }
+      }
+    }
+#pragma unroll
+    for (int g = 0; g < 2; ++g) {
+      float v[32];
+#pragma unroll
+      for (int t = 0; t < 32; ++t) v[t] = acc[2 * g + t / ROWS][t % ROWS];
+      const float dot = reduce_transpose32(v, lane);  // lane l: query row q0 + 2 g + l / 16, news row l % 16
+      const int q = q0 + 2 * g + lane / ROWS;
+      if (q < q_dim) mine[g] += __fmul_rn(query[q], tanhf(dot + bias[q]));
+    }
+  }
+  part[warp * (QG * ROWS) + lane] = mine[0];
+  part[warp * (QG * ROWS) + 32 + lane] = mine[1];
+  __syncthreads();
+  if (threadIdx.x < ROWS) {
+    // fixed summation order: warps, then the QG query-row slots -> deterministic
+    float total = 0.f;
+    for (int w = 0; w < WARPS; ++w)
+#pragma unroll
+      for (int a = 0; a < QG; ++a) total += part[w * (QG * ROWS) + a * ROWS + threadIdx.x];
+    const long long row = row0 + threadIdx.x;
+    if (row <= n_rows) out[row] = total;  // row == n_rows: the all-zero row = the pad logit
+  }
+}
+
+// out[0] = sum over steps of the step's loss value, out[1] = number of steps (one block, fixed order).
+__global__ void __launch_bounds__(256) step_loss_kernel(const float* __restrict__ loss, long long n_impr, int step, int kind,
+                                                        double* __restrict__ out) {
+  __shared__ double sh[256];
+  const long long n_steps = (n_impr + step - 1) / step;
+  double acc = 0.0;
+  for (long long s = threadIdx.x; s < n_steps; s += 256) {
+    const long long lo = s * step, hi = min(n_impr, lo + step);
+    double sum = 0.0;
+    int cnt = 0;
+    for (long long i = lo; i < hi; ++i) {
+      const float l = loss[i];
+      if (kind == MB200_LOSS_SUPCON) {
+        if (l > 0.f) sum += (double)l, ++cnt;  // AvgNonZeroReducer
+      } else {
+        sum += (double)l, ++cnt;
+      }
+    }
+    // the reference takes the step mean in fp32 and hands it to a fp32 MeanMetric
+    acc += cnt ? (double)(float)(sum / cnt) : 0.0;
+  }
+  sh[threadIdx.x] = acc;
+  __syncthreads();
+  for (int s = 128; s > 0; s >>= 1) {
+    if (threadIdx.x < s) sh[threadIdx.x] += sh[threadIdx.x + s];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) out[0] = sh[0], out[1] = (double)n_steps;
+}
+
+int attention_logits(const void* table, int dtype, int dim, long long row_stride, long long n_rows, const float* weight, const float* bias,
+                     const float* query, int q_dim, float* out, cudaStream_t stream) {
+  if (!table || !weight || !bias || !query || !out || n_rows < 0 || dim <= 0 || q_dim <= 0 || row_stride < dim) return MB200_ERR_INVALID_ARG;
+  if (dtype != MB200_F32 && dtype != MB200_BF16) return MB200_ERR_INVALID_ARG;
+  if (dim % 4 != 0 || dim > att::MAX_DIM || q_dim > 1024) return MB200_ERR_UNSUPPORTED;
+  if (((uintptr_t)weight & 15) != 0) return MB200_ERR_INVALID_ARG;
+  int st = use_device_of(out, nullptr);
+  if (st != MB200_OK) return st;
+  const size_t smem = ((size_t)att::ROWS * dim + att::WARPS * att::QG * att::ROWS) * sizeof(float);
+  const unsigned grid = (unsigned)((n_rows + 1 + att::ROWS - 1) / att::ROWS);  // + 1: the all-zero pad row
+  if (dtype == MB200_F32) {
+    auto kern = attention_logits_kernel<float>;
+    if ((st = cuda_status(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "cudaFuncSetAttribute")) != MB200_OK) return st;
+    kern<<<grid, att::WARPS * 32, smem, stream>>>(reinterpret_cast<const float*>(table), row_stride, n_rows, dim, weight, bias, query, q_dim, out);
+  } else {
+    auto kern = attention_logits_kernel<__nv_bfloat16>;
+    if ((st = cuda_status(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "cudaFuncSetAttribute")) != MB200_OK) return st;
+    kern<<<grid, att::WARPS * 32, smem, stream>>>(reinterpret_cast<const __nv_bfloat16*>(table), row_stride, n_rows, dim, weight, bias, query, q_dim, out);
+  }
+  note_launch(1);
+  return cuda_status(cudaGetLastError(), "attention_logits_kernel");
+}
+
+int step_loss(const float* loss, long long n_impr, int step, int kind, double* out, cudaStream_t stream) {
+  if (!loss || !out || n_impr < 0 || step < 1 || (kind != MB200_LOSS_CE && kind != MB200_LOSS_SUPCON)) return MB200_ERR_INVALID_ARG;
+  int st = use_device_of(out, nullptr);
+  if (st != MB200_OK) return st;
+  step_loss_kernel<<<1, 256, 0, stream>>>(loss, n_impr, step, kind, out);
+  note_launch(1);
+  return cuda_status(cudaGetLastError(), "step_loss_kernel");
+}
+
+}  // namespace mb200

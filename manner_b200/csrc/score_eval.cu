@@ -38,6 +38,10 @@ struct EvalParams {
   const float* weights;
   const int32_t* news_category;
   const int32_t* news_sentiment;
+  const float* attn_logits[MB200_MAX_MODULES];  // [n_news + 1] per module, or null (late fusion)
+  const int32_t* hist_pad;
+  const int32_t* cand_pad;
+  float* loss_per_impr;
   float* scores;
   float* per_impr;
   double* partials;  // [total_warps][W][MB200_NUM_METRICS]
@@ -59,6 +63,8 @@ struct EvalParams {
   int num_categ, num_sent;
   int smem_per_warp;  // bytes
   int acc_bytes;      // bytes of the per-warp fp64 accumulators (16-byte multiple)
+  int loss_kind;
+  float loss_temperature;
 };
 
 template <typename T>
@@ -218,10 +224,14 @@ __device__ __noinline__ float personalization_value(const uint8_t* top, int kk, 
 // The loops are branch-free on purpose: a batch always loads R rows (slots past the end re-read the
 // batch's first row and are masked out), so the R*NV 16-byte loads stay in registers and are all in
 // flight before the first use.  Returns MB200_FLAG_* bits.
-template <typename T, int NV, int R, bool EXACT, int POLICY>
+//
+// ATTN (early fusion, cr_module.py:124-125): when `logits` is given the history rows are combined with the
+// additive-attention weights softmax(logits of the H history rows and of n_pad zero rows) instead of 1/H
+// (attention.py:20-27; the reference's softmax runs over the PADDED history, so the pad rows take mass).
+template <typename T, int NV, int R, bool EXACT, int POLICY, bool ATTN>
 __device__ __forceinline__ int gather_pool_score(const T* __restrict__ table, long long row_stride, int vec_per_row, long long n_news,
                                                  const int32_t* __restrict__ hist_ids, int H, const int32_t* __restrict__ cand_ids, int C,
-                                                 float* __restrict__ s_out) {
+                                                 float* __restrict__ s_out, const float* __restrict__ logits, int n_pad) {
   constexpr int E = Elem<T>::E;
   const int lane = threadIdx.x & 31;
   int flags = 0;
@@ -240,11 +250,39 @@ __device__ __forceinline__ int gather_pool_score(const T* __restrict__ table, lo
 #pragma unroll
   for (int t = 0; t < NV * E; ++t) u[t] = 0.f;
 
+  // softmax statistics of the attention logits: maximum and sum of exp over history + pad rows
+  float att_max = 0.f, att_sum = 1.f;
+  const bool attn = ATTN && logits != nullptr;
+  if (ATTN && attn) {
+    const float pad_logit = logits[n_news];
+    float mx = n_pad > 0 ? pad_logit : -INFINITY;
+#pragma unroll 1
+    for (int h = lane; h < H; h += 32) {
+      int id = hist_ids[h];
+      if ((unsigned long long)(long long)id >= (unsigned long long)n_news) id = 0;
+      mx = fmaxf(mx, logits[id]);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(kFull, mx, o));
+    float se = 0.f;
+#pragma unroll 1
+    for (int h = lane; h < H; h += 32) {
+      int id = hist_ids[h];
+      if ((unsigned long long)(long long)id >= (unsigned long long)n_news) id = 0;
+      se += expf(logits[id] - mx);
+    }
+    se = warp_sum(se);
+    if (n_pad > 0) se = __fadd_rn(se, __fmul_rn((float)n_pad, expf(pad_logit - mx)));
+    att_max = mx, att_sum = se;
+  }
+
 #pragma unroll 1
   for (int b0 = 0; b0 < H; b0 += 32) {
     const int cnt = min(32, H - b0);
     int my_id = hist_ids[b0 + ((lane < cnt) ? lane : 0)];
     if ((unsigned long long)(long long)my_id >= (unsigned long long)n_news) my_id = 0, flags |= MB200_FLAG_BAD_ID;
+    float my_w = 1.0f;  // weight of this lane's history row: softmax weight (early fusion) or 1 (late fusion divides by H below)
+    if (ATTN && attn) my_w = __fdiv_rn(expf(logits[my_id] - att_max), att_sum);
 #pragma unroll 1
     for (int r0 = 0; r0 < cnt; r0 += R) {
       uint4 buf[R][NV];
@@ -258,14 +296,15 @@ __device__ __forceinline__ int gather_pool_score(const T* __restrict__ table, lo
       }
 #pragma unroll
       for (int r = 0; r < R; ++r) {
-        const float keep = (r0 + r < cnt) ? 1.0f : 0.0f;
+        float keep = (r0 + r < cnt) ? 1.0f : 0.0f;
+        if (ATTN) keep *= __shfl_sync(kFull, my_w, (r0 + r < cnt) ? (r0 + r) : 0);
 #pragma unroll
         for (int v = 0; v < NV; ++v) {
           float f[E];
           Elem<T>::unpack(buf[r][v], f);
           const float k = EXACT ? keep : keep * vmask[v];
 #pragma unroll
-          for (int e = 0; e < E; ++e) u[v * E + e] = fmaf(f[e], k, u[v * E + e]);  // k is 1 or 0: exact add or no-op
+          for (int e = 0; e < E; ++e) u[v * E + e] = fmaf(f[e], k, u[v * E + e]);  // late fusion: k is 1 or 0, an exact add or a no-op
         }
       }
     }
@@ -274,12 +313,14 @@ __device__ __forceinline__ int gather_pool_score(const T* __restrict__ table, lo
   // correctly rounded quotient x / h is produced without the generic division subroutine: with
   // rh = RN(1/h), q = RN(x rh), r = x - q h (exact, one FMA), RN(q + r rh) is the IEEE quotient for
   // integer-valued h < 2^23 (Markstein; checked against true fp32 division on 15 M cases).
-  const float hf = (float)H;
-  const float rh = __frcp_rn(hf);
+  if (!(ATTN && attn)) {
+    const float hf = (float)H;
+    const float rh = __frcp_rn(hf);
 #pragma unroll
-  for (int t = 0; t < NV * E; ++t) {
-    const float q = __fmul_rn(u[t], rh);
-    u[t] = __fmaf_rn(__fmaf_rn(-q, hf, u[t]), rh, q);
+    for (int t = 0; t < NV * E; ++t) {
+      const float q = __fmul_rn(u[t], rh);
+      u[t] = __fmaf_rn(__fmaf_rn(-q, hf, u[t]), rh, q);
+    }
   }
   if (!EXACT) {
 #pragma unroll
@@ -455,6 +496,44 @@ __device__ __noinline__ int sweep_weightings(const EvalParams& p, const WarpSmem
   return flags;
 }
 
+// Loss of one impression on its final scores (cr_module.py:140-171), fp32 terms, fp64 accumulation.
+//   cross entropy: -sum over positives of log_softmax(s)_p, the softmax running over the C real columns and the
+//                  n_pad zero columns the reference's dense batch appends (torch CrossEntropyLoss with the 0/1 label
+//                  matrix as class probabilities; the batch mean is taken by mb200_step_loss)
+//   SupCon:        -(sum over positives of (s_p / T - logsumexp over the real candidates of s / T)) / P, 0 when P = 0
+//                  (components/losses.py:19-40)
+__device__ __noinline__ float impression_loss(const EvalParams& p, const float* s, const uint8_t* lab, int C, int i, int lane) {
+  __builtin_assume(__isShared(s));
+  __builtin_assume(__isShared(lab));
+  const bool ce = p.loss_kind == MB200_LOSS_CE;
+  const int n_pad = (ce && p.cand_pad) ? p.cand_pad[i] : 0;
+  const float T = ce ? 1.0f : p.loss_temperature;
+  float mx = n_pad > 0 ? 0.f : -INFINITY;
+#pragma unroll 1
+  for (int j = lane; j < C; j += 32) mx = fmaxf(mx, ce ? s[j] : __fdiv_rn(s[j], T));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(kFull, mx, o));
+  double se = 0.0, sp = 0.0;
+  int n_pos = 0;
+#pragma unroll 1
+  for (int j = lane; j < C; j += 32) {
+    const float x = __fsub_rn(ce ? s[j] : __fdiv_rn(s[j], T), mx);
+    se += (double)expf(x);
+    if (lab[j] != 0) sp += (double)x, ++n_pos;
+  }
+  se = warp_sum(se), sp = warp_sum(sp);
+  n_pos = __reduce_add_sync(kFull, n_pos);
+  if (n_pad > 0) se += (double)n_pad * (double)expf(-mx);
+  float loss = 0.f;
+  if (n_pos > 0) {
+    const double lse = (double)logf((float)se);
+    const double total = (double)n_pos * lse - sp;  // -sum over positives of (x_p - lse)
+    loss = ce ? (float)total : (float)(total / (double)n_pos);
+  }
+  if (p.loss_per_impr && lane == 0) p.loss_per_impr[i] = loss;
+  return loss;
+}
+
 // Everything after the per-module scores of impression i sit in shared memory: z-scores are already
 // applied; combine per weighting, rank, metrics, accumulate.  Not inlined (see gather_pool_score).
 __device__ __noinline__ int rank_and_metrics(const EvalParams& p, const WarpSmem& sm, int i, int h0, int H, int c0, int C) {
@@ -551,6 +630,9 @@ __device__ __noinline__ int rank_and_metrics(const EvalParams& p, const WarpSmem
       if (outside) warp_flags |= MB200_FLAG_OUTSIDE_UNIT;
     }
 
+    float loss = 0.f;
+    if (p.loss_kind != MB200_LOSS_NONE && w == p.scores_weighting) loss = impression_loss(p, scores_w, lab, C, i, lane);
+
     int n_pos = 0, min_rank = 0x7fffffff;
     unsigned hit_mask = 0;
     long long gauc2 = 0;  // sum over positives of 2 * (#neg below) + (#neg equal)
@@ -622,6 +704,8 @@ __device__ __noinline__ int rank_and_metrics(const EvalParams& p, const WarpSmem
       if (lane == MB200_M_GAUC) mine = (float)((double)gauc2 / (2.0 * (double)n_pos * (double)(C - n_pos)));
       if (lane == MB200_M_GAUC_VALID) mine = 1.f;
     }
+    if (lane == MB200_M_LOSS) mine = loss;
+    if (lane == MB200_M_LOSS_NONZERO) mine = loss > 0.f ? 1.f : 0.f;
     if (aspects) {
       const int kk0 = min(p.k0, C), kk1 = min(p.k1, C);
       if (categ_group_ok) {
@@ -649,7 +733,7 @@ __device__ __noinline__ int rank_and_metrics(const EvalParams& p, const WarpSmem
   return warp_flags;
 }
 
-template <typename T, int NV, int R, bool EXACT, int POLICY, int MINB>
+template <typename T, int NV, int R, bool EXACT, int POLICY, int MINB, bool ATTN = false>
 __global__ void __launch_bounds__(kThreads, MINB) score_eval_kernel(const __grid_constant__ EvalParams p) {
   extern __shared__ __align__(16) unsigned char smem[];
   const int lane = threadIdx.x & 31;
@@ -696,8 +780,10 @@ __global__ void __launch_bounds__(kThreads, MINB) score_eval_kernel(const __grid
       for (int m = 0; m < p.n_modules; ++m) {
         if (!((p.active_mask >> m) & 1)) continue;
         float* s_m = sm.sc + (size_t)slot * p.cpad;
-        warp_flags |= gather_pool_score<T, NV, R, EXACT, POLICY>(reinterpret_cast<const T*>(p.tables[m]), p.row_stride, p.vec_per_row,
-                                                                 p.n_news, p.hist_ids + h0, H, p.cand_ids + c0, C, s_m);
+        warp_flags |= gather_pool_score<T, NV, R, EXACT, POLICY, ATTN>(reinterpret_cast<const T*>(p.tables[m]), p.row_stride, p.vec_per_row,
+                                                                       p.n_news, p.hist_ids + h0, H, p.cand_ids + c0, C, s_m,
+                                                                       ATTN ? p.attn_logits[m] : nullptr,
+                                                                       (ATTN && p.hist_pad) ? p.hist_pad[i] : 0);
         __syncwarp();
         if (p.zscore) {
           zscore_inplace(s_m, C, lane);
@@ -825,6 +911,9 @@ static int validate(const mb200_eval_desc* d) {
   if (d->news_category &&
       (d->num_categ_classes < 1 || d->num_categ_classes > MB200_MAX_CLASSES || d->num_sent_classes < 1 || d->num_sent_classes > MB200_MAX_CLASSES))
     return MB200_ERR_INVALID_ARG;
+  if (d->loss_kind < MB200_LOSS_NONE || d->loss_kind > MB200_LOSS_SUPCON) return MB200_ERR_INVALID_ARG;
+  if (d->loss_kind == MB200_LOSS_SUPCON && !(d->loss_temperature > 0.f)) return MB200_ERR_INVALID_ARG;
+  if (d->loss_kind != MB200_LOSS_NONE && (d->scores_weighting < 0 || d->scores_weighting >= d->n_weightings)) return MB200_ERR_INVALID_ARG;
   const int esz = d->dtype == MB200_F32 ? 4 : 2;
   for (int m = 0; m < d->n_modules; ++m) {
     if (((d->active_modules_mask >> m) & 1) && (d->tables[m] == nullptr || ((uintptr_t)d->tables[m] & 15))) return MB200_ERR_INVALID_ARG;
@@ -841,16 +930,18 @@ using KernelFn = void (*)(const EvalParams);
 // predicate-free kernels in a few rows-in-flight / occupancy trade-offs (mb200_set_tuning key 1); every
 // other width runs a predicated kernel whose per-lane vector count is rounded up to 1, 2, 4 or 8.
 template <typename T, int NV>
-static KernelFn generic_kernel() {
+static KernelFn generic_kernel(bool attn) {
   constexpr int R = (NV <= 2) ? 8 : (NV <= 4) ? 6 : 3;
+  if (attn) return score_eval_kernel<T, NV, R, false, 0, 3, true>;
   return score_eval_kernel<T, NV, R, false, 0, 3>;
 }
 
 template <typename T>
-static KernelFn select_kernel(int vec_per_row) {
+static KernelFn select_kernel(int vec_per_row, bool attn) {
   constexpr int kRefNV = 768 / Elem<T>::E / 32;  // 6 (fp32) or 3 (bf16)
   constexpr int R = (kRefNV == 6) ? 4 : 8;
   constexpr int R3 = (R * 3 + 3) / 4, R2 = (R + 1) / 2;
+  if (vec_per_row == kRefNV * 32 && attn) return score_eval_kernel<T, kRefNV, R3, true, 0, 4, true>;  // early fusion (separate code: the late-fusion kernels keep their tuning)
   if (vec_per_row == kRefNV * 32) {
     switch (tuning().variant) {
       case 0: return score_eval_kernel<T, kRefNV, R, true, 0, 3>;
@@ -860,10 +951,10 @@ static KernelFn select_kernel(int vec_per_row) {
     }
   }
   const int nv = (vec_per_row + 31) / 32;
-  if (nv <= 1) return generic_kernel<T, 1>();
-  if (nv <= 2) return generic_kernel<T, 2>();
-  if (nv <= 4) return generic_kernel<T, 4>();
-  return generic_kernel<T, 8>();
+  if (nv <= 1) return generic_kernel<T, 1>(attn);
+  if (nv <= 2) return generic_kernel<T, 2>(attn);
+  if (nv <= 4) return generic_kernel<T, 4>(attn);
+  return generic_kernel<T, 8>(attn);
 }
 
 static int sm_count_of(int device, int* out) {
@@ -925,7 +1016,9 @@ int score_eval(const mb200_eval_desc* d, cudaStream_t stream) {
   if (st != MB200_OK) return st;
   if (sms > 160) return MB200_ERR_UNSUPPORTED;
   const int vec_per_row = d->dim * (d->dtype == MB200_F32 ? 4 : 2) / 16;
-  KernelFn kern = (d->dtype == MB200_F32) ? select_kernel<float>(vec_per_row) : select_kernel<__nv_bfloat16>(vec_per_row);
+  bool attn = false;
+  for (int m = 0; m < d->n_modules; ++m) attn |= ((d->active_modules_mask >> m) & 1) && d->attn_logits[m] != nullptr;
+  KernelFn kern = (d->dtype == MB200_F32) ? select_kernel<float>(vec_per_row, attn) : select_kernel<__nv_bfloat16>(vec_per_row, attn);
   LaunchPlan plan;
   st = make_plan(d, sms, 1, &plan);  // shared-memory sizes first: they decide how many CTAs fit
   if (st != MB200_OK) return st;
@@ -959,6 +1052,9 @@ int score_eval(const mb200_eval_desc* d, cudaStream_t stream) {
   p.k0 = d->k0, p.k1 = d->k1, p.cpad = plan.cpad, p.max_cand = d->max_cand, p.n_chunks = plan.n_chunks;
   p.num_categ = d->num_categ_classes, p.num_sent = d->num_sent_classes;
   p.smem_per_warp = plan.smem_per_warp, p.acc_bytes = plan.acc_bytes;
+  for (int m = 0; m < MB200_MAX_MODULES; ++m) p.attn_logits[m] = (m < d->n_modules) ? d->attn_logits[m] : nullptr;
+  p.hist_pad = d->hist_pad, p.cand_pad = d->cand_pad, p.loss_per_impr = d->loss_per_impression;
+  p.loss_kind = d->loss_kind, p.loss_temperature = d->loss_temperature;
 
   partition_kernel<<<(plan.n_chunks + 1 + 255) / 256, 256, 0, stream>>>(d->hist_offsets, d->cand_offsets, p.n_impr, plan.n_chunks,
                                                                        reinterpret_cast<int32_t*>(d->workspace));

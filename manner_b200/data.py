@@ -99,6 +99,18 @@ class Behaviours:
         return b + (4 * self.n_cand if scores_written else 0)
 
 
+def step_pads(offsets: np.ndarray, step: int) -> np.ndarray:
+    """int32 [B]: how many zero rows / columns the reference's dense batch appends to each impression when the
+    impressions are processed in steps of ``step`` (configs/data/mind_rec.yaml:51; ``to_dense_batch`` pads every
+    segment of a step to the step's longest, cr_module.py:108-114,142)."""
+    sizes = np.diff(np.asarray(offsets, dtype=np.int64))
+    out = np.empty(sizes.shape[0], dtype=np.int32)
+    for lo in range(0, sizes.shape[0], step):
+        seg = sizes[lo : lo + step]
+        out[lo : lo + step] = seg.max() - seg
+    return out
+
+
 def from_segment_ids(batch_hist: torch.Tensor, hist_rows: torch.Tensor, batch_cand: torch.Tensor, cand_rows: torch.Tensor, labels: torch.Tensor) -> Behaviours:
     """Convert the reference's MINDRecBatch segment-id contract (mind_batch.py:6-12;
     ``batch = repeat_interleave(arange(B), sizes)``, sorted) to CSR.  ``B = batch.max() + 1`` exactly

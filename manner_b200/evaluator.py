@@ -27,7 +27,7 @@ from torch import Tensor
 from . import _native as nat
 from . import dist as mdist
 from . import ops
-from .data import NUM_CATEG_CLASSES, NUM_SENT_CLASSES, Behaviours
+from .data import NUM_CATEG_CLASSES, NUM_SENT_CLASSES, Behaviours, step_pads
 
 # log keys of the reference (cr_module.py:79-89 prefix "test/"; ensemble_module.py:50-84) by metric slot
 SLOT_KEYS = {
@@ -59,6 +59,11 @@ class DeviceBehaviours:
     h2d_bytes: int = 0
     n_pos: int = 0  # positives in this shard (host-known from the labels)
     pos_cap: Optional[int] = None  # agreed upper bound on any rank's positives (multi-GPU pooled AUC)
+    # only for early fusion / the loss: the reference's step structure (configs/data/mind_rec.yaml:51) and the zero
+    # rows / columns its dense batches append per impression
+    step_batch: int = 8
+    hist_pad: Optional[Tensor] = None
+    cand_pad: Optional[Tensor] = None
 
 
 @dataclass
@@ -70,6 +75,7 @@ class EvalResult:
     has_aspects: bool
     auc: Optional[float] = None  # pooled AUROC (reference "auc"), weighting `scores_weighting`
     auc_counts: Optional[Tuple[int, int]] = None  # (positives, negatives)
+    loss: Optional[float] = None  # the reference's test/loss: MeanMetric over its steps (cr_module.py:253-259)
     scores: Optional[Tensor] = None  # device fp32 [sum C] of this rank
     per_impression: Optional[Tensor] = None  # device fp32 [W, B, NUM_METRICS] of this rank
     d2h_bytes: int = 0
@@ -86,6 +92,8 @@ class EvalResult:
         out[prefix + "gauc"] = float(s[nat.M_GAUC] / s[nat.M_GAUC_VALID]) if s[nat.M_GAUC_VALID] > 0 else 0.0
         if self.auc is not None:
             out[prefix + "auc"] = self.auc
+        if self.loss is not None:
+            out[prefix + "loss"] = self.loss
         return out
 
 
@@ -101,6 +109,7 @@ class PendingEval:
     auc_stats: Optional[Tensor]
     scores: Optional[Tensor]
     per_impression: Optional[Tensor]
+    loss_stats: Optional[Tensor] = None  # fp64 [2]: sum of step losses, number of steps (all ranks)
 
 
 class ScoreEvaluator:
@@ -119,6 +128,7 @@ class ScoreEvaluator:
         num_categ_classes: int = NUM_CATEG_CLASSES,
         num_sent_classes: int = NUM_SENT_CLASSES,
         ks: Tuple[int, int] = (5, 10),
+        attention: Optional[Sequence[Optional[Tuple[Tensor, Tensor, Tensor]]]] = None,
     ) -> None:
         nat.lib()  # fail now, loudly, if the CUDA library is not built
         if not torch.cuda.is_available():
@@ -134,6 +144,14 @@ class ScoreEvaluator:
         self.news_sentiment = self._aspect(news_sentiment)
         if (self.news_category is None) != (self.news_sentiment is None):
             raise ValueError("give both aspect label arrays or neither")
+        # early fusion (late_fusion=False, cr_module.py:63-68,124-125): attention[m] = (linear.weight [Q, D], linear.bias [Q],
+        # query [Q]) of module m's NAMLUserEncoder.additive_attention, or None for late fusion.  The per-news logits are
+        # computed once here and cached next to the table.
+        self.attn_logits: Optional[List[Optional[Tensor]]] = None
+        if attention is not None and any(a is not None for a in attention):
+            if len(attention) != len(self.tables):
+                raise ValueError("attention needs one entry per table")
+            self.attn_logits = [None if a is None else ops.attention_logits(t, *a) for t, a in zip(self.tables, attention)]
 
     def _aspect(self, a: Optional[Union[Tensor, np.ndarray]]) -> Optional[Tensor]:
         if a is None:
@@ -144,26 +162,34 @@ class ScoreEvaluator:
         return t.to(self.device).contiguous()
 
     # -- inputs ----------------------------------------------------------------------------------------------
-    def upload(self, bhv: Behaviours, pinned: Optional[Dict[str, object]] = None, pos_cap: Optional[int] = None) -> DeviceBehaviours:
+    def upload(self, bhv: Behaviours, pinned: Optional[Dict[str, object]] = None, pos_cap: Optional[int] = None,
+               step_batch: Optional[int] = None) -> DeviceBehaviours:
         """Host CSR -> device (asynchronous on the current stream).  ``pinned`` lets a caller reuse
         page-locked staging tensors (see ``pin``); ``pos_cap`` is the multi-GPU bound of
-        ``dist.agree_pos_cap`` when the caller already has it."""
-        src = pinned if pinned is not None else self.pin(bhv)
+        ``dist.agree_pos_cap`` when the caller already has it.  ``step_batch`` (the reference's eval batch size)
+        additionally uploads the per-impression pad counts early fusion and the cross-entropy loss need."""
+        src = pinned if pinned is not None else self.pin(bhv, step_batch)
         dev = {k: v.to(self.device, non_blocking=True) for k, v in src.items() if isinstance(v, Tensor)}
         nbytes = sum(v.numel() * v.element_size() for v in src.values() if isinstance(v, Tensor))
         return DeviceBehaviours(
             dev["hist_offsets"], dev["hist_ids"], dev["cand_offsets"], dev["cand_ids"], dev["labels"],
             bhv.n_impressions, src["max_cand"], nbytes, src["n_pos"], pos_cap,
+            src.get("step_batch", 8), dev.get("hist_pad"), dev.get("cand_pad"),
         )
 
     @staticmethod
-    def pin(bhv: Behaviours) -> Dict[str, object]:
+    def pin(bhv: Behaviours, step_batch: Optional[int] = None) -> Dict[str, object]:
         """Page-locked staging copies of the CSR arrays + the two host-side facts a launch needs
         (largest candidate list, number of positives), computed once here rather than per upload."""
         arrays = dict(hist_offsets=bhv.hist_offsets, hist_ids=bhv.hist_ids, cand_offsets=bhv.cand_offsets, cand_ids=bhv.cand_ids, labels=bhv.labels)
+        if step_batch is not None:
+            arrays["hist_pad"] = step_pads(bhv.hist_offsets, step_batch)
+            arrays["cand_pad"] = step_pads(bhv.cand_offsets, step_batch)
         out: Dict[str, object] = {k: torch.from_numpy(np.ascontiguousarray(v)).pin_memory() for k, v in arrays.items()}
         out["max_cand"] = max(bhv.max_cand, 1)
         out["n_pos"] = int(bhv.labels.sum())
+        if step_batch is not None:
+            out["step_batch"] = int(step_batch)
         return out
 
     # -- the hot path ----------------------------------------------------------------------------------------
@@ -178,9 +204,15 @@ class ScoreEvaluator:
         scores_weighting: int = 0,
         group: Optional["torch.distributed.ProcessGroup"] = None,
         distributed: bool = False,
+        loss: Optional[str] = None,
+        temperature: float = 0.1,
     ) -> "PendingEval":
         """Enqueue one pass on the current stream and return device-side results without waiting for
-        them.  ``weights`` may be a device fp32 tensor [W, n_modules] (then every module is gathered)."""
+        them.  ``weights`` may be a device fp32 tensor [W, n_modules] (then every module is gathered).
+        ``loss`` = "ce" | "supcon" adds the reference's test/loss (cr_module.py:140-171,253-259; ``temperature`` for
+        SupCon); it and early fusion need ``upload(..., step_batch=...)``."""
+        if (loss == "ce" or self.attn_logits is not None) and bhv.hist_pad is None:
+            raise ValueError("early fusion / the cross-entropy loss depend on the reference's step padding: upload(..., step_batch=8)")
         n_mod = len(self.tables)
         w_dev: Optional[Tensor] = None
         active = (1 << n_mod) - 1
@@ -195,11 +227,21 @@ class ScoreEvaluator:
                     active |= 1 << m
             w_dev = w_host.to(self.device, non_blocking=True).contiguous()
         need_scores = want_scores or pooled_auc
-        scores, per_impr, sums, flags = torch.ops.manner_b200.score_eval(
+        loss_kind = {None: nat.LOSS_NONE, "ce": nat.LOSS_CE, "supcon": nat.LOSS_SUPCON}[loss]
+        scores, per_impr, sums, flags, loss_per_impr = torch.ops.manner_b200.score_eval(
             self.tables, bhv.hist_offsets, bhv.hist_ids, bhv.cand_offsets, bhv.cand_ids, bhv.labels, w_dev, zscore,
             bhv.max_cand, active, self.ks[0], self.ks[1], need_scores, scores_weighting, want_per_impression,
-            self.news_category, self.news_sentiment, self.num_categ_classes, self.num_sent_classes, distributed,
+            self.news_category, self.news_sentiment, self.num_categ_classes, self.num_sent_classes,
+            self.attn_logits if self.attn_logits is not None else [], distributed,
+            bhv.hist_pad if self.attn_logits is not None else None, loss_kind, float(temperature),
+            bhv.cand_pad if loss == "ce" else None,
         )
+        loss_stats: Optional[Tensor] = None
+        if loss is not None:
+            # MeanMetric over the reference's steps (cr_module.py:253-259): (sum of step losses, number of steps)
+            loss_stats = ops.step_loss(loss_per_impr, bhv.step_batch, loss_kind)
+            if distributed:
+                torch.distributed.all_reduce(loss_stats, op=torch.distributed.ReduceOp.SUM, group=group)
         n_w = 1 if w_dev is None else w_dev.shape[0]
         auc_stats: Optional[Tensor] = None
         if distributed:
@@ -212,7 +254,7 @@ class ScoreEvaluator:
         elif pooled_auc:
             auc_stats = torch.ops.manner_b200.pooled_auc(scores, bhv.labels, 2, flags)
         return PendingEval(sums, flags, n_w, bhv.n_impressions, distributed, auc_stats,
-                           scores if want_scores else None, per_impr if want_per_impression else None)
+                           scores if want_scores else None, per_impr if want_per_impression else None, loss_stats)
 
     def finish(self, pending: "PendingEval") -> EvalResult:
         """The one device -> host read of a pass: metric sums, flag word, AUC statistics."""
@@ -235,6 +277,11 @@ class ScoreEvaluator:
                 a = pending.auc_stats.cpu().numpy()
                 d2h += a.size * 8
                 auc, counts = float(a[0]), (int(a[1]), int(a[2]))
+        loss_value = None
+        if pending.loss_stats is not None:
+            ls = pending.loss_stats.cpu().numpy()
+            d2h += 16
+            loss_value = float(ls[0] / ls[1]) if ls[1] > 0 else 0.0
         if flags_h & (nat.FLAG_BAD_ID | nat.FLAG_CAND_OVERFLOW | nat.FLAG_BAD_ASPECT):
             raise nat.NativeError(
                 f"manner_b200 kernels flagged bad input (flags={flags_h}): "
@@ -242,7 +289,7 @@ class ScoreEvaluator:
             )
         return EvalResult(
             sums=sums_h, n_impressions=int(n_total), flags=flags_h, ks=self.ks, has_aspects=self.news_category is not None,
-            auc=auc, auc_counts=counts, scores=pending.scores, per_impression=pending.per_impression, d2h_bytes=d2h,
+            auc=auc, auc_counts=counts, scores=pending.scores, per_impression=pending.per_impression, d2h_bytes=d2h, loss=loss_value,
         )
 
     def evaluate(self, bhv: DeviceBehaviours, **kwargs) -> EvalResult:

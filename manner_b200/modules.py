@@ -101,9 +101,9 @@ class StepScorer:
             cat = torch.cat([batch["x_hist"]["category"], batch["x_cand"]["category"]]).to(dev, torch.int32)
             sent = torch.cat([batch["x_hist"]["sentiment"], batch["x_cand"]["sentiment"]]).to(dev, torch.int32)
             self.has_aspects = True
-        scores, _, sums, flags = torch.ops.manner_b200.score_eval(
+        scores, _, sums, flags, _ = torch.ops.manner_b200.score_eval(
             tables, hist_off, hist_ids, cand_off, cand_ids, labels, w_dev, self.zscore, max(n_cand, 1), active,
-            self.ks[0], self.ks[1], True, 0, False, cat, sent, self.num_categ_classes, self.num_sent_classes,
+            self.ks[0], self.ks[1], True, 0, False, cat, sent, self.num_categ_classes, self.num_sent_classes, [],
         )
         self.sums = sums if self.sums is None else self.sums + sums
         self.flags = flags if self.flags is None else self.flags | flags

@@ -62,12 +62,23 @@ def score_eval(
     news_sentiment: Optional[Tensor],
     num_categ_classes: int,
     num_sent_classes: int,
+    attn_logits: Sequence[Optional[Tensor]],
     pack_payload: bool = False,
-) -> Tuple[Tensor, Tensor, Tensor, Tensor]:
+    hist_pad: Optional[Tensor] = None,
+    loss_kind: int = 0,
+    loss_temperature: float = 1.0,
+    cand_pad: Optional[Tensor] = None,
+) -> Tuple[Tensor, Tensor, Tensor, Tensor, Tensor]:
     """Fused gather / pool / score / z-score / ensemble / per-impression metrics (include/manner_b200.h,
-    mb200_score_eval).  Returns (scores fp32 [sum C] or empty, per_impression fp32 [W, B, 13] or empty,
-    sums fp64 [W, 13], flags int32 [1]).  With ``pack_payload`` the sums come back flat, fp64 [W*13 + 5],
-    with the impression count and the flag bits appended: the buffer a multi-GPU caller all-reduces."""
+    mb200_score_eval).  Returns (scores fp32 [sum C] or empty, per_impression fp32 [W, B, NUM_METRICS] or empty,
+    sums fp64 [W, NUM_METRICS], flags int32 [1], loss_per_impression fp32 [B] or empty).  With ``pack_payload``
+    the sums come back flat, fp64 [W*NUM_METRICS + 5], with the impression count and the flag bits appended: the
+    buffer a multi-GPU caller all-reduces.
+
+    Early fusion (cr_module.py:124-125): ``attn_logits`` is ``[]`` (late fusion everywhere) or one entry per table: ``attn_logits[m]`` = the [n_news + 1] logits of ``attention_logits`` for
+    module m (None keeps module m on late fusion) and ``hist_pad`` [B] int32 = zero rows the reference's
+    step batch pads impression i's history with.  ``loss_kind`` (nat.LOSS_CE / LOSS_SUPCON) adds the per-impression
+    loss of cr_module.py:140-171 (``cand_pad`` [B]: padded candidate columns, cross entropy only)."""
     lib = nat.lib()
     if len(tables) < 1 or len(tables) > nat.MAX_MODULES:
         raise ValueError(f"1..{nat.MAX_MODULES} embedding tables expected")
@@ -99,6 +110,19 @@ def score_eval(
     if news_category is not None:
         _require_cuda("news_category", news_category, torch.int32)
         _require_cuda("news_sentiment", news_sentiment, torch.int32)
+    if len(attn_logits):
+        if len(attn_logits) != len(tables):
+            raise ValueError("attn_logits needs one entry per table (None = late fusion for that module)")
+        for a in attn_logits:
+            if a is not None:
+                _require_cuda("attn_logits", a, torch.float32)
+                if a.numel() != t0.shape[0] + 1:
+                    raise ValueError("attn_logits[m] must hold n_news + 1 floats (ops.attention_logits)")
+    for name, t in (("hist_pad", hist_pad), ("cand_pad", cand_pad)):
+        if t is not None:
+            _require_cuda(name, t, torch.int32)
+            if t.numel() != n_impr:
+                raise ValueError(f"{name} must have one entry per impression")
 
     with torch.cuda.device(dev):
         stream = torch.cuda.current_stream(dev).cuda_stream
@@ -106,8 +130,14 @@ def score_eval(
         per_impr = torch.empty((n_w, n_impr, nat.NUM_METRICS) if want_per_impression else (0,), dtype=torch.float32, device=dev)
         sums = torch.empty(n_w * nat.NUM_METRICS + nat.PAYLOAD_TAIL if pack_payload else (n_w, nat.NUM_METRICS), dtype=torch.float64, device=dev)
         flags = torch.zeros(1, dtype=torch.int32, device=dev)
+        loss_out = torch.empty(n_impr if loss_kind else 0, dtype=torch.float32, device=dev)
 
         d = nat.EvalDesc()
+        for m, a in enumerate(attn_logits):
+            d.attn_logits[m] = _ptr(a)
+        d.hist_pad, d.cand_pad = _ptr(hist_pad), _ptr(cand_pad)
+        d.loss_kind, d.loss_temperature = int(loss_kind), float(loss_temperature)
+        d.loss_per_impression = loss_out.data_ptr() if loss_kind else None
         d.pack_payload = int(pack_payload)
         d.struct_size = ctypes.sizeof(nat.EvalDesc)
         d.n_modules = len(tables)
@@ -142,13 +172,13 @@ def score_eval(
         ws = _workspace(dev, stream, "eval", need)
         d.workspace, d.workspace_bytes = ws.data_ptr(), ws.numel()
         nat.check(lib.mb200_score_eval(ctypes.byref(d), stream), "mb200_score_eval")
-    return scores, per_impr, sums, flags
+    return scores, per_impr, sums, flags, loss_out
 
 
 @score_eval.register_fake
 def _(tables, hist_offsets, hist_ids, cand_offsets, cand_ids, labels, weights, zscore, max_cand, active_mask, k0, k1,
       want_scores, scores_weighting, want_per_impression, news_category, news_sentiment, num_categ_classes, num_sent_classes,
-      pack_payload=False):
+      attn_logits, pack_payload=False, hist_pad=None, loss_kind=0, loss_temperature=1.0, cand_pad=None):
     dev = tables[0].device
     n_w = 1 if weights is None else weights.shape[0]
     n_impr = hist_offsets.numel() - 1
@@ -157,7 +187,47 @@ def _(tables, hist_offsets, hist_ids, cand_offsets, cand_ids, labels, weights, z
         torch.empty((n_w, n_impr, nat.NUM_METRICS) if want_per_impression else (0,), dtype=torch.float32, device=dev),
         torch.empty(n_w * nat.NUM_METRICS + nat.PAYLOAD_TAIL if pack_payload else (n_w, nat.NUM_METRICS), dtype=torch.float64, device=dev),
         torch.empty(1, dtype=torch.int32, device=dev),
+        torch.empty(n_impr if loss_kind else 0, dtype=torch.float32, device=dev),
     )
+
+
+def attention_logits(table: Tensor, weight: Tensor, bias: Tensor, query: Tensor) -> Tensor:
+    """fp32 [n_rows + 1]: query . tanh(weight x_n + bias) for every row of ``table`` and, last, for an all-zero row
+    (mb200_attention_logits) -- the per-news part of NAMLUserEncoder's additive attention (attention.py:20-24)."""
+    lib = nat.lib()
+    if not table.is_cuda:
+        raise RuntimeError("manner_b200: `table` must be a CUDA tensor (there is no CPU path)")
+    if table.dtype not in (torch.float32, torch.bfloat16) or table.dim() != 2 or table.stride(1) != 1:
+        raise TypeError("table must be [n_rows, dim] float32 or bfloat16 with unit inner stride")
+    dev = table.device
+    w = weight.detach().to(dev, torch.float32).contiguous()
+    b = bias.detach().to(dev, torch.float32).contiguous()
+    q = query.detach().to(dev, torch.float32).contiguous()
+    if w.dim() != 2 or w.shape[1] != table.shape[1] or b.numel() != w.shape[0] or q.numel() != w.shape[0]:
+        raise ValueError("weight [Q, dim], bias [Q], query [Q] expected")
+    with torch.cuda.device(dev):
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        out = torch.empty(table.shape[0] + 1, dtype=torch.float32, device=dev)
+        nat.check(
+            lib.mb200_attention_logits(table.data_ptr(), nat.F32 if table.dtype == torch.float32 else nat.BF16, table.shape[1], table.stride(0),
+                                       table.shape[0], w.data_ptr(), b.data_ptr(), q.data_ptr(), w.shape[0], out.data_ptr(), stream),
+            "mb200_attention_logits",
+        )
+    return out
+
+
+def step_loss(loss_per_impression: Tensor, step: int, loss_kind: int) -> Tensor:
+    """fp64 [2] = (sum over the reference's steps of the step loss, number of steps): what MeanMetric averages into
+    test/loss (cr_module.py:253-259); mb200_step_loss."""
+    lib = nat.lib()
+    _require_cuda("loss_per_impression", loss_per_impression, torch.float32)
+    dev = loss_per_impression.device
+    with torch.cuda.device(dev):
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        out = torch.empty(2, dtype=torch.float64, device=dev)
+        nat.check(lib.mb200_step_loss(loss_per_impression.data_ptr(), loss_per_impression.numel(), int(step), int(loss_kind), out.data_ptr(), stream),
+                  "mb200_step_loss")
+    return out
 
 
 @torch.library.custom_op("manner_b200::pooled_auc", mutates_args=())

@@ -76,7 +76,7 @@ def test_product_refuses_to_run_without_cuda():
     i32 = torch.zeros(2, dtype=torch.int32)
     with pytest.raises(RuntimeError, match="no CPU path"):
         torch.ops.manner_b200.score_eval([t], i32, i32, i32, i32, torch.zeros(2, dtype=torch.uint8), None, False, 4, 1, 5, 10,
-                                         False, 0, False, None, None, 19, 4)
+                                         False, 0, False, None, None, 19, 4, [])
     if not torch.cuda.is_available():
         from manner_b200.evaluator import ScoreEvaluator
 
