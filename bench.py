@@ -17,6 +17,7 @@ host cores and prints the same line with "impl": "reference".
 from __future__ import annotations
 
 import argparse
+import gc
 import json
 import os
 import statistics
@@ -250,6 +251,8 @@ def run_gpu_arm(args) -> None:
 
     # end to end: pinned host CSR -> device, pass, metric sums back to the host, every step
     barrier()
+    gc.collect()
+    gc.disable()  # a generation-2 collection of the interpreter (tens of ms) inside a 2 ms step is host noise, not the path
     e2e_events = []
     for i in range(max(args.steps, 10) + 1):
         flush.fill_(rank + 1)
@@ -261,6 +264,7 @@ def run_gpu_arm(args) -> None:
         torch.cuda.synchronize(dev)
         if i > 0:
             e2e_events.append(e0.elapsed_time(e1))
+    gc.enable()
     e2e_median_ms = statistics.median(e2e_events)
     e2e_ms = torch.tensor([sum(e2e_events) / len(e2e_events)], dtype=torch.float64, device=dev)
     if distributed:
@@ -308,6 +312,7 @@ def run_gpu_arm(args) -> None:
         "e2e": {
             "value": n_impr_total / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": dev_bhv.h2d_bytes,
             "d2h_bytes_per_step": r.d2h_bytes, "ms_per_step": e2e_ms, "ms_per_step_median_rank0": e2e_median_ms, "steps": len(e2e_events),
+            "ms_each_rank0": [round(x, 3) for x in e2e_events],
         },
         "gpu_launches": launches1[0] - launches0[0],
         "library_launches": launches1[1] - launches0[1],
@@ -389,9 +394,9 @@ def run_retrieval_arm(args) -> None:
         e1.record()
         k_events.append((e0, e1))
     barrier()
+    clocks = sampler.stop() if sampler is not None else None  # sampled during the device-timed regions only
     e2e_events = [step(True)[:2] for _ in range(args.steps + 1)][1:]
     barrier()
-    clocks = sampler.stop() if sampler is not None else None
 
     def max_over_ranks(ms: float) -> float:
         t = torch.tensor([ms], dtype=torch.float64, device=dev)

@@ -65,13 +65,17 @@ class StepScorer:
     Replaces, per step, cr_module.py:108-131,173-182 / ensemble_module.py:116-149,155-192 and, at the
     end, cr_module.py:266-274 / ensemble_module.py:214-238."""
 
-    def __init__(self, zscore: bool, ks=(5, 10), with_auc: bool = True, num_categ_classes: int = 19, num_sent_classes: int = 4) -> None:
+    def __init__(self, zscore: bool, ks=(5, 10), with_auc: bool = True, num_categ_classes: int = 19, num_sent_classes: int = 4,
+                 loss: Optional[str] = None, temperature: float = 0.1) -> None:
         nat.lib()
         self.zscore, self.ks, self.with_auc = zscore, (int(ks[0]), int(ks[1])), with_auc
         self.num_categ_classes, self.num_sent_classes = num_categ_classes, num_sent_classes
+        self.loss_kind = {None: nat.LOSS_NONE, "ce": nat.LOSS_CE, "supcon": nat.LOSS_SUPCON}[loss]
+        self.temperature = float(temperature)
         self.reset()
 
     def reset(self) -> None:
+        self.loss_stats: Optional[Tensor] = None  # fp64 [2]: sum of the step losses, number of steps
         self.sums: Optional[Tensor] = None
         self.n_impressions = 0
         self.flags: Optional[Tensor] = None
@@ -80,9 +84,12 @@ class StepScorer:
         self.has_aspects = False
 
     @torch.no_grad()
-    def step(self, hist_vecs: Sequence[Tensor], cand_vecs: Sequence[Tensor], batch: Dict[str, Any], weights: Optional[Sequence[float]] = None) -> Tensor:
+    def step(self, hist_vecs: Sequence[Tensor], cand_vecs: Sequence[Tensor], batch: Dict[str, Any], weights: Optional[Sequence[float]] = None,
+             attention: Optional[Sequence[Optional[Sequence[Tensor]]]] = None) -> Tensor:
         """``hist_vecs[m]`` / ``cand_vecs[m]``: module m's news vectors for ``batch['x_hist']`` / ``['x_cand']``
-        ([sum H, D] / [sum C, D]).  Returns the flat combined scores [sum C] (the reference's ``preds``)."""
+        ([sum H, D] / [sum C, D]).  ``attention[m]`` = (linear.weight, linear.bias, query) of module m's additive
+        attention for early fusion (cr_module.py:124-125), None for late fusion.  Returns the flat combined scores
+        [sum C] (the reference's ``preds``)."""
         dev = cand_vecs[0].device
         batch_hist, batch_cand = batch["batch_hist"].to(dev), batch["batch_cand"].to(dev)
         n_hist, n_cand = hist_vecs[0].shape[0], cand_vecs[0].shape[0]
@@ -101,10 +108,26 @@ class StepScorer:
             cat = torch.cat([batch["x_hist"]["category"], batch["x_cand"]["category"]]).to(dev, torch.int32)
             sent = torch.cat([batch["x_hist"]["sentiment"], batch["x_cand"]["sentiment"]]).to(dev, torch.int32)
             self.has_aspects = True
-        scores, _, sums, flags, _ = torch.ops.manner_b200.score_eval(
+        attn_logits: List[Optional[Tensor]] = []
+        hist_pad = cand_pad = None
+        if attention is not None and any(a is not None for a in attention):
+            from . import ops
+
+            attn_logits = [None if a is None else ops.attention_logits(t, *a) for t, a in zip(tables, attention)]
+        if attn_logits or self.loss_kind == nat.LOSS_CE:
+            # the step IS the reference's dense batch: every impression is padded to the step's longest (to_dense_batch)
+            h_len, c_len = hist_off[1:] - hist_off[:-1], cand_off[1:] - cand_off[:-1]
+            hist_pad, cand_pad = (h_len.max() - h_len).to(torch.int32), (c_len.max() - c_len).to(torch.int32)
+        scores, _, sums, flags, loss_per_impr = torch.ops.manner_b200.score_eval(
             tables, hist_off, hist_ids, cand_off, cand_ids, labels, w_dev, self.zscore, max(n_cand, 1), active,
-            self.ks[0], self.ks[1], True, 0, False, cat, sent, self.num_categ_classes, self.num_sent_classes, [],
+            self.ks[0], self.ks[1], True, 0, False, cat, sent, self.num_categ_classes, self.num_sent_classes, attn_logits,
+            False, hist_pad if attn_logits else None, self.loss_kind, self.temperature, cand_pad if self.loss_kind == nat.LOSS_CE else None,
         )
+        if self.loss_kind != nat.LOSS_NONE:
+            from . import ops
+
+            st = ops.step_loss(loss_per_impr, n_impr, self.loss_kind)  # this step's value for the MeanMetric (cr_module.py:255-259)
+            self.loss_stats = st if self.loss_stats is None else self.loss_stats + st
         self.sums = sums if self.sums is None else self.sums + sums
         self.flags = flags if self.flags is None else self.flags | flags
         self.n_impressions += n_impr
@@ -133,6 +156,9 @@ class StepScorer:
         out[prefix + "gauc"] = float(s[nat.M_GAUC] / s[nat.M_GAUC_VALID]) if s[nat.M_GAUC_VALID] > 0 else 0.0
         if auc_stats is not None:
             out[prefix + "auc"] = float(auc_stats.cpu()[0])
+        if self.loss_stats is not None:
+            ls = self.loss_stats.cpu().numpy()
+            out[prefix + "loss"] = float(ls[0] / ls[1]) if ls[1] > 0 else 0.0
         return out
 
 
@@ -150,8 +176,17 @@ class B200EvalMixin:
                 self._b200_zscore, with_auc=self._b200_with_auc,
                 num_categ_classes=int(hp.get("num_categ_classes", 19)) if hasattr(hp, "get") else 19,
                 num_sent_classes=int(hp.get("num_sent_classes", 4)) if hasattr(hp, "get") else 4,
+                loss=self._b200_loss(), temperature=float(hp.get("temperature", 0.1)) if hasattr(hp, "get") else 0.1,
             )
         return self._b200_step_scorer
+
+    def _b200_loss(self) -> Optional[str]:
+        """"ce" | "supcon" | None: the step loss logged as test/loss (cr_module.py:72-76,253-259)."""
+        return None
+
+    def _b200_attention(self) -> Optional[List[Optional[Sequence[Tensor]]]]:
+        """Per module: (linear.weight, linear.bias, query) of its early-fusion additive attention, or None."""
+        return None
 
     def _b200_encoders(self) -> List[torch.nn.Module]:  # pragma: no cover - overridden
         raise NotImplementedError
@@ -163,7 +198,7 @@ class B200EvalMixin:
         encoders = self._b200_encoders()
         hist = [enc(batch["x_hist"]) for enc in encoders]
         cand = [enc(batch["x_cand"]) for enc in encoders]
-        self._b200_scorer().step(hist, cand, batch, self._b200_weights())
+        self._b200_scorer().step(hist, cand, batch, self._b200_weights(), self._b200_attention())
 
     def on_test_epoch_end(self) -> None:
         scorer = self._b200_scorer()
@@ -173,17 +208,24 @@ class B200EvalMixin:
 
 
 class CRModuleB200(B200EvalMixin, _RefCRModule):
-    """CRModule (late fusion) with the B200 test path.  Extra keyword: ``scorer`` ("b200" | "reference")
-    to fall back to the reference's own test path for A/B comparison."""
+    """CRModule (late or early fusion, CE or SupCon loss) with the B200 test path.  Extra keyword: ``scorer``
+    ("b200" | "reference") to fall back to the reference's own test path for A/B comparison."""
 
     def __init__(self, *args: Any, scorer: str = "b200", **kwargs: Any) -> None:
         super().__init__(*args, **kwargs)
         self._b200_enabled = scorer == "b200"
-        if self._b200_enabled and not self.hparams.late_fusion:
-            raise ValueError("CRModuleB200 accelerates the late-fusion path (late_fusion=True); early fusion is not built yet")
 
     def _b200_encoders(self) -> List[torch.nn.Module]:
         return [self.news_encoder]
+
+    def _b200_loss(self) -> Optional[str]:
+        return "supcon" if self.hparams.supcon_loss else "ce"
+
+    def _b200_attention(self) -> Optional[List[Optional[Sequence[Tensor]]]]:
+        if self.hparams.late_fusion:
+            return None
+        att = self.user_encoder.additive_attention  # NAMLUserEncoder (user_encoder.py:9-21) -> AdditiveAttention (attention.py:6-13)
+        return [(att.linear.weight, att.linear.bias, att.query)]
 
     def test_step(self, batch: Dict[str, Any], batch_idx: int) -> None:
         if not self._b200_enabled:

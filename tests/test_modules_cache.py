@@ -103,6 +103,46 @@ def test_cr_step_mode_dropin_logs_the_reference_values(golden_dir, name):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("name", ["cr_ef_d128", "cr_d768"])
+def test_cr_step_mode_early_fusion_and_loss(golden_dir, name):
+    """Step mode with late_fusion=False (attention parameters taken from the module) and test/loss: the values the
+    reference's CRModule logged."""
+    from manner_b200.modules import B200EvalMixin
+
+    z = np.load(os.path.join(golden_dir, name + ".npz"))
+    early = "att_weight" in z.files
+
+    class FakeCR(B200EvalMixin, torch.nn.Module):
+        def __init__(self, table):
+            super().__init__()
+            self.news_encoder = TableEncoder(table)
+            if early:
+                self.att = torch.nn.ParameterList([torch.nn.Parameter(torch.from_numpy(z[k])) for k in ("att_weight", "att_bias", "att_query")])
+            self.logged = {}
+
+        def _b200_encoders(self):
+            return [self.news_encoder]
+
+        def _b200_loss(self):
+            return "ce"
+
+        def _b200_attention(self):
+            return [tuple(self.att)] if early else None
+
+        def log_dict(self, values, **kw):
+            self.logged.update(values)
+
+    bhv = _bhv(z)
+    model = FakeCR(torch.from_numpy(z["table"])).cuda()
+    for i, lo in enumerate(range(0, bhv.n_impressions, 8)):
+        model.test_step(mo.step_batch(bhv, lo, min(lo + 8, bhv.n_impressions)), i)
+    model.on_test_epoch_end()
+    for k in ("auc", "mrr", "ndcg@5", "ndcg@10"):
+        assert abs(model.logged["test/" + k] - float(z["test_" + k])) <= 1e-6, k
+    assert abs(model.logged["test/loss"] - float(z["test_loss"])) <= 1e-5 * abs(float(z["test_loss"]))
+
+
+@pytest.mark.gpu
 def test_ensemble_step_mode_dropin_logs_the_reference_values(golden_dir):
     from manner_b200.modules import B200EvalMixin
 
