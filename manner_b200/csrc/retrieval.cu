@@ -25,22 +25,27 @@ namespace mb200 {
 namespace rt {
 constexpr int BLOCK_M = 128, BLOCK_N = 256, BLOCK_K = 64, UMMA_K = 16, STAGES = 4;
 constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2, B_BYTES = BLOCK_N * BLOCK_K * 2, STAGE_BYTES = A_BYTES + B_BYTES;
-constexpr int CAP = 256;          // per-row candidate buffer entries
+constexpr int CAP = 256;          // per-row candidate buffer entries (hard limit: a row is compacted before a chunk could overflow it)
+constexpr int SOFT_CAP = 160;     // soft limit (> MAX_K): from here on a row is compacted between tiles, one row per tile and warp
 constexpr int MAX_K = 128;        // top-k limit (k <= CAP / 2)
-constexpr int THREADS = 192;      // warp 0: TMA producer, warp 1: MMA issuer + TMEM owner, warps 2-5: epilogue
+constexpr int EPI_GROUPS = 2;     // epilogue warpgroups: group g drains accumulator stage g (every second catalogue tile)
+constexpr int THREADS = 64 + EPI_GROUPS * 128;  // warp 0: TMA producer, warp 1: MMA issuer + TMEM owner, warps 2-9: epilogue
 constexpr int TMEM_COLS = 512;    // two 128 x 256 fp32 accumulators
 constexpr int SCRATCH_BYTES = 0;
-constexpr int SMEM_BYTES = 1024 /*alignment slack*/ + STAGES * STAGE_BYTES + SCRATCH_BYTES + 256 /*barriers*/;
+constexpr int SHARE_BYTES = EPI_GROUPS * BLOCK_M * 8;  // per (group, row): published admission threshold + list length
+constexpr int SMEM_BYTES = 1024 /*alignment slack*/ + STAGES * STAGE_BYTES + SHARE_BYTES + 256 /*barriers*/;
 constexpr unsigned long long WAIT_LIMIT_NS = 2000ull * 1000 * 1000;
 }  // namespace rt
 
 struct RetrievalParams {
   float* out_scores;       // [n_users, k]
   long long* out_ids;      // [n_users, k]
-  float* cand_scores;      // workspace [grid][128][CAP]
-  int* cand_ids;           // workspace [grid][128][CAP]
+  float* cand_scores;      // workspace [grid][EPI_GROUPS][128][CAP]
+  int* cand_ids;           // workspace [grid][EPI_GROUPS][128][CAP]
   float* debug_scores;     // optional [n_users, n_catalog]
   int* error_flag;
+  unsigned long long* stats;  // diag == 4: [0] cycles in compactions, [1] in the admission slow path, [2] waiting for an accumulator,
+                              // [3] compactions, [4] slow chunks, [5] epilogue cycles in total (summed over epilogue warps, lane 0)
   long long n_users, n_catalog, id_offset;
   int dim, k, m_tiles, n_tiles;
   int diag;  // Tuning::retrieval_diag
@@ -249,7 +254,9 @@ retrieve_topk_kernel(const __grid_constant__ CUtensorMap tmap_users, const __gri
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   unsigned char* stage_base = smem;                                   // STAGES x (A | B), 1024-aligned
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  float* thr_sh = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES);  // [EPI_GROUPS][BLOCK_M] published admission thresholds
+  int* cnt_sh = reinterpret_cast<int*>(thr_sh + EPI_GROUPS * BLOCK_M);     // [EPI_GROUPS][BLOCK_M] list lengths at the end of a sweep
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES + SHARE_BYTES);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tmem_full = empty_bar + STAGES;   // [2]
   uint64_t* tmem_empty = tmem_full + 2;       // [2]
@@ -263,6 +270,7 @@ retrieve_topk_kernel(const __grid_constant__ CUtensorMap tmap_users, const __gri
     for (int s = 0; s < 2; ++s) mbar_init(&tmem_full[s], 1), mbar_init(&tmem_empty[s], 4);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
+  for (int t = threadIdx.x; t < EPI_GROUPS * BLOCK_M; t += THREADS) thr_sh[t] = -CUDART_INF_F;
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)TMEM_COLS) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -317,26 +325,52 @@ retrieve_topk_kernel(const __grid_constant__ CUtensorMap tmap_users, const __gri
       }
     }
   } else {
-    // ===== epilogue: 4 warps x 32 lanes = the 128 accumulator rows; warp w may touch TMEM lanes 32 (w % 4) .. + 31 =====
+    // ===== epilogue: 2 warpgroups x (4 warps x 32 lanes = the 128 accumulator rows); warp w may touch TMEM lanes
+    // 32 (w % 4) .. + 31.  Group g owns accumulator stage g, i.e. every second catalogue tile, so a tile's epilogue has two
+    // tile times to finish and every scheduler holds two epilogue warps.  A user row therefore has one candidate list per
+    // group; the groups publish their admission thresholds to each other (an item below EITHER group's k-th best can not be in
+    // the row's top k) and the two lists are merged at the end of the sweep. =====
+    const int g = (warp - 2) >> 2;
     const int quarter = warp & 3;
     const int row_in_tile = quarter * 32 + lane;
-    float* my_cs = p.cand_scores + ((size_t)blockIdx.x * BLOCK_M + row_in_tile) * CAP;
-    int* my_ci = p.cand_ids + ((size_t)blockIdx.x * BLOCK_M + row_in_tile) * CAP;
-    int as = 0;
-    uint32_t aphase = 0;
+    const size_t list0 = ((size_t)blockIdx.x * EPI_GROUPS + g) * BLOCK_M;
+    float* my_cs = p.cand_scores + (list0 + row_in_tile) * CAP;
+    int* my_ci = p.cand_ids + (list0 + row_in_tile) * CAP;
+    volatile float* thr_mine = thr_sh + g * BLOCK_M + row_in_tile;
+    volatile float* thr_other = thr_sh + (g ^ 1) * BLOCK_M + row_in_tile;
+    int tile = 0;  // tiles this CTA has seen so far: stage = tile & 1, phase = (tile >> 1) & 1
+    const bool st_on = p.diag == 4;
+    long long st_comp = 0, st_slow = 0, st_wait = 0, st_ncomp = 0, st_nslow = 0;
+    const long long st_t0 = clock64();
     for (int mt = blockIdx.x; mt < p.m_tiles; mt += gridDim.x) {
       const long long user = (long long)mt * BLOCK_M + row_in_tile;
       const bool row_valid = user < p.n_users;
-      float thr = -CUDART_INF_F;  // admission threshold: the row's k-th best score at its last compaction
+      float thr = -CUDART_INF_F;  // admission threshold: the best k-th best score either group has established for this row
       int cnt = 0;
-      for (int nt = 0; nt < p.n_tiles; ++nt) {
-        mbar_wait<20>(&tmem_full[as], aphase, p.error_flag);
+      for (int nt = 0; nt < p.n_tiles; ++nt, ++tile) {
+        if ((tile & 1) != g) continue;
+        long long c0 = st_on ? clock64() : 0;
+        mbar_wait<20>(&tmem_full[g], (uint32_t)(tile >> 1) & 1u, p.error_flag);
+        if (st_on) st_wait += clock64() - c0;
         tc_fence_after();
+        {
+          // The other group's k-th best bounds this row too, but only NON-strictly: its lists may already hold items with
+          // HIGHER catalogue ids than the ones seen here (the groups run concurrently), and an equal score with a lower id
+          // must still be admitted.  "s >= other" == "s > the float just below other".
+          const float other = *thr_other;
+          if (other > -CUDART_INF_F) {
+            uint32_t kk = score_key(other) - 1u;
+            if (kk == 0x7fffffffu) kk = 0x7ffffffeu;  // skip -0.0: it compares equal to +0.0
+            thr = fmaxf(thr, key_score(kk));
+          }
+        }
         const bool last_tile = nt == p.n_tiles - 1;
 #pragma unroll 1
         for (int c = 0; c < BLOCK_N / 32; ++c) {
           // make room for a whole 32-column chunk in every row of the warp before looking at it
           unsigned need = __ballot_sync(kFull, cnt > CAP - 32);
+          if (st_on && need) c0 = clock64(), st_ncomp += __popc(need);
+          const unsigned need0 = need;
           while (need) {
             const int src = __ffs(need) - 1;
             need &= need - 1;
@@ -344,11 +378,15 @@ retrieve_topk_kernel(const __grid_constant__ CUtensorMap tmap_users, const __gri
             float* cs = reinterpret_cast<float*>(__shfl_sync(kFull, reinterpret_cast<unsigned long long>(my_cs), src));
             int* ci = reinterpret_cast<int*>(__shfl_sync(kFull, reinterpret_cast<unsigned long long>(my_ci), src));
             const float kth = compact_row(cs, ci, n_src, p.k, lane);
-            if (lane == src) thr = kth, cnt = min(n_src, p.k);
+            if (lane == src) {
+              thr = fmaxf(thr, kth), cnt = min(n_src, p.k);
+              *thr_mine = thr;
+            }
           }
+          if (st_on && need0) st_comp += clock64() - c0;
           if (p.diag == 2) continue;
           uint32_t v[32];
-          tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * BLOCK_N + c * 32), v);
+          tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(g * BLOCK_N + c * 32), v);
           const int col0 = nt * BLOCK_N + c * 32;
           if (p.debug_scores != nullptr && row_valid) {
 #pragma unroll
@@ -361,47 +399,92 @@ retrieve_topk_kernel(const __grid_constant__ CUtensorMap tmap_users, const __gri
               if (col0 + t >= p.n_catalog) v[t] = 0xff800000u;  // -inf
           }
           // two-level filter: the maxima of the four 8-column groups, then only the groups that can hold an admission
-          float g[4];
+          float gm[4];
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
             const float a0 = fmaxf(__uint_as_float(v[8 * q + 0]), __uint_as_float(v[8 * q + 1])), a1 = fmaxf(__uint_as_float(v[8 * q + 2]), __uint_as_float(v[8 * q + 3]));
             const float a2 = fmaxf(__uint_as_float(v[8 * q + 4]), __uint_as_float(v[8 * q + 5])), a3 = fmaxf(__uint_as_float(v[8 * q + 6]), __uint_as_float(v[8 * q + 7]));
-            g[q] = fmaxf(fmaxf(a0, a1), fmaxf(a2, a3));
+            gm[q] = fmaxf(fmaxf(a0, a1), fmaxf(a2, a3));
           }
-          float mx = fmaxf(fmaxf(g[0], g[1]), fmaxf(g[2], g[3]));
+          float mx = fmaxf(fmaxf(gm[0], gm[1]), fmaxf(gm[2], gm[3]));
           if (p.diag == 1 || !row_valid) mx = -CUDART_INF_F;
+          const bool any_slow = st_on && __any_sync(kFull, mx > thr);
+          if (any_slow) c0 = clock64(), ++st_nslow;
           if (mx > thr) {
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
-              if (g[q] > thr) {
+              if (gm[q] > thr) {
 #pragma unroll
                 for (int t = 8 * q; t < 8 * q + 8; ++t) {
-                  const float s = __uint_as_float(v[t]);
-                  if (s > thr) my_cs[cnt] = s, my_ci[cnt] = col0 + t, ++cnt;
+                  const float sc = __uint_as_float(v[t]);
+                  if (sc > thr) my_cs[cnt] = sc, my_ci[cnt] = col0 + t, ++cnt;
                 }
               }
             }
           }
           __syncwarp();
+          if (any_slow) st_slow += clock64() - c0;
         }
         // accumulator drained: hand the TMEM buffer back to the MMA warp
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&tmem_empty[as]);
-        if (++as == 2) as = 0, aphase ^= 1;
+        if (lane == 0) mbar_arrive(&tmem_empty[g]);
+        // Off the critical path (the accumulator is already released): compact at most ONE row per tile, the fullest one
+        // above the soft limit.  Rows of a warp fill up at similar times; compacting them all when they hit the hard limit
+        // (above) would hold the accumulator stage for ~32 compactions and stall the MMA pipeline.
+        {
+          const int worst = __reduce_max_sync(kFull, cnt);
+          if (worst > SOFT_CAP) {
+            if (st_on) c0 = clock64(), ++st_ncomp;
+            const int src = __ffs(__ballot_sync(kFull, cnt == worst)) - 1;
+            float* cs = reinterpret_cast<float*>(__shfl_sync(kFull, reinterpret_cast<unsigned long long>(my_cs), src));
+            int* ci = reinterpret_cast<int*>(__shfl_sync(kFull, reinterpret_cast<unsigned long long>(my_ci), src));
+            const float kth = compact_row(cs, ci, worst, p.k, lane);
+            if (lane == src) {
+              thr = fmaxf(thr, kth), cnt = min(worst, p.k);
+              *thr_mine = thr;
+            }
+            if (st_on) st_comp += clock64() - c0;
+          }
+        }
       }
-      // end of the sweep for this user tile: every row is cut to its best k and written in order
+      // end of the sweep for this user tile: cut every list to its best k, merge the two groups' lists, write in order
       __syncwarp();
       for (int src = 0; src < 32; ++src) {
         const int n_src = __shfl_sync(kFull, cnt, src);
-        float* cs = reinterpret_cast<float*>(__shfl_sync(kFull, reinterpret_cast<unsigned long long>(my_cs), src));
-        int* ci = reinterpret_cast<int*>(__shfl_sync(kFull, reinterpret_cast<unsigned long long>(my_ci), src));
-        const long long u_src = (long long)mt * BLOCK_M + quarter * 32 + src;
-        if (u_src >= p.n_users) continue;  // warp-uniform
-        compact_row(cs, ci, n_src, p.k, lane);
-        write_sorted_row(cs, ci, min(n_src, p.k), p.k, p.out_scores + u_src * p.k, p.out_ids + u_src * p.k, p.id_offset, lane);
+        if (n_src > p.k) {  // warp-uniform
+          float* cs = reinterpret_cast<float*>(__shfl_sync(kFull, reinterpret_cast<unsigned long long>(my_cs), src));
+          int* ci = reinterpret_cast<int*>(__shfl_sync(kFull, reinterpret_cast<unsigned long long>(my_ci), src));
+          compact_row(cs, ci, n_src, p.k, lane);
+        }
+      }
+      cnt_sh[g * BLOCK_M + row_in_tile] = min(cnt, p.k);
+      __threadfence_block();
+      asm volatile("bar.sync 1, %0;" ::"n"(EPI_GROUPS * 128) : "memory");  // both groups' lists are final
+      // warp (g, quarter) finishes rows quarter * 32 + 16 g .. + 15
+      for (int rr = 0; rr < 16; ++rr) {
+        const int row = quarter * 32 + g * 16 + rr;
+        const long long u_row = (long long)mt * BLOCK_M + row;
+        if (u_row >= p.n_users) break;  // warp-uniform
+        const int n0 = cnt_sh[row], n1 = cnt_sh[BLOCK_M + row];
+        float* cs0 = p.cand_scores + ((size_t)blockIdx.x * EPI_GROUPS * BLOCK_M + row) * CAP;
+        int* ci0 = p.cand_ids + ((size_t)blockIdx.x * EPI_GROUPS * BLOCK_M + row) * CAP;
+        const float* cs1 = cs0 + (size_t)BLOCK_M * CAP;
+        const int* ci1 = ci0 + (size_t)BLOCK_M * CAP;
+        for (int t = lane; t < n1; t += 32) cs0[n0 + t] = cs1[t], ci0[n0 + t] = ci1[t];  // n0 + n1 <= 2 k <= CAP
+        const int n = n0 + n1;
+        if (n > p.k) compact_row(cs0, ci0, n, p.k, lane); else __syncwarp();
+        write_sorted_row(cs0, ci0, min(n, p.k), p.k, p.out_scores + u_row * p.k, p.out_ids + u_row * p.k, p.id_offset, lane);
         __syncwarp();
       }
+      *thr_mine = -CUDART_INF_F;  // the next user tile starts from scratch
+      __threadfence_block();
+      asm volatile("bar.sync 1, %0;" ::"n"(EPI_GROUPS * 128) : "memory");  // lists and thresholds may be reused
+    }
+    if (st_on && lane == 0) {
+      atomicAdd(p.stats + 0, (unsigned long long)st_comp), atomicAdd(p.stats + 1, (unsigned long long)st_slow);
+      atomicAdd(p.stats + 2, (unsigned long long)st_wait), atomicAdd(p.stats + 3, (unsigned long long)st_ncomp);
+      atomicAdd(p.stats + 4, (unsigned long long)st_nslow), atomicAdd(p.stats + 5, (unsigned long long)(clock64() - st_t0));
     }
   }
 
@@ -529,7 +612,7 @@ size_t retrieval_workspace_bytes(const mb200_retrieval_desc* d) {
   if (d == nullptr || d->struct_size != sizeof(mb200_retrieval_desc) || d->n_users <= 0) return 0;
   const long long m_tiles = (d->n_users + rt::BLOCK_M - 1) / rt::BLOCK_M;
   const long long grid = m_tiles < 160 ? m_tiles : 160;
-  return (size_t)grid * rt::BLOCK_M * rt::CAP * 8 + 256;
+  return (size_t)grid * rt::EPI_GROUPS * rt::BLOCK_M * rt::CAP * 8 + 256;
 }
 
 int retrieve_topk(const mb200_retrieval_desc* d, cudaStream_t stream) {
@@ -553,8 +636,9 @@ int retrieve_topk(const mb200_retrieval_desc* d, cudaStream_t stream) {
   const int grid = retrieval_grid(device, d->n_users);
   unsigned char* ws = reinterpret_cast<unsigned char*>(d->workspace);
   p.error_flag = reinterpret_cast<int*>(ws);
+  p.stats = reinterpret_cast<unsigned long long*>(ws + 64);
   p.cand_scores = reinterpret_cast<float*>(ws + 256);
-  p.cand_ids = reinterpret_cast<int*>(ws + 256 + (size_t)grid * rt::BLOCK_M * rt::CAP * 4);
+  p.cand_ids = reinterpret_cast<int*>(ws + 256 + (size_t)grid * rt::EPI_GROUPS * rt::BLOCK_M * rt::CAP * 4);
   p.out_scores = d->out_scores, p.out_ids = reinterpret_cast<long long*>(d->out_ids), p.debug_scores = d->debug_scores;
   p.n_users = d->n_users, p.n_catalog = d->n_catalog, p.id_offset = d->catalog_id_offset;
   p.dim = d->dim, p.k = d->k;

@@ -70,9 +70,16 @@ def test_retrieval_ties_break_by_lower_id(rt):
     users = _rand_bf16(70, 128, 4)
     s, i, _ = _check(rt, users, catalog, 12)
     assert np.all(i[:, 0] < 40) and np.all(i[:, 1] == i[:, 0] + 40)
+    # the same across many catalogue tiles (the two epilogue warpgroups own alternating tiles and exchange thresholds):
+    # every score appears 8 times, 300 rows apart
+    catalog2 = _rand_bf16(300, 128, 5).repeat(8, 1)
+    s, i, _ = _check(rt, _rand_bf16(200, 128, 6), catalog2, 20)
+    assert np.all(i[:, 0] < 300) and np.all(i[:, 1] == i[:, 0] + 300) and np.all(i[:, 7] == i[:, 0] + 2100)
     # all-equal scores (zero users): ids 0..k-1 in order
     s, i, _ = _check(rt, torch.zeros(5, 128, dtype=torch.bfloat16), catalog, 12)
     np.testing.assert_array_equal(i, np.tile(np.arange(12), (5, 1)))
+    s, i, _ = _check(rt, torch.zeros(5, 128, dtype=torch.bfloat16), catalog2, 100)
+    np.testing.assert_array_equal(i, np.tile(np.arange(100), (5, 1)))
 
 
 def test_retrieval_slice_4096_by_65536(rt):
