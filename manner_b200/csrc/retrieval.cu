@@ -28,13 +28,15 @@ constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2, B_BYTES = BLOCK_N * BLOCK_K * 2, 
 constexpr int CAP = 256;          // per-row candidate buffer entries (hard limit: a row is compacted before a chunk could overflow it)
 constexpr int SOFT_CAP = 160;     // soft limit (> MAX_K): from here on a row is compacted between tiles, one row per tile and warp
 constexpr int MAX_K = 128;        // top-k limit (k <= CAP / 2)
-constexpr int EPI_GROUPS = 2;     // epilogue warpgroups: group g drains accumulator stage g (every second catalogue tile)
+constexpr int EPI_GROUPS = 2;     // epilogue warpgroups: group g scans columns 128 g .. 128 g + 127 of every accumulator tile
+constexpr int EPI_COLS = BLOCK_N / EPI_GROUPS;
 constexpr int THREADS = 64 + EPI_GROUPS * 128;  // warp 0: TMA producer, warp 1: MMA issuer + TMEM owner, warps 2-9: epilogue
 constexpr int TMEM_COLS = 512;    // two 128 x 256 fp32 accumulators
 constexpr int SCRATCH_BYTES = 0;
 constexpr int SHARE_BYTES = EPI_GROUPS * BLOCK_M * 8;  // per (group, row): published admission threshold + list length
 constexpr int SMEM_BYTES = 1024 /*alignment slack*/ + STAGES * STAGE_BYTES + SHARE_BYTES + 256 /*barriers*/;
 constexpr unsigned long long WAIT_LIMIT_NS = 2000ull * 1000 * 1000;
+constexpr uint32_t WAIT_HINT_NS = 20000;  // upper bound of one hardware-suspended try_wait
 }  // namespace rt
 
 struct RetrievalParams {
@@ -69,6 +71,9 @@ __device__ __forceinline__ unsigned long long global_ns() {
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
   return t;
 }
+// `try_wait` with a suspend-time hint parks the thread in hardware until the phase completes (or the hint expires), so
+// the ten mostly-waiting warps of this kernel do not burn issue slots and power spinning -- the kernel runs under the
+// 1 kW power cap, where every wasted instruction lowers the tensor-core clock.
 template <int SLEEP_NS = 0>
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int* error_flag) {
   const uint32_t addr = smem_u32(bar);
@@ -77,14 +82,13 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int* e
     uint32_t done;
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(done)
-        : "r"(addr), "r"(parity)
+        : "r"(addr), "r"(parity), "r"(rt::WAIT_HINT_NS)
         : "memory");
     if (done) return;
-    if (SLEEP_NS > 0) __nanosleep(SLEEP_NS);  // waits that are off the critical path give their issue slots to the epilogue warps
-    if ((spin & 1023u) == 1023u) {
+    if ((spin & 63u) == 63u) {
       const unsigned long long now = global_ns();
       if (t0 == 0) t0 = now;
       if (now - t0 > rt::WAIT_LIMIT_NS) {
@@ -126,7 +130,12 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+#define MB200_R32(r) \
+  r[0], r[1], r[2], r[3], r[4], r[5], r[6], r[7], r[8], r[9], r[10], r[11], r[12], r[13], r[14], r[15], r[16], r[17], r[18], r[19], r[20], r[21], \
+      r[22], r[23], r[24], r[25], r[26], r[27], r[28], r[29], r[30], r[31]
+// Asynchronous TMEM -> register load of 32 consecutive columns of this thread's lane; the registers are valid only after
+// tmem_ld_wait on the same array (which names them as in/out operands so no use can be scheduled above the wait).
+__device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
       "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
@@ -137,7 +146,15 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
         "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
       : "r"(taddr)
       : "memory");
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait(uint32_t (&r)[32]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]), "+r"(r[9]),
+                 "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]), "+r"(r[16]), "+r"(r[17]), "+r"(r[18]),
+                 "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]), "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]),
+                 "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
+               :
+               : "memory");
 }
 
 // ---- per-row candidate lists -------------------------------------------------------------------------
@@ -152,11 +169,21 @@ __device__ __forceinline__ float key_score(uint32_t k) { return __uint_as_float(
 constexpr int kPerLane = rt::CAP / 32;  // candidate entries a lane holds during a compaction
 
 // Largest T with |{key >= T}| >= kk over the warp's 32 x kPerLane keys (kk >= 1; absent entries are 0 and never
-// count): the kk-th largest key, found bit by bit -- 32 rounds of kPerLane compares + one REDUX.
-__device__ __forceinline__ uint32_t kth_largest(const uint32_t (&key)[kPerLane], int kk) {
-  uint32_t t = 0;
+// count): the kk-th largest key, found bit by bit -- one round = kPerLane compares + one REDUX.  The bits all present keys
+// share (sign, exponent and a few mantissa bits of an already filtered list) are skipped, and with max_rounds < 32 the
+// search stops early: T is then a lower bound of the kk-th largest key with its remaining low bits zero.
+__device__ __forceinline__ uint32_t kth_largest(const uint32_t (&key)[kPerLane], int kk, int max_rounds = 32) {
+  uint32_t all_or = 0, all_and = 0xffffffffu;
+#pragma unroll
+  for (int j = 0; j < kPerLane; ++j) all_or |= key[j], all_and &= key[j] ? key[j] : 0xffffffffu;
+  all_or = __reduce_or_sync(kFull, all_or), all_and = __reduce_and_sync(kFull, all_and);
+  const uint32_t diff = all_or ^ all_and;
+  if (diff == 0) return all_or;  // all present keys are equal
+  const int hi = 31 - __clz(diff);
+  uint32_t t = all_or & ~((2u << hi) - 1u);  // the common prefix (hi == 31: 2u << 31 == 0 wraps to an all-ones mask, t = 0)
+  const int lo = max(0, hi - max_rounds + 1);
 #pragma unroll 4
-  for (int b = 31; b >= 0; --b) {
+  for (int b = hi; b >= lo; --b) {
     const uint32_t trial = t | (1u << b);
     int c = 0;
 #pragma unroll
@@ -166,10 +193,16 @@ __device__ __forceinline__ uint32_t kth_largest(const uint32_t (&key)[kPerLane],
   return t;
 }
 
-// Warp-cooperative compaction of one row's candidate buffer (n <= CAP entries, unsorted, in global memory):
-// keeps exactly min(n, k) best entries, still unsorted, at the front.  Returns the k-th best score (the new
-// admission threshold), or -inf while fewer than k entries exist.
-__device__ float compact_row(float* cs, int* ci, int n, int k, int lane) {
+// Warp-cooperative compaction of one row's candidate buffer (n <= CAP entries, unsorted, in global memory).
+//   exact:   keeps exactly min(n, k) best entries (ties at the boundary resolved towards the lower id), still unsorted,
+//            at the front; returns the k-th best score (-inf while fewer than k entries exist).
+//   !exact:  the k-th largest key is only located to kApproxRounds bits below the keys' common prefix; every entry >= that
+//            lower bound is kept (k entries or a few more) and the bound is returned -- a valid, slightly conservative
+//            admission threshold at less than half the latency.  Used between tiles; the hard limit and the end of the
+//            sweep use the exact form.
+// Returns the new length through *n_out.
+constexpr int kApproxRounds = 12;
+__device__ float compact_row(float* cs, int* ci, int n, int k, int lane, bool exact, int* n_out) {
   __syncwarp();  // the owning lane's appends to cs / ci become visible to the whole warp
   float sc[kPerLane];
   int id[kPerLane];
@@ -181,20 +214,24 @@ __device__ float compact_row(float* cs, int* ci, int n, int k, int lane) {
     id[j] = t < n ? ci[t] : 0;
     key[j] = t < n ? score_key(sc[j]) : 0u;
   }
+  *n_out = n;
   if (n <= k) return -CUDART_INF_F;  // nothing to drop (warp-uniform)
-  const uint32_t kth = kth_largest(key, k);
-  int c_gt = 0, c_eq = 0;
+  const uint32_t kth = kth_largest(key, k, exact ? 32 : kApproxRounds);
+  if (!exact && kth == 0u) return -CUDART_INF_F;  // no usable bound at this precision: leave the list as it is
+  uint32_t id_floor = 0;  // on (0x80000000 - id): larger = lower id
+  if (exact) {
+    int c_gt = 0, c_eq = 0;
 #pragma unroll
-  for (int j = 0; j < kPerLane; ++j) c_gt += key[j] > kth ? 1 : 0, c_eq += key[j] == kth ? 1 : 0;
-  c_gt = (int)__reduce_add_sync(kFull, (unsigned)c_gt);
-  c_eq = (int)__reduce_add_sync(kFull, (unsigned)c_eq);
-  const int need = k - c_gt;  // 1 <= need <= c_eq entries of score == kth survive: the ones with the lowest ids
-  uint32_t id_floor = 0;      // on (0x80000000 - id): larger = lower id
-  if (c_eq > need) {
-    uint32_t rid[kPerLane];
+    for (int j = 0; j < kPerLane; ++j) c_gt += key[j] > kth ? 1 : 0, c_eq += key[j] == kth ? 1 : 0;
+    c_gt = (int)__reduce_add_sync(kFull, (unsigned)c_gt);
+    c_eq = (int)__reduce_add_sync(kFull, (unsigned)c_eq);
+    const int need = k - c_gt;  // 1 <= need <= c_eq entries of score == kth survive: the ones with the lowest ids
+    if (c_eq > need) {
+      uint32_t rid[kPerLane];
 #pragma unroll
-    for (int j = 0; j < kPerLane; ++j) rid[j] = key[j] == kth ? 0x80000000u - (uint32_t)id[j] : 0u;
-    id_floor = kth_largest(rid, need);
+      for (int j = 0; j < kPerLane; ++j) rid[j] = key[j] == kth ? 0x80000000u - (uint32_t)id[j] : 0u;
+      id_floor = kth_largest(rid, need);
+    }
   }
   __syncwarp();
   int base = 0;
@@ -210,7 +247,14 @@ __device__ float compact_row(float* cs, int* ci, int n, int k, int lane) {
     base += __popc(m);
   }
   __syncwarp();
-  return key_score(kth);
+  *n_out = base;
+  // approximate form: entries equal to the bound were kept, so the strict admission test must use the float just below it
+  uint32_t bound = kth;
+  if (!exact) {
+    bound = kth - 1u;
+    if (bound == 0x7fffffffu) bound = 0x7ffffffeu;  // skip -0.0 (compares equal to +0.0)
+  }
+  return key_score(bound);
 }
 
 // Final pass over one row: its (already compacted, n <= k <= 128) entries are ranked by counting -- (score desc,
@@ -267,7 +311,7 @@ retrieve_topk_kernel(const __grid_constant__ CUtensorMap tmap_users, const __gri
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) mbar_init(&full_bar[s], 1), mbar_init(&empty_bar[s], 1);
-    for (int s = 0; s < 2; ++s) mbar_init(&tmem_full[s], 1), mbar_init(&tmem_empty[s], 4);
+    for (int s = 0; s < 2; ++s) mbar_init(&tmem_full[s], 1), mbar_init(&tmem_empty[s], 4 * EPI_GROUPS);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   for (int t = threadIdx.x; t < EPI_GROUPS * BLOCK_M; t += THREADS) thr_sh[t] = -CUDART_INF_F;
@@ -326,10 +370,11 @@ retrieve_topk_kernel(const __grid_constant__ CUtensorMap tmap_users, const __gri
     }
   } else {
     // ===== epilogue: 2 warpgroups x (4 warps x 32 lanes = the 128 accumulator rows); warp w may touch TMEM lanes
-    // 32 (w % 4) .. + 31.  Group g owns accumulator stage g, i.e. every second catalogue tile, so a tile's epilogue has two
-    // tile times to finish and every scheduler holds two epilogue warps.  A user row therefore has one candidate list per
-    // group; the groups publish their admission thresholds to each other (an item below EITHER group's k-th best can not be in
-    // the row's top k) and the two lists are merged at the end of the sweep. =====
+    // 32 (w % 4) .. + 31.  Group g scans one half of the columns of EVERY tile: the MMA of tile t + 2 reuses the accumulator of
+    // tile t, so a tile's epilogue has to finish within ONE tile time (the MMA of tile t + 1) -- splitting the columns halves
+    // its latency and gives every scheduler two epilogue warps.  A user row therefore has one candidate list per group; the
+    // groups publish their admission thresholds to each other (an item below EITHER group's k-th best can not be in the
+    // row's top k) and the two lists are merged at the end of the sweep. =====
     const int g = (warp - 2) >> 2;
     const int quarter = warp & 3;
     const int row_in_tile = quarter * 32 + lane;
@@ -348,9 +393,9 @@ retrieve_topk_kernel(const __grid_constant__ CUtensorMap tmap_users, const __gri
       float thr = -CUDART_INF_F;  // admission threshold: the best k-th best score either group has established for this row
       int cnt = 0;
       for (int nt = 0; nt < p.n_tiles; ++nt, ++tile) {
-        if ((tile & 1) != g) continue;
+        const int as = tile & 1;
         long long c0 = st_on ? clock64() : 0;
-        mbar_wait<20>(&tmem_full[g], (uint32_t)(tile >> 1) & 1u, p.error_flag);
+        mbar_wait<20>(&tmem_full[as], (uint32_t)(tile >> 1) & 1u, p.error_flag);
         if (st_on) st_wait += clock64() - c0;
         tc_fence_after();
         {
@@ -365,29 +410,29 @@ retrieve_topk_kernel(const __grid_constant__ CUtensorMap tmap_users, const __gri
           }
         }
         const bool last_tile = nt == p.n_tiles - 1;
-#pragma unroll 1
-        for (int c = 0; c < BLOCK_N / 32; ++c) {
-          // make room for a whole 32-column chunk in every row of the warp before looking at it
+        // make room for a whole 32-column chunk in every row of the warp before looking at it (hard limit; see SOFT_CAP below)
+        auto make_room = [&]() {
           unsigned need = __ballot_sync(kFull, cnt > CAP - 32);
-          if (st_on && need) c0 = clock64(), st_ncomp += __popc(need);
-          const unsigned need0 = need;
+          if (need == 0) return;
+          if (st_on) c0 = clock64(), st_ncomp += __popc(need);
           while (need) {
             const int src = __ffs(need) - 1;
             need &= need - 1;
             const int n_src = __shfl_sync(kFull, cnt, src);
             float* cs = reinterpret_cast<float*>(__shfl_sync(kFull, reinterpret_cast<unsigned long long>(my_cs), src));
             int* ci = reinterpret_cast<int*>(__shfl_sync(kFull, reinterpret_cast<unsigned long long>(my_ci), src));
-            const float kth = compact_row(cs, ci, n_src, p.k, lane);
+            int n_new;
+            const float kth = compact_row(cs, ci, n_src, p.k, lane, true, &n_new);
             if (lane == src) {
-              thr = fmaxf(thr, kth), cnt = min(n_src, p.k);
+              thr = fmaxf(thr, kth), cnt = n_new;
               *thr_mine = thr;
             }
           }
-          if (st_on && need0) st_comp += clock64() - c0;
-          if (p.diag == 2) continue;
-          uint32_t v[32];
-          tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(g * BLOCK_N + c * 32), v);
-          const int col0 = nt * BLOCK_N + c * 32;
+          if (st_on) st_comp += clock64() - c0;
+        };
+        // one chunk: 32 consecutive scores of this thread's user row
+        auto process = [&](uint32_t (&v)[32], int c) {
+          const int col0 = nt * BLOCK_N + g * EPI_COLS + c * 32;
           if (p.debug_scores != nullptr && row_valid) {
 #pragma unroll
             for (int t = 0; t < 32; ++t)
@@ -424,11 +469,29 @@ retrieve_topk_kernel(const __grid_constant__ CUtensorMap tmap_users, const __gri
           }
           __syncwarp();
           if (any_slow) st_slow += clock64() - c0;
+        };
+        if (p.diag != 2) {
+          // software pipeline over this group's 4 chunks of the tile: the TMEM load of chunk c + 1 is in flight while chunk c is scanned
+          const uint32_t t0 = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * BLOCK_N + g * EPI_COLS);
+          uint32_t va[32], vb[32];
+          tmem_ld32_issue(t0, va);
+          tmem_ld_wait(va);
+#pragma unroll 1
+          for (int c = 0; c < EPI_COLS / 32; c += 2) {
+            tmem_ld32_issue(t0 + (uint32_t)((c + 1) * 32), vb);
+            make_room();
+            process(va, c);
+            tmem_ld_wait(vb);
+            if (c + 2 < EPI_COLS / 32) tmem_ld32_issue(t0 + (uint32_t)((c + 2) * 32), va);
+            make_room();
+            process(vb, c + 1);
+            if (c + 2 < EPI_COLS / 32) tmem_ld_wait(va);
+          }
         }
         // accumulator drained: hand the TMEM buffer back to the MMA warp
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&tmem_empty[g]);
+        if (lane == 0) mbar_arrive(&tmem_empty[as]);
         // Off the critical path (the accumulator is already released): compact at most ONE row per tile, the fullest one
         // above the soft limit.  Rows of a warp fill up at similar times; compacting them all when they hit the hard limit
         // (above) would hold the accumulator stage for ~32 compactions and stall the MMA pipeline.
@@ -439,9 +502,10 @@ retrieve_topk_kernel(const __grid_constant__ CUtensorMap tmap_users, const __gri
             const int src = __ffs(__ballot_sync(kFull, cnt == worst)) - 1;
             float* cs = reinterpret_cast<float*>(__shfl_sync(kFull, reinterpret_cast<unsigned long long>(my_cs), src));
             int* ci = reinterpret_cast<int*>(__shfl_sync(kFull, reinterpret_cast<unsigned long long>(my_ci), src));
-            const float kth = compact_row(cs, ci, worst, p.k, lane);
+            int n_new;
+            const float kth = compact_row(cs, ci, worst, p.k, lane, false, &n_new);
             if (lane == src) {
-              thr = fmaxf(thr, kth), cnt = min(worst, p.k);
+              thr = fmaxf(thr, kth), cnt = n_new;
               *thr_mine = thr;
             }
             if (st_on) st_comp += clock64() - c0;
@@ -455,7 +519,8 @@ retrieve_topk_kernel(const __grid_constant__ CUtensorMap tmap_users, const __gri
         if (n_src > p.k) {  // warp-uniform
           float* cs = reinterpret_cast<float*>(__shfl_sync(kFull, reinterpret_cast<unsigned long long>(my_cs), src));
           int* ci = reinterpret_cast<int*>(__shfl_sync(kFull, reinterpret_cast<unsigned long long>(my_ci), src));
-          compact_row(cs, ci, n_src, p.k, lane);
+          int n_new;
+          compact_row(cs, ci, n_src, p.k, lane, true, &n_new);
         }
       }
       cnt_sh[g * BLOCK_M + row_in_tile] = min(cnt, p.k);
@@ -473,7 +538,8 @@ retrieve_topk_kernel(const __grid_constant__ CUtensorMap tmap_users, const __gri
         const int* ci1 = ci0 + (size_t)BLOCK_M * CAP;
         for (int t = lane; t < n1; t += 32) cs0[n0 + t] = cs1[t], ci0[n0 + t] = ci1[t];  // n0 + n1 <= 2 k <= CAP
         const int n = n0 + n1;
-        if (n > p.k) compact_row(cs0, ci0, n, p.k, lane); else __syncwarp();
+        int n_new;
+        if (n > p.k) compact_row(cs0, ci0, n, p.k, lane, true, &n_new); else __syncwarp();
         write_sorted_row(cs0, ci0, min(n, p.k), p.k, p.out_scores + u_row * p.k, p.out_ids + u_row * p.k, p.id_offset, lane);
         __syncwarp();
       }
