@@ -47,7 +47,8 @@ struct RetrievalParams {
   float* debug_scores;     // optional [n_users, n_catalog]
   int* error_flag;
   unsigned long long* stats;  // diag == 4: [0] cycles in compactions, [1] in the admission slow path, [2] waiting for an accumulator,
-                              // [3] compactions, [4] slow chunks, [5] epilogue cycles in total (summed over epilogue warps, lane 0)
+                              // [3] compactions, [4] slow chunks, [5] epilogue cycles in total (summed over epilogue warps, lane 0);
+                              // [6] / [7] cycles the MMA thread waited for a free accumulator / for operands (summed over CTAs)
   long long n_users, n_catalog, id_offset;
   int dim, k, m_tiles, n_tiles;
   int diag;  // Tuning::retrieval_diag
@@ -347,13 +348,19 @@ retrieve_topk_kernel(const __grid_constant__ CUtensorMap tmap_users, const __gri
     if (lane == 0) {
       int stage = 0, as = 0;
       uint32_t phase = 0, aphase = 0;
+      const bool st_on = p.diag == 4;
+      long long w_acc = 0, w_feed = 0, c0 = 0;
       for (int mt = blockIdx.x; mt < p.m_tiles; mt += gridDim.x) {
         for (int nt = 0; nt < p.n_tiles; ++nt) {
+          if (st_on) c0 = clock64();
           mbar_wait(&tmem_empty[as], aphase ^ 1, p.error_flag);
+          if (st_on) w_acc += clock64() - c0;
           tc_fence_after();
           const uint32_t d_tmem = tmem_base + as * BLOCK_N;
           for (int kb = 0; kb < k_blocks; ++kb) {
+            if (st_on) c0 = clock64();
             mbar_wait(&full_bar[stage], phase, p.error_flag);
+            if (st_on) w_feed += clock64() - c0;
             tc_fence_after();
             const uint32_t a_addr = smem_u32(stage_base + stage * STAGE_BYTES);
             const uint64_t adesc = umma_desc(a_addr), bdesc = umma_desc(a_addr + A_BYTES);
@@ -367,6 +374,7 @@ retrieve_topk_kernel(const __grid_constant__ CUtensorMap tmap_users, const __gri
           if (++as == 2) as = 0, aphase ^= 1;
         }
       }
+      if (st_on) atomicAdd(p.stats + 6, (unsigned long long)w_acc), atomicAdd(p.stats + 7, (unsigned long long)w_feed);
     }
   } else {
     // ===== epilogue: 2 warpgroups x (4 warps x 32 lanes = the 128 accumulator rows); warp w may touch TMEM lanes
