@@ -38,6 +38,7 @@ UNIT = "impressions/s"
 CATEG_WEIGHT = 0.4  # model.categ_weight (the YAMLs ship 0 and are swept by CLI override; 0 would not load the A-Module)
 FALLBACK_HBM_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md
 FALLBACK_BF16_TFLOPS = 1590.0
+FALLBACK_BF16_TFLOPS_SUSTAINED = 1400.0
 
 
 def workload_config(args) -> dict:
@@ -254,7 +255,8 @@ def run_gpu_arm(args) -> None:
     gc.collect()
     gc.disable()  # a generation-2 collection of the interpreter (tens of ms) inside a 2 ms step is host noise, not the path
     e2e_events = []
-    for i in range(max(args.steps, 10) + 1):
+    e2e_warm = max(args.warmup, 3)  # the end-to-end path gets its own warm-up steps (first uploads, allocator growth, sampler teardown)
+    for i in range(max(args.steps, 10) + e2e_warm):
         flush.fill_(rank + 1)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
@@ -262,7 +264,7 @@ def run_gpu_arm(args) -> None:
         r = ev.evaluate(step_bhv, **kw)  # includes the device -> host read of sums / AUC statistics
         e1.record()
         torch.cuda.synchronize(dev)
-        if i > 0:
+        if i >= e2e_warm:
             e2e_events.append(e0.elapsed_time(e1))
     gc.enable()
     e2e_median_ms = statistics.median(e2e_events)
@@ -399,7 +401,7 @@ def run_retrieval_arm(args) -> None:
         k_events.append((e0, e1))
     barrier()
     clocks = sampler.stop() if sampler is not None else None  # sampled during the device-timed regions only
-    e2e_events = [step(True)[:2] for _ in range(args.steps + 1)][1:]
+    e2e_events = [step(True)[:2] for _ in range(args.steps + 3)][3:]  # 3 warm-up steps of the end-to-end path
     barrier()
 
     def max_over_ranks(ms: float) -> float:
@@ -412,11 +414,15 @@ def run_retrieval_arm(args) -> None:
     kern_ms = max_over_ranks(sum(a.elapsed_time(b) for a, b in k_events)) / args.steps
     e2e_ms = max_over_ranks(sum(a.elapsed_time(b) for a, b in e2e_events) / len(e2e_events))
     if rank == 0:
-        peak, peak_kind = FALLBACK_BF16_TFLOPS, "fallback"
+        # the kernel runs for ~60 ms per launch, launches back to back, SM clock ~1.4 GHz under sw_power_cap: the regime of
+        # the SUSTAINED cuBLAS figure (B200_PROFILING.md); the burst figure is reported beside it
+        peak, peak_kind, burst = FALLBACK_BF16_TFLOPS_SUSTAINED, "fallback sustained", FALLBACK_BF16_TFLOPS
         path = os.path.join(ROOT, "MEASURED_PEAKS.json")
         if os.path.exists(path):
             with open(path) as f:
-                peak, peak_kind = float(json.load(f)["bf16_tflops"]), "measured (burst: kernel timed alone)"
+                mp = json.load(f)
+            burst = float(mp["bf16_tflops"])
+            peak, peak_kind = float(mp.get("bf16_tflops_sustained", burst)), "measured sustained (long kernel under the power cap; see frac_of_burst)"
         flops = 2.0 * n_users * n_shard * dim  # per launch, per GPU
         achieved = flops / (kern_ms * 1e-3) / 1e12
         cpu = None
@@ -442,7 +448,7 @@ def run_retrieval_arm(args) -> None:
                     "d2h_bytes_per_step": (n_users if (not distributed or args.exchange == "all_gather") else -(-n_users // world)) * k * 12, "ms_per_step": e2e_ms},
             "gpu_launches": launches1[0] - launches0[0],
             "roofline": {"bound": "tensor", "kernel": "retrieve_topk_kernel", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                         "peak_kind": peak_kind, "traffic": None, "flops_per_launch": flops, "kernel_ms": kern_ms,
+                         "peak_kind": peak_kind, "peak_burst": burst, "frac_of_burst": achieved / burst, "traffic": None, "flops_per_launch": flops, "kernel_ms": kern_ms,
                          "kernel_share_of_step": kern_ms * args.steps / total_ms if total_ms > 0 else None},
             "cpu_baseline": cpu, "clocks": clocks,
         }

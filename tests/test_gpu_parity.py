@@ -186,6 +186,37 @@ def test_edge_cases_and_error_reporting(evaluator_cls):
         torch.ops.manner_b200.pooled_auc(torch.rand(4), torch.zeros(4, dtype=torch.uint8), 0, None)
 
 
+def test_empty_and_extreme_inputs(evaluator_cls):
+    """Empty call, the largest impression shapes the reference's data can produce, and all-positive / no-positive lists."""
+    table = mdata.synth_table(512, 768, 3)
+    ev = evaluator_cls([table])
+    empty = mdata.Behaviours(np.zeros(1, np.int32), np.zeros(0, np.int32), np.zeros(1, np.int32), np.zeros(0, np.int32), np.zeros(0, np.uint8))
+    res = ev.evaluate(ev.upload(empty), pooled_auc=True, want_scores=True, want_per_impression=True)
+    assert res.n_impressions == 0 and not res.sums.any() and res.scores.numel() == 0 and res.auc == 0.0
+    assert all(v == 0.0 for v in res.metrics().values())
+    # H = 50 (the reference's truncation, mind_rec_dataset.py:92), C = 300 candidates, every label pattern
+    rng = np.random.default_rng(9)
+    hs, cs = [50, 1, 50, 7], [300, 300, 2, 299]
+    labels = [np.ones(300, np.uint8), np.zeros(300, np.uint8), np.array([0, 1], np.uint8), (rng.random(299) < 0.5).astype(np.uint8)]
+    off = lambda xs: np.concatenate([[0], np.cumsum(xs)]).astype(np.int32)
+    bhv = mdata.Behaviours(off(hs), rng.integers(0, 512, sum(hs)).astype(np.int32), off(cs),
+                           np.concatenate([rng.permutation(512)[:c] for c in cs]).astype(np.int32), np.concatenate(labels))
+    res = ev.evaluate(ev.upload(bhv), pooled_auc=True, want_scores=True, want_per_impression=True)
+    ob = mo.Behaviours(bhv.hist_offsets, bhv.hist_ids, bhv.cand_offsets, bhv.cand_ids, bhv.labels)
+    ref = mo.cr_eval_epoch(table, ob, step=4)
+    scores = res.scores.cpu().numpy()
+    assert np.all(np.abs(scores.astype(np.float64) - ref["scores"]) <= _score_tol(table, bhv, ref["scores"]))
+    per = mo.per_impression_metrics(scores, bhv.labels, bhv.cand_offsets)
+    np.testing.assert_array_equal(res.per_impression.cpu().numpy()[0][:, :3], per[:, :3])
+    assert per[1, 0] == 0.0 and per[1, 1] == 0.0  # no positive: MRR = nDCG = 0 (empty_target_action="neg")
+    assert per[0, 0] == 1.0 and per[0, 1] == 1.0  # all positive
+    # an impression longer than the declared max_cand is skipped and flagged, never read out of bounds
+    dev_bhv = ev.upload(bhv)
+    dev_bhv.max_cand = 100
+    with pytest.raises(nat.NativeError, match="flagged bad input"):
+        ev.evaluate(dev_bhv)
+
+
 def test_small_shape_properties_full_size(evaluator_cls):
     """BASELINE.json's MIND-small shape (73 152 impressions, 768-d): size-independent properties."""
     tables, bhv = mdata.synth_workload("small", n_modules=1)
