@@ -65,8 +65,6 @@ struct EvalParams {
   int acc_bytes;      // bytes of the per-warp fp64 accumulators (16-byte multiple)
   int loss_kind;
   float loss_temperature;
-  int ring_slots;      // stream kernel: rows in flight per warp
-  int ring_row_bytes;  // stream kernel: bytes of one staged row (16-byte multiple)
 };
 
 template <typename T>
@@ -803,247 +801,6 @@ __global__ void __launch_bounds__(kThreads, MINB) score_eval_kernel(const __grid
   if (lane == 0 && warp_flags && p.flags) atomicOr(p.flags, warp_flags);
 }
 
-
-// ------------------------------------------------------------------------------------------------------
-// Streaming variant of the fused kernel (reference width, late fusion): the rows are not loaded into
-// registers batch by batch but staged through a per-warp ring in shared memory with asynchronous copies
-// (cp.async 16 B per lane: 512 B per warp instruction, six per fp32 row; one commit group per row).  The warp runs an
-// issue cursor S rows ahead of the row it is consuming, across history / candidate / impression boundaries and
-// across the ranking + metrics phase, so its share of the L2 -> SM pipe never drains: the register-batch kernel
-// above has a bubble after every batch (all loads issued, then waited for) and no loads in flight at all while an
-// impression is being ranked.  Registers hold only the pooled user vectors (one per active module: the stream is
-// module-inner, so every history / candidate id is read once and strictly in order).
-// (A first version staged the rows with the bulk-copy engine, cp.async.bulk + mbarrier per slot: correct but 3.5 x
-// slower -- about 170 cycles of engine time per 3 KB copy and SM, 5 TB/s chip-wide; profiles/r1_v5_stream_bulk.log.)
-// ------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() {
-  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
-}
-
-// 32-wide sliding window over an id array: lane l holds ids[base + l], the following 32 are already on their way.
-struct IdWindow {
-  const int32_t* ids;
-  int limit;  // number of valid entries in ids
-  int base;
-  int cur, nxt;
-  __device__ __forceinline__ int load(int at, int lane) const {
-    const int k = at + lane;
-    return k < limit ? __ldg(ids + k) : 0;
-  }
-  __device__ __forceinline__ void start(const int32_t* a, int first, int n, int lane) {
-    ids = a, limit = n, base = first;
-    cur = load(base, lane), nxt = load(base + 32, lane);
-  }
-  // id at absolute position `at` (non-decreasing across calls, warp-uniform)
-  __device__ __forceinline__ int get(int at, int lane) {
-    while (at >= base + 32) {
-      base += 32;
-      cur = nxt;
-      nxt = load(base + 32, lane);
-    }
-    return __shfl_sync(kFull, cur, at - base);
-  }
-};
-
-template <typename T, int NV, int NM, int S>
-__global__ void __launch_bounds__(kThreads, 2) score_eval_stream_kernel(const __grid_constant__ EvalParams p) {
-  constexpr int E = Elem<T>::E;
-  extern __shared__ __align__(128) unsigned char smem[];
-  const int lane = threadIdx.x & 31;
-  const int warp = threadIdx.x >> 5;
-  const int gw = blockIdx.x * kWarpsPerCta + warp;
-  const int W = p.n_weightings;
-  constexpr uint32_t row_bytes = NV * 32 * 16;
-
-  // per-warp shared memory: [ring: S rows][the scratch of the register-batch kernel]
-  constexpr size_t ring_bytes = (size_t)S * row_bytes;
-  const size_t per_warp = ring_bytes + (size_t)p.smem_per_warp;
-  unsigned char* wbase = smem + (size_t)warp * per_warp;
-  unsigned char* ring = wbase;
-  unsigned char* base = wbase + ring_bytes;
-  WarpSmem sm;
-  sm.acc = reinterpret_cast<double*>(base);
-  sm.sc = reinterpret_cast<float*>(base + p.acc_bytes);
-  sm.comb = sm.sc + (size_t)NM * p.cpad;
-  sm.lab = reinterpret_cast<uint8_t*>(sm.comb + p.cpad);
-  sm.ccat = sm.lab + p.cpad;
-  sm.csent = sm.ccat + p.cpad;
-  sm.hist_cat = reinterpret_cast<int*>(sm.csent + p.cpad);
-  sm.hist_sent = sm.hist_cat + MB200_MAX_CLASSES;
-  sm.top_cat = reinterpret_cast<uint8_t*>(sm.hist_sent + MB200_MAX_CLASSES);
-  sm.top_sent = sm.top_cat + 32;
-
-  for (int t = lane; t < W * MB200_NUM_METRICS; t += 32) sm.acc[t] = 0.0;
-  __syncwarp();
-
-  // tables of the active modules, in slot order
-  const T* tab[NM];
-  {
-    int sl = 0;
-#pragma unroll
-    for (int m = 0; m < MB200_MAX_MODULES; ++m)
-      if (((p.active_mask >> m) & 1) && sl < NM) tab[sl++] = reinterpret_cast<const T*>(p.tables[m]);
-  }
-
-  int warp_flags = 0;
-  const int i_begin = gw < p.n_chunks ? p.bounds[gw] : 0;
-  const int i_end = gw < p.n_chunks ? p.bounds[gw + 1] : 0;
-
-  // ---- issue cursor: (impression, row q of the impression's NM * (H + C) rows) ----
-  int is_i = i_begin, is_q = 0, is_n = 0, is_h0 = 0, is_H = 0, is_c0 = 0;
-  int issued = 0, consumed = 0;
-  IdWindow hwin, cwin;
-  auto rows_of = [&](int h0, int h1, int c0, int c1) {
-    const int H = h1 - h0, C = c1 - c0;
-    return (C > p.max_cand || C <= 0 || H < 0) ? 0 : NM * (H + C);
-  };
-  auto issuer_enter = [&]() {  // position the cursor on the first row of impression is_i or a later one that has rows
-    while (is_i < i_end) {
-      const int h0 = p.hist_offsets[is_i], h1 = p.hist_offsets[is_i + 1];
-      const int c0 = p.cand_offsets[is_i], c1 = p.cand_offsets[is_i + 1];
-      is_n = rows_of(h0, h1, c0, c1);
-      is_h0 = h0, is_H = h1 - h0, is_c0 = c0, is_q = 0;
-      if (is_n > 0) return;
-      ++is_i;
-    }
-  };
-  auto issue_ahead = [&](int consumer_i) {
-    // at most S rows in flight, and never more than one impression ahead of the consumer
-    while (issued - consumed < S && is_i < i_end && is_i <= consumer_i + 1) {
-      const int nh = NM * is_H;
-      int id, m;
-      if (is_q < nh) {
-        id = hwin.get(is_h0 + is_q / NM, lane), m = is_q % NM;
-      } else {
-        const int r = is_q - nh;
-        id = cwin.get(is_c0 + r / NM, lane), m = r % NM;
-      }
-      if ((unsigned long long)(long long)id >= (unsigned long long)p.n_news) id = 0, warp_flags |= MB200_FLAG_BAD_ID;
-      const int slot = issued % S;
-      {
-        const T* src = tab[0];
-#pragma unroll
-        for (int k = 1; k < NM; ++k) src = (m == k) ? tab[k] : src;
-        const uint4* row = reinterpret_cast<const uint4*>(src + (long long)id * p.row_stride);
-        const uint32_t dst = smem_addr(ring + (size_t)slot * row_bytes) + (uint32_t)lane * 16u;
-#pragma unroll
-        for (int v = 0; v < NV; ++v) cp_async16(dst + (uint32_t)v * 512u, row + lane + 32 * v);
-        cp_async_commit();  // one group per row: groups complete in order
-      }
-      ++issued;
-      if (++is_q == is_n) {
-        ++is_i;
-        issuer_enter();
-      }
-    }
-  };
-  // the next staged row: waits for it and returns its shared-memory address.  With the ring full, "at most S - 1 groups
-  // pending" means the oldest row has landed; with fewer rows in flight (end of the warp's range) everything is awaited.
-  auto next_row = [&]() -> const uint4* {
-    const int slot = consumed % S;
-    if (issued - consumed == S) cp_async_wait<S - 1>(); else cp_async_wait<0>();
-    // no warp synchronisation: a lane reads back exactly the 16-byte vectors it copied itself (lane + 32 v)
-    return reinterpret_cast<const uint4*>(ring + (size_t)slot * row_bytes);
-  };
-
-  if (i_begin < i_end) {
-    hwin.start(p.hist_ids, p.hist_offsets[i_begin], p.hist_offsets[p.n_impr], lane);
-    cwin.start(p.cand_ids, p.cand_offsets[i_begin], p.cand_offsets[p.n_impr], lane);
-    issuer_enter();
-    issue_ahead(i_begin);
-  }
-
-  for (int i = i_begin; i < i_end; ++i) {
-    const int h0 = p.hist_offsets[i], h1 = p.hist_offsets[i + 1];
-    const int c0 = p.cand_offsets[i], c1 = p.cand_offsets[i + 1];
-    const int H = h1 - h0, C = c1 - c0;
-    if (C > p.max_cand || C <= 0 || H < 0) {
-      warp_flags |= MB200_FLAG_CAND_OVERFLOW;
-      if (p.per_impr)
-        for (int t = lane; t < W * MB200_NUM_METRICS; t += 32)
-          p.per_impr[((size_t)(t / MB200_NUM_METRICS) * p.n_impr + i) * MB200_NUM_METRICS + t % MB200_NUM_METRICS] = 0.f;
-      issue_ahead(i);
-      continue;
-    }
-    __syncwarp();
-    for (int j = lane; j < C; j += 32) sm.lab[j] = p.labels[c0 + j];
-
-    // ---- history: u_m = sum of the module's rows (module-inner stream) ----
-    float u[NM][NV * E];
-#pragma unroll
-    for (int m = 0; m < NM; ++m)
-#pragma unroll
-      for (int t = 0; t < NV * E; ++t) u[m][t] = 0.f;
-#pragma unroll 1
-    for (int h = 0; h < H; ++h) {
-#pragma unroll
-      for (int m = 0; m < NM; ++m) {
-        const uint4* row = next_row();
-#pragma unroll
-        for (int v = 0; v < NV; ++v) {
-          float f[E];
-          Elem<T>::unpack(row[lane + 32 * v], f);
-#pragma unroll
-          for (int e = 0; e < E; ++e) u[m][v * E + e] += f[e];
-        }
-        ++consumed;
-        issue_ahead(i);
-      }
-    }
-    {
-      const float hf = (float)H;  // true division, as in gather_pool_score
-      const float rh = __frcp_rn(hf);
-#pragma unroll
-      for (int m = 0; m < NM; ++m)
-#pragma unroll
-        for (int t = 0; t < NV * E; ++t) {
-          const float q = __fmul_rn(u[m][t], rh);
-          u[m][t] = __fmaf_rn(__fmaf_rn(-q, hf, u[m][t]), rh, q);
-        }
-    }
-    // ---- candidates: s^m_j = u_m . row ----
-#pragma unroll 1
-    for (int j = 0; j < C; ++j) {
-#pragma unroll
-      for (int m = 0; m < NM; ++m) {
-        const uint4* row = next_row();
-        float part = 0.f;
-#pragma unroll
-        for (int v = 0; v < NV; ++v) {
-          float f[E];
-          Elem<T>::unpack(row[lane + 32 * v], f);
-#pragma unroll
-          for (int e = 0; e < E; ++e) part = fmaf(u[m][v * E + e], f[e], part);
-        }
-        ++consumed;
-        issue_ahead(i);
-        part = warp_sum(part);
-        if (lane == 0) sm.sc[(size_t)m * p.cpad + j] = part;
-      }
-    }
-    __syncwarp();
-    if (p.zscore) {
-#pragma unroll 1
-      for (int m = 0; m < NM; ++m) {
-        zscore_inplace(sm.sc + (size_t)m * p.cpad, C, lane);
-        __syncwarp();
-      }
-    }
-    warp_flags |= rank_and_metrics(p, sm, i, h0, H, c0, C);
-  }
-
-  __syncwarp();
-  for (int t = lane; t < W * MB200_NUM_METRICS; t += 32) p.partials[(size_t)gw * W * MB200_NUM_METRICS + t] = sm.acc[t];
-  warp_flags = __reduce_or_sync(kFull, warp_flags);
-  if (lane == 0 && warp_flags && p.flags) atomicOr(p.flags, warp_flags);
-}
-
 // bounds[c] = first impression whose work prefix reaches c/n_chunks of the total; work = rows gathered
 // (+ a per-impression constant), so chunks are balanced by sum(H_i + C_i), not by count.
 __global__ void partition_kernel(const int32_t* __restrict__ hist_offsets, const int32_t* __restrict__ cand_offsets, int n_impr,
@@ -1200,32 +957,6 @@ static KernelFn select_kernel(int vec_per_row, bool attn) {
   return generic_kernel<T, 8>(attn);
 }
 
-constexpr int kStreamCtasPerSm = 2;
-
-template <typename T, int S>
-static KernelFn select_stream_kernel_s(int n_active) {
-  constexpr int kRefNV = 768 / Elem<T>::E / 32;  // 6 (fp32) or 3 (bf16)
-  switch (n_active) {
-    case 1: return score_eval_stream_kernel<T, kRefNV, 1, S>;
-    case 2: return score_eval_stream_kernel<T, kRefNV, 2, S>;
-    case 3: return score_eval_stream_kernel<T, kRefNV, 3, S>;
-  }
-  return nullptr;
-}
-
-// ring depths that are compiled (cp.async.wait_group needs an immediate): the largest that fits is used
-
-template <typename T>
-static KernelFn select_stream_kernel(int vec_per_row, int n_active, int max_slots, int* slots) {
-  constexpr int kRefNV = 768 / Elem<T>::E / 32;
-  *slots = 0;
-  if (vec_per_row != kRefNV * 32) return nullptr;
-  if (max_slots >= 12) return *slots = 12, select_stream_kernel_s<T, 12>(n_active);
-  if (max_slots >= 7) return *slots = 7, select_stream_kernel_s<T, 7>(n_active);
-  if (max_slots >= 4) return *slots = 4, select_stream_kernel_s<T, 4>(n_active);
-  return nullptr;
-}
-
 static int sm_count_of(int device, int* out) {
   static int cached[64] = {0};
   if (device >= 0 && device < 64 && cached[device]) {
@@ -1291,24 +1022,6 @@ int score_eval(const mb200_eval_desc* d, cudaStream_t stream) {
   LaunchPlan plan;
   st = make_plan(d, sms, 1, &plan);  // shared-memory sizes first: they decide how many CTAs fit
   if (st != MB200_OK) return st;
-  // Streaming kernel (rows staged through a shared-memory ring by the bulk-copy engine): reference width, late fusion,
-  // <= 3 active modules, one contiguous impression range per warp, and room for a ring of at least kMinRingSlots rows.
-  const int n_active = __builtin_popcount((unsigned)d->active_modules_mask);
-  const int row_bytes = vec_per_row * 16;
-  int ring_slots = 0;
-  KernelFn stream_kern = nullptr;
-  if (tuning().variant == 4 && !attn && n_active <= 3 && tuning().chunks_per_warp <= 1) {
-    const size_t per_warp_budget = ((size_t)227 * 1024 / kStreamCtasPerSm - 1024) / kWarpsPerCta;
-    const size_t fixed = (size_t)plan.smem_per_warp;
-    const int max_slots = per_warp_budget > fixed ? (int)((per_warp_budget - fixed) / row_bytes) : 0;
-    stream_kern = (d->dtype == MB200_F32) ? select_stream_kernel<float>(vec_per_row, n_active, max_slots, &ring_slots)
-                                          : select_stream_kernel<__nv_bfloat16>(vec_per_row, n_active, max_slots, &ring_slots);
-    if (stream_kern == nullptr) ring_slots = 0;
-  }
-  if (ring_slots > 0) {
-    kern = stream_kern;
-    plan.smem_per_cta = ((size_t)ring_slots * row_bytes + plan.smem_per_warp) * kWarpsPerCta;
-  }
   if (plan.smem_per_cta > 48 * 1024) {
     st = cuda_status(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem_per_cta), "cudaFuncSetAttribute");
     if (st != MB200_OK) return st;
@@ -1319,15 +1032,8 @@ int score_eval(const mb200_eval_desc* d, cudaStream_t stream) {
   if (st != MB200_OK) return st;
   if (resident < 1) return MB200_ERR_UNSUPPORTED;
   const int want = tuning().ctas_per_sm > 0 ? tuning().ctas_per_sm : resident;
-  {
-    const size_t smem_per_cta = plan.smem_per_cta;
-    st = make_plan(d, sms, want < resident ? want : resident, &plan);
-    if (st != MB200_OK) return st;
-    if (ring_slots > 0) {
-      plan.smem_per_cta = smem_per_cta;
-      if (plan.n_chunks > plan.total_warps) plan.n_chunks = plan.total_warps;
-    }
-  }
+  st = make_plan(d, sms, want < resident ? want : resident, &plan);
+  if (st != MB200_OK) return st;
   const size_t need = plan.bounds_bytes + plan.partials_bytes;
   if (d->workspace == nullptr || ((uintptr_t)d->workspace & 255) || d->workspace_bytes < need) return MB200_ERR_WORKSPACE;
 
@@ -1349,7 +1055,6 @@ int score_eval(const mb200_eval_desc* d, cudaStream_t stream) {
   for (int m = 0; m < MB200_MAX_MODULES; ++m) p.attn_logits[m] = (m < d->n_modules) ? d->attn_logits[m] : nullptr;
   p.hist_pad = d->hist_pad, p.cand_pad = d->cand_pad, p.loss_per_impr = d->loss_per_impression;
   p.loss_kind = d->loss_kind, p.loss_temperature = d->loss_temperature;
-  p.ring_slots = ring_slots, p.ring_row_bytes = row_bytes;
 
   partition_kernel<<<(plan.n_chunks + 1 + 255) / 256, 256, 0, stream>>>(d->hist_offsets, d->cand_offsets, p.n_impr, plan.n_chunks,
                                                                        reinterpret_cast<int32_t*>(d->workspace));

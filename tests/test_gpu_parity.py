@@ -255,53 +255,3 @@ def test_small_shape_properties_full_size(evaluator_cls):
     else:
         print(f"near-tie rank flips between device and oracle scores: {flips}")
         assert flips <= 4
-
-
-@pytest.mark.parametrize("n_modules,dtype", [(1, torch.float32), (2, torch.float32), (3, torch.float32), (2, torch.bfloat16)])
-def test_streaming_kernel_is_bit_identical_to_the_register_batch_kernel(evaluator_cls, n_modules, dtype):
-    """Tuning variant 4 stages the rows through a shared-memory ring with the bulk-copy engine (score_eval_stream_kernel);
-    it adds the history rows and the dot-product terms in the same order, so every output must match bit for bit --
-    and the register-batch kernel is the one pinned on the reference's goldens."""
-    from manner_b200 import ops
-
-    n_news = 3000
-    bhv = mdata.synth_behaviours(n_news, 700, seed=31 + n_modules, cand_window=900)
-    tables = [mdata.synth_table(n_news, 768, s).to(dtype) for s in mdata.TABLE_SEEDS[:n_modules]]
-    aspects = mdata.synth_aspects(n_news)
-    weights = [[1.0, 0.3, 0.6][:n_modules], [1.0, 0.0, 0.2][:n_modules]]
-    ev = evaluator_cls(tables, news_category=aspects["category"], news_sentiment=aspects["sentiment"])
-    dev_bhv = ev.upload(bhv, step_batch=8)
-    out = {}
-    try:
-        for variant in (2, 4):
-            ops.set_tuning(variant=variant)
-            a = ev.evaluate(dev_bhv, weights=weights, zscore=True, want_scores=True, want_per_impression=True, pooled_auc=True, scores_weighting=1)
-            b = ev.evaluate(dev_bhv, want_scores=True, loss="ce") if n_modules == 1 else None
-            out[variant] = (a, b)
-    finally:
-        ops.set_tuning(variant=2)
-    (a2, b2), (a4, b4) = out[2], out[4]
-    assert torch.equal(a2.scores, a4.scores)
-    assert torch.equal(a2.per_impression, a4.per_impression)
-    np.testing.assert_array_equal(a2.sums, a4.sums)
-    assert a2.auc == a4.auc
-    if b2 is not None:
-        assert torch.equal(b2.scores, b4.scores) and b2.loss == b4.loss
-    # an out-of-range id and an over-long impression are flagged the same way
-    bad = mdata.Behaviours(bhv.hist_offsets, bhv.hist_ids.copy(), bhv.cand_offsets, bhv.cand_ids.copy(), bhv.labels)
-    bad.cand_ids[5] = n_news
-    try:
-        ops.set_tuning(variant=4)
-        with pytest.raises(nat.NativeError, match="flagged bad input"):
-            ev.evaluate(ev.upload(bad))
-        over = ev.upload(bhv)
-        over.max_cand = 40
-        with pytest.raises(nat.NativeError, match="flagged bad input"):
-            ev.evaluate(over)
-        # a single impression / fewer impressions than warps
-        tiny = ev.evaluate(ev.upload(bhv.slice(3, 4)), want_scores=True)
-        ops.set_tuning(variant=2)
-        tiny2 = ev.evaluate(ev.upload(bhv.slice(3, 4)), want_scores=True)
-        assert torch.equal(tiny.scores, tiny2.scores)
-    finally:
-        ops.set_tuning(variant=2)
