@@ -49,6 +49,8 @@ def workload_config(args) -> dict:
         "categ_weight": CATEG_WEIGHT,
         "metrics": "ndcg@5 ndcg@10 mrr gauc + pooled auroc",
         "ids": "uniform" if args.uniform_ids else "zipf(1.05)",
+        "fusion": "early (additive attention, cached logits)" if getattr(args, "early_fusion", False) else "late (mean)",
+        "loss": getattr(args, "loss", None),
         "weightings": (max(2, int(round(args.sweep ** 0.5))) ** 2 if args.sweep else 1),
         "l2": "flushed between timed steps (256 MiB write); table 200 MB/module > 126 MB L2",
     }
@@ -185,14 +187,25 @@ def run_gpu_arm(args) -> None:
     else:
         # weak scaling: every rank scores its own MIND-small-shaped shard (different behaviour seed), tables replicated
         tables, bhv = mdata.synth_workload(args.workload, n_modules=args.modules, seed_offset=rank, uniform_ids=args.uniform_ids)
-    ev = ScoreEvaluator(tables, dev)
-    pinned = ev.pin(bhv)
+    attention = None
+    if args.early_fusion:
+        # late_fusion=False (configs/experiment/cr_module_mind_all_scl_ef.yaml): additive attention with query_vector_dim 200 on the CR
+        # module; the per-news logits are computed once here (ops.attention_logits), like the embedding table
+        ga = torch.Generator().manual_seed(77)
+        dim = tables[0].shape[1]
+        attention = [(torch.randn(200, dim, generator=ga) * dim ** -0.5, torch.randn(200, generator=ga) * 0.1, torch.rand(200, generator=ga) * 0.2 - 0.1)]
+        attention += [None] * (len(tables) - 1)
+    step_batch = 8 if (args.early_fusion or args.loss) else None  # configs/data/mind_rec.yaml:51
+    ev = ScoreEvaluator(tables, dev, attention=attention)
+    pinned = ev.pin(bhv, step_batch)
     # multi-GPU pooled AUC: agree once (outside the timed loop) on the largest per-rank positive count
     pos_cap = mdist.agree_pos_cap(int(bhv.labels.sum()), dev) if distributed else None
     dev_bhv = ev.upload(bhv, pinned, pos_cap)
     weights = [[1.0, CATEG_WEIGHT] + [0.0] * (args.modules - 2)][0][: args.modules]
     w_dev = torch.tensor([weights], dtype=torch.float32, device=dev)
     kw = dict(weights=w_dev, zscore=True, pooled_auc=True, distributed=distributed)
+    if args.loss:
+        kw.update(loss=args.loss, temperature=0.36)
     if args.sweep:
         # BASELINE.json configs[3]: aspect-weight sweep, every weighting re-scored from the one gather
         side = max(2, int(round(args.sweep ** 0.5)))
@@ -468,6 +481,8 @@ def main() -> None:
     ap.add_argument("--modules", type=int, default=2)
     ap.add_argument("--shard", action="store_true", help="strong scaling: shard one workload over the ranks instead of one workload per rank")
     ap.add_argument("--sweep", type=int, default=0, help="aspect-weight sweep with about this many weightings (configs[3]); no pooled AUC")
+    ap.add_argument("--early-fusion", action="store_true", help="CR module with late_fusion=False: additive-attention pooling from cached per-news logits")
+    ap.add_argument("--loss", default=None, choices=["ce", "supcon"], help="also compute the reference's test/loss on device")
     ap.add_argument("--uniform-ids", action="store_true", help="draw ids uniformly over the catalogue (no L2-friendly head)")
     ap.add_argument("--cpu-sample", type=int, default=8192)
     ap.add_argument("--no-cpu-baseline", action="store_true")

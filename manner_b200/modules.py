@@ -169,16 +169,17 @@ class B200EvalMixin:
     _b200_zscore = False
     _b200_with_auc = True
 
-    def _b200_scorer(self) -> StepScorer:
-        if getattr(self, "_b200_step_scorer", None) is None:
+    def _b200_scorer(self, stage: str = "test") -> StepScorer:
+        scorers = self.__dict__.setdefault("_b200_step_scorers", {})
+        if stage not in scorers:
             hp = getattr(self, "hparams", {})
-            self._b200_step_scorer = StepScorer(
+            scorers[stage] = StepScorer(
                 self._b200_zscore, with_auc=self._b200_with_auc,
                 num_categ_classes=int(hp.get("num_categ_classes", 19)) if hasattr(hp, "get") else 19,
                 num_sent_classes=int(hp.get("num_sent_classes", 4)) if hasattr(hp, "get") else 4,
                 loss=self._b200_loss(), temperature=float(hp.get("temperature", 0.1)) if hasattr(hp, "get") else 0.1,
             )
-        return self._b200_step_scorer
+        return scorers[stage]
 
     def _b200_loss(self) -> Optional[str]:
         """"ce" | "supcon" | None: the step loss logged as test/loss (cr_module.py:72-76,253-259)."""
@@ -194,17 +195,45 @@ class B200EvalMixin:
     def _b200_weights(self) -> Optional[List[float]]:
         return None
 
-    def test_step(self, batch: Dict[str, Any], batch_idx: int) -> None:
+    def _b200_step(self, stage: str, batch: Dict[str, Any]) -> None:
         encoders = self._b200_encoders()
         hist = [enc(batch["x_hist"]) for enc in encoders]
         cand = [enc(batch["x_cand"]) for enc in encoders]
-        self._b200_scorer().step(hist, cand, batch, self._b200_weights(), self._b200_attention())
+        self._b200_scorer(stage).step(hist, cand, batch, self._b200_weights(), self._b200_attention())
+
+    def _b200_epoch_end(self, stage: str) -> Dict[str, float]:
+        scorer = self._b200_scorer(stage)
+        values = scorer.compute(prefix=stage + "/")
+        scorer.reset()
+        return values
+
+    def test_step(self, batch: Dict[str, Any], batch_idx: int) -> None:
+        self._b200_step("test", batch)
 
     def on_test_epoch_end(self) -> None:
-        scorer = self._b200_scorer()
-        values = scorer.compute(prefix="test/")
-        scorer.reset()
+        self.log_dict(self._b200_epoch_end("test"), on_step=False, on_epoch=True, prog_bar=True, logger=True)
+
+    def validation_step(self, batch: Dict[str, Any], batch_idx: int) -> None:
+        """cr_module.py:214-225: val/loss is what `ModelCheckpoint(monitor="val/loss")` watches (configs/callbacks/default.yaml)."""
+        self._b200_step("val", batch)
+
+    def on_validation_epoch_end(self) -> None:
+        """cr_module.py:227-251: val/loss, the best val/loss so far (MinMetric), then the validation metrics."""
+        values = self._b200_epoch_end("val")
+        if "val/loss" in values:
+            best = min(self.__dict__.get("_b200_val_loss_best", float("inf")), values["val/loss"])
+            self.__dict__["_b200_val_loss_best"] = best
+            values["val/loss_best"] = best
         self.log_dict(values, on_step=False, on_epoch=True, prog_bar=True, logger=True)
+
+    def on_train_start(self) -> None:
+        """cr_module.py:133-138: forget what Lightning's sanity-check validation steps accumulated."""
+        self.__dict__.pop("_b200_val_loss_best", None)
+        if "val" in self.__dict__.get("_b200_step_scorers", {}):
+            self._b200_scorer("val").reset()
+        parent = getattr(super(), "on_train_start", None)
+        if callable(parent):
+            parent()
 
 
 class CRModuleB200(B200EvalMixin, _RefCRModule):
@@ -237,6 +266,17 @@ class CRModuleB200(B200EvalMixin, _RefCRModule):
             return _RefCRModule.on_test_epoch_end(self)
         return B200EvalMixin.on_test_epoch_end(self)
 
+    def validation_step(self, batch: Dict[str, Any], batch_idx: int) -> None:
+        if not self._b200_enabled:
+            return _RefCRModule.validation_step(self, batch, batch_idx)
+        with torch.no_grad():
+            return B200EvalMixin.validation_step(self, batch, batch_idx)
+
+    def on_validation_epoch_end(self) -> None:
+        if not self._b200_enabled:
+            return _RefCRModule.on_validation_epoch_end(self)
+        return B200EvalMixin.on_validation_epoch_end(self)
+
 
 class EnsembleModuleB200(B200EvalMixin, _RefEnsembleModule):
     """EnsembleModule (CR + category / sentiment A-Modules, z-score, aspect weights) with the B200 test
@@ -252,6 +292,12 @@ class EnsembleModuleB200(B200EvalMixin, _RefEnsembleModule):
         if self.hparams.sent_weight != 0:
             encs.append(self.a_module_sent.news_encoder)
         return encs
+
+    def validation_step(self, batch: Dict[str, Any], batch_idx: int) -> None:  # ensemble_module.py:199-200: the ensemble is never validated
+        pass
+
+    def on_validation_epoch_end(self) -> None:
+        pass
 
     def _b200_weights(self) -> Optional[List[float]]:
         w = [1.0]

@@ -140,6 +140,20 @@ def test_cr_step_mode_early_fusion_and_loss(golden_dir, name):
     for k in ("auc", "mrr", "ndcg@5", "ndcg@10"):
         assert abs(model.logged["test/" + k] - float(z["test_" + k])) <= 1e-6, k
     assert abs(model.logged["test/loss"] - float(z["test_loss"])) <= 1e-5 * abs(float(z["test_loss"]))
+    # the validation path (cr_module.py:214-251) logs the same numbers under val/ plus the best val/loss so far
+    for epoch, n_steps in enumerate((2, None)):  # a short first "epoch", then the full one
+        for i, lo in enumerate(range(0, bhv.n_impressions, 8)):
+            if n_steps is not None and i >= n_steps:
+                break
+            model.validation_step(mo.step_batch(bhv, lo, min(lo + 8, bhv.n_impressions)), i)
+        model.on_validation_epoch_end()
+        if epoch == 0:
+            first = model.logged["val/loss"]
+            assert abs(first - float(np.mean(z["step_losses"][:2]))) <= 1e-5 * abs(first)
+    for k in ("auc", "mrr", "ndcg@5", "ndcg@10"):
+        assert abs(model.logged["val/" + k] - float(z["test_" + k])) <= 1e-6, k
+    assert abs(model.logged["val/loss"] - float(z["test_loss"])) <= 1e-5 * abs(float(z["test_loss"]))
+    assert model.logged["val/loss_best"] == min(first, model.logged["val/loss"])
 
 
 @pytest.mark.gpu
