@@ -484,7 +484,7 @@ def main() -> None:
     ap.add_argument("--early-fusion", action="store_true", help="CR module with late_fusion=False: additive-attention pooling from cached per-news logits")
     ap.add_argument("--loss", default=None, choices=["ce", "supcon"], help="also compute the reference's test/loss on device")
     ap.add_argument("--uniform-ids", action="store_true", help="draw ids uniformly over the catalogue (no L2-friendly head)")
-    ap.add_argument("--cpu-sample", type=int, default=8192)
+    ap.add_argument("--cpu-sample", type=int, default=24576, help="impressions of the workload the CPU baseline is timed on (~12 s on 16 cores)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--mode", default="eval", choices=["eval", "retrieval"], help="retrieval: BASELINE.json configs[4] (tcgen05 GEMM + fused top-100)")
     ap.add_argument("--users", type=int, default=37888, help="retrieval mode: users per step (37 888 = 2 full waves of 148 CTAs x 128 rows)")
