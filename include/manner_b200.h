@@ -192,6 +192,41 @@ MB200_API int mb200_attention_logits(const void* table, int dtype, int dim, int6
 MB200_API int mb200_step_loss(const float* loss_per_impression, int64_t n_impressions, int step, int loss_kind, double* out, void* stream);
 
 /*
+ * Ranking metrics on scores that already exist: the seam of torchmetrics' `update(preds, target, indexes)` / `compute()` that
+ * every module of the reference -- CRModule, EnsembleModule and the nine baseline recommenders -- ends its epoch with
+ * (cr_module.py:266-274, ensemble_module.py:214-256, nrms_plm_module.py:275-313), and of the in-repo Diversity /
+ * Personalization (metrics/diversity.py, metrics/personalization.py, metrics/base.py:62-129).  Same ranking rule, same
+ * per-impression arithmetic and the same `sums` layout as mb200_score_eval, without the gather: `preds` is the flat [sum C]
+ * prediction vector with every impression's candidates contiguous (`cand_offsets` = prefix sums of `cand_news_size`).
+ * Aspect metrics take per-ROW labels as the reference's metric objects do (`target_categories`, `hist_categories`, ...).
+ * The pooled AUROC of the same vector is mb200_pooled_auc.
+ */
+typedef struct mb200_metrics_desc {
+  uint32_t struct_size; /* = sizeof(mb200_metrics_desc) */
+  int32_t k0, k1;       /* 1..MB200_MAX_K */
+  int32_t max_cand;     /* upper bound on candidates per impression */
+  int64_t n_impressions;
+  const float* preds;          /* [sum C] */
+  const uint8_t* labels;       /* [sum C] 0 / 1 */
+  const int32_t* cand_offsets; /* [n_impressions + 1] */
+  /* optional: all five or none */
+  const int32_t* cand_category;  /* [sum C] in [0, num_categ_classes) */
+  const int32_t* cand_sentiment; /* [sum C] */
+  const int32_t* hist_offsets;   /* [n_impressions + 1] */
+  const int32_t* hist_category;  /* [sum H] */
+  const int32_t* hist_sentiment; /* [sum H] */
+  int32_t num_categ_classes, num_sent_classes;
+  float* per_impression; /* optional [n_impressions, MB200_NUM_METRICS] */
+  double* sums;          /* [MB200_NUM_METRICS] */
+  int32_t* flags;        /* optional; the caller zeroes it */
+  void* workspace;       /* >= mb200_metrics_workspace_bytes(desc), 256-byte aligned */
+  size_t workspace_bytes;
+} mb200_metrics_desc;
+
+MB200_API size_t mb200_metrics_workspace_bytes(const mb200_metrics_desc* desc);
+MB200_API int mb200_rank_metrics(const mb200_metrics_desc* desc, void* stream);
+
+/*
  * Pooled AUROC exactly as torchmetrics 0.11.4 `AUROC(task="binary")` defines it (cr_module.py:81,273;
  * SURVEY a12/A6): all candidate rows of the epoch in one pool, fp32 sigmoid applied iff some pred is
  * outside [0,1], ties get half credit.  Evaluated as the exact rank statistic

@@ -76,6 +76,33 @@ class EvalDesc(Structure):
     ]
 
 
+class MetricsDesc(Structure):
+    """mb200_metrics_desc, field for field."""
+
+    _fields_ = [
+        ("struct_size", c_uint32),
+        ("k0", c_int32),
+        ("k1", c_int32),
+        ("max_cand", c_int32),
+        ("n_impressions", c_int64),
+        ("preds", c_void_p),
+        ("labels", c_void_p),
+        ("cand_offsets", c_void_p),
+        ("cand_category", c_void_p),
+        ("cand_sentiment", c_void_p),
+        ("hist_offsets", c_void_p),
+        ("hist_category", c_void_p),
+        ("hist_sentiment", c_void_p),
+        ("num_categ_classes", c_int32),
+        ("num_sent_classes", c_int32),
+        ("per_impression", c_void_p),
+        ("sums", c_void_p),
+        ("flags", c_void_p),
+        ("workspace", c_void_p),
+        ("workspace_bytes", c_size_t),
+    ]
+
+
 class RetrievalDesc(Structure):
     """mb200_retrieval_desc, field for field."""
 
@@ -116,6 +143,8 @@ SIGNATURES = {
     "mb200_merge_topk": (c_int, [c_void_p, c_void_p, c_int, c_int64, c_int, c_void_p, c_void_p, c_void_p]),
     "mb200_attention_logits": (c_int, [c_void_p, c_int, c_int, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
     "mb200_step_loss": (c_int, [c_void_p, c_int64, c_int, c_int, c_void_p, c_void_p]),
+    "mb200_metrics_workspace_bytes": (c_size_t, [POINTER(MetricsDesc)]),
+    "mb200_rank_metrics": (c_int, [POINTER(MetricsDesc), c_void_p]),
     "mb200_dcg_discount": (c_float, [c_int]),
     "mb200_launch_count": (c_int64, []),
     "mb200_library_launch_count": (c_int64, []),

@@ -59,6 +59,8 @@ int pool_users(const void*, int, int, long long, long long, const int32_t*, cons
 int merge_topk(const float*, const long long*, int, long long, int, float*, long long*, cudaStream_t);
 int attention_logits(const void*, int, int, long long, long long, const float*, const float*, const float*, int, float*, cudaStream_t);
 int step_loss(const float*, long long, int, int, double*, cudaStream_t);
+size_t metrics_workspace_bytes(const mb200_metrics_desc* d);
+int rank_metrics(const mb200_metrics_desc* d, cudaStream_t stream);
 
 }  // namespace mb200
 
@@ -151,6 +153,10 @@ int mb200_attention_logits(const void* table, int dtype, int dim, int64_t row_st
 int mb200_step_loss(const float* loss_per_impression, int64_t n_impressions, int step, int loss_kind, double* out, void* stream) {
   return step_loss(loss_per_impression, n_impressions, step, loss_kind, out, static_cast<cudaStream_t>(stream));
 }
+
+size_t mb200_metrics_workspace_bytes(const mb200_metrics_desc* desc) { return metrics_workspace_bytes(desc); }
+
+int mb200_rank_metrics(const mb200_metrics_desc* desc, void* stream) { return rank_metrics(desc, static_cast<cudaStream_t>(stream)); }
 
 float mb200_dcg_discount(int rank) { return host_dcg_discount(rank); }
 int64_t mb200_launch_count(void) { return g_launches.load(); }

@@ -38,6 +38,9 @@ struct EvalParams {
   const float* weights;
   const int32_t* news_category;
   const int32_t* news_sentiment;
+  const int32_t* flat_cand_aspect[2];  // rank_metrics: per-row category / sentiment labels instead of per-news tables
+  const int32_t* flat_hist_aspect[2];
+  const float* scores_in;  // rank_metrics: flat predictions
   const float* attn_logits[MB200_MAX_MODULES];  // [n_news + 1] per module, or null (late fusion)
   const int32_t* hist_pad;
   const int32_t* cand_pad;
@@ -541,7 +544,8 @@ __device__ __noinline__ int rank_and_metrics(const EvalParams& p, const WarpSmem
   const int W = p.n_weightings;
   const int n_active = __popc(p.active_mask);
   const int kmax = max(p.k0, p.k1);
-  const bool aspects = p.news_category != nullptr;
+  const bool flat = p.flat_cand_aspect[0] != nullptr;  // labels per row (mb200_rank_metrics) instead of per news id
+  const bool aspects = p.news_category != nullptr || flat;
   float* sc = sm.sc;
   float* comb = sm.comb;
   const uint8_t* lab = sm.lab;
@@ -566,9 +570,14 @@ __device__ __noinline__ int rank_and_metrics(const EvalParams& p, const WarpSmem
     int cat_sum = 0, sent_sum = 0;
 #pragma unroll 1
     for (int j = lane; j < C; j += 32) {
-      int id = p.cand_ids[c0 + j];
-      if ((unsigned long long)(long long)id >= (unsigned long long)p.n_news) id = 0;
-      int a = p.news_category[id], b = p.news_sentiment[id];
+      int a, b;
+      if (flat) {
+        a = p.flat_cand_aspect[0][c0 + j], b = p.flat_cand_aspect[1][c0 + j];
+      } else {
+        int id = p.cand_ids[c0 + j];
+        if ((unsigned long long)(long long)id >= (unsigned long long)p.n_news) id = 0;
+        a = p.news_category[id], b = p.news_sentiment[id];
+      }
       if ((unsigned)a >= (unsigned)p.num_categ) a = 0, warp_flags |= MB200_FLAG_BAD_ASPECT;
       if ((unsigned)b >= (unsigned)p.num_sent) b = 0, warp_flags |= MB200_FLAG_BAD_ASPECT;
       sm.ccat[j] = (uint8_t)a, sm.csent[j] = (uint8_t)b;
@@ -576,9 +585,14 @@ __device__ __noinline__ int rank_and_metrics(const EvalParams& p, const WarpSmem
     }
 #pragma unroll 1
     for (int h = lane; h < H; h += 32) {
-      int id = p.hist_ids[h0 + h];
-      if ((unsigned long long)(long long)id >= (unsigned long long)p.n_news) id = 0;
-      int a = p.news_category[id], b = p.news_sentiment[id];
+      int a, b;
+      if (flat) {
+        a = p.flat_hist_aspect[0][h0 + h], b = p.flat_hist_aspect[1][h0 + h];
+      } else {
+        int id = p.hist_ids[h0 + h];
+        if ((unsigned long long)(long long)id >= (unsigned long long)p.n_news) id = 0;
+        a = p.news_category[id], b = p.news_sentiment[id];
+      }
       if ((unsigned)a >= (unsigned)p.num_categ) a = 0, warp_flags |= MB200_FLAG_BAD_ASPECT;
       if ((unsigned)b >= (unsigned)p.num_sent) b = 0, warp_flags |= MB200_FLAG_BAD_ASPECT;
       atomicAdd(&sm.hist_cat[a], 1);
@@ -797,6 +811,53 @@ __global__ void __launch_bounds__(kThreads, MINB) score_eval_kernel(const __grid
 
   __syncwarp();
   for (int t = lane; t < W * MB200_NUM_METRICS; t += 32) p.partials[(size_t)gw * W * MB200_NUM_METRICS + t] = sm.acc[t];
+  warp_flags = __reduce_or_sync(kFull, warp_flags);
+  if (lane == 0 && warp_flags && p.flags) atomicOr(p.flags, warp_flags);
+}
+
+
+// mb200_rank_metrics: the ranking / metrics half of the fused kernel on predictions that already exist (one warp per
+// impression, same shared-memory layout, rank_and_metrics unchanged).
+__global__ void __launch_bounds__(kThreads) rank_metrics_kernel(const __grid_constant__ EvalParams p) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const int gw = blockIdx.x * kWarpsPerCta + warp;
+  const int total_warps = gridDim.x * kWarpsPerCta;
+  unsigned char* base = smem + (size_t)warp * p.smem_per_warp;
+  WarpSmem sm;
+  sm.acc = reinterpret_cast<double*>(base);
+  sm.sc = reinterpret_cast<float*>(base + p.acc_bytes);
+  sm.comb = sm.sc + p.cpad;
+  sm.lab = reinterpret_cast<uint8_t*>(sm.comb + p.cpad);
+  sm.ccat = sm.lab + p.cpad;
+  sm.csent = sm.ccat + p.cpad;
+  sm.hist_cat = reinterpret_cast<int*>(sm.csent + p.cpad);
+  sm.hist_sent = sm.hist_cat + MB200_MAX_CLASSES;
+  sm.top_cat = reinterpret_cast<uint8_t*>(sm.hist_sent + MB200_MAX_CLASSES);
+  sm.top_sent = sm.top_cat + 32;
+  for (int t = lane; t < MB200_NUM_METRICS; t += 32) sm.acc[t] = 0.0;
+  __syncwarp();
+  int warp_flags = 0;
+  for (int chunk = gw; chunk < p.n_chunks; chunk += total_warps) {
+    for (int i = p.bounds[chunk]; i < p.bounds[chunk + 1]; ++i) {
+      const int c0 = p.cand_offsets[i], C = p.cand_offsets[i + 1] - c0;
+      const int h0 = p.flat_hist_aspect[0] ? p.hist_offsets[i] : 0;
+      const int H = p.flat_hist_aspect[0] ? p.hist_offsets[i + 1] - h0 : 0;
+      if (C > p.max_cand || C <= 0 || H < 0) {
+        warp_flags |= MB200_FLAG_CAND_OVERFLOW;
+        if (p.per_impr)
+          for (int t = lane; t < MB200_NUM_METRICS; t += 32) p.per_impr[(size_t)i * MB200_NUM_METRICS + t] = 0.f;
+        continue;
+      }
+      __syncwarp();
+      for (int j = lane; j < C; j += 32) sm.sc[j] = p.scores_in[c0 + j], sm.lab[j] = p.labels[c0 + j];
+      __syncwarp();
+      warp_flags |= rank_and_metrics(p, sm, i, h0, H, c0, C);
+    }
+  }
+  __syncwarp();
+  for (int t = lane; t < MB200_NUM_METRICS; t += 32) p.partials[(size_t)gw * MB200_NUM_METRICS + t] = sm.acc[t];
   warp_flags = __reduce_or_sync(kFull, warp_flags);
   if (lane == 0 && warp_flags && p.flags) atomicOr(p.flags, warp_flags);
 }
@@ -1071,6 +1132,67 @@ int score_eval(const mb200_eval_desc* d, cudaStream_t stream) {
                                                               d->pack_payload);
   st = cuda_status(cudaGetLastError(), "reduce_partials_kernel");
   if (st != MB200_OK) return st;
+  note_launch(3);
+  return MB200_OK;
+}
+
+// ---- mb200_rank_metrics ---------------------------------------------------------------------------------
+static int metrics_plan(const mb200_metrics_desc* d, int sms, LaunchPlan* plan) {
+  if (d == nullptr || d->struct_size != sizeof(mb200_metrics_desc)) return MB200_ERR_INVALID_ARG;
+  if (d->n_impressions < 0 || d->n_impressions > 0x7ffffff0ll || d->max_cand < 1 || !d->cand_offsets || !d->sums) return MB200_ERR_INVALID_ARG;
+  if (d->n_impressions > 0 && (!d->preds || !d->labels)) return MB200_ERR_INVALID_ARG;
+  if (d->k0 < 1 || d->k0 > MB200_MAX_K || d->k1 < 1 || d->k1 > MB200_MAX_K) return MB200_ERR_INVALID_ARG;
+  const int n_aspect = (d->cand_category != nullptr) + (d->cand_sentiment != nullptr) + (d->hist_offsets != nullptr) + (d->hist_category != nullptr) +
+                       (d->hist_sentiment != nullptr);
+  if (n_aspect != 0 && n_aspect != 5) return MB200_ERR_INVALID_ARG;
+  if (n_aspect == 5 && (d->num_categ_classes < 1 || d->num_categ_classes > MB200_MAX_CLASSES || d->num_sent_classes < 1 ||
+                        d->num_sent_classes > MB200_MAX_CLASSES))
+    return MB200_ERR_INVALID_ARG;
+  mb200_eval_desc e{};  // the plan only looks at these fields
+  e.active_modules_mask = 1, e.max_cand = d->max_cand, e.n_weightings = 1, e.n_impressions = d->n_impressions;
+  return make_plan(&e, sms, 4, plan);
+}
+
+size_t metrics_workspace_bytes(const mb200_metrics_desc* d) {
+  LaunchPlan plan;
+  if (metrics_plan(d, 160, &plan) != MB200_OK) return 0;
+  return plan.bounds_bytes + plan.partials_bytes + 256;
+}
+
+int rank_metrics(const mb200_metrics_desc* d, cudaStream_t stream) {
+  LaunchPlan plan;
+  int st = metrics_plan(d, 160, &plan);
+  if (st != MB200_OK) return st;
+  int device = 0;
+  if ((st = use_device_of(d->sums, &device)) != MB200_OK) return st;
+  int sms = 0;
+  if ((st = sm_count_of(device, &sms)) != MB200_OK) return st;
+  if (sms > 160) return MB200_ERR_UNSUPPORTED;
+  if ((st = metrics_plan(d, sms, &plan)) != MB200_OK) return st;
+  if (plan.smem_per_cta > 48 * 1024) {
+    st = cuda_status(cudaFuncSetAttribute(rank_metrics_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem_per_cta), "cudaFuncSetAttribute");
+    if (st != MB200_OK) return st;
+  }
+  if (d->workspace == nullptr || ((uintptr_t)d->workspace & 255) || d->workspace_bytes < plan.bounds_bytes + plan.partials_bytes) return MB200_ERR_WORKSPACE;
+  EvalParams p{};
+  p.cand_offsets = d->cand_offsets, p.hist_offsets = d->hist_offsets ? d->hist_offsets : d->cand_offsets;
+  p.labels = d->labels, p.scores_in = d->preds;
+  p.flat_cand_aspect[0] = d->cand_category, p.flat_cand_aspect[1] = d->cand_sentiment;
+  p.flat_hist_aspect[0] = d->hist_category, p.flat_hist_aspect[1] = d->hist_sentiment;
+  p.per_impr = d->per_impression, p.flags = d->flags;
+  p.bounds = reinterpret_cast<int32_t*>(d->workspace);
+  p.partials = reinterpret_cast<double*>(reinterpret_cast<unsigned char*>(d->workspace) + plan.bounds_bytes);
+  p.n_impr = (int)d->n_impressions, p.n_modules = 1, p.active_mask = 1, p.n_weightings = 1;
+  p.k0 = d->k0, p.k1 = d->k1, p.cpad = plan.cpad, p.max_cand = d->max_cand, p.n_chunks = plan.n_chunks;
+  p.num_categ = d->num_categ_classes, p.num_sent = d->num_sent_classes;
+  p.smem_per_warp = plan.smem_per_warp, p.acc_bytes = plan.acc_bytes;
+  partition_kernel<<<(plan.n_chunks + 1 + 255) / 256, 256, 0, stream>>>(p.hist_offsets, d->cand_offsets, p.n_impr, plan.n_chunks,
+                                                                       reinterpret_cast<int32_t*>(d->workspace));
+  if ((st = cuda_status(cudaGetLastError(), "partition_kernel")) != MB200_OK) return st;
+  rank_metrics_kernel<<<plan.grid, kThreads, plan.smem_per_cta, stream>>>(p);
+  if ((st = cuda_status(cudaGetLastError(), "rank_metrics_kernel")) != MB200_OK) return st;
+  reduce_partials_kernel<<<1, 256, 0, stream>>>(p.partials, plan.total_warps, 1, d->sums, d->flags, p.n_impr, 0);
+  if ((st = cuda_status(cudaGetLastError(), "reduce_partials_kernel")) != MB200_OK) return st;
   note_launch(3);
   return MB200_OK;
 }

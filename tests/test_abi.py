@@ -141,3 +141,28 @@ def test_retrieval_refuses_cpu_tensors():
     assert rt.catalog_shard_bounds(1000, 3) == [(0, 512), (512, 768), (768, 1000)]
     assert rt.catalog_shard_bounds(100, 4) == [(0, 100), (100, 100), (100, 100), (100, 100)]
     assert rt.catalog_shard_bounds(10_000_000, 8)[-1][1] == 10_000_000
+
+
+def test_metrics_desc_layout_and_validation_without_a_gpu(tmp_path):
+    src = tmp_path / "msz.c"
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "manner_b200.h"\nint main(){printf("%zu %zu %zu %zu %zu",'
+                   "sizeof(mb200_metrics_desc),offsetof(mb200_metrics_desc,preds),offsetof(mb200_metrics_desc,hist_offsets),"
+                   "offsetof(mb200_metrics_desc,num_categ_classes),offsetof(mb200_metrics_desc,workspace_bytes));return 0;}\n")
+    exe = tmp_path / "msz"
+    subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    got = [int(x) for x in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()]
+    M = nat.MetricsDesc
+    assert got == [ctypes.sizeof(M), M.preds.offset, M.hist_offsets.offset, M.num_categ_classes.offset, M.workspace_bytes.offset]
+    lib = nat.lib()
+    d = M()
+    assert lib.mb200_metrics_workspace_bytes(ctypes.byref(d)) == 0 and lib.mb200_rank_metrics(ctypes.byref(d), None) == nat.ERR_INVALID_ARG
+    assert lib.mb200_rank_metrics(None, None) == nat.ERR_INVALID_ARG
+    from manner_b200 import metrics
+
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        metrics.rank_metrics(torch.rand(4), torch.zeros(4, dtype=torch.uint8), torch.tensor([0, 4], dtype=torch.int32), 4)
+    # the host-side grouping mirrors torchmetrics: sort by index, group sizes in ascending index order
+    off, perm, mx = metrics._offsets_from_indexes(torch.tensor([5, 5, 2, 9, 2, 2]))
+    assert off.tolist() == [0, 3, 5, 6] and perm.tolist() == [2, 4, 5, 0, 1, 3] and mx == 3
+    off, perm, mx = metrics._offsets_from_indexes(torch.tensor([0, 0, 1, 3, 3]))
+    assert off.tolist() == [0, 2, 3, 5] and perm is None and mx == 2
