@@ -66,6 +66,7 @@ struct EvalParams {
   int num_categ, num_sent;
   int smem_per_warp;  // bytes
   int acc_bytes;      // bytes of the per-warp fp64 accumulators (16-byte multiple)
+  int acc_stride;     // doubles per weighting in the accumulators: MB200_NUM_METRICS, or kSweepSlots in the aspect-weight sweep mode
   int loss_kind;
   float loss_temperature;
 };
@@ -382,6 +383,8 @@ struct WarpSmem {
 };
 
 constexpr int kSweepMinWeightings = 16;  // from here on lanes own weightings instead of candidates
+constexpr int kSweepSlots = MB200_M_GAUC_VALID + 1;  // metric slots the sweep mode fills: its accumulators are packed to these,
+                                                      // which keeps 121 weightings at 4 resident CTAs per SM instead of 2
 constexpr int kSweepPos = 2;             // positives ranked per pass over the candidates (91 % of MIND impressions have <= 2)
 
 // s = w0 * z0 ; s += w_m * z_m for m >= 1 when w_m != 0  (ensemble_module.py:97-107): separate multiply
@@ -485,7 +488,7 @@ __device__ __noinline__ int sweep_weightings(const EvalParams& p, const WarpSmem
     const float nd1 = ndcg_at(hit_mask, n_pos, C, p.k1);
     const bool gvalid = n_pos > 0 && n_pos < C;
     const float g = gvalid ? (float)((double)gauc2 / (2.0 * (double)n_pos * (double)(C - n_pos))) : 0.f;
-    double* a = sm.acc + (size_t)w * MB200_NUM_METRICS;
+    double* a = sm.acc + (size_t)w * p.acc_stride;
     a[MB200_M_MRR] += (double)mrr, a[MB200_M_NDCG_K0] += (double)nd0, a[MB200_M_NDCG_K1] += (double)nd1;
     a[MB200_M_GAUC] += (double)g, a[MB200_M_GAUC_VALID] += gvalid ? 1.0 : 0.0;
     if (p.per_impr) {
@@ -739,7 +742,7 @@ __device__ __noinline__ int rank_and_metrics(const EvalParams& p, const WarpSmem
       __syncwarp();
     }
     if (lane < MB200_NUM_METRICS) {
-      sm.acc[w * MB200_NUM_METRICS + lane] += (double)mine;
+      sm.acc[w * p.acc_stride + lane] += (double)mine;
       if (p.per_impr) p.per_impr[((size_t)w * p.n_impr + i) * MB200_NUM_METRICS + lane] = mine;
     }
     __syncwarp();
@@ -770,7 +773,7 @@ __global__ void __launch_bounds__(kThreads, MINB) score_eval_kernel(const __grid
   sm.top_cat = reinterpret_cast<uint8_t*>(sm.hist_sent + MB200_MAX_CLASSES);
   sm.top_sent = sm.top_cat + 32;
 
-  for (int t = lane; t < W * MB200_NUM_METRICS; t += 32) sm.acc[t] = 0.0;
+  for (int t = lane; t < W * p.acc_stride; t += 32) sm.acc[t] = 0.0;
   __syncwarp();
 
   int warp_flags = 0;
@@ -810,11 +813,13 @@ __global__ void __launch_bounds__(kThreads, MINB) score_eval_kernel(const __grid
   }
 
   __syncwarp();
-  for (int t = lane; t < W * MB200_NUM_METRICS; t += 32) p.partials[(size_t)gw * W * MB200_NUM_METRICS + t] = sm.acc[t];
+  for (int t = lane; t < W * MB200_NUM_METRICS; t += 32) {
+    const int w = t / MB200_NUM_METRICS, k = t % MB200_NUM_METRICS;
+    p.partials[(size_t)gw * W * MB200_NUM_METRICS + t] = k < p.acc_stride ? sm.acc[w * p.acc_stride + k] : 0.0;
+  }
   warp_flags = __reduce_or_sync(kFull, warp_flags);
   if (lane == 0 && warp_flags && p.flags) atomicOr(p.flags, warp_flags);
 }
-
 
 // mb200_rank_metrics: the ranking / metrics half of the fused kernel on predictions that already exist (one warp per
 // impression, same shared-memory layout, rank_and_metrics unchanged).
@@ -927,6 +932,7 @@ struct LaunchPlan {
   int n_chunks = 0;
   int cpad = 0;
   int acc_bytes = 0;
+  int acc_stride = MB200_NUM_METRICS;
   int smem_per_warp = 0;
   size_t smem_per_cta = 0;
   size_t bounds_bytes = 0, partials_bytes = 0;
@@ -937,7 +943,10 @@ static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 static int make_plan(const mb200_eval_desc* d, int sm_count, int ctas, LaunchPlan* plan) {
   const int n_active = __builtin_popcount((unsigned)d->active_modules_mask);
   plan->cpad = (int)align_up((size_t)(d->max_cand > 0 ? d->max_cand : 1), 32);
-  plan->acc_bytes = (int)align_up((size_t)d->n_weightings * MB200_NUM_METRICS * sizeof(double), 16);
+  // the aspect-weight sweep (lane per weighting: rank_and_metrics -> sweep_weightings) fills only the first kSweepSlots slots
+  const bool sweep = d->weights != nullptr && d->n_weightings >= kSweepMinWeightings && d->news_category == nullptr;
+  plan->acc_stride = sweep ? kSweepSlots : MB200_NUM_METRICS;
+  plan->acc_bytes = (int)align_up((size_t)d->n_weightings * plan->acc_stride * sizeof(double), 16);
   size_t per_warp = (size_t)plan->acc_bytes + (size_t)(n_active + 1) * plan->cpad * sizeof(float) + 3 * (size_t)plan->cpad +
                     2 * MB200_MAX_CLASSES * sizeof(int) + 64;
   per_warp = align_up(per_warp, 16);
@@ -1112,7 +1121,7 @@ int score_eval(const mb200_eval_desc* d, cudaStream_t stream) {
   p.zscore = d->zscore, p.n_weightings = d->n_weightings, p.scores_weighting = d->scores_weighting;
   p.k0 = d->k0, p.k1 = d->k1, p.cpad = plan.cpad, p.max_cand = d->max_cand, p.n_chunks = plan.n_chunks;
   p.num_categ = d->num_categ_classes, p.num_sent = d->num_sent_classes;
-  p.smem_per_warp = plan.smem_per_warp, p.acc_bytes = plan.acc_bytes;
+  p.smem_per_warp = plan.smem_per_warp, p.acc_bytes = plan.acc_bytes, p.acc_stride = plan.acc_stride;
   for (int m = 0; m < MB200_MAX_MODULES; ++m) p.attn_logits[m] = (m < d->n_modules) ? d->attn_logits[m] : nullptr;
   p.hist_pad = d->hist_pad, p.cand_pad = d->cand_pad, p.loss_per_impr = d->loss_per_impression;
   p.loss_kind = d->loss_kind, p.loss_temperature = d->loss_temperature;
@@ -1185,7 +1194,7 @@ int rank_metrics(const mb200_metrics_desc* d, cudaStream_t stream) {
   p.n_impr = (int)d->n_impressions, p.n_modules = 1, p.active_mask = 1, p.n_weightings = 1;
   p.k0 = d->k0, p.k1 = d->k1, p.cpad = plan.cpad, p.max_cand = d->max_cand, p.n_chunks = plan.n_chunks;
   p.num_categ = d->num_categ_classes, p.num_sent = d->num_sent_classes;
-  p.smem_per_warp = plan.smem_per_warp, p.acc_bytes = plan.acc_bytes;
+  p.smem_per_warp = plan.smem_per_warp, p.acc_bytes = plan.acc_bytes, p.acc_stride = plan.acc_stride;
   partition_kernel<<<(plan.n_chunks + 1 + 255) / 256, 256, 0, stream>>>(p.hist_offsets, d->cand_offsets, p.n_impr, plan.n_chunks,
                                                                        reinterpret_cast<int32_t*>(d->workspace));
   if ((st = cuda_status(cudaGetLastError(), "partition_kernel")) != MB200_OK) return st;
