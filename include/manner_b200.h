@@ -138,7 +138,7 @@ typedef struct mb200_eval_desc {
   /* outputs (any may be NULL except sums) */
   float* scores;            /* [sum C] combined scores of weighting `scores_weighting` == the reference's flat `preds` */
   int32_t scores_weighting;
-  int32_t pack_payload;     /* != 0: `sums` has MB200_PAYLOAD_TAIL more doubles behind the [W, 13] block:
+  int32_t pack_payload;     /* != 0: `sums` has MB200_PAYLOAD_TAIL more doubles behind the [W, MB200_NUM_METRICS] block:
                                n_impressions, then one 0/1 double per MB200_FLAG_* bit (1, 2, 4, 8) -- everything
                                a multi-GPU caller sum-reduces, in one buffer, with no host-side packing */
   float* per_impression;    /* [W, n_impressions, MB200_NUM_METRICS] */

@@ -4,7 +4,7 @@ The reference is single-device (every trainer config has ``devices: 1``, configs
 so there is no reference behaviour to match beyond "same numbers as one GPU".  Impressions are
 independent, hence no data-path collective.  What does cross NVLink, once per evaluation:
 
-* one all-reduce (sum) of the fp64 metric sums + impression count + flag bits  -- (W*13 + 5) doubles;
+* one all-reduce (sum) of the fp64 metric sums + impression count + flag bits  -- (W*NUM_METRICS + 5) doubles;
 * pooled AUROC only (it is not a sum of per-impression terms): an all-gather of the POSITIVE keys
   (about 4 % of the rows; the negatives never move) and an all-reduce of three int64
   (rank statistic, positives, negatives).
@@ -35,7 +35,7 @@ def shard_for_rank(bhv: Behaviours, rank: int, world_size: int) -> Behaviours:
 
 
 def pack_metric_payload(sums: Tensor, flags: Tensor, n_impressions: int) -> Tensor:
-    """[W, 13] sums, the impression count and the flag word's bits as one fp64 vector (all additive)."""
+    """[W, NUM_METRICS] sums, the impression count and the flag word's bits as one fp64 vector (all additive)."""
     bits = ((flags.to(torch.int64).reshape(1) >> torch.arange(N_FLAG_BITS, device=flags.device)) & 1).to(torch.float64)
     count = torch.full((1,), float(n_impressions), dtype=torch.float64, device=sums.device)
     return torch.cat([sums.reshape(-1), count, bits])

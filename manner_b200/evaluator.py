@@ -101,7 +101,7 @@ class EvalResult:
 class PendingEval:
     """Device-side results of an enqueued pass (no host synchronisation yet)."""
 
-    sums: Tensor  # [W, 13], or the packed all-reduced payload [W*13 + 5] when distributed
+    sums: Tensor  # [W, NUM_METRICS], or the packed all-reduced payload [W*NUM_METRICS + 5] when distributed
     flags: Tensor
     n_weightings: int
     n_impressions: int  # of this rank
@@ -245,7 +245,7 @@ class ScoreEvaluator:
         n_w = 1 if w_dev is None else w_dev.shape[0]
         auc_stats: Optional[Tensor] = None
         if distributed:
-            # `sums` is the packed payload [W*13 sums, impression count, 4 flag bits]: one NCCL all-reduce
+            # `sums` is the packed payload [W*NUM_METRICS sums, impression count, 4 flag bits]: one NCCL all-reduce
             torch.distributed.all_reduce(sums, op=torch.distributed.ReduceOp.SUM, group=group)
             if pooled_auc:
                 outside = n_w * nat.NUM_METRICS + 1 + 2  # bit index of MB200_FLAG_OUTSIDE_UNIT in the tail
