@@ -377,6 +377,8 @@ def run_retrieval_arm(args) -> None:
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     if args.retrieval_diag:
         ops.set_tuning(retrieval_diag=args.retrieval_diag)
+    if args.retrieval_pair is not None:
+        ops.set_tuning(retrieval_pair=args.retrieval_pair)
 
     def barrier() -> None:
         if distributed:
@@ -490,6 +492,7 @@ def main() -> None:
     ap.add_argument("--users", type=int, default=37888, help="retrieval mode: users per step (37 888 = 2 full waves of 148 CTAs x 128 rows)")
     ap.add_argument("--catalog-per-gpu", type=int, default=1_250_000, help="retrieval mode: catalogue rows per GPU (10 M over 8)")
     ap.add_argument("--exchange", default="all_gather", choices=["all_gather", "all_to_all"])
+    ap.add_argument("--retrieval-pair", type=int, default=None, help="retrieval kernel: 1 = CTA pairs (cta_group::2), 0 = one CTA per tile")
     ap.add_argument("--retrieval-diag", type=int, default=0, help="DIAGNOSTIC: 1/2 disable parts of the retrieval epilogue (results invalid)")
     ap.add_argument("--variant", type=int, default=None)
     ap.add_argument("--chunks-per-warp", type=int, default=None)

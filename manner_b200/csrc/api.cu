@@ -172,6 +172,7 @@ int mb200_set_tuning(int key, int value) {
     case 2: prev = tuning().ctas_per_sm, tuning().ctas_per_sm = value; break;
     case 3: prev = tuning().time_kernel, tuning().time_kernel = value; break;
     case 4: prev = tuning().retrieval_diag, tuning().retrieval_diag = value; break;
+    case 5: prev = tuning().retrieval_pair, tuning().retrieval_pair = value; break;
   }
   return prev;
 }

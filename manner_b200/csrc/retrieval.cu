@@ -23,8 +23,20 @@
 namespace mb200 {
 
 namespace rt {
-constexpr int BLOCK_M = 128, BLOCK_N = 256, BLOCK_K = 64, UMMA_K = 16, STAGES = 4;
-constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2, B_BYTES = BLOCK_N * BLOCK_K * 2, STAGE_BYTES = A_BYTES + B_BYTES;
+constexpr int BLOCK_M = 128, BLOCK_N = 256, BLOCK_K = 64, UMMA_K = 16;
+constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;
+// One CTA per tile (cta_group::1): B = 256 catalogue rows per stage, 4 stages of 48 KB.  CTA pair (cta_group::2, UMMA M = 256):
+// every CTA stages its own 128 users and HALF of the catalogue tile, 6 stages of 32 KB -- a third less L2 -> SM traffic and half
+// the shared-memory reads of B per flop.
+template <bool PAIR> struct Ring {
+  static constexpr int STAGES = PAIR ? 6 : 4;
+  static constexpr int B_ROWS = PAIR ? BLOCK_N / 2 : BLOCK_N;
+  static constexpr int B_BYTES = B_ROWS * BLOCK_K * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+};
+constexpr int RING_BYTES = 4 * (A_BYTES + BLOCK_N * BLOCK_K * 2);  // 192 KB either way
+static_assert(Ring<false>::STAGES * Ring<false>::STAGE_BYTES == RING_BYTES && Ring<true>::STAGES * Ring<true>::STAGE_BYTES == RING_BYTES, "ring size");
+constexpr int MAX_STAGES = 6;
 constexpr int CAP = 256;          // per-row candidate buffer entries (hard limit: a row is compacted before a chunk could overflow it)
 constexpr int SOFT_CAP = 160;     // soft limit (> MAX_K): from here on a row is compacted between tiles, one row per tile and warp
 constexpr int MAX_K = 128;        // top-k limit (k <= CAP / 2)
@@ -34,7 +46,7 @@ constexpr int THREADS = 64 + EPI_GROUPS * 128;  // warp 0: TMA producer, warp 1:
 constexpr int TMEM_COLS = 512;    // two 128 x 256 fp32 accumulators
 constexpr int SCRATCH_BYTES = 0;
 constexpr int SHARE_BYTES = EPI_GROUPS * BLOCK_M * 8;  // per (group, row): published admission threshold + list length
-constexpr int SMEM_BYTES = 1024 /*alignment slack*/ + STAGES * STAGE_BYTES + SHARE_BYTES + 256 /*barriers*/;
+constexpr int SMEM_BYTES = 1024 /*alignment slack*/ + RING_BYTES + SHARE_BYTES + 256 /*barriers*/;
 constexpr unsigned long long WAIT_LIMIT_NS = 2000ull * 1000 * 1000;
 constexpr uint32_t WAIT_HINT_NS = 20000;  // upper bound of one hardware-suspended try_wait
 }  // namespace rt
@@ -107,6 +119,33 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m
                : "memory");
 }
 
+// CTA-pair variants.  In a cluster the 32-bit shared-window address carries the CTA's rank within the pair in bit 24; clearing it
+// addresses the same offset in the leader CTA (rank 0) -- the convention of CUTLASS' SM100_TMA_2SM_LOAD (Sm100MmaPeerBitMask).
+constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;
+__device__ __forceinline__ void tma_load_2d_pair(void* smem_dst, const CUtensorMap* map, uint64_t* leader_bar, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+                   smem_u32(smem_dst)),
+               "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(leader_bar) & kPeerBitMask), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// arrive on the barrier at the same shared-memory offset in CTA `rank` of the cluster
+__device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t rank) {
+  asm volatile(
+      "{\n\t.reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t}" ::"r"(smem_u32(bar)),
+      "r"(rank)
+      : "memory");
+}
+
 // K-major operand tile in shared memory with 128-byte swizzle: rows of 64 bf16 (128 B), 8-row groups 1024 B
 // apart.  Descriptor: start >> 4, LBO = 1 (unused for swizzled K-major), SBO = 1024 >> 4, version 1 (sm_100),
 // layout SWIZZLE_128B.  Advancing by one UMMA_K (16 bf16 = 32 B) adds 2 to the start field.
@@ -124,6 +163,23 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64
       "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
       "l"(adesc), "l"(bdesc), "r"(kIdesc), "r"(accumulate)
       : "memory");
+}
+// CTA pair: one instruction drives both SMs' tensor cores (M = 256: 128 rows of A and 128 of the 256 rows of B from each CTA's
+// shared memory, 128 x 256 accumulator rows into each CTA's TMEM); issued by the leader CTA only.
+constexpr uint32_t kIdescPair = (1u << 4) | (1u << 7) | (1u << 10) | ((rt::BLOCK_N >> 3) << 17) | (((2 * rt::BLOCK_M) >> 4) << 24);
+__device__ __forceinline__ void umma_f16_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(kIdescPair), "r"(accumulate)
+      : "memory");
+}
+// arrives on the barrier at this offset in BOTH CTAs of the pair once the MMAs issued so far have completed
+__device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
+               "h"((unsigned short)3)
+               : "memory");
 }
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -293,17 +349,24 @@ __device__ void write_sorted_row(const float* cs, const int* ci, int n, int k, f
   }
 }
 
+template <bool PAIR>
 __global__ void __launch_bounds__(rt::THREADS, 1)
 retrieve_topk_kernel(const __grid_constant__ CUtensorMap tmap_users, const __grid_constant__ CUtensorMap tmap_catalog, const RetrievalParams p) {
   using namespace rt;
+  constexpr int STAGES = Ring<PAIR>::STAGES, STAGE_BYTES = Ring<PAIR>::STAGE_BYTES;
+  // tiles of this CTA: unit u = blockIdx.x / UNIT + j * (gridDim.x / UNIT); a unit is one user tile, or a pair of them for a CTA pair
+  constexpr int UNIT = PAIR ? 2 : 1;
+  const uint32_t rank = PAIR ? cluster_ctarank() : 0u;  // 0 = leader of the pair
+  const int unit0 = (int)blockIdx.x / UNIT, unit_step = (int)gridDim.x / UNIT;
+  const int n_units = (p.m_tiles + UNIT - 1) / UNIT;
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   unsigned char* stage_base = smem;                                   // STAGES x (A | B), 1024-aligned
-  float* thr_sh = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES);  // [EPI_GROUPS][BLOCK_M] published admission thresholds
+  float* thr_sh = reinterpret_cast<float*>(smem + RING_BYTES);  // [EPI_GROUPS][BLOCK_M] published admission thresholds
   int* cnt_sh = reinterpret_cast<int*>(thr_sh + EPI_GROUPS * BLOCK_M);     // [EPI_GROUPS][BLOCK_M] list lengths at the end of a sweep
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES + SHARE_BYTES);
-  uint64_t* empty_bar = full_bar + STAGES;
-  uint64_t* tmem_full = empty_bar + STAGES;   // [2]
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + RING_BYTES + SHARE_BYTES);
+  uint64_t* empty_bar = full_bar + MAX_STAGES;
+  uint64_t* tmem_full = empty_bar + MAX_STAGES;   // [2]
   uint64_t* tmem_empty = tmem_full + 2;       // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
 
@@ -312,16 +375,22 @@ retrieve_topk_kernel(const __grid_constant__ CUtensorMap tmap_users, const __gri
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) mbar_init(&full_bar[s], 1), mbar_init(&empty_bar[s], 1);
-    for (int s = 0; s < 2; ++s) mbar_init(&tmem_full[s], 1), mbar_init(&tmem_empty[s], 4 * EPI_GROUPS);
+    // the leader's tmem_empty collects the epilogue warps of both CTAs of a pair
+    for (int s = 0; s < 2; ++s) mbar_init(&tmem_full[s], 1), mbar_init(&tmem_empty[s], 4 * EPI_GROUPS * UNIT);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   for (int t = threadIdx.x; t < EPI_GROUPS * BLOCK_M; t += THREADS) thr_sh[t] = -CUDART_INF_F;
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)TMEM_COLS) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if constexpr (PAIR) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)TMEM_COLS) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)TMEM_COLS) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   tc_fence_before();
-  __syncthreads();
+  if constexpr (PAIR) cluster_sync_all(); else __syncthreads();  // pair: the peer's barriers must exist before anything signals them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -330,14 +399,22 @@ retrieve_topk_kernel(const __grid_constant__ CUtensorMap tmap_users, const __gri
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int mt = blockIdx.x; mt < p.m_tiles; mt += gridDim.x) {
+      for (int unit = unit0; unit < n_units; unit += unit_step) {
+        const int mt = unit * UNIT + (int)rank;  // a pair's second tile may lie past the last user tile: TMA zero-fills it
         for (int nt = 0; nt < p.n_tiles; ++nt) {
           for (int kb = 0; kb < k_blocks; ++kb) {
             mbar_wait<64>(&empty_bar[stage], phase ^ 1, p.error_flag);
             unsigned char* a = stage_base + stage * STAGE_BYTES;
-            mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
-            tma_load_2d(a, &tmap_users, &full_bar[stage], kb * BLOCK_K, mt * BLOCK_M);
-            tma_load_2d(a + A_BYTES, &tmap_catalog, &full_bar[stage], kb * BLOCK_K, nt * BLOCK_N);
+            if constexpr (PAIR) {
+              // both CTAs' bytes are counted on the LEADER's barrier (the MMA is issued there)
+              if (rank == 0) mbar_expect_tx(&full_bar[stage], 2 * STAGE_BYTES);
+              tma_load_2d_pair(a, &tmap_users, &full_bar[stage], kb * BLOCK_K, mt * BLOCK_M);
+              tma_load_2d_pair(a + A_BYTES, &tmap_catalog, &full_bar[stage], kb * BLOCK_K, nt * BLOCK_N + (int)rank * (BLOCK_N / 2));
+            } else {
+              mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
+              tma_load_2d(a, &tmap_users, &full_bar[stage], kb * BLOCK_K, mt * BLOCK_M);
+              tma_load_2d(a + A_BYTES, &tmap_catalog, &full_bar[stage], kb * BLOCK_K, nt * BLOCK_N);
+            }
             if (++stage == STAGES) stage = 0, phase ^= 1;
           }
         }
@@ -345,12 +422,12 @@ retrieve_topk_kernel(const __grid_constant__ CUtensorMap tmap_users, const __gri
     }
   } else if (warp == 1) {
     // ===== MMA issuer =====
-    if (lane == 0) {
+    if (lane == 0 && rank == 0) {
       int stage = 0, as = 0;
       uint32_t phase = 0, aphase = 0;
       const bool st_on = p.diag == 4;
       long long w_acc = 0, w_feed = 0, c0 = 0;
-      for (int mt = blockIdx.x; mt < p.m_tiles; mt += gridDim.x) {
+      for (int unit = unit0; unit < n_units; unit += unit_step) {
         for (int nt = 0; nt < p.n_tiles; ++nt) {
           if (st_on) c0 = clock64();
           mbar_wait(&tmem_empty[as], aphase ^ 1, p.error_flag);
@@ -365,12 +442,15 @@ retrieve_topk_kernel(const __grid_constant__ CUtensorMap tmap_users, const __gri
             const uint32_t a_addr = smem_u32(stage_base + stage * STAGE_BYTES);
             const uint64_t adesc = umma_desc(a_addr), bdesc = umma_desc(a_addr + A_BYTES);
 #pragma unroll
-            for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
-              umma_f16(d_tmem, adesc + (uint64_t)(k * (UMMA_K * 2 / 16)), bdesc + (uint64_t)(k * (UMMA_K * 2 / 16)), (kb | k) != 0);
-            umma_commit(&empty_bar[stage]);  // frees the stage once these MMAs have read it
+            for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+              if constexpr (PAIR) umma_f16_pair(d_tmem, adesc + (uint64_t)(k * (UMMA_K * 2 / 16)), bdesc + (uint64_t)(k * (UMMA_K * 2 / 16)), (kb | k) != 0);
+              else umma_f16(d_tmem, adesc + (uint64_t)(k * (UMMA_K * 2 / 16)), bdesc + (uint64_t)(k * (UMMA_K * 2 / 16)), (kb | k) != 0);
+            }
+            // frees the stage (in both CTAs of a pair) once these MMAs have read it
+            if constexpr (PAIR) umma_commit_pair(&empty_bar[stage]); else umma_commit(&empty_bar[stage]);
             if (++stage == STAGES) stage = 0, phase ^= 1;
           }
-          umma_commit(&tmem_full[as]);  // accumulator complete
+          if constexpr (PAIR) umma_commit_pair(&tmem_full[as]); else umma_commit(&tmem_full[as]);  // accumulator complete
           if (++as == 2) as = 0, aphase ^= 1;
         }
       }
@@ -395,7 +475,8 @@ retrieve_topk_kernel(const __grid_constant__ CUtensorMap tmap_users, const __gri
     const bool st_on = p.diag == 4;
     long long st_comp = 0, st_slow = 0, st_wait = 0, st_ncomp = 0, st_nslow = 0;
     const long long st_t0 = clock64();
-    for (int mt = blockIdx.x; mt < p.m_tiles; mt += gridDim.x) {
+    for (int unit = unit0; unit < n_units; unit += unit_step) {
+      const int mt = unit * UNIT + (int)rank;
       const long long user = (long long)mt * BLOCK_M + row_in_tile;
       const bool row_valid = user < p.n_users;
       float thr = -CUDART_INF_F;  // admission threshold: the best k-th best score either group has established for this row
@@ -499,7 +580,9 @@ retrieve_topk_kernel(const __grid_constant__ CUtensorMap tmap_users, const __gri
         // accumulator drained: hand the TMEM buffer back to the MMA warp
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&tmem_empty[as]);
+        if (lane == 0) {
+          if (PAIR && rank != 0) mbar_arrive_remote(&tmem_empty[as], 0); else mbar_arrive(&tmem_empty[as]);
+        }
         // Off the critical path (the accumulator is already released): compact at most ONE row per tile, the fullest one
         // above the soft limit.  Rows of a warp fill up at similar times; compacting them all when they hit the hard limit
         // (above) would hold the accumulator stage for ~32 compactions and stall the MMA pipeline.
@@ -563,10 +646,11 @@ retrieve_topk_kernel(const __grid_constant__ CUtensorMap tmap_users, const __gri
   }
 
   tc_fence_before();
-  __syncthreads();
+  if constexpr (PAIR) cluster_sync_all(); else __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS) : "memory");
+    if constexpr (PAIR) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS) : "memory");
+    else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS) : "memory");
   }
 }
 
@@ -675,17 +759,21 @@ static int make_map(CUtensorMap* map, const void* base, long long rows, int dim,
   return r == CUDA_SUCCESS ? MB200_OK : MB200_ERR_CUDA;
 }
 
-static int retrieval_grid(int device, long long n_users) {
+// persistent grid: one CTA per SM, never more CTAs than user tiles; a CTA-pair launch needs an even grid
+static int retrieval_grid(int device, long long n_users, bool pair) {
   int sms = 148;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
   const long long m_tiles = (n_users + rt::BLOCK_M - 1) / rt::BLOCK_M;
-  return (int)(m_tiles < sms ? m_tiles : sms);
+  if (!pair) return (int)(m_tiles < sms ? m_tiles : sms);
+  const long long units = (m_tiles + 1) / 2;
+  const long long pairs = units < sms / 2 ? units : sms / 2;
+  return (int)(2 * pairs);
 }
 
 size_t retrieval_workspace_bytes(const mb200_retrieval_desc* d) {
   if (d == nullptr || d->struct_size != sizeof(mb200_retrieval_desc) || d->n_users <= 0) return 0;
   const long long m_tiles = (d->n_users + rt::BLOCK_M - 1) / rt::BLOCK_M;
-  const long long grid = m_tiles < 160 ? m_tiles : 160;
+  const long long grid = m_tiles + 1 < 160 ? m_tiles + 1 : 160;  // + 1: a CTA pair rounds the tile count up to even
   return (size_t)grid * rt::EPI_GROUPS * rt::BLOCK_M * rt::CAP * 8 + 256;
 }
 
@@ -702,12 +790,14 @@ int retrieve_topk(const mb200_retrieval_desc* d, cudaStream_t stream) {
   const size_t need = retrieval_workspace_bytes(d);
   if (d->workspace == nullptr || ((uintptr_t)d->workspace & 255) || d->workspace_bytes < need) return MB200_ERR_WORKSPACE;
 
+  // CTA pairs (cta_group::2) when there are at least two user tiles; tuning key 5: 0 = never, 1 = when possible
+  const bool pair = tuning().retrieval_pair != 0 && d->n_users > rt::BLOCK_M;
   CUtensorMap map_u, map_c;
   if ((st = make_map(&map_u, d->users, d->n_users, d->dim, rt::BLOCK_M)) != MB200_OK) return st;
-  if ((st = make_map(&map_c, d->catalog, d->n_catalog, d->dim, rt::BLOCK_N)) != MB200_OK) return st;
+  if ((st = make_map(&map_c, d->catalog, d->n_catalog, d->dim, pair ? rt::BLOCK_N / 2 : rt::BLOCK_N)) != MB200_OK) return st;
 
   RetrievalParams p{};
-  const int grid = retrieval_grid(device, d->n_users);
+  const int grid = retrieval_grid(device, d->n_users, pair);
   unsigned char* ws = reinterpret_cast<unsigned char*>(d->workspace);
   p.error_flag = reinterpret_cast<int*>(ws);
   p.stats = reinterpret_cast<unsigned long long*>(ws + 64);
@@ -721,9 +811,22 @@ int retrieve_topk(const mb200_retrieval_desc* d, cudaStream_t stream) {
   p.n_tiles = (int)((d->n_catalog + rt::BLOCK_N - 1) / rt::BLOCK_N);
   st = cuda_status(cudaMemsetAsync(p.error_flag, 0, 256, stream), "cudaMemsetAsync");
   if (st != MB200_OK) return st;
-  st = cuda_status(cudaFuncSetAttribute(retrieve_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, rt::SMEM_BYTES), "cudaFuncSetAttribute");
+  if (pair) {
+    st = cuda_status(cudaFuncSetAttribute(retrieve_topk_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, rt::SMEM_BYTES), "cudaFuncSetAttribute");
+    if (st != MB200_OK) return st;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)grid), cfg.blockDim = dim3(rt::THREADS), cfg.dynamicSmemBytes = rt::SMEM_BYTES, cfg.stream = stream;
+    cudaLaunchAttribute attr{};
+    attr.id = cudaLaunchAttributeClusterDimension;
+    attr.val.clusterDim.x = 2, attr.val.clusterDim.y = 1, attr.val.clusterDim.z = 1;
+    cfg.attrs = &attr, cfg.numAttrs = 1;
+    st = cuda_status(cudaLaunchKernelEx(&cfg, retrieve_topk_kernel<true>, map_u, map_c, p), "retrieve_topk_kernel<pair>");
+    note_launch(1);
+    return st;
+  }
+  st = cuda_status(cudaFuncSetAttribute(retrieve_topk_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, rt::SMEM_BYTES), "cudaFuncSetAttribute");
   if (st != MB200_OK) return st;
-  retrieve_topk_kernel<<<grid, rt::THREADS, rt::SMEM_BYTES, stream>>>(map_u, map_c, p);
+  retrieve_topk_kernel<false><<<grid, rt::THREADS, rt::SMEM_BYTES, stream>>>(map_u, map_c, p);
   note_launch(1);
   return cuda_status(cudaGetLastError(), "retrieve_topk_kernel");
 }

@@ -310,8 +310,8 @@ def last_score_kernel_ms() -> float:
 
 
 def set_tuning(chunks_per_warp: Optional[int] = None, variant: Optional[int] = None, ctas_per_sm: Optional[int] = None,
-               time_kernel: Optional[int] = None, retrieval_diag: Optional[int] = None) -> None:
+               time_kernel: Optional[int] = None, retrieval_diag: Optional[int] = None, retrieval_pair: Optional[int] = None) -> None:
     lib = nat.lib()
-    for key, val in ((0, chunks_per_warp), (1, variant), (2, ctas_per_sm), (3, time_kernel), (4, retrieval_diag)):
+    for key, val in ((0, chunks_per_warp), (1, variant), (2, ctas_per_sm), (3, time_kernel), (4, retrieval_diag), (5, retrieval_pair)):
         if val is not None:
             lib.mb200_set_tuning(key, int(val))

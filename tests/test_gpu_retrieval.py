@@ -27,6 +27,17 @@ def rt():
     return retrieval
 
 
+@pytest.fixture(autouse=True, params=[0, 1], ids=["cta_group1", "cta_pair"])
+def pair_mode(request, rt):
+    """Every test runs on both GEMM pipelines: one CTA per user tile (tcgen05 cta_group::1) and CTA pairs (cta_group::2,
+    UMMA M = 256, operands split across the two CTAs' shared memory)."""
+    from manner_b200 import ops
+
+    ops.set_tuning(retrieval_pair=request.param)
+    yield request.param
+    ops.set_tuning(retrieval_pair=1)  # the library default
+
+
 def _rand_bf16(n, d, seed, scale=None):
     g = torch.Generator().manual_seed(seed)
     return (torch.randn(n, d, generator=g) * (scale if scale is not None else d ** -0.5)).to(torch.bfloat16)
