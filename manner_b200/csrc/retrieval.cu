@@ -184,6 +184,11 @@ __device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+__device__ __forceinline__ float fmax3(float a, float b, float c) {
+  float d;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+  return d;
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
@@ -535,12 +540,13 @@ retrieve_topk_kernel(const __grid_constant__ CUtensorMap tmap_users, const __gri
           // two-level filter: the maxima of the four 8-column groups, then only the groups that can hold an admission
           float gm[4];
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const float a0 = fmaxf(__uint_as_float(v[8 * q + 0]), __uint_as_float(v[8 * q + 1])), a1 = fmaxf(__uint_as_float(v[8 * q + 2]), __uint_as_float(v[8 * q + 3]));
-            const float a2 = fmaxf(__uint_as_float(v[8 * q + 4]), __uint_as_float(v[8 * q + 5])), a3 = fmaxf(__uint_as_float(v[8 * q + 6]), __uint_as_float(v[8 * q + 7]));
-            gm[q] = fmaxf(fmaxf(a0, a1), fmaxf(a2, a3));
+          for (int q = 0; q < 4; ++q) {  // three-input max (FMNMX3): 4 instructions per 8 columns instead of 7
+            const float a0 = fmax3(__uint_as_float(v[8 * q + 0]), __uint_as_float(v[8 * q + 1]), __uint_as_float(v[8 * q + 2]));
+            const float a1 = fmax3(__uint_as_float(v[8 * q + 3]), __uint_as_float(v[8 * q + 4]), __uint_as_float(v[8 * q + 5]));
+            const float a2 = fmaxf(__uint_as_float(v[8 * q + 6]), __uint_as_float(v[8 * q + 7]));
+            gm[q] = fmax3(a0, a1, a2);
           }
-          float mx = fmaxf(fmaxf(gm[0], gm[1]), fmaxf(gm[2], gm[3]));
+          float mx = fmaxf(fmax3(gm[0], gm[1], gm[2]), gm[3]);
           if (p.diag == 1 || !row_valid) mx = -CUDART_INF_F;
           const bool any_slow = st_on && __any_sync(kFull, mx > thr);
           if (any_slow) c0 = clock64(), ++st_nslow;
