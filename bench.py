@@ -43,7 +43,7 @@ FALLBACK_BF16_TFLOPS_SUSTAINED = 1400.0
 
 def workload_config(args) -> dict:
     return {
-        "workload": f"MIND-{args.workload}-shaped synthetic impressions, CR + category A-Module z-score ensemble, fp32 768-d tables",
+        "workload": f"MIND-{args.workload}-shaped synthetic impressions, CR + category A-Module z-score ensemble, {getattr(args, 'table_dtype', 'f32').replace('f32', 'fp32')} 768-d tables",
         "shape": args.workload,
         "n_modules": args.modules,
         "categ_weight": CATEG_WEIGHT,
@@ -126,7 +126,7 @@ def cpu_reference_pass(tables, bhv, n_sample: int, threads: int) -> tuple:
     ob = mo.Behaviours(head.hist_offsets, head.hist_ids, head.cand_offsets, head.cand_ids, head.labels)
     weights = [1.0, CATEG_WEIGHT] + [0.0] * (len(tables) - 2)
     t0 = time.perf_counter()
-    mo.ensemble_eval_epoch(tables, weights[: len(tables)], ob, double_compute=True, reference_only=True)
+    mo.ensemble_eval_epoch([t.float() for t in tables], weights[: len(tables)], ob, double_compute=True, reference_only=True)
     dt = time.perf_counter() - t0
     return head.n_impressions / dt, dt, head.n_impressions
 
@@ -179,14 +179,15 @@ def run_gpu_arm(args) -> None:
     dev = torch.device(f"cuda:{local_rank}")
     distributed = world > 1
 
+    tdtype = torch.bfloat16 if args.table_dtype == "bf16" else torch.float32
     if args.shard:
         # strong scaling (BASELINE.json configs[2]): ONE set of impressions, sharded over the ranks by rows gathered
-        tables, full = mdata.synth_workload(args.workload, n_modules=args.modules, uniform_ids=args.uniform_ids)
+        tables, full = mdata.synth_workload(args.workload, n_modules=args.modules, uniform_ids=args.uniform_ids, dtype=tdtype)
         bhv = mdist.shard_for_rank(full, rank, world)
         del full
     else:
         # weak scaling: every rank scores its own MIND-small-shaped shard (different behaviour seed), tables replicated
-        tables, bhv = mdata.synth_workload(args.workload, n_modules=args.modules, seed_offset=rank, uniform_ids=args.uniform_ids)
+        tables, bhv = mdata.synth_workload(args.workload, n_modules=args.modules, seed_offset=rank, uniform_ids=args.uniform_ids, dtype=tdtype)
     attention = None
     if args.early_fusion:
         # late_fusion=False (configs/experiment/cr_module_mind_all_scl_ef.yaml): additive attention with query_vector_dim 200 on the CR
@@ -299,7 +300,7 @@ def run_gpu_arm(args) -> None:
         return
 
     hbm_peak, peak_kind = peaks()
-    algo_bytes = bhv.algorithmic_bytes(args.modules, tables[0].shape[1], 4, scores_written=True)
+    algo_bytes = bhv.algorithmic_bytes(args.modules, tables[0].shape[1], tables[0].element_size(), scores_written=True)
     k_ms = sum(kernel_ms) / len(kernel_ms)
     achieved = algo_bytes / (k_ms * 1e-3) / 1e9
     traffic, l2_note = None, None
@@ -324,7 +325,7 @@ def run_gpu_arm(args) -> None:
     line = {
         "metric": METRIC, "value": n_impr_total * args.steps / (total_ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "strong" if args.shard else "weak",
-        "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(args),
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(args),  # arithmetic is fp32 for either table dtype
         "e2e": {
             "value": n_impr_total / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": dev_bhv.h2d_bytes,
             "d2h_bytes_per_step": r.d2h_bytes, "ms_per_step": e2e_ms, "ms_per_step_median_rank0": e2e_median_ms, "steps": len(e2e_events),
@@ -485,6 +486,7 @@ def main() -> None:
     ap.add_argument("--sweep", type=int, default=0, help="aspect-weight sweep with about this many weightings (configs[3]); no pooled AUC")
     ap.add_argument("--early-fusion", action="store_true", help="CR module with late_fusion=False: additive-attention pooling from cached per-news logits")
     ap.add_argument("--loss", default=None, choices=["ce", "supcon"], help="also compute the reference's test/loss on device")
+    ap.add_argument("--table-dtype", default="f32", choices=["f32", "bf16"], help="storage type of the embedding tables (arithmetic stays fp32)")
     ap.add_argument("--uniform-ids", action="store_true", help="draw ids uniformly over the catalogue (no L2-friendly head)")
     ap.add_argument("--cpu-sample", type=int, default=24576, help="impressions of the workload the CPU baseline is timed on (~12 s on 16 cores)")
     ap.add_argument("--no-cpu-baseline", action="store_true")

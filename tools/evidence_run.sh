@@ -8,9 +8,10 @@ timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smok
 python bench.py --steps 20 --warmup 3 > gpurun_out/bench_zipf.json 2> gpurun_out/bench_zipf.err
 python bench.py --steps 20 --warmup 3 --uniform-ids --no-cpu-baseline > gpurun_out/bench_uniform.json 2>/dev/null
 python bench.py --steps 20 --warmup 3 --no-cpu-baseline --modules 3 --sweep 121 > gpurun_out/bench_sweep121.json 2>/dev/null
+python bench.py --steps 20 --warmup 3 --no-cpu-baseline --table-dtype bf16 > gpurun_out/bench_bf16.json 2>/dev/null
 python bench.py --mode retrieval --steps 5 --warmup 3 > gpurun_out/bench_retrieval.json 2> gpurun_out/bench_retrieval.err
 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_reference.json 2>/dev/null
-for f in bench_zipf bench_uniform bench_sweep121 bench_retrieval bench_reference; do python -c "import sys,json; d=json.loads(open('gpurun_out/$f.json').read()); print('$f', d['value'], d['ms_per_step'], (d.get('roofline') or {}).get('kernel_ms'), (d.get('roofline') or {}).get('achieved'), (d.get('roofline') or {}).get('frac'), d['e2e']['value'])"; done
+for f in bench_zipf bench_uniform bench_sweep121 bench_bf16 bench_retrieval bench_reference; do python -c "import sys,json; d=json.loads(open('gpurun_out/$f.json').read()); print('$f', d['value'], d['ms_per_step'], (d.get('roofline') or {}).get('kernel_ms'), (d.get('roofline') or {}).get('achieved'), (d.get('roofline') or {}).get('frac'), d['e2e']['value'])"; done
 C="python bench.py --steps 3 --warmup 3 --no-cpu-baseline"
 $C > gpurun_out/plain.log 2>&1 && ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv $C > gpurun_out/ncu_launches.log 2>&1
 $C > gpurun_out/plain2.log 2>&1 && ncu --set full --clock-control none --import-source on -k regex:score_eval_kernel -s 3 -c 2 -o gpurun_out/prof_zipf $C > gpurun_out/ncu_full.log 2>&1
