@@ -447,7 +447,7 @@ def run_retrieval_arm(args) -> None:
 
             threads = os.cpu_count() or 1
             torch.set_num_threads(threads)
-            nu, nc = min(n_users, 2048), min(n_shard, 131072)
+            nu, nc = min(n_users, 16384), min(n_shard, 262144)  # ~10 s of host work
             t0 = time.perf_counter()
             sc = mo.retrieval_scores(users_host[:nu], catalog[:nc].cpu())
             torch.topk(sc, k, dim=1)
