@@ -249,10 +249,15 @@ def synth_workload(shape: str, n_modules: int = 1, dim: int = 768, dtype: torch.
     return tables, synth_behaviours(n_news, n_impr, seed + seed_offset, uniform_ids=uniform_ids)
 
 
-def balanced_shard_bounds(bhv: Behaviours, world_size: int) -> np.ndarray:
+def balanced_shard_bounds(bhv: Behaviours, world_size: int, align: int = 1) -> np.ndarray:
     """Contiguous impression ranges per rank balanced by rows gathered, sum(H_i + C_i), not by count
-    (SURVEY 8(e)).  Returns int64 [world_size + 1] impression boundaries."""
+    (SURVEY 8(e)).  Returns int64 [world_size + 1] impression boundaries.  ``align`` > 1 rounds the inner boundaries
+    to multiples of the reference's step size: early fusion and the losses depend on which impressions share a step
+    (pads, MeanMetric over steps), so a shard must start on a step boundary to reproduce the single-GPU numbers."""
     work = bhv.hist_offsets.astype(np.int64) + bhv.cand_offsets.astype(np.int64)
     targets = work[-1] * np.arange(1, world_size, dtype=np.float64) / world_size
     cuts = np.searchsorted(work, targets, side="left")
+    if align > 1:
+        cuts = np.minimum((cuts + align // 2) // align * align, bhv.n_impressions)
+        cuts = np.maximum.accumulate(cuts)
     return np.concatenate([[0], cuts, [bhv.n_impressions]]).astype(np.int64)

@@ -27,10 +27,11 @@ from .data import Behaviours, balanced_shard_bounds
 N_FLAG_BITS = 4
 
 
-def shard_for_rank(bhv: Behaviours, rank: int, world_size: int) -> Behaviours:
+def shard_for_rank(bhv: Behaviours, rank: int, world_size: int, align: int = 1) -> Behaviours:
     """This rank's contiguous impression range, balanced by rows gathered (not by impression count),
-    offsets rebased to 0."""
-    bounds = balanced_shard_bounds(bhv, world_size)
+    offsets rebased to 0.  Pass ``align=step_batch`` when early fusion or a loss is evaluated (see
+    ``balanced_shard_bounds``)."""
+    bounds = balanced_shard_bounds(bhv, world_size, align)
     return bhv.slice(int(bounds[rank]), int(bounds[rank + 1]))
 
 

@@ -65,6 +65,21 @@ def test_shards_are_balanced_by_rows_and_cover_everything():
             p.validate(4096)
 
 
+def test_step_aligned_shards_keep_the_references_step_structure():
+    """Early fusion / losses: pads and step means of a shard equal the corresponding slice of the whole set's only when
+    the shard starts on a step boundary."""
+    bhv = mdata.synth_behaviours(2048, 1003, seed=6)
+    whole_h, whole_c = mdata.step_pads(bhv.hist_offsets, 8), mdata.step_pads(bhv.cand_offsets, 8)
+    for world in (2, 3, 5):
+        b = mdata.balanced_shard_bounds(bhv, world, align=8)
+        assert b[0] == 0 and b[-1] == bhv.n_impressions and np.all(np.diff(b) >= 0) and np.all(b[1:-1] % 8 == 0)
+        for r in range(world):
+            part = bhv.slice(int(b[r]), int(b[r + 1]))
+            np.testing.assert_array_equal(mdata.step_pads(part.hist_offsets, 8), whole_h[b[r]:b[r + 1]])
+            np.testing.assert_array_equal(mdata.step_pads(part.cand_offsets, 8), whole_c[b[r]:b[r + 1]])
+    assert mdata.step_pads(np.array([0, 3, 4, 9, 9]), 2).tolist() == [0, 2, 0, 5]
+
+
 def test_algorithmic_bytes_formula():
     bhv = mdata.synth_behaviours(1024, 100, seed=2)
     rows = bhv.n_hist + bhv.n_cand
