@@ -1,0 +1,60 @@
+#!/usr/bin/env python
+"""Multi-GPU check of the evaluation path (run under torchrun, one rank per GPU): one behaviour set sharded over the ranks
+(step-aligned) must give the single-GPU numbers -- metric sums within 1e-12 relative, pooled AUROC exactly, test/loss within
+fp64 regrouping -- for late fusion + ensemble and for early fusion + SupCon / cross-entropy loss.
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29541 tools/dist_eval_check.py
+"""
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from manner_b200 import data as mdata
+from manner_b200 import dist as mdist
+from manner_b200.evaluator import ScoreEvaluator
+
+
+def main() -> None:
+    rank, local_rank, world = mdist.init_from_env("nccl")
+    dev = torch.device(f"cuda:{local_rank}")
+    n_news, dim = 5000, 768
+    bhv = mdata.synth_behaviours(n_news, 20011, seed=3, cand_window=1500)
+    tables = [mdata.synth_table(n_news, dim, s) for s in mdata.TABLE_SEEDS[:2]]
+    g = torch.Generator().manual_seed(5)
+    att = (torch.randn(200, dim, generator=g) * dim ** -0.5, torch.randn(200, generator=g) * 0.1, torch.rand(200, generator=g) * 0.2 - 0.1)
+    shard = mdist.shard_for_rank(bhv, rank, world, align=8)
+    pos_cap = mdist.agree_pos_cap(int(shard.labels.sum()), dev)
+    out = {"world": world}
+    cases = {
+        "ensemble": (dict(tables=tables), dict(weights=[[1.0, 0.4]], zscore=True, pooled_auc=True)),
+        "early_fusion_supcon": (dict(tables=tables[:1], attention=[att]), dict(pooled_auc=True, loss="supcon", temperature=0.36)),
+        "late_fusion_ce": (dict(tables=tables[:1]), dict(pooled_auc=True, loss="ce")),
+    }
+    for name, (ctor, kw) in cases.items():
+        ev = ScoreEvaluator(ctor["tables"], dev, attention=ctor.get("attention"))
+        one = ev.evaluate(ev.upload(bhv, step_batch=8), **kw)  # the whole set on this GPU
+        many = ev.evaluate(ev.upload(shard, pos_cap=pos_cap, step_batch=8), distributed=True, **kw)
+        ok = many.n_impressions == one.n_impressions and np.allclose(many.sums, one.sums, rtol=1e-12, atol=1e-9) and many.auc == one.auc
+        if one.loss is not None:
+            ok = ok and abs(many.loss - one.loss) <= 1e-12 * abs(one.loss)
+        t = torch.tensor([int(ok)], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        out[name] = bool(t.item())
+        out[name + "_metrics"] = {k: round(v, 6) for k, v in many.metrics().items()}
+    if rank == 0:
+        print(json.dumps(out))
+    dist.barrier()
+    dist.destroy_process_group()
+    if not all(v for k, v in out.items() if isinstance(v, bool)):
+        raise SystemExit(1)
+
+
+if __name__ == "__main__":
+    main()
