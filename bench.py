@@ -30,7 +30,6 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-import numpy as np
 import torch
 
 METRIC = "impressions/sec (pool+score+ensemble+metrics)"

@@ -16,12 +16,10 @@ from __future__ import annotations
 
 from typing import Callable, Optional, Tuple
 
-import numpy as np
 import torch
 import torch.distributed as dist
 from torch import Tensor
 
-from . import _native as nat
 from .data import Behaviours, balanced_shard_bounds
 
 N_FLAG_BITS = 4

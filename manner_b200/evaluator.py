@@ -17,7 +17,7 @@ results are all-reduced over NCCL (dist.py); nothing else crosses GPUs.
 """
 from __future__ import annotations
 
-from dataclasses import dataclass, field
+from dataclasses import dataclass
 from typing import Dict, List, Optional, Sequence, Tuple, Union
 
 import numpy as np

@@ -3,7 +3,7 @@
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
-from manner_b200 import ops, retrieval as rt
+from manner_b200 import ops, retrieval  # noqa: F401  (retrieval registers torch.ops.manner_b200.retrieve_topk)
 
 dev = torch.device("cuda:0")
 n_users, n_cat, dim = int(sys.argv[1]) if len(sys.argv) > 1 else 37888, int(sys.argv[2]) if len(sys.argv) > 2 else 1_250_000, 768
