@@ -439,6 +439,13 @@ def run_retrieval_arm(args) -> None:
             burst = float(mp["bf16_tflops"])
             peak, peak_kind = float(mp.get("bf16_tflops_sustained", burst)), "measured sustained (long kernel under the power cap; see frac_of_burst)"
         flops = 2.0 * n_users * n_shard * dim  # per launch, per GPU
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "traffic_retrieval.json")
+        if os.path.exists(tpath):
+            with open(tpath) as f:
+                t = json.load(f)
+            if t.get("users") == n_users and t.get("catalog_per_gpu") == n_shard and t.get("dim") == dim:
+                traffic = t.get("dram_bytes_per_launch")
         achieved = flops / (kern_ms * 1e-3) / 1e12
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
@@ -463,7 +470,7 @@ def run_retrieval_arm(args) -> None:
                     "d2h_bytes_per_step": (n_users if (not distributed or args.exchange == "all_gather") else -(-n_users // world)) * k * 12, "ms_per_step": e2e_ms},
             "gpu_launches": launches1[0] - launches0[0],
             "roofline": {"bound": "tensor", "kernel": "retrieve_topk_kernel", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                         "peak_kind": peak_kind, "peak_burst": burst, "frac_of_burst": achieved / burst, "traffic": None, "flops_per_launch": flops, "kernel_ms": kern_ms,
+                         "peak_kind": peak_kind, "peak_burst": burst, "frac_of_burst": achieved / burst, "traffic": traffic, "flops_per_launch": flops, "kernel_ms": kern_ms,
                          "kernel_share_of_step": kern_ms * args.steps / total_ms if total_ms > 0 else None},
             "cpu_baseline": cpu, "clocks": clocks,
         }
