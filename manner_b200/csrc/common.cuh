@@ -25,7 +25,7 @@ constexpr unsigned kFull = 0xffffffffu;
 
 struct Tuning {
   int chunks_per_warp = 1;  // work-balanced impression chunks per resident warp (1: one contiguous range per warp)
-  int variant = 2;          // reference-width kernel: 0 = 4 rows in flight / 3 CTAs per SM, 1 = same with L1::no_allocate loads,
+  int variant = -1;         // reference-width kernel: -1 = by table type (fp32: 2, bf16: 3), 0 = 4 rows in flight / 3 CTAs per SM, 1 = same with L1::no_allocate loads,
                             // 2 = 3 rows / 4 CTAs (default: best on Zipf-shaped ids), 3 = 2 rows / 5 CTAs
   int ctas_per_sm = 0;      // CTAs (of kWarpsPerCta warps) per SM; 0 = as many as are resident (occupancy query)
   int time_kernel = 0;      // 1: bracket the fused kernel with CUDA events (mb200_last_score_kernel_ms)

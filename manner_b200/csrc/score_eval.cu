@@ -1013,10 +1013,16 @@ static KernelFn select_kernel(int vec_per_row, bool attn) {
   constexpr int R3 = (R * 3 + 3) / 4, R2 = (R + 1) / 2;
   if (vec_per_row == kRefNV * 32 && attn) return score_eval_kernel<T, kRefNV, R3, true, 0, 4, true>;  // early fusion (separate code: the late-fusion kernels keep their tuning)
   if (vec_per_row == kRefNV * 32) {
-    switch (tuning().variant) {
+    int variant = tuning().variant;
+    // default: fp32 rows sit at the L2 -> SM limit with 3 rows x 4 CTAs; bf16 rows (half the bytes) are latency bound and
+    // want more resident warps: 4 rows x 5 CTAs (measured: profiles/r1_v6_bench_bf16_variants.log)
+    if (variant < 0) variant = (Elem<T>::E == 8) ? 3 : 2;
+    switch (variant) {
       case 0: return score_eval_kernel<T, kRefNV, R, true, 0, 3>;
       case 1: return score_eval_kernel<T, kRefNV, R, true, 1, 3>;
       case 3: return score_eval_kernel<T, kRefNV, R2, true, 0, 5>;
+      case 5: return score_eval_kernel<T, kRefNV, 3, true, 0, 6>;
+      case 6: return score_eval_kernel<T, kRefNV, 2, true, 0, 7>;
       default: return score_eval_kernel<T, kRefNV, R3, true, 0, 4>;
     }
   }
