@@ -26,6 +26,20 @@ def news_row_map(news_ids: Iterable[str]) -> Dict[str, int]:
     return {nid: row for row, nid in enumerate(news_ids)}
 
 
+def unique_news_ids(behaviors: Any, max_history_length: int = MAX_HISTORY) -> List[str]:
+    """The news a split's behaviours refer to (history cut to ``max_history_length`` like the dataset does,
+    mind_rec_dataset.py:92), in first-appearance order -- the set ``MINDNewsDataset`` builds (mind_news_dataset.py:16-25)."""
+    seen: Dict[str, None] = {}
+    for h, c in zip(behaviors["history"].tolist(), behaviors["candidates"].tolist()):
+        h = parse_id_list(h) if isinstance(h, str) else list(h)
+        c = parse_id_list(c) if isinstance(c, str) else list(c)
+        for nid in h[:max_history_length]:
+            seen.setdefault(nid, None)
+        for nid in c:
+            seen.setdefault(nid, None)
+    return list(seen)
+
+
 def parse_id_list(text: str) -> List[str]:
     """One ``history`` / ``candidates`` cell of ``parsed_behaviors.tsv`` -- a stringified Python list --
     exactly as the reference's converters read it (mind_dataframe.py:283-286)."""

@@ -14,12 +14,14 @@ The evaluation logic lives in ``B200EvalMixin`` and ``StepScorer``, which do not
 reference package and its dependencies (lightning, torchmetrics, torch_geometric, ...) are optional
 imports, so this file is importable -- and testable -- without them.
 
-Two ways to feed the kernel:
-  * step mode (default): the unchanged DataModule delivers ``MINDRecBatch`` es (mind_batch.py:6-12);
+Two ways to feed the kernel (constructor keyword / YAML key ``scorer``):
+  * step mode (``scorer: b200``, default): the unchanged DataModule delivers ``MINDRecBatch`` es (mind_batch.py:6-12);
     the module runs its PLM ``news_encoder`` on ``x_hist`` / ``x_cand`` exactly as the reference does
     (cr_module.py:107,113) and uses the resulting [sum H + sum C, D] matrix as the step's table;
-  * cached mode: ``manner_b200.cache`` builds the table once per epoch and the CSR behaviours once per
-    dataset; ``ScoreEvaluator.evaluate`` then scores the whole epoch in one call (the PLM leaves the loop).
+  * cached mode (``scorer: b200_cached``): in ``on_test_start`` the module runs its news encoder(s) once over the UNIQUE
+    news of the split (``manner_b200.cache``), converts the datamodule's behaviours frame to CSR and scores the whole epoch
+    with one ``ScoreEvaluator.evaluate`` call; ``test_step`` then does nothing -- the PLM leaves the loop (65 k encoder
+    rows instead of 4.3 M on MIND-small).
 """
 from __future__ import annotations
 
@@ -207,11 +209,74 @@ class B200EvalMixin:
         scorer.reset()
         return values
 
+    # ---- cached mode: the PLM runs once per unique news, the whole epoch is ONE evaluation call ----
+    _b200_cached = False       # scorer == "b200_cached"
+    _b200_news_batch = 256     # news per encoder call while the table is built
+
+    def _b200_evaluate_cached(self, stage: str) -> Dict[str, float]:
+        """Builds the embedding table(s) with the module's own news encoders over the UNIQUE news of the split, converts
+        the split's behaviours frame to CSR and scores the whole epoch with one ``ScoreEvaluator.evaluate`` call.  Uses
+        only what the reference's datamodule already has: the dataset's ``news`` / ``behaviors`` frames and the collate's
+        tokeniser (mind_rec_dataset.py:81-99,114-168)."""
+        from . import cache
+        from .evaluator import ScoreEvaluator
+
+        dm = self.trainer.datamodule
+        loader = dm.test_dataloader() if stage == "test" else dm.val_dataloader()
+        ds, collate = loader.dataset, loader.collate_fn
+        step = int(getattr(loader, "batch_size", 8) or 8)
+        news_ids = cache.unique_news_ids(ds.behaviors, ds.max_history_length)
+        nid2row = cache.news_row_map(news_ids)
+        device = getattr(self, "device", None)  # LightningModule.device; plain modules: wherever their tensors live
+        if not isinstance(device, torch.device):
+            import itertools
+
+            device = next(itertools.chain(self.parameters(), self.buffers())).device
+        encoders = self._b200_encoders()
+
+        def news_batches():
+            for lo in range(0, len(news_ids), self._b200_news_batch):
+                yield collate._tokenize_df(ds.news.loc[news_ids[lo : lo + self._b200_news_batch]])
+
+        tables = []
+        for enc in encoders:
+            first = next(iter(news_batches()))
+            with torch.no_grad():
+                was = enc.training
+                enc.eval()
+                dim = int(enc(cache._to_device(first, device)).shape[1])
+                enc.train(was)
+            tables.append(cache.build_embedding_table(enc, news_batches(), len(news_ids), dim, device))
+        bhv = cache.behaviours_frame_to_csr(ds.behaviors, nid2row, ds.max_history_length)
+        aspects = {}
+        if self._b200_zscore and "category_label" in ds.news.columns and "sentiment_label" in ds.news.columns:
+            cat, sent = cache.aspect_arrays(ds.news, nid2row)
+            hp = getattr(self, "hparams", {})
+            aspects = dict(news_category=cat, news_sentiment=sent,
+                           num_categ_classes=int(hp.get("num_categ_classes", 19)) if hasattr(hp, "get") else 19,
+                           num_sent_classes=int(hp.get("num_sent_classes", 4)) if hasattr(hp, "get") else 4)
+        ev = ScoreEvaluator(tables, device, attention=self._b200_attention(), **aspects)
+        weights = self._b200_weights()
+        hp = getattr(self, "hparams", {})
+        res = ev.evaluate(
+            ev.upload(bhv, step_batch=step), weights=None if weights is None else [weights], zscore=self._b200_zscore,
+            pooled_auc=self._b200_with_auc, loss=None if self._b200_zscore else self._b200_loss(),
+            temperature=float(hp.get("temperature", 0.1)) if hasattr(hp, "get") else 0.1,
+        )
+        return res.metrics(prefix=stage + "/")
+
+    def on_test_start(self) -> None:
+        if self._b200_cached:
+            self.__dict__["_b200_cached_values"] = self._b200_evaluate_cached("test")
+
     def test_step(self, batch: Dict[str, Any], batch_idx: int) -> None:
+        if self._b200_cached:
+            return  # the epoch was scored in on_test_start; the batch (and its tokenisation) is not needed
         self._b200_step("test", batch)
 
     def on_test_epoch_end(self) -> None:
-        self.log_dict(self._b200_epoch_end("test"), on_step=False, on_epoch=True, prog_bar=True, logger=True)
+        values = self.__dict__.pop("_b200_cached_values", None) if self._b200_cached else self._b200_epoch_end("test")
+        self.log_dict(values or {}, on_step=False, on_epoch=True, prog_bar=True, logger=True)
 
     def validation_step(self, batch: Dict[str, Any], batch_idx: int) -> None:
         """cr_module.py:214-225: val/loss is what `ModelCheckpoint(monitor="val/loss")` watches (configs/callbacks/default.yaml)."""
@@ -242,7 +307,10 @@ class CRModuleB200(B200EvalMixin, _RefCRModule):
 
     def __init__(self, *args: Any, scorer: str = "b200", **kwargs: Any) -> None:
         super().__init__(*args, **kwargs)
-        self._b200_enabled = scorer == "b200"
+        if scorer not in ("b200", "b200_cached", "reference"):
+            raise ValueError("scorer must be 'b200' (per step), 'b200_cached' (table built once, one call per epoch) or 'reference'")
+        self._b200_enabled = scorer != "reference"
+        self._b200_cached = scorer == "b200_cached"
 
     def _b200_encoders(self) -> List[torch.nn.Module]:
         return [self.news_encoder]
@@ -284,6 +352,12 @@ class EnsembleModuleB200(B200EvalMixin, _RefEnsembleModule):
 
     _b200_zscore = True
     _b200_with_auc = False  # the reference's EnsembleModule has no AUROC (ensemble_module.py:50-55)
+
+    def __init__(self, *args: Any, scorer: str = "b200", **kwargs: Any) -> None:
+        super().__init__(*args, **kwargs)
+        if scorer not in ("b200", "b200_cached"):
+            raise ValueError("scorer must be 'b200' (per step) or 'b200_cached' (tables built once, one call per epoch)")
+        self._b200_cached = scorer == "b200_cached"
 
     def _b200_encoders(self) -> List[torch.nn.Module]:
         encs = [self.cr_module.news_encoder]

@@ -215,3 +215,124 @@ def test_cached_mode_table_builder_feeds_the_evaluator(golden_dir):
     m = ev.evaluate(ev.upload(csr), pooled_auc=True).metrics()
     for k in ("auc", "mrr", "ndcg@5", "ndcg@10"):
         assert abs(m["test/" + k] - float(z["test_" + k])) <= 1e-6, k
+
+
+class _FakeLoader:
+    def __init__(self, dataset, collate_fn, batch_size):
+        self.dataset, self.collate_fn, self.batch_size = dataset, collate_fn, batch_size
+
+
+def _fake_datamodule(z, with_aspects=False):
+    """The parts of the reference's datamodule the cached mode touches: the test dataset's ``news`` / ``behaviors`` frames and
+    ``max_history_length`` (mind_rec_dataset.py:81-99) and the collate's ``_tokenize_df`` (:146-168)."""
+    import pandas as pd
+
+    n_news = z["table0" if "table0" in z.files else "table"].shape[0]
+    ids = [f"N{i}" for i in range(n_news)]
+    news = pd.DataFrame({"row": np.arange(n_news)}, index=ids)
+    if with_aspects:
+        news["category_label"], news["sentiment_label"] = z["category"], z["sentiment"]
+    ho, co = z["hist_offsets"], z["cand_offsets"]
+    beh = pd.DataFrame({
+        "history": [[ids[j] for j in z["hist_ids"][ho[i]:ho[i + 1]]] for i in range(len(ho) - 1)],
+        "candidates": [[ids[j] for j in z["cand_ids"][co[i]:co[i + 1]]] for i in range(len(co) - 1)],
+        "labels": [z["labels"][co[i]:co[i + 1]].tolist() for i in range(len(co) - 1)],
+    })
+    ds = types.SimpleNamespace(news=news, behaviors=beh, max_history_length=50)
+    collate = types.SimpleNamespace(_tokenize_df=lambda df: {"news_row": torch.from_numpy(df["row"].to_numpy().copy())})
+    loader = _FakeLoader(ds, collate, 8)
+    return types.SimpleNamespace(test_dataloader=lambda: loader, val_dataloader=lambda: loader)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["cr_d768", "cr_ef_d128"])
+def test_cached_mode_scores_the_epoch_in_one_call(golden_dir, name):
+    """scorer=b200_cached: table built from the unique news in on_test_start, behaviours frame -> CSR, one evaluation call;
+    test_step is a no-op.  Logs the values the reference logged."""
+    from manner_b200.modules import B200EvalMixin
+
+    z = np.load(os.path.join(golden_dir, name + ".npz"))
+    early = "att_weight" in z.files
+    calls = {"encoder": 0}
+
+    class CountingEncoder(TableEncoder):
+        def forward(self, x):
+            calls["encoder"] += 1
+            return super().forward(x)
+
+    class FakeCR(B200EvalMixin, torch.nn.Module):
+        _b200_cached = True
+        _b200_news_batch = 32
+
+        def __init__(self, table):
+            super().__init__()
+            self.news_encoder = CountingEncoder(table)
+            if early:
+                self.att = torch.nn.ParameterList([torch.nn.Parameter(torch.from_numpy(z[k])) for k in ("att_weight", "att_bias", "att_query")])
+            self.logged = {}
+
+        def _b200_encoders(self):
+            return [self.news_encoder]
+
+        def _b200_loss(self):
+            return "ce"
+
+        def _b200_attention(self):
+            return [tuple(self.att)] if early else None
+
+        def log_dict(self, values, **kw):
+            self.logged.update(values)
+
+    model = FakeCR(torch.from_numpy(z["table"])).cuda()
+    model.trainer = types.SimpleNamespace(datamodule=_fake_datamodule(z))
+    model.on_test_start()
+    n_encoder_calls = calls["encoder"]
+    model.test_step({"never": "looked at"}, 0)
+    model.on_test_epoch_end()
+    assert calls["encoder"] == n_encoder_calls  # test_step did not touch the encoder
+    for k in ("auc", "mrr", "ndcg@5", "ndcg@10"):
+        assert abs(model.logged["test/" + k] - float(z["test_" + k])) <= 1e-6, k
+    assert abs(model.logged["test/loss"] - float(z["test_loss"])) <= 1e-5 * abs(float(z["test_loss"]))
+
+
+@pytest.mark.gpu
+def test_cached_mode_ensemble_with_aspects(golden_dir):
+    from manner_b200.modules import B200EvalMixin
+
+    z = np.load(os.path.join(golden_dir, "ensemble_d128.npz"))
+
+    class FakeEnsemble(B200EvalMixin, torch.nn.Module):
+        _b200_zscore = True
+        _b200_with_auc = False
+        _b200_cached = True
+
+        def __init__(self, tables, weights):
+            super().__init__()
+            self.encs = torch.nn.ModuleList([TableEncoder(t) for t in tables])
+            self.w, self.logged = weights, {}
+
+        def _b200_encoders(self):
+            return [e for e, w in zip(self.encs, self.w) if w != 0]
+
+        def _b200_weights(self):
+            return [w for w in self.w if w != 0]
+
+        def log_dict(self, values, **kw):
+            self.logged.update(values)
+
+    tabs = [torch.from_numpy(z[f"table{m}"]) for m in range(3)]
+    for w, (wc, ws) in enumerate(z["weightings"].tolist()):
+        model = FakeEnsemble(tabs, [1.0, wc, ws]).cuda()
+        model.trainer = types.SimpleNamespace(datamodule=_fake_datamodule(z, with_aspects=True))
+        model.on_test_start()
+        model.on_test_epoch_end()
+        for k in ("ndcg@5", "ndcg@10", "categ_div@5", "categ_div@10", "sent_div@5", "sent_div@10",
+                  "categ_pers@5", "categ_pers@10", "sent_pers@5", "sent_pers@10"):
+            assert abs(model.logged["test/" + k] - float(z[f"w{w}_test_{k}"])) <= 1e-6, (w, k)
+
+
+def test_unique_news_ids_follow_the_history_truncation():
+    import pandas as pd
+
+    beh = pd.DataFrame({"history": [["N3", "N1", "N9"], "['N1', 'N4']"], "candidates": [["N5"], "['N3', 'N6']"]})
+    assert mcache.unique_news_ids(beh, max_history_length=2) == ["N3", "N1", "N5", "N4", "N6"]  # N9 is cut off
