@@ -278,13 +278,19 @@ class B200EvalMixin:
         values = self.__dict__.pop("_b200_cached_values", None) if self._b200_cached else self._b200_epoch_end("test")
         self.log_dict(values or {}, on_step=False, on_epoch=True, prog_bar=True, logger=True)
 
+    def on_validation_start(self) -> None:
+        if self._b200_cached:  # the encoder weights changed since the last validation: the table is rebuilt every time
+            self.__dict__["_b200_cached_val_values"] = self._b200_evaluate_cached("val")
+
     def validation_step(self, batch: Dict[str, Any], batch_idx: int) -> None:
         """cr_module.py:214-225: val/loss is what `ModelCheckpoint(monitor="val/loss")` watches (configs/callbacks/default.yaml)."""
+        if self._b200_cached:
+            return
         self._b200_step("val", batch)
 
     def on_validation_epoch_end(self) -> None:
         """cr_module.py:227-251: val/loss, the best val/loss so far (MinMetric), then the validation metrics."""
-        values = self._b200_epoch_end("val")
+        values = (self.__dict__.pop("_b200_cached_val_values", None) or {}) if self._b200_cached else self._b200_epoch_end("val")
         if "val/loss" in values:
             best = min(self.__dict__.get("_b200_val_loss_best", float("inf")), values["val/loss"])
             self.__dict__["_b200_val_loss_best"] = best

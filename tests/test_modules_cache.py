@@ -293,6 +293,12 @@ def test_cached_mode_scores_the_epoch_in_one_call(golden_dir, name):
     for k in ("auc", "mrr", "ndcg@5", "ndcg@10"):
         assert abs(model.logged["test/" + k] - float(z["test_" + k])) <= 1e-6, k
     assert abs(model.logged["test/loss"] - float(z["test_loss"])) <= 1e-5 * abs(float(z["test_loss"]))
+    # validation in cached mode: same numbers under val/, val/loss_best tracked across epochs
+    model.on_validation_start()
+    model.validation_step({"never": "looked at"}, 0)
+    model.on_validation_epoch_end()
+    assert abs(model.logged["val/ndcg@10"] - float(z["test_ndcg@10"])) <= 1e-6
+    assert model.logged["val/loss_best"] == model.logged["val/loss"]
 
 
 @pytest.mark.gpu
