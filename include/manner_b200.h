@@ -39,6 +39,7 @@ extern "C" {
 #define MB200_MAX_MODULES 4 /* CR-Module + up to 3 A-Modules (reference: CR, category, sentiment) */
 #define MB200_MAX_K 31      /* largest ranking cut-off k for nDCG / diversity / personalization */
 #define MB200_MAX_CLASSES 64
+#define MB200_MAX_TABLE_SHARDS 8 /* GPUs of one NVSwitch box a row-sharded embedding table may be spread over */
 
 /* ---- status codes ------------------------------------------------------------------------------ */
 #define MB200_OK 0
@@ -163,6 +164,15 @@ typedef struct mb200_eval_desc {
   const int32_t* cand_pad;  /* optional [n_impressions]: zero columns the step batch appends to impression i's candidates
                                (cross entropy only); NULL = none */
   float* loss_per_impression; /* optional [n_impressions] */
+
+  /* Row-sharded embedding tables, for catalogues too large to replicate on every GPU: news row n of module m lives
+     in table_shards[m][n >> table_shard_shift] at local row n & ((1 << table_shard_shift) - 1).  The pointers are device pointers
+     valid in THIS process: the local shard and peer GPUs' shards opened through CUDA IPC / peer access; the kernel reads a row
+     where it lives (plain loads over NVLink / NVSwitch for remote shards), there is no separate exchange step.  n_table_shards
+     <= 1: `tables[]` is used (replicated table).  Reference width (768), late fusion. */
+  int32_t n_table_shards;
+  int32_t table_shard_shift;
+  const void* table_shards[MB200_MAX_MODULES][MB200_MAX_TABLE_SHARDS];
 } mb200_eval_desc;
 
 MB200_API int mb200_abi_version(void);
@@ -289,6 +299,17 @@ MB200_API int mb200_pool_users(const void* table, int dtype, int dim, int64_t ro
 /* merge of per-shard top-k lists [shards, n_users, k] (each sorted as above) into the global top-k (shards <= 32) */
 MB200_API int mb200_merge_topk(const float* scores, const int64_t* ids, int shards, int64_t n_users, int k, float* out_scores,
                                int64_t* out_ids, void* stream);
+
+/* Lets kernels running on `device` load from memory that lives on `peer` (cudaDeviceEnablePeerAccess; "already enabled" is
+ * not an error): needed once per pair of GPUs before row-sharded tables (mb200_eval_desc.table_shards) are used. */
+MB200_API int mb200_enable_peer_access(int device, int peer);
+
+/* CUDA IPC for row-sharded tables: `mb200_ipc_export` describes the allocation that contains `ptr` (64-byte IPC handle of its
+ * base + the offset of `ptr` in it); a PEER PROCESS passes both to `mb200_ipc_open`, which maps the allocation with
+ * cudaIpcMemLazyEnablePeerAccess while `device` (the GPU whose kernels will read it) is current and returns the address of
+ * `ptr` in the calling process.  The exporter keeps the memory alive; mappings live until the process exits. */
+MB200_API int mb200_ipc_export(const void* ptr, unsigned char handle[64], int64_t* offset);
+MB200_API int mb200_ipc_open(const unsigned char handle[64], int64_t offset, int device, void** out_ptr);
 
 /* ---- introspection ------------------------------------------------------------------------------- */
 /* 1 / log2(rank + 1) as fp32, rank = 1..MB200_MAX_K: the discount table the kernels use for

@@ -14,6 +14,7 @@ LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libm
 
 ABI_VERSION = 2
 MAX_MODULES = 4
+MAX_TABLE_SHARDS = 8
 MAX_K = 31
 MAX_CLASSES = 64
 NUM_METRICS = 15
@@ -73,6 +74,9 @@ class EvalDesc(Structure):
         ("loss_temperature", c_float),
         ("cand_pad", c_void_p),
         ("loss_per_impression", c_void_p),
+        ("n_table_shards", c_int32),
+        ("table_shard_shift", c_int32),
+        ("table_shards", (c_void_p * MAX_TABLE_SHARDS) * MAX_MODULES),
     ]
 
 
@@ -145,6 +149,9 @@ SIGNATURES = {
     "mb200_step_loss": (c_int, [c_void_p, c_int64, c_int, c_int, c_void_p, c_void_p]),
     "mb200_metrics_workspace_bytes": (c_size_t, [POINTER(MetricsDesc)]),
     "mb200_rank_metrics": (c_int, [POINTER(MetricsDesc), c_void_p]),
+    "mb200_enable_peer_access": (c_int, [c_int, c_int]),
+    "mb200_ipc_export": (c_int, [c_void_p, c_char_p, POINTER(c_int64)]),
+    "mb200_ipc_open": (c_int, [c_char_p, c_int64, c_int, POINTER(c_void_p)]),
     "mb200_dcg_discount": (c_float, [c_int]),
     "mb200_launch_count": (c_int64, []),
     "mb200_library_launch_count": (c_int64, []),

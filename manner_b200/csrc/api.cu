@@ -158,6 +158,60 @@ size_t mb200_metrics_workspace_bytes(const mb200_metrics_desc* desc) { return me
 
 int mb200_rank_metrics(const mb200_metrics_desc* desc, void* stream) { return rank_metrics(desc, static_cast<cudaStream_t>(stream)); }
 
+int mb200_enable_peer_access(int device, int peer) {
+  int can = 0;
+  int st = cuda_status(cudaDeviceCanAccessPeer(&can, device, peer), "cudaDeviceCanAccessPeer");
+  if (st != MB200_OK) return st;
+  if (!can) return MB200_ERR_UNSUPPORTED;
+  int prev = 0;
+  cudaGetDevice(&prev);
+  if ((st = cuda_status(cudaSetDevice(device), "cudaSetDevice")) != MB200_OK) return st;
+  const cudaError_t e = cudaDeviceEnablePeerAccess(peer, 0);
+  cudaSetDevice(prev);
+  if (e == cudaErrorPeerAccessAlreadyEnabled) {
+    (void)cudaGetLastError();
+    return MB200_OK;
+  }
+  return cuda_status(e, "cudaDeviceEnablePeerAccess");
+}
+
+int mb200_ipc_export(const void* ptr, unsigned char handle[64], int64_t* offset) {
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  if (!ptr || !handle || !offset) return MB200_ERR_INVALID_ARG;
+  int st = use_device_of(ptr, nullptr);
+  if (st != MB200_OK) return st;
+  typedef int (*RangeFn)(unsigned long long*, size_t*, unsigned long long);
+  void* sym = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  if (cudaGetDriverEntryPoint("cuMemGetAddressRange", &sym, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess || sym == nullptr)
+    return MB200_ERR_CUDA;
+  unsigned long long base = 0;
+  size_t size = 0;
+  if (reinterpret_cast<RangeFn>(sym)(&base, &size, (unsigned long long)(uintptr_t)ptr) != 0) return MB200_ERR_CUDA;
+  cudaIpcMemHandle_t h;
+  st = cuda_status(cudaIpcGetMemHandle(&h, reinterpret_cast<void*>((uintptr_t)base)), "cudaIpcGetMemHandle");
+  if (st != MB200_OK) return st;
+  memcpy(handle, &h, 64);
+  *offset = (int64_t)((unsigned long long)(uintptr_t)ptr - base);
+  return MB200_OK;
+}
+
+int mb200_ipc_open(const unsigned char handle[64], int64_t offset, int device, void** out_ptr) {
+  if (!handle || !out_ptr || offset < 0) return MB200_ERR_INVALID_ARG;
+  int prev = 0;
+  cudaGetDevice(&prev);
+  int st = cuda_status(cudaSetDevice(device), "cudaSetDevice");
+  if (st != MB200_OK) return st;
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle, 64);
+  void* base = nullptr;
+  st = cuda_status(cudaIpcOpenMemHandle(&base, h, cudaIpcMemLazyEnablePeerAccess), "cudaIpcOpenMemHandle");
+  cudaSetDevice(prev);
+  if (st != MB200_OK) return st;
+  *out_ptr = static_cast<unsigned char*>(base) + offset;
+  return MB200_OK;
+}
+
 float mb200_dcg_discount(int rank) { return host_dcg_discount(rank); }
 int64_t mb200_launch_count(void) { return g_launches.load(); }
 int64_t mb200_library_launch_count(void) { return g_library_launches.load(); }

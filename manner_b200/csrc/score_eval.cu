@@ -30,6 +30,8 @@ float host_dcg_discount(int rank) { return (rank >= 1 && rank <= MB200_MAX_K) ? 
 
 struct EvalParams {
   const void* tables[MB200_MAX_MODULES];
+  const void* shard_base[MB200_MAX_MODULES][MB200_MAX_TABLE_SHARDS];  // row-sharded tables: shard s of module m (own or peer-GPU memory)
+  int shard_shift;  // rows per shard = 1 << shard_shift
   const int32_t* hist_offsets;
   const int32_t* hist_ids;
   const int32_t* cand_offsets;
@@ -235,7 +237,8 @@ __device__ __noinline__ float personalization_value(const uint8_t* top, int kk, 
 template <typename T, int NV, int R, bool EXACT, int POLICY, bool ATTN>
 __device__ __forceinline__ int gather_pool_score(const T* __restrict__ table, long long row_stride, int vec_per_row, long long n_news,
                                                  const int32_t* __restrict__ hist_ids, int H, const int32_t* __restrict__ cand_ids, int C,
-                                                 float* __restrict__ s_out, const float* __restrict__ logits, int n_pad) {
+                                                 float* __restrict__ s_out, const float* __restrict__ logits, int n_pad,
+                                                 const void* const* __restrict__ shard_base, int shard_shift) {
   constexpr int E = Elem<T>::E;
   const int lane = threadIdx.x & 31;
   int flags = 0;
@@ -294,7 +297,11 @@ __device__ __forceinline__ int gather_pool_score(const T* __restrict__ table, lo
       for (int r = 0; r < R; ++r) {
         const int src = (r0 + r < cnt) ? (r0 + r) : 0;
         const int id = __shfl_sync(kFull, my_id, src);
-        const uint4* row = reinterpret_cast<const uint4*>(table + (long long)id * row_stride);
+        // POLICY 3: the table is row-sharded over the GPUs of the box; the row is read where it lives -- a plain load from the
+        // owner's memory over NVLink / NVSwitch peer access when it is not this GPU's shard
+        const T* tbase = POLICY == 3 ? reinterpret_cast<const T*>(shard_base[id >> shard_shift]) : table;
+        const long long lrow = POLICY == 3 ? (long long)(id & ((1 << shard_shift) - 1)) : (long long)id;
+        const uint4* row = reinterpret_cast<const uint4*>(tbase + lrow * row_stride);
 #pragma unroll
         for (int v = 0; v < NV; ++v) buf[r][v] = load_row_vec<POLICY>(row + (EXACT ? lane + 32 * v : voff[v]));
       }
@@ -345,7 +352,11 @@ __device__ __forceinline__ int gather_pool_score(const T* __restrict__ table, lo
       for (int r = 0; r < R; ++r) {
         const int src = (r0 + r < cnt) ? (r0 + r) : 0;
         const int id = __shfl_sync(kFull, my_id, src);
-        const uint4* row = reinterpret_cast<const uint4*>(table + (long long)id * row_stride);
+        // POLICY 3: the table is row-sharded over the GPUs of the box; the row is read where it lives -- a plain load from the
+        // owner's memory over NVLink / NVSwitch peer access when it is not this GPU's shard
+        const T* tbase = POLICY == 3 ? reinterpret_cast<const T*>(shard_base[id >> shard_shift]) : table;
+        const long long lrow = POLICY == 3 ? (long long)(id & ((1 << shard_shift) - 1)) : (long long)id;
+        const uint4* row = reinterpret_cast<const uint4*>(tbase + lrow * row_stride);
 #pragma unroll
         for (int v = 0; v < NV; ++v) buf[r][v] = load_row_vec<POLICY>(row + (EXACT ? lane + 32 * v : voff[v]));
       }
@@ -800,7 +811,7 @@ __global__ void __launch_bounds__(kThreads, MINB) score_eval_kernel(const __grid
         warp_flags |= gather_pool_score<T, NV, R, EXACT, POLICY, ATTN>(reinterpret_cast<const T*>(p.tables[m]), p.row_stride, p.vec_per_row,
                                                                        p.n_news, p.hist_ids + h0, H, p.cand_ids + c0, C, s_m,
                                                                        ATTN ? p.attn_logits[m] : nullptr,
-                                                                       (ATTN && p.hist_pad) ? p.hist_pad[i] : 0);
+                                                                       (ATTN && p.hist_pad) ? p.hist_pad[i] : 0, p.shard_base[m], p.shard_shift);
         __syncwarp();
         if (p.zscore) {
           zscore_inplace(s_m, C, lane);
@@ -981,12 +992,19 @@ static int validate(const mb200_eval_desc* d) {
   if (d->news_category &&
       (d->num_categ_classes < 1 || d->num_categ_classes > MB200_MAX_CLASSES || d->num_sent_classes < 1 || d->num_sent_classes > MB200_MAX_CLASSES))
     return MB200_ERR_INVALID_ARG;
+  if (d->n_table_shards < 0 || d->n_table_shards > MB200_MAX_TABLE_SHARDS) return MB200_ERR_INVALID_ARG;
+  if (d->n_table_shards > 1) {
+    if (d->table_shard_shift < 1 || d->table_shard_shift > 30 || ((long long)d->n_table_shards << d->table_shard_shift) < d->n_news) return MB200_ERR_INVALID_ARG;
+    for (int m = 0; m < d->n_modules; ++m)
+      for (int sh = 0; sh < d->n_table_shards; ++sh)
+        if (((d->active_modules_mask >> m) & 1) && (d->table_shards[m][sh] == nullptr || ((uintptr_t)d->table_shards[m][sh] & 15))) return MB200_ERR_INVALID_ARG;
+  }
   if (d->loss_kind < MB200_LOSS_NONE || d->loss_kind > MB200_LOSS_SUPCON) return MB200_ERR_INVALID_ARG;
   if (d->loss_kind == MB200_LOSS_SUPCON && !(d->loss_temperature > 0.f)) return MB200_ERR_INVALID_ARG;
   if (d->loss_kind != MB200_LOSS_NONE && (d->scores_weighting < 0 || d->scores_weighting >= d->n_weightings)) return MB200_ERR_INVALID_ARG;
   const int esz = d->dtype == MB200_F32 ? 4 : 2;
   for (int m = 0; m < d->n_modules; ++m) {
-    if (((d->active_modules_mask >> m) & 1) && (d->tables[m] == nullptr || ((uintptr_t)d->tables[m] & 15))) return MB200_ERR_INVALID_ARG;
+    if (d->n_table_shards <= 1 && ((d->active_modules_mask >> m) & 1) && (d->tables[m] == nullptr || ((uintptr_t)d->tables[m] & 15))) return MB200_ERR_INVALID_ARG;
   }
   if ((d->row_stride * esz) % 16 != 0 || (d->dim * esz) % 16 != 0) return MB200_ERR_UNSUPPORTED;
   const int vec_per_row = d->dim * esz / 16;
@@ -1007,10 +1025,11 @@ static KernelFn generic_kernel(bool attn) {
 }
 
 template <typename T>
-static KernelFn select_kernel(int vec_per_row, bool attn) {
+static KernelFn select_kernel(int vec_per_row, bool attn, bool sharded) {
   constexpr int kRefNV = 768 / Elem<T>::E / 32;  // 6 (fp32) or 3 (bf16)
   constexpr int R = (kRefNV == 6) ? 4 : 8;
   constexpr int R3 = (R * 3 + 3) / 4, R2 = (R + 1) / 2;
+  if (sharded) return (vec_per_row == kRefNV * 32 && !attn) ? score_eval_kernel<T, kRefNV, R3, true, 3, 4> : nullptr;
   if (vec_per_row == kRefNV * 32 && attn) return score_eval_kernel<T, kRefNV, R3, true, 0, 4, true>;  // early fusion (separate code: the late-fusion kernels keep their tuning)
   if (vec_per_row == kRefNV * 32) {
     int variant = tuning().variant;
@@ -1085,7 +1104,7 @@ int score_eval(const mb200_eval_desc* d, cudaStream_t stream) {
   int st = validate(d);
   if (st != MB200_OK) return st;
   int device = 0;
-  st = use_device_of(d->tables[0], &device);
+  st = use_device_of(d->n_table_shards > 1 ? (const void*)d->sums : d->tables[0], &device);  // sharded tables: peers own most shards
   if (st != MB200_OK) return st;
   int sms = 0;
   st = sm_count_of(device, &sms);
@@ -1094,7 +1113,9 @@ int score_eval(const mb200_eval_desc* d, cudaStream_t stream) {
   const int vec_per_row = d->dim * (d->dtype == MB200_F32 ? 4 : 2) / 16;
   bool attn = false;
   for (int m = 0; m < d->n_modules; ++m) attn |= ((d->active_modules_mask >> m) & 1) && d->attn_logits[m] != nullptr;
-  KernelFn kern = (d->dtype == MB200_F32) ? select_kernel<float>(vec_per_row, attn) : select_kernel<__nv_bfloat16>(vec_per_row, attn);
+  const bool sharded = d->n_table_shards > 1;
+  KernelFn kern = (d->dtype == MB200_F32) ? select_kernel<float>(vec_per_row, attn, sharded) : select_kernel<__nv_bfloat16>(vec_per_row, attn, sharded);
+  if (kern == nullptr) return MB200_ERR_UNSUPPORTED;  // row-sharded tables: reference width, late fusion only
   LaunchPlan plan;
   st = make_plan(d, sms, 1, &plan);  // shared-memory sizes first: they decide how many CTAs fit
   if (st != MB200_OK) return st;
@@ -1115,6 +1136,11 @@ int score_eval(const mb200_eval_desc* d, cudaStream_t stream) {
 
   EvalParams p{};
   for (int m = 0; m < MB200_MAX_MODULES; ++m) p.tables[m] = d->tables[m];
+  if (sharded) {
+    for (int m = 0; m < d->n_modules; ++m)
+      for (int sh = 0; sh < d->n_table_shards; ++sh) p.shard_base[m][sh] = d->table_shards[m][sh];
+    p.shard_shift = d->table_shard_shift;
+  }
   p.hist_offsets = d->hist_offsets, p.hist_ids = d->hist_ids, p.cand_offsets = d->cand_offsets, p.cand_ids = d->cand_ids;
   p.labels = d->labels, p.weights = d->weights;
   p.news_category = d->news_category, p.news_sentiment = d->news_sentiment;

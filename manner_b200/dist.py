@@ -33,6 +33,48 @@ def shard_for_rank(bhv: Behaviours, rank: int, world_size: int, align: int = 1) 
     return bhv.slice(int(bounds[rank]), int(bounds[rank + 1]))
 
 
+class _PeerMemory:
+    """A peer GPU's memory mapped into this process, presented to torch through the CUDA array interface (zero copy)."""
+
+    def __init__(self, ptr: int, shape, dtype: torch.dtype) -> None:
+        typestr = {torch.float32: "<f4", torch.bfloat16: "<u2", torch.float16: "<f2"}[dtype]
+        self.__cuda_array_interface__ = {"data": (int(ptr), False), "shape": tuple(shape), "typestr": typestr, "version": 2, "strides": None}
+
+
+def share_table_shards(local_shard: Tensor, group: Optional[dist.ProcessGroup] = None) -> list:
+    """Row-sharded embedding table over the GPUs of one box: every rank contributes the shard it holds ([2**s, dim],
+    contiguous, on its GPU) and gets back the list of ALL shards as tensors whose memory its own GPU's kernels can read --
+    the peers' shards are mapped through CUDA IPC with peer access (mb200_ipc_export / mb200_ipc_open), so the fused kernel
+    loads remote rows directly over NVLink / NVSwitch.  No data moves here; keep ``local_shard`` alive while any rank uses it."""
+    import ctypes
+
+    from . import _native as nat
+
+    lib = nat.lib()
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    if not local_shard.is_cuda or not local_shard.is_contiguous():
+        raise ValueError("the local shard must be a contiguous CUDA tensor")
+    handle = ctypes.create_string_buffer(64)
+    offset = ctypes.c_int64(0)
+    nat.check(lib.mb200_ipc_export(local_shard.data_ptr(), handle, ctypes.byref(offset)), "mb200_ipc_export")
+    mine = (bytes(handle.raw), int(offset.value), local_shard.device.index, tuple(local_shard.shape), local_shard.dtype)
+    gathered: list = [None] * world
+    dist.all_gather_object(gathered, mine, group=group)
+    shards = []
+    for r, (h, off, peer_dev, shape, dtype) in enumerate(gathered):
+        if r == rank:
+            shards.append(local_shard)
+            continue
+        nat.check(lib.mb200_enable_peer_access(local_shard.device.index, peer_dev), "mb200_enable_peer_access")
+        ptr = ctypes.c_void_p()
+        nat.check(lib.mb200_ipc_open(h, off, local_shard.device.index, ctypes.byref(ptr)), "mb200_ipc_open")
+        t = torch.as_tensor(_PeerMemory(ptr.value, shape, dtype), device=torch.device("cuda", peer_dev))
+        shards.append(t.view(torch.bfloat16) if dtype == torch.bfloat16 else t)
+    torch.cuda.synchronize(local_shard.device)
+    dist.barrier(group=group)
+    return shards
+
+
 def pack_metric_payload(sums: Tensor, flags: Tensor, n_impressions: int) -> Tensor:
     """[W, NUM_METRICS] sums, the impression count and the flag word's bits as one fp64 vector (all additive)."""
     bits = ((flags.to(torch.int64).reshape(1) >> torch.arange(N_FLAG_BITS, device=flags.device)) & 1).to(torch.float64)

@@ -129,15 +129,34 @@ class ScoreEvaluator:
         num_sent_classes: int = NUM_SENT_CLASSES,
         ks: Tuple[int, int] = (5, 10),
         attention: Optional[Sequence[Optional[Tuple[Tensor, Tensor, Tensor]]]] = None,
+        table_shards: Optional[Sequence[Sequence[Tensor]]] = None,
+        n_news: Optional[int] = None,
     ) -> None:
+        """``table_shards`` (instead of ``tables``): row-sharded tables for catalogues too large to replicate --
+        ``table_shards[m]`` = the R shards of module m, each [2**s, dim] on ITS OWN GPU (this rank's shard plus the peers'
+        opened with ``dist.share_table_shards``), ``n_news`` the catalogue size; row n lives in shard n >> s.  The kernel
+        reads remote rows over NVLink.  Late fusion, reference width."""
         nat.lib()  # fail now, loudly, if the CUDA library is not built
         if not torch.cuda.is_available():
             raise RuntimeError("manner_b200.ScoreEvaluator needs a CUDA device; there is no CPU path")
         self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
-        if not 1 <= len(tables) <= nat.MAX_MODULES:
-            raise ValueError(f"1..{nat.MAX_MODULES} tables expected")
-        self.tables: List[Tensor] = [t.to(self.device, non_blocking=True).contiguous() for t in tables]
-        self.n_news, self.dim = self.tables[0].shape
+        self.n_table_shards, self.table_shard_shift = 1, 0
+        if table_shards is not None:
+            if attention is not None or n_news is None:
+                raise ValueError("row-sharded tables need n_news and support late fusion only")
+            r, rows = len(table_shards[0]), table_shards[0][0].shape[0]
+            if rows & (rows - 1) or any(len(s) != r for s in table_shards) or not 1 <= len(table_shards) <= nat.MAX_MODULES:
+                raise ValueError("every module needs the same number of shards of 2**s rows each")
+            self.n_modules = len(table_shards)
+            self.tables = [t for shards in table_shards for t in shards]  # module-major, as ops.score_eval takes them
+            self.n_table_shards, self.table_shard_shift = r, rows.bit_length() - 1
+            self.n_news, self.dim = int(n_news), self.tables[0].shape[1]
+        else:
+            if not 1 <= len(tables) <= nat.MAX_MODULES:
+                raise ValueError(f"1..{nat.MAX_MODULES} tables expected")
+            self.tables: List[Tensor] = [t.to(self.device, non_blocking=True).contiguous() for t in tables]
+            self.n_modules = len(self.tables)
+            self.n_news, self.dim = self.tables[0].shape
         self.ks = (int(ks[0]), int(ks[1]))
         self.num_categ_classes, self.num_sent_classes = int(num_categ_classes), int(num_sent_classes)
         self.news_category = self._aspect(news_category)
@@ -213,7 +232,7 @@ class ScoreEvaluator:
         SupCon); it and early fusion need ``upload(..., step_batch=...)``."""
         if (loss == "ce" or self.attn_logits is not None) and bhv.hist_pad is None:
             raise ValueError("early fusion / the cross-entropy loss depend on the reference's step padding: upload(..., step_batch=8)")
-        n_mod = len(self.tables)
+        n_mod = self.n_modules
         w_dev: Optional[Tensor] = None
         active = (1 << n_mod) - 1
         if isinstance(weights, Tensor) and weights.is_cuda:
@@ -234,7 +253,7 @@ class ScoreEvaluator:
             self.news_category, self.news_sentiment, self.num_categ_classes, self.num_sent_classes,
             self.attn_logits if self.attn_logits is not None else [], distributed,
             bhv.hist_pad if self.attn_logits is not None else None, loss_kind, float(temperature),
-            bhv.cand_pad if loss == "ce" else None,
+            bhv.cand_pad if loss == "ce" else None, self.n_table_shards, self.table_shard_shift, self.n_news,
         )
         loss_stats: Optional[Tensor] = None
         if loss is not None:

@@ -68,6 +68,9 @@ def score_eval(
     loss_kind: int = 0,
     loss_temperature: float = 1.0,
     cand_pad: Optional[Tensor] = None,
+    n_table_shards: int = 1,
+    table_shard_shift: int = 0,
+    n_news: int = 0,
 ) -> Tuple[Tensor, Tensor, Tensor, Tensor, Tensor]:
     """Fused gather / pool / score / z-score / ensemble / per-impression metrics (include/manner_b200.h,
     mb200_score_eval).  Returns (scores fp32 [sum C] or empty, per_impression fp32 [W, B, NUM_METRICS] or empty,
@@ -78,9 +81,16 @@ def score_eval(
     Early fusion (cr_module.py:124-125): ``attn_logits`` is ``[]`` (late fusion everywhere) or one entry per table: ``attn_logits[m]`` = the [n_news + 1] logits of ``attention_logits`` for
     module m (None keeps module m on late fusion) and ``hist_pad`` [B] int32 = zero rows the reference's
     step batch pads impression i's history with.  ``loss_kind`` (nat.LOSS_CE / LOSS_SUPCON) adds the per-impression
-    loss of cr_module.py:140-171 (``cand_pad`` [B]: padded candidate columns, cross entropy only)."""
+    loss of cr_module.py:140-171 (``cand_pad`` [B]: padded candidate columns, cross entropy only).
+
+    Row-sharded tables (``n_table_shards`` = R > 1): ``tables`` then holds R tensors per module, module-major, each
+    [1 << table_shard_shift, dim] -- this GPU's shard and the peers' shards opened over CUDA IPC (dist.share_table_shards);
+    ``n_news`` is the size of the whole catalogue.  The kernel reads remote rows directly over NVLink."""
     lib = nat.lib()
-    if len(tables) < 1 or len(tables) > nat.MAX_MODULES:
+    n_modules = len(tables) // max(n_table_shards, 1)
+    if n_table_shards > 1 and (n_table_shards > nat.MAX_TABLE_SHARDS or n_modules * n_table_shards != len(tables) or n_news <= 0):
+        raise ValueError("row-sharded tables: pass n_modules x n_table_shards tensors (module-major) and the catalogue size n_news")
+    if n_modules < 1 or n_modules > nat.MAX_MODULES:
         raise ValueError(f"1..{nat.MAX_MODULES} embedding tables expected")
     t0 = tables[0]
     if t0.dtype not in (torch.float32, torch.bfloat16):
@@ -90,7 +100,7 @@ def score_eval(
             raise RuntimeError("manner_b200: embedding tables must be CUDA tensors (there is no CPU path)")
         if t.dtype != t0.dtype or t.shape != t0.shape or t.dim() != 2 or t.stride(1) != 1 or t.stride(0) != t0.stride(0):
             raise ValueError(f"table {m}: all tables must share dtype, shape [n_news, dim] and row stride")
-    dev = t0.device
+    dev = hist_offsets.device if n_table_shards > 1 else t0.device  # sharded: tables[0] may be a peer GPU's shard
     for name, t, dt in (
         ("hist_offsets", hist_offsets, torch.int32), ("hist_ids", hist_ids, torch.int32),
         ("cand_offsets", cand_offsets, torch.int32), ("cand_ids", cand_ids, torch.int32), ("labels", labels, torch.uint8),
@@ -102,7 +112,7 @@ def score_eval(
     n_w = 1
     if weights is not None:
         _require_cuda("weights", weights, torch.float32)
-        if weights.dim() != 2 or weights.shape[1] != len(tables):
+        if weights.dim() != 2 or weights.shape[1] != n_modules:
             raise ValueError("weights must be [n_weightings, n_modules]")
         n_w = weights.shape[0]
     if (news_category is None) != (news_sentiment is None):
@@ -111,7 +121,7 @@ def score_eval(
         _require_cuda("news_category", news_category, torch.int32)
         _require_cuda("news_sentiment", news_sentiment, torch.int32)
     if len(attn_logits):
-        if len(attn_logits) != len(tables):
+        if len(attn_logits) != n_modules:
             raise ValueError("attn_logits needs one entry per table (None = late fusion for that module)")
         for a in attn_logits:
             if a is not None:
@@ -140,14 +150,22 @@ def score_eval(
         d.loss_per_impression = loss_out.data_ptr() if loss_kind else None
         d.pack_payload = int(pack_payload)
         d.struct_size = ctypes.sizeof(nat.EvalDesc)
-        d.n_modules = len(tables)
+        d.n_modules = n_modules
         d.dtype = nat.F32 if t0.dtype == torch.float32 else nat.BF16
         d.dim = t0.shape[1]
         d.active_modules_mask = active_mask
-        d.n_news = t0.shape[0]
         d.row_stride = t0.stride(0)
-        for m, t in enumerate(tables):
-            d.tables[m] = t.data_ptr()
+        if n_table_shards > 1:
+            if t0.shape[0] != (1 << table_shard_shift):
+                raise ValueError("every table shard must hold 1 << table_shard_shift rows")
+            d.n_news, d.n_table_shards, d.table_shard_shift = n_news, n_table_shards, table_shard_shift
+            for m in range(n_modules):
+                for sh in range(n_table_shards):
+                    d.table_shards[m][sh] = tables[m * n_table_shards + sh].data_ptr()
+        else:
+            d.n_news = t0.shape[0]
+            for m, t in enumerate(tables):
+                d.tables[m] = t.data_ptr()
         d.n_impressions = n_impr
         d.hist_offsets, d.hist_ids = hist_offsets.data_ptr(), hist_ids.data_ptr()
         d.cand_offsets, d.cand_ids, d.labels = cand_offsets.data_ptr(), cand_ids.data_ptr(), labels.data_ptr()
@@ -178,7 +196,8 @@ def score_eval(
 @score_eval.register_fake
 def _(tables, hist_offsets, hist_ids, cand_offsets, cand_ids, labels, weights, zscore, max_cand, active_mask, k0, k1,
       want_scores, scores_weighting, want_per_impression, news_category, news_sentiment, num_categ_classes, num_sent_classes,
-      attn_logits, pack_payload=False, hist_pad=None, loss_kind=0, loss_temperature=1.0, cand_pad=None):
+      attn_logits, pack_payload=False, hist_pad=None, loss_kind=0, loss_temperature=1.0, cand_pad=None, n_table_shards=1,
+      table_shard_shift=0, n_news=0):
     dev = tables[0].device
     n_w = 1 if weights is None else weights.shape[0]
     n_impr = hist_offsets.numel() - 1
