@@ -166,3 +166,28 @@ def test_metrics_desc_layout_and_validation_without_a_gpu(tmp_path):
     assert off.tolist() == [0, 3, 5, 6] and perm.tolist() == [2, 4, 5, 0, 1, 3] and mx == 3
     off, perm, mx = metrics._offsets_from_indexes(torch.tensor([0, 0, 1, 3, 3]))
     assert off.tolist() == [0, 2, 3, 5] and perm is None and mx == 2
+
+
+def test_ipc_and_sharded_table_entry_points_reject_bad_arguments_without_a_gpu():
+    lib = nat.lib()
+    buf = ctypes.create_string_buffer(64)
+    off = ctypes.c_int64(0)
+    out = ctypes.c_void_p()
+    assert lib.mb200_ipc_export(None, buf, ctypes.byref(off)) == nat.ERR_INVALID_ARG
+    assert lib.mb200_ipc_open(None, 0, 0, ctypes.byref(out)) == nat.ERR_INVALID_ARG
+    assert lib.mb200_ipc_open(buf.raw, -1, 0, ctypes.byref(out)) == nat.ERR_INVALID_ARG
+    # descriptor validation of row-sharded tables is host-side
+    d = nat.EvalDesc()
+    d.struct_size = ctypes.sizeof(nat.EvalDesc)
+    d.n_modules, d.dtype, d.dim, d.active_modules_mask, d.n_news, d.row_stride = 1, nat.F32, 768, 1, 5000, 768
+    d.n_impressions, d.max_cand, d.n_weightings, d.k0, d.k1 = 4, 10, 1, 5, 10
+    for name in ("hist_offsets", "hist_ids", "cand_offsets", "cand_ids", "labels", "sums"):
+        setattr(d, name, 0x1000)
+    d.n_table_shards, d.table_shard_shift = 2, 12
+    assert lib.mb200_eval_workspace_bytes(ctypes.byref(d)) == 0  # shard pointers missing
+    d.table_shards[0][0], d.table_shards[0][1] = 0x10000, 0x20000
+    assert lib.mb200_eval_workspace_bytes(ctypes.byref(d)) > 0
+    d.table_shard_shift = 11  # 2 x 2048 rows < 5000 news
+    assert lib.mb200_eval_workspace_bytes(ctypes.byref(d)) == 0
+    d.table_shard_shift, d.n_table_shards = 12, 9
+    assert lib.mb200_eval_workspace_bytes(ctypes.byref(d)) == 0
