@@ -319,8 +319,11 @@ MB200_API float mb200_dcg_discount(int rank);
  * separately by mb200_library_launch_count). */
 MB200_API int64_t mb200_launch_count(void);
 MB200_API int64_t mb200_library_launch_count(void);
-/* tuning knobs (key: 0 = chunks per warp, 1 = row-load cache policy, 2 = CTAs per SM, 3 = time the fused
- * kernel with CUDA events); returns the previous value */
+/* tuning knobs; returns the previous value.  key 0 = impression chunks per warp; 1 = variant of the reference-width fused
+ * kernel (-1 = by table type [default], 0/2/3/5/6 = rows in flight x resident CTAs per SM: 4x3, 3x4, 2x5, 3x6, 2x7 for fp32
+ * rows, twice the rows for bf16; 1 = 4x3 with L1::no_allocate loads); 2 = cap on CTAs per SM; 3 = time the fused kernel with
+ * CUDA events; 4 = retrieval diagnostics (1, 2: parts of the epilogue disabled, RESULTS INVALID; 4: cycle counters in the
+ * workspace header, results valid); 5 = retrieval pipeline (1 = CTA pairs / tcgen05 cta_group::2 [default], 0 = one CTA per tile) */
 MB200_API int mb200_set_tuning(int key, int value);
 
 /* duration in ms of the most recent fused score/eval kernel launched while tuning key 3 was on
