@@ -339,6 +339,9 @@ def run_gpu_arm(args) -> None:
             # zipf-shaped ids: ~83 % of the gathered sectors hit the 126 MB L2, so `achieved` (algorithmic bytes / time) exceeds the
             # HBM copy peak and the binding resource is L2 -> SM bandwidth; --uniform-ids is the HBM-bound case
             "l2": l2_note,
+            # what actually crossed the HBM interface per second (ncu DRAM bytes of the same launch / live kernel time)
+            "dram_achieved": (traffic / (k_ms * 1e-3) / 1e9) if traffic else None,
+            "dram_frac": (traffic / (k_ms * 1e-3) / 1e9 / hbm_peak) if traffic else None,
         },
         "cpu_baseline": cpu,
         "clocks": clocks,
