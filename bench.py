@@ -306,10 +306,12 @@ def run_gpu_arm(args) -> None:
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tpath):
         with open(tpath) as f:
-            t = json.load(f)
-        if t.get("shape") == args.workload and t.get("n_modules") == args.modules and bool(t.get("uniform_ids")) == args.uniform_ids:
-            traffic = t.get("dram_bytes_per_launch")
-            l2_note = t.get("l2")
+            entries = json.load(f).get("entries", [])
+        for t in entries:  # ncu captures of this exact workload (fp32 tables, default kernel)
+            if (t.get("shape") == args.workload and t.get("n_modules") == args.modules and bool(t.get("uniform_ids")) == args.uniform_ids
+                    and args.table_dtype == "f32" and not args.sweep and not args.early_fusion):
+                traffic = t.get("dram_bytes_per_launch")
+                l2_note = t.get("l2")
 
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
