@@ -53,7 +53,10 @@ class LightningModule(torch.nn.Module):
     def save_hyperparameters(self, *args: Any, logger: bool = True, **kwargs: Any) -> None:
         frame = inspect.currentframe().f_back
         local = frame.f_locals
-        names = [n for n in inspect.signature(type(self).__init__).parameters if n != "self"]
+        # like Lightning: the arguments of the __init__ whose frame called us (the class that owns the frame), so a
+        # subclass with an (*args, **kwargs) constructor still records the reference module's own keywords
+        owner = local.get("__class__", type(self))
+        names = [n for n in inspect.signature(owner.__init__).parameters if n != "self"]
         self.hparams.update({n: local[n] for n in names if n in local})
 
     def log(self, name: str, value: Any, *args: Any, **kwargs: Any) -> None:

@@ -1,0 +1,63 @@
+"""CPU, only where the reference checkout exists (this container, not the GPU box): the drop-in modules really are
+subclasses of the reference's own CRModule -- same constructor keywords, same parameter names (so Lightning checkpoints
+load), B200 hooks first in the method resolution order.  The reference's heavy dependencies are shimmed exactly as for the
+golden generator (oracle/ref_stubs.py); the PLM encoder is replaced by a small module.  Runs in a subprocess: installing the
+shims changes sys.modules / sys.path for good."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REFERENCE = "/root/reference"
+pytestmark = pytest.mark.skipif(not os.path.isdir(os.path.join(REFERENCE, "manner")), reason="reference checkout not present")
+
+SCRIPT = r'''
+import sys
+sys.path.insert(0, %(root)r)
+import torch
+from oracle import ref_stubs
+ref_stubs.install(%(ref)r)
+import manner.models.cr_module as ref_cr
+
+
+class TinyEncoder(torch.nn.Module):
+    def __init__(self, *args, **kwargs):
+        super().__init__()
+        self.proj = torch.nn.Linear(4, 8)
+
+
+ref_cr.MannerNewsEncoder = TinyEncoder
+from manner_b200 import modules
+assert modules.HAVE_REFERENCE
+KW = dict(supcon_loss=True, late_fusion=False, temperature=0.36, plm_model="", frozen_layers=[], dropout_probability=0.2,
+          use_entities=False, pretrained_entity_embeddings_path="", entity_embedding_dim=100, num_attention_heads=10,
+          query_vector_dim=16, text_embedding_dim=8, optimizer=None)
+ref = ref_cr.CRModule(**KW)
+ours = modules.CRModuleB200(**KW)  # same keywords; `scorer` is defaulted
+assert isinstance(ours, ref_cr.CRModule)
+assert list(ours.state_dict().keys()) == list(ref.state_dict().keys())  # checkpoints of the reference load unchanged
+ours.load_state_dict(ref.state_dict())
+assert ours.hparams["temperature"] == 0.36 and ours.hparams["late_fusion"] is False  # the reference's own hparams are recorded
+mro = [c.__name__ for c in type(ours).__mro__]
+assert mro.index("B200EvalMixin") < mro.index("CRModule")
+assert ours._b200_loss() == "supcon" and ours._b200_cached is False
+att = ours._b200_attention()  # early fusion: the module's own additive-attention parameters
+assert att is not None and att[0][0] is ours.user_encoder.additive_attention.linear.weight
+assert att[0][2] is ours.user_encoder.additive_attention.query
+late = modules.CRModuleB200(**dict(KW, late_fusion=True, supcon_loss=False), scorer="b200_cached")
+assert late._b200_attention() is None and late._b200_loss() == "ce" and late._b200_cached is True
+assert modules.CRModuleB200(**KW, scorer="reference")._b200_enabled is False
+try:
+    modules.CRModuleB200(**KW, scorer="cpu")
+    raise SystemExit("a bad scorer was accepted")
+except ValueError:
+    pass
+print("dropin ok")
+'''
+
+
+def test_cr_module_b200_is_the_reference_module_with_b200_hooks():
+    out = subprocess.run([sys.executable, "-c", SCRIPT % {"root": ROOT, "ref": REFERENCE}], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and "dropin ok" in out.stdout, out.stderr[-3000:]
