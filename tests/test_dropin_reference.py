@@ -54,6 +54,30 @@ try:
     raise SystemExit("a bad scorer was accepted")
 except ValueError:
     pass
+
+# ---- EnsembleModuleB200 on the reference's EnsembleModule (sub-modules come from checkpoints: patched like make_golden.py) ----
+import manner.models.a_module as ref_a
+import manner.models.ensemble_module as ref_ens
+
+
+class Sub(torch.nn.Module):
+    def __init__(self, tag):
+        super().__init__()
+        self.news_encoder = TinyEncoder()
+        self.tag = tag
+
+
+ref_cr.CRModule.load_from_checkpoint = classmethod(lambda cls, checkpoint_path, **kw: Sub(checkpoint_path))
+ref_a.AModule.load_from_checkpoint = classmethod(lambda cls, checkpoint_path, **kw: Sub(checkpoint_path))
+EKW = dict(cr_module_module_ckpt="cr", a_module_categ_ckpt="categ", a_module_sent_ckpt="sent", categ_weight=0.3, sent_weight=0,
+           num_categ_classes=19, num_sent_classes=4)
+ens = modules.EnsembleModuleB200(**EKW)
+assert isinstance(ens, ref_ens.EnsembleModule) and ens.hparams["categ_weight"] == 0.3
+assert list(ens.state_dict().keys()) == list(ref_ens.EnsembleModule(**EKW).state_dict().keys())
+encs = ens._b200_encoders()
+assert len(encs) == 2 and encs[0] is ens.cr_module.news_encoder and encs[1] is ens.a_module_categ.news_encoder  # sent_weight 0: not loaded
+assert ens._b200_weights() == [1.0, 0.3] and ens._b200_zscore and not ens._b200_with_auc and ens._b200_loss() is None
+assert modules.EnsembleModuleB200(**dict(EKW, sent_weight=0.5), scorer="b200_cached")._b200_weights() == [1.0, 0.3, 0.5]
 print("dropin ok")
 '''
 
