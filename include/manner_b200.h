@@ -288,6 +288,19 @@ typedef struct mb200_retrieval_desc {
   float* debug_scores;  /* optional [n_users, n_catalog] fp32: the full score matrix (tests only) */
   void* workspace;      /* >= mb200_retrieval_workspace_bytes(desc), 256-byte aligned */
   size_t workspace_bytes;
+
+  /* Fused exchange for a row-sharded catalogue (replaces the NCCL all-gather of the per-shard lists): when n_peers > 1 every
+     finished user row is also STORED into the gather buffers of the other GPUs over NVLink / NVSwitch peer memory, while
+     the kernel keeps scoring the next user tiles.  peer_scores[r] / peer_ids[r] = GPU r's gather buffers
+     [n_peers, peer_rows, k] as seen from this process (mb200_ipc_open); this rank writes slot `my_rank`, rows
+     [0, n_users).  out_scores / out_ids must then be this rank's own slot of its own gather buffer
+     (peer_scores[my_rank] + my_rank * peer_rows * k).  After a cross-GPU completion signal (any collective on the same
+     stream) each GPU merges its buffer with mb200_merge_topk. */
+  int32_t n_peers; /* 0 / 1 = no fused exchange */
+  int32_t my_rank;
+  int64_t peer_rows;
+  float* peer_scores[MB200_MAX_TABLE_SHARDS];
+  int64_t* peer_ids[MB200_MAX_TABLE_SHARDS];
 } mb200_retrieval_desc;
 
 MB200_API size_t mb200_retrieval_workspace_bytes(const mb200_retrieval_desc* desc);

@@ -125,6 +125,11 @@ class RetrievalDesc(Structure):
         ("debug_scores", c_void_p),
         ("workspace", c_void_p),
         ("workspace_bytes", c_size_t),
+        ("n_peers", c_int32),
+        ("my_rank", c_int32),
+        ("peer_rows", c_int64),
+        ("peer_scores", c_void_p * MAX_TABLE_SHARDS),
+        ("peer_ids", c_void_p * MAX_TABLE_SHARDS),
     ]
 
 

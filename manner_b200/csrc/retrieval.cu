@@ -64,6 +64,11 @@ struct RetrievalParams {
   long long n_users, n_catalog, id_offset;
   int dim, k, m_tiles, n_tiles;
   int diag;  // Tuning::retrieval_diag
+  // fused exchange: gather buffers of the peer GPUs ([n_peers][peer_rows][k], this rank writes slot my_rank); 0 = off
+  int n_peers, my_rank;
+  long long peer_rows;
+  float* peer_scores[MB200_MAX_TABLE_SHARDS];
+  long long* peer_ids[MB200_MAX_TABLE_SHARDS];
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -639,6 +644,17 @@ retrieve_topk_kernel(const __grid_constant__ CUtensorMap tmap_users, const __gri
         if (n > p.k) compact_row(cs0, ci0, n, p.k, lane, true, &n_new); else __syncwarp();
         write_sorted_row(cs0, ci0, min(n, p.k), p.k, p.out_scores + u_row * p.k, p.out_ids + u_row * p.k, p.id_offset, lane);
         __syncwarp();
+        if (p.n_peers > 1) {
+          // fused exchange: the finished list goes straight into slot `my_rank` of every other GPU's gather buffer (peer
+          // stores over NVLink / NVSwitch), overlapped with the MMA of the user tiles this CTA still has to sweep
+          for (int t = lane; t < p.k; t += 32) {
+            const float sv = p.out_scores[u_row * p.k + t];
+            const long long iv = p.out_ids[u_row * p.k + t];
+            const size_t at = ((size_t)p.my_rank * p.peer_rows + u_row) * p.k + t;
+            for (int r = 0; r < p.n_peers; ++r)
+              if (r != p.my_rank) p.peer_scores[r][at] = sv, p.peer_ids[r][at] = iv;
+          }
+        }
       }
       *thr_mine = -CUDART_INF_F;  // the next user tile starts from scratch
       __threadfence_block();
@@ -790,6 +806,11 @@ int retrieve_topk(const mb200_retrieval_desc* d, cudaStream_t stream) {
   if (d->dim < rt::BLOCK_K || d->dim % rt::BLOCK_K != 0) return MB200_ERR_UNSUPPORTED;
   if (d->n_catalog > 0x7fffff00ll || d->n_users > 0x7fffff00ll * (long long)rt::BLOCK_M) return MB200_ERR_UNSUPPORTED;
   if (((uintptr_t)d->users & 15) || ((uintptr_t)d->catalog & 15)) return MB200_ERR_INVALID_ARG;
+  if (d->n_peers > 1) {
+    if (d->n_peers > MB200_MAX_TABLE_SHARDS || d->my_rank < 0 || d->my_rank >= d->n_peers || d->peer_rows < d->n_users) return MB200_ERR_INVALID_ARG;
+    for (int r = 0; r < d->n_peers; ++r)
+      if (!d->peer_scores[r] || !d->peer_ids[r]) return MB200_ERR_INVALID_ARG;
+  }
   int device = 0;
   int st = use_device_of(d->users, &device);
   if (st != MB200_OK) return st;
@@ -813,6 +834,8 @@ int retrieve_topk(const mb200_retrieval_desc* d, cudaStream_t stream) {
   p.n_users = d->n_users, p.n_catalog = d->n_catalog, p.id_offset = d->catalog_id_offset;
   p.dim = d->dim, p.k = d->k;
   p.diag = tuning().retrieval_diag;
+  p.n_peers = d->n_peers > 1 ? d->n_peers : 0, p.my_rank = d->my_rank, p.peer_rows = d->peer_rows;
+  for (int r = 0; r < p.n_peers; ++r) p.peer_scores[r] = d->peer_scores[r], p.peer_ids[r] = reinterpret_cast<long long*>(d->peer_ids[r]);
   p.m_tiles = (int)((d->n_users + rt::BLOCK_M - 1) / rt::BLOCK_M);
   p.n_tiles = (int)((d->n_catalog + rt::BLOCK_N - 1) / rt::BLOCK_N);
   st = cuda_status(cudaMemsetAsync(p.error_flag, 0, 256, stream), "cudaMemsetAsync");

@@ -37,12 +37,13 @@ class _PeerMemory:
     """A peer GPU's memory mapped into this process, presented to torch through the CUDA array interface (zero copy)."""
 
     def __init__(self, ptr: int, shape, dtype: torch.dtype) -> None:
-        typestr = {torch.float32: "<f4", torch.bfloat16: "<u2", torch.float16: "<f2"}[dtype]
+        typestr = {torch.float32: "<f4", torch.bfloat16: "<u2", torch.float16: "<f2", torch.int64: "<i8", torch.int32: "<i4"}[dtype]
         self.__cuda_array_interface__ = {"data": (int(ptr), False), "shape": tuple(shape), "typestr": typestr, "version": 2, "strides": None}
 
 
 def share_table_shards(local_shard: Tensor, group: Optional[dist.ProcessGroup] = None) -> list:
-    """Row-sharded embedding table over the GPUs of one box: every rank contributes the shard it holds ([2**s, dim],
+    """(Also used for any other buffer the peers' kernels read or write directly, e.g. the retrieval gather buffers.)
+    Row-sharded embedding table over the GPUs of one box: every rank contributes the shard it holds ([2**s, dim],
     contiguous, on its GPU) and gets back the list of ALL shards as tensors whose memory its own GPU's kernels can read --
     the peers' shards are mapped through CUDA IPC with peer access (mb200_ipc_export / mb200_ipc_open), so the fused kernel
     loads remote rows directly over NVLink / NVSwitch.  No data moves here; keep ``local_shard`` alive while any rank uses it."""

@@ -16,14 +16,17 @@ merge kernel:
 
   * ``exchange="all_gather"``  every rank ends with the merged lists of all users (the north star's wording);
   * ``exchange="all_to_all"``  rank r ends with the merged lists of its 1/R slice of every user block
-                               (1/R of the NVLink bytes and of the merge work).
+                               (1/R of the NVLink bytes and of the merge work);
+  * ``exchange="p2p"``         the exchange is fused into the kernel: every finished list is stored straight into all
+                               GPUs' gather buffers over NVLink / NVSwitch peer memory (CUDA IPC) while the kernel keeps
+                               scoring; the only collective left is a 4-byte completion signal.
 
 torch is plumbing (memory, streams, NCCL); the arithmetic is in manner_b200/csrc/retrieval.cu.
 """
 from __future__ import annotations
 
 import ctypes
-from typing import Callable, Optional, Tuple
+from typing import Callable, Optional, Sequence, Tuple
 
 import torch
 from torch import Tensor
@@ -102,6 +105,38 @@ def _(users, catalog, k, catalog_id_offset=0, want_scores_matrix=False):
     )
 
 
+def retrieve_topk_p2p(users: Tensor, catalog: Tensor, k: int, catalog_id_offset: int, gather_scores: Sequence[Tensor],
+                      gather_ids: Sequence[Tensor], my_rank: int) -> None:
+    """mb200_retrieve_topk with the fused exchange: ``gather_scores[r]`` / ``gather_ids[r]`` are GPU r's gather buffers
+    [R, rows, k] (fp32 / int64) as this process sees them (``dist.share_table_shards``); the kernel writes this rank's lists
+    into slot ``my_rank`` of ALL of them -- its own through ordinary stores, the peers' over NVLink -- while it is still
+    scoring.  Nothing is returned: after a completion signal on the stream the caller merges its own buffer."""
+    lib = nat.lib()
+    _require_cuda("users", users, torch.bfloat16)
+    _require_cuda("catalog", catalog, torch.bfloat16)
+    world = len(gather_scores)
+    mine_s, mine_i = gather_scores[my_rank], gather_ids[my_rank]
+    rows = mine_s.shape[1]
+    if mine_s.shape != (world, rows, k) or mine_i.shape != (world, rows, k) or users.shape[0] > rows:
+        raise ValueError("gather buffers must be [world, rows >= n_users, k]")
+    dev = users.device
+    with torch.cuda.device(dev):
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        d = nat.RetrievalDesc()
+        d.struct_size = ctypes.sizeof(nat.RetrievalDesc)
+        d.dim, d.k = users.shape[1], k
+        d.n_users, d.n_catalog, d.catalog_id_offset = users.shape[0], catalog.shape[0], catalog_id_offset
+        d.users, d.catalog = users.data_ptr(), catalog.data_ptr()
+        d.out_scores, d.out_ids = mine_s[my_rank].data_ptr(), mine_i[my_rank].data_ptr()
+        d.n_peers, d.my_rank, d.peer_rows = world, my_rank, rows
+        for r in range(world):
+            d.peer_scores[r], d.peer_ids[r] = gather_scores[r].data_ptr(), gather_ids[r].data_ptr()
+        need = lib.mb200_retrieval_workspace_bytes(ctypes.byref(d))
+        ws = _workspace(dev, stream, "retrieval", max(need, 256))
+        d.workspace, d.workspace_bytes = ws.data_ptr(), ws.numel()
+        nat.check(lib.mb200_retrieve_topk(ctypes.byref(d), stream), "mb200_retrieve_topk")
+
+
 def merge_topk(scores: Tensor, ids: Tensor) -> Tuple[Tensor, Tensor]:
     """Merges per-shard sorted lists [R, U, k] into the global top-k [U, k] (mb200_merge_topk)."""
     lib = nat.lib()
@@ -175,12 +210,29 @@ class CatalogRetriever:
         nat.lib()
         if not 1 <= k <= MAX_K:
             raise ValueError(f"k must be in 1..{MAX_K}")
-        if exchange not in ("all_gather", "all_to_all"):
-            raise ValueError("exchange must be 'all_gather' or 'all_to_all'")
+        if exchange not in ("all_gather", "all_to_all", "p2p"):
+            raise ValueError("exchange must be 'all_gather', 'all_to_all' or 'p2p'")
         _require_cuda("catalog", catalog, torch.bfloat16)
         self.catalog, self.k, self.offset = catalog, int(k), int(catalog_id_offset)
         self.distributed, self.group, self.exchange = bool(distributed), group, exchange
         self.user_block = int(user_block)
+        self._gather = None  # exchange == "p2p": two sets of gather buffers shared over CUDA IPC (double buffered over user blocks)
+
+    def _p2p_buffers(self):
+        import torch.distributed as dist
+
+        from . import dist as mdist
+
+        if self._gather is None:
+            world = dist.get_world_size(self.group)
+            dev = self.catalog.device
+            self._gather = []
+            for _ in range(2):
+                s = torch.full((world, self.user_block, self.k), float("-inf"), dtype=torch.float32, device=dev)
+                i = torch.full((world, self.user_block, self.k), -1, dtype=torch.int64, device=dev)
+                self._gather.append((mdist.share_table_shards(s, self.group), mdist.share_table_shards(i, self.group)))
+            self._token = torch.zeros(1, dtype=torch.int32, device=dev)
+        return self._gather
 
     def local_topk(self, users: Tensor) -> Tuple[Tensor, Tensor]:
         """Top-k of ``users`` against this rank's shard only (global ids)."""
@@ -194,6 +246,22 @@ class CatalogRetriever:
         if not self.distributed:
             return self.local_topk(users)
         out_s, out_i = [], []
+        if self.exchange == "p2p":
+            # fused exchange: the kernel stores every finished list into all GPUs' gather buffers over NVLink while it is
+            # still scoring; the only collective is a 4-byte all-reduce that tells every rank the others' kernels are done
+            import torch.distributed as dist
+
+            rank = dist.get_rank(self.group)
+            bufs = self._p2p_buffers()
+            for b, lo in enumerate(range(0, users.shape[0], self.user_block)):
+                blk = users[lo : lo + self.user_block]
+                gs, gi = bufs[b % 2]
+                retrieve_topk_p2p(blk, self.catalog, self.k, self.offset, gs, gi, rank)
+                dist.all_reduce(self._token, group=self.group)
+                n = blk.shape[0]
+                ms, mi = merge_topk(gs[rank][:, :n].contiguous(), gi[rank][:, :n].contiguous())
+                out_s.append(ms), out_i.append(mi)
+            return torch.cat(out_s), torch.cat(out_i)
         for lo in range(0, users.shape[0], self.user_block):
             s, i = self.local_topk(users[lo : lo + self.user_block])
             ms, mi = exchange_topk(s, i, self.group, self.exchange)

@@ -32,10 +32,10 @@ def main() -> None:
     whole = rt.CatalogRetriever(catalog.to(dev), k=k)
     ref_s, ref_i = whole.retrieve(users)
     out = {"world": world, "n_users": n_users, "n_catalog": n_catalog}
-    for exchange in ("all_gather", "all_to_all"):
+    for exchange in ("all_gather", "all_to_all", "p2p"):
         r = rt.CatalogRetriever(shard, k=k, catalog_id_offset=lo, distributed=True, exchange=exchange, user_block=2048)
         s, i = r.retrieve(users)
-        if exchange == "all_gather":
+        if exchange in ("all_gather", "p2p"):
             ok = bool(torch.equal(i, ref_i) and torch.equal(s, ref_s))
         else:
             idx = torch.tensor(rt.CatalogRetriever.user_slice(n_users, 2048, rank, world), device=dev)
@@ -47,7 +47,7 @@ def main() -> None:
         print(json.dumps(out))
     dist.barrier()
     dist.destroy_process_group()
-    if not (out["all_gather"] and out["all_to_all"]):
+    if not (out["all_gather"] and out["all_to_all"] and out["p2p"]):
         raise SystemExit(1)
 
 
