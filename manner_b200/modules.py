@@ -5,7 +5,7 @@
 
 ``CRModuleB200`` / ``EnsembleModuleB200`` subclass the reference's ``CRModule`` / ``EnsembleModule``
 (manner/models/cr_module.py:19, ensemble_module.py:17) -- same constructor keywords (plus defaulted
-ones), same ``news_encoder.*`` parameters, so existing experiment YAMLs and Lightning checkpoints
+ones; the YAMLs inherit the reference's model configs through Hydra's `defaults` list), same ``news_encoder.*`` parameters, so existing experiment YAMLs and Lightning checkpoints
 load unchanged -- and replace only the test path: ``test_step`` / ``on_test_epoch_end`` (and
 ``validation_step`` metrics for the CR module) hand the batch's news vectors to the fused sm_100a
 kernel instead of ``to_dense_batch`` + per-row Python loops + ``bmm`` + torchmetrics' group loops.
