@@ -13,6 +13,14 @@ in HBM; ``e2e`` is the same pass through ScoreEvaluator.upload + evaluate from p
 copies inside the timed region.  ``--impl reference`` times the oracle port of the reference's own CPU
 path (steps of 8 impressions, per-row Python loops, torchmetrics-style group loop run twice) on the
 host cores and prints the same line with "impl": "reference".
+
+Other workloads of BASELINE.json (not the default line):
+  --workload large --shard          configs[2]: MIND-large shape, one set sharded over the ranks (strong scaling)
+  --modules 3 --sweep 121           configs[3]: aspect-weight sweep, 121 weightings from one gather
+  --mode retrieval [--users U --catalog-per-gpu N --exchange all_gather|all_to_all|p2p]
+                                    configs[4]: users x catalogue bf16 GEMM on tcgen05 + fused top-100, catalogue row-sharded
+  --early-fusion / --loss ce|supcon late_fusion=False pooling and the reference's test/loss on device
+  --uniform-ids / --table-dtype bf16  the HBM-bound id distribution / bf16 table storage
 """
 from __future__ import annotations
 
