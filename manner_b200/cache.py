@@ -97,6 +97,28 @@ def behaviours_frame_to_csr(behaviors: Any, nid2row: Dict[str, int], max_history
     return behaviours_to_csr(col("history", parse_id_list), col("candidates", parse_id_list), col("labels", parse_label_list), nid2row, max_history_length)
 
 
+def read_parsed_behaviors(path: str, nid2row: Dict[str, int], max_history_length: int = MAX_HISTORY) -> Behaviours:
+    """``parsed_behaviors.tsv`` (the file the reference caches with ``to_tsv`` and reloads in
+    ``MINDDataFrame._load_behaviors``, mind_dataframe.py:278-288,360-366: tab separated, columns ``user``, ``history``,
+    ``candidates``, ``labels`` with stringified Python lists) -> CSR, without going through pandas objects per cell."""
+    import csv
+
+    histories: List[List[str]] = []
+    candidates: List[List[str]] = []
+    labels: List[List[int]] = []
+    with open(path, newline="") as f:
+        reader = csv.reader(f, delimiter="\t")
+        header = next(reader)
+        col = {name: header.index(name) for name in ("history", "candidates", "labels")}
+        for row in reader:
+            if not row:
+                continue
+            histories.append(parse_id_list(row[col["history"]]))
+            candidates.append(parse_id_list(row[col["candidates"]]))
+            labels.append(parse_label_list(row[col["labels"]]))
+    return behaviours_to_csr(histories, candidates, labels, nid2row, max_history_length)
+
+
 @torch.no_grad()
 def build_embedding_table(
     news_encoder: torch.nn.Module,

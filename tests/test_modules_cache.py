@@ -62,6 +62,23 @@ def test_parsed_behaviours_to_csr_follows_the_reference_format():
         mcache.behaviours_to_csr([[]], [["N1"]], [[1]], nid2row)
 
 
+def test_read_parsed_behaviors_file(tmp_path):
+    """The reference's cached parsed_behaviors.tsv (pandas ``to_csv(sep="\\t")`` of list-valued cells) -> CSR."""
+    import pandas as pd
+
+    beh = pd.DataFrame({"user": [3, 7], "history": [["N1", "N2", "N3"], ["N4"]], "candidates": [["N5", "N6"], ["N7", "N8", "N9"]],
+                        "labels": [[0, 1], [1, 0, 0]]})
+    path = tmp_path / "parsed_behaviors.tsv"
+    beh.to_csv(path, sep="\t", index=False)  # what mind_dataframe.py's to_tsv writes
+    nid2row = mcache.news_row_map([f"N{i}" for i in range(10)])
+    bhv = mcache.read_parsed_behaviors(str(path), nid2row, max_history_length=2)
+    same = mcache.behaviours_frame_to_csr(pd.read_table(path), nid2row, max_history_length=2)
+    for a, b in ((bhv.hist_offsets, same.hist_offsets), (bhv.hist_ids, same.hist_ids), (bhv.cand_offsets, same.cand_offsets),
+                 (bhv.cand_ids, same.cand_ids), (bhv.labels, same.labels)):
+        np.testing.assert_array_equal(a, b)
+    assert bhv.hist_ids.tolist() == [1, 2, 4] and bhv.cand_ids.tolist() == [5, 6, 7, 8, 9] and bhv.labels.tolist() == [0, 1, 1, 0, 0]
+
+
 def test_build_embedding_table_on_cpu_plumbing():
     table = torch.randn(10, 16)
     enc = TableEncoder(table)
