@@ -250,6 +250,28 @@ def main() -> None:
             fixture[f"w{w}_" + k.replace("/", "_")] = v
     save("ensemble_d128", **fixture)
 
+    # ---- ensemble at the reference's width (D = 768: the exact-width kernels), 2 weightings, with aspects -----------
+    rng = np.random.default_rng(2030)
+    n_news, dim = 120, 768
+    hs, cs, ps = ragged_sizes(rng, 24, cmax=40)
+    cs = [max(c, 2) for c in cs]
+    bhv = make_behaviours(rng, n_news, hs, cs, ps)
+    tabs = [table(n_news, dim, s) for s in (1234, 1235, 1236)]
+    aspects = {
+        "category": rng.integers(1, 19, n_news).astype(np.int32),
+        "sentiment": rng.integers(1, 4, n_news).astype(np.int32),
+    }
+    weightings = [(0.4, 0.0), (0.25, 0.6)]
+    fixture = dict(bhv_arrays(bhv), weightings=np.asarray(weightings, dtype=np.float64), category=aspects["category"], sentiment=aspects["sentiment"])
+    for m, t in enumerate(tabs):
+        fixture[f"table{m}"] = t.numpy()
+    for w, (wc, ws) in enumerate(weightings):
+        with stable_argsort():
+            ref = run_reference_ensemble(tabs, wc, ws, bhv, aspects)
+        for k, v in ref.items():
+            fixture[f"w{w}_" + k.replace("/", "_")] = v
+    save("ensemble_d768", **fixture)
+
     # ---- functional level ------------------------------------------------------------------------------
     g = torch.Generator().manual_seed(5)
     user = torch.randn(6, 1, 64, generator=g)

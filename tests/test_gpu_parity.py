@@ -91,6 +91,27 @@ def test_ensemble_matches_reference_golden(golden_dir, evaluator_cls):
         np.testing.assert_allclose(sweep.sums[w], single.sums[0], rtol=0, atol=1e-9)
 
 
+def test_ensemble_at_reference_width_matches_reference_golden(golden_dir, evaluator_cls):
+    """D = 768 (text_embedding_dim of the reference's configs): the exact-width kernels against what the reference's own
+    EnsembleModule logged.  Scores within 2e-5 (z-scores are O(1)); metrics within 1e-6 unless a near-tie (|ds| below the score
+    tolerance) ranks differently on the two sides, which is reported and bounded instead of hidden."""
+    z = np.load(os.path.join(golden_dir, "ensemble_d768.npz"))
+    tabs = [torch.from_numpy(z[f"table{m}"]) for m in range(3)]
+    bhv = _bhv(z)
+    ev = evaluator_cls(tabs, news_category=z["category"], news_sentiment=z["sentiment"])
+    dev_bhv = ev.upload(bhv)
+    for w, (wc, ws) in enumerate(z["weightings"].tolist()):
+        res = ev.evaluate(dev_bhv, weights=[[1.0, wc, ws]], zscore=True, want_scores=True)
+        got, ref = res.scores.cpu().numpy(), z[f"w{w}_preds"]
+        assert np.all(np.abs(got.astype(np.float64) - ref.astype(np.float64)) <= 2e-5 * np.maximum(1.0, np.abs(ref))), w
+        flips = int((mo.stable_ranks(got, bhv.cand_offsets) != mo.stable_ranks(ref, bhv.cand_offsets)).sum())
+        m = res.metrics()
+        for k in ("ndcg@5", "ndcg@10", "categ_div@5", "categ_div@10", "sent_div@5", "sent_div@10",
+                  "categ_pers@5", "categ_pers@10", "sent_pers@5", "sent_pers@10"):
+            tol = METRIC_ATOL if flips == 0 else 2.0 / bhv.n_impressions
+            assert abs(m["test/" + k] - float(z[f"w{w}_test_{k}"])) <= tol, (w, k, flips)
+
+
 def test_weight_sweep_path_equals_single_weighting_calls(golden_dir, evaluator_cls):
     """BASELINE.json configs[3]: >= 16 weightings take the lane-per-weighting path; it must give exactly
     what one call per weighting gives (and therefore what the reference logs per weighting)."""

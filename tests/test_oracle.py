@@ -78,8 +78,9 @@ def test_supcon_restatement_known_answers():
     assert float(mo.supcon_step_loss(torch.tensor([[0.3, 0.1]]), mo.step_batch(bhv2, 0, 1), T)) == 0.0
 
 
-def test_ensemble_epoch_matches_reference_golden(golden_dir):
-    z = np.load(os.path.join(golden_dir, "ensemble_d128.npz"))
+@pytest.mark.parametrize("name", ["ensemble_d128", "ensemble_d768"])
+def test_ensemble_epoch_matches_reference_golden(golden_dir, name):
+    z = np.load(os.path.join(golden_dir, name + ".npz"))
     tabs = [torch.from_numpy(z[f"table{m}"]) for m in range(3)]
     aspects = {"category": z["category"], "sentiment": z["sentiment"]}
     for w, (wc, ws) in enumerate(z["weightings"].tolist()):
