@@ -33,6 +33,9 @@ def shard_for_rank(bhv: Behaviours, rank: int, world_size: int, align: int = 1) 
     return bhv.slice(int(bounds[rank]), int(bounds[rank + 1]))
 
 
+_ipc_bases: dict = {}  # (IPC handle, local device) -> base address of the mapping in this process
+
+
 class _PeerMemory:
     """A peer GPU's memory mapped into this process, presented to torch through the CUDA array interface (zero copy)."""
 
@@ -67,9 +70,13 @@ def share_table_shards(local_shard: Tensor, group: Optional[dist.ProcessGroup] =
             shards.append(local_shard)
             continue
         nat.check(lib.mb200_enable_peer_access(local_shard.device.index, peer_dev), "mb200_enable_peer_access")
-        ptr = ctypes.c_void_p()
-        nat.check(lib.mb200_ipc_open(h, off, local_shard.device.index, ctypes.byref(ptr)), "mb200_ipc_open")
-        t = torch.as_tensor(_PeerMemory(ptr.value, shape, dtype), device=torch.device("cuda", peer_dev))
+        # several tensors of a peer can live in one allocation (torch's caching allocator): every allocation is mapped once
+        key = (h, local_shard.device.index)
+        if key not in _ipc_bases:
+            base = ctypes.c_void_p()
+            nat.check(lib.mb200_ipc_open(h, 0, local_shard.device.index, ctypes.byref(base)), "mb200_ipc_open")
+            _ipc_bases[key] = int(base.value)
+        t = torch.as_tensor(_PeerMemory(_ipc_bases[key] + off, shape, dtype), device=torch.device("cuda", peer_dev))
         shards.append(t.view(torch.bfloat16) if dtype == torch.bfloat16 else t)
     torch.cuda.synchronize(local_shard.device)
     dist.barrier(group=group)
