@@ -247,6 +247,9 @@ class ScoreEvaluator:
             w_dev = w_host.to(self.device, non_blocking=True).contiguous()
         need_scores = want_scores or pooled_auc
         loss_kind = {None: nat.LOSS_NONE, "ce": nat.LOSS_CE, "supcon": nat.LOSS_SUPCON}[loss]
+        if loss is not None and w_dev is not None and w_dev.shape[0] >= 16 and self.news_category is None:
+            # >= 16 weightings without aspects take the lane-per-weighting sweep path, which fills the ranking slots only
+            raise ValueError("the loss is not computed in the aspect-weight sweep mode: evaluate it with a single weighting")
         scores, per_impr, sums, flags, loss_per_impr = torch.ops.manner_b200.score_eval(
             self.tables, bhv.hist_offsets, bhv.hist_ids, bhv.cand_offsets, bhv.cand_ids, bhv.labels, w_dev, zscore,
             bhv.max_cand, active, self.ks[0], self.ks[1], need_scores, scores_weighting, want_per_impression,
