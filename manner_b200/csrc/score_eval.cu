@@ -71,7 +71,25 @@ struct EvalParams {
   int acc_stride;     // doubles per weighting in the accumulators: MB200_NUM_METRICS, or kSweepSlots in the aspect-weight sweep mode
   int loss_kind;
   float loss_temperature;
+  // hot-row cache of the streaming kernel (score_eval_stream_kernel): the rows gathered most often in THIS behaviour set are
+  // kept in shared memory for the whole launch
+  const struct HotDir* hot_dir;   // counters written by hot_select_kernel
+  const int32_t* hot_ids;         // [hot_cap] news id cached in slot s
+  const uint8_t* slot_of;         // [n_news] slot of a news id, kHotCold = not cached
+  int hot_cap;                    // slots per module the launch reserved shared memory for
+  int hot_bytes;                  // bytes of the cache at the front of the CTA's shared memory
+  int has_aspects;                // the per-warp area holds the aspect buffers
+  int comb_alias;                 // one weighting: the combined scores overwrite module 0's (no separate buffer)
 };
+
+struct HotDir {
+  int32_t n_hot;    // rows cached this launch (0: cache off, e.g. uniform ids)
+  int32_t total;    // sampled row reads
+  int32_t covered;  // of which go to the cached rows
+  int32_t reserved;
+};
+constexpr int kHotCold = 255;
+constexpr int kHotMaxSlots = 254;
 
 template <typename T>
 struct Elem;
@@ -832,6 +850,339 @@ __global__ void __launch_bounds__(kThreads, MINB) score_eval_kernel(const __grid
   if (lane == 0 && warp_flags && p.flags) atomicOr(p.flags, warp_flags);
 }
 
+// ------------------------------------------------------------------------------------------------------
+// Streaming variant for the reference width (dim 768), late fusion, replicated tables: the product path.
+//
+// (1) Hot-row cache.  News popularity is heavy-tailed (a few dozen rows carry a quarter of all row reads of a
+//     MIND-shaped behaviour set), but the L1 cannot hold on to them: every SM streams ~180 MB through it per launch.  One
+//     CTA of 16 warps per SM therefore keeps the most frequently gathered rows of THIS behaviour set (found per launch by
+//     hot_count_kernel / hot_select_kernel) in shared memory -- everything the per-warp score areas leave of the 227 KB --
+//     and a gathered row is read from there (LDS.128) instead of through the L2 -> SM crossbar, which is the binding
+//     resource on Zipf-shaped ids.  The arithmetic does not depend on where a row is read from:
+//     outputs are bit-identical with the cache on or off.
+// (2) Rotating row pipeline.  History and candidate rows of a module form ONE stream of slots; R rows are in flight per warp
+//     and a row's registers are refilled with the row R slots ahead as soon as it is consumed, so candidate rows are already
+//     arriving while the user vector is finished and there is no issue-all / wait-all bubble per batch.  Ids (and their
+//     cache slots) are fetched 32 at a time one chunk ahead of the rows that need them.
+// ------------------------------------------------------------------------------------------------------
+
+constexpr int kStreamWarps = 16;
+
+struct StreamSrc {
+  const int32_t* hist_ids;  // of this impression
+  const int32_t* cand_ids;
+  int H, Hp, C, n_slots;    // Hp = H rounded up to R: candidate slots start R-aligned; slots [H, Hp) are empty
+  long long n_news;
+  const uint8_t* slot_of;   // null = cache off
+};
+
+// ref of stream slot base + lane: news id (>= 0), ~cache slot (< 0), or 0 for an empty slot; OR-s MB200_FLAG_BAD_ID into flags
+__device__ __noinline__ int stream_fetch_refs(const StreamSrc& s, int base, int& flags) {
+  const int t = base + (threadIdx.x & 31);
+  int id = 0;
+  bool valid = false;
+  if (t < s.H) id = s.hist_ids[t], valid = true;
+  else if (t >= s.Hp && t < s.n_slots) id = s.cand_ids[t - s.Hp], valid = true;
+  if ((unsigned long long)(long long)id >= (unsigned long long)s.n_news) id = 0, flags |= MB200_FLAG_BAD_ID;
+  int ref = id;
+  if (s.slot_of != nullptr && valid) {
+    const int sl = s.slot_of[id];
+    if (sl != kHotCold) ref = ~sl;
+  }
+  return ref;
+}
+
+template <typename T, int NV, int R>
+__device__ __forceinline__ int stream_pool_score(const T* __restrict__ table, const unsigned char* hot_rows, const StreamSrc& src,
+                                                 int ref_first, float* __restrict__ s_out) {
+  constexpr int E = Elem<T>::E;
+  constexpr int kRowBytes = NV * 32 * 16;  // rows are contiguous (row stride == dim): a row's address is one multiply-add
+  const int lane = threadIdx.x & 31;
+  int flags = 0;
+  const int H = src.H, Hp = src.Hp, n_slots = src.n_slots;
+  const unsigned char* gbase = reinterpret_cast<const unsigned char*>(table) + lane * 16;  // this lane's first vector of row 0
+  const unsigned char* sbase = hot_rows + lane * 16;
+
+  float u[NV * E];
+#pragma unroll
+  for (int t = 0; t < NV * E; ++t) u[t] = 0.f;
+
+  uint4 buf[R][NV];
+  int ref_cur = 0, ref_nxt = ref_first;
+
+  // issue the loads of slot sn (if it holds a row) into b; advances the id window when sn enters a new chunk of 32
+  auto refill = [&](uint4 (&b)[NV], int sn) {
+    if (sn < n_slots) {
+      if ((sn & 31) == 0) {
+        ref_cur = ref_nxt;
+        if (sn + 32 < n_slots) ref_nxt = stream_fetch_refs(src, sn + 32, flags);
+      }
+      if (sn < H || sn >= Hp) {
+        const int ref = __shfl_sync(kFull, ref_cur, sn & 31);
+        if (ref < 0) {
+          const uint4* row = reinterpret_cast<const uint4*>(sbase + (unsigned)(~ref) * (unsigned)kRowBytes);
+#pragma unroll
+          for (int v = 0; v < NV; ++v) b[v] = row[32 * v];
+        } else {
+          const uint4* row = reinterpret_cast<const uint4*>(gbase + (unsigned long long)(unsigned)ref * (unsigned long long)kRowBytes);
+#pragma unroll
+          for (int v = 0; v < NV; ++v) b[v] = __ldg(row + 32 * v);
+        }
+      }
+    }
+  };
+
+#pragma unroll
+  for (int r = 0; r < R; ++r) refill(buf[r], r);
+
+  // history: u = sum of the rows (cr_module.py:116-123)
+#pragma unroll 1
+  for (int t0 = 0; t0 < Hp; t0 += R) {
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const int t = t0 + r;
+      if (t < H) {
+#pragma unroll
+        for (int v = 0; v < NV; ++v) {
+          float f[E];
+          Elem<T>::unpack(buf[r][v], f);
+#pragma unroll
+          for (int e = 0; e < E; ++e) u[v * E + e] = __fadd_rn(u[v * E + e], f[e]);
+        }
+      }
+      refill(buf[r], t + R);
+    }
+  }
+  // true division by the history length (see gather_pool_score)
+  {
+    const float hf = (float)H;
+    const float rh = __frcp_rn(hf);
+#pragma unroll
+    for (int t = 0; t < NV * E; ++t) {
+      const float q = __fmul_rn(u[t], rh);
+      u[t] = __fmaf_rn(__fmaf_rn(-q, hf, u[t]), rh, q);
+    }
+  }
+  // candidates: s_j = u . row_j (click_predictors.py:12)
+#pragma unroll 1
+  for (int t0 = Hp; t0 < n_slots; t0 += R) {
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const int t = t0 + r;
+      if (t < n_slots) {
+        float part = 0.f;
+#pragma unroll
+        for (int v = 0; v < NV; ++v) {
+          float f[E];
+          Elem<T>::unpack(buf[r][v], f);
+#pragma unroll
+          for (int e = 0; e < E; ++e) part = fmaf(u[v * E + e], f[e], part);
+        }
+        part = warp_sum(part);
+        if (lane == 0) s_out[t - Hp] = part;
+        refill(buf[r], t + R);
+      }
+    }
+  }
+  return flags;
+}
+
+__device__ __forceinline__ WarpSmem warp_smem_of(unsigned char* base, const EvalParams& p, int n_active) {
+  WarpSmem sm;
+  sm.acc = reinterpret_cast<double*>(base);
+  sm.sc = reinterpret_cast<float*>(base + p.acc_bytes);
+  sm.comb = p.comb_alias ? sm.sc : sm.sc + (size_t)n_active * p.cpad;
+  sm.lab = reinterpret_cast<uint8_t*>(sm.sc + (size_t)(n_active + (p.comb_alias ? 0 : 1)) * p.cpad);
+  sm.ccat = sm.lab + p.cpad;
+  sm.csent = sm.ccat + p.cpad;
+  sm.hist_cat = reinterpret_cast<int*>(sm.csent + p.cpad);  // cpad is a multiple of 32: 4-byte aligned
+  sm.hist_sent = sm.hist_cat + MB200_MAX_CLASSES;
+  sm.top_cat = reinterpret_cast<uint8_t*>(sm.hist_sent + MB200_MAX_CLASSES);
+  sm.top_sent = sm.top_cat + 32;
+  if (!p.has_aspects) sm.ccat = sm.csent = sm.top_cat = sm.top_sent = sm.lab, sm.hist_cat = sm.hist_sent = reinterpret_cast<int*>(sm.sc);  // never touched
+  return sm;
+}
+
+template <typename T, int NV, int R, bool HOT>
+__global__ void __launch_bounds__(kStreamWarps * 32, 1) score_eval_stream_kernel(const __grid_constant__ EvalParams p) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  constexpr int kVecPerRow = NV * 32;
+  constexpr int kRowBytes = kVecPerRow * 16;
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const int gw = blockIdx.x * kStreamWarps + warp;
+  const int total_warps = gridDim.x * kStreamWarps;
+  const int W = p.n_weightings;
+  const int n_active = __popc(p.active_mask);
+
+  // ---- fill the hot-row cache: slot s of active module a at smem[(a * hot_cap + s) * row bytes] --------------------
+  int n_hot = 0;
+  if (HOT) {
+    n_hot = min(p.hot_dir->n_hot, p.hot_cap);
+    const int per_module = n_hot * kVecPerRow;
+    int a = 0;
+    for (int m = 0; m < p.n_modules; ++m) {
+      if (!((p.active_mask >> m) & 1)) continue;
+      const T* table = reinterpret_cast<const T*>(p.tables[m]);
+      uint4* dst = reinterpret_cast<uint4*>(smem + (size_t)a * p.hot_cap * kRowBytes);
+      for (int idx = threadIdx.x; idx < per_module; idx += kStreamWarps * 32) {
+        const int s = idx / kVecPerRow, v = idx - s * kVecPerRow;
+        const int id = p.hot_ids[s];
+        dst[idx] = __ldg(reinterpret_cast<const uint4*>(table + (long long)id * p.row_stride) + v);
+      }
+      ++a;
+    }
+    __syncthreads();
+  }
+
+  WarpSmem sm = warp_smem_of(smem + p.hot_bytes + (size_t)warp * p.smem_per_warp, p, n_active);
+  for (int t = lane; t < W * p.acc_stride; t += 32) sm.acc[t] = 0.0;
+  __syncwarp();
+
+  int warp_flags = 0;
+  for (int chunk = gw; chunk < p.n_chunks; chunk += total_warps) {
+    const int i_begin = p.bounds[chunk], i_end = p.bounds[chunk + 1];
+    if (i_begin >= i_end) continue;
+    // offsets one impression ahead: (h0, c0) of impression i and the ends of i and i + 1 are in registers when i starts
+    int h0 = p.hist_offsets[i_begin], c0 = p.cand_offsets[i_begin];
+    int h1 = p.hist_offsets[i_begin + 1], c1 = p.cand_offsets[i_begin + 1];
+    for (int i = i_begin; i < i_end; ++i) {
+      const int nxt = min(i + 2, p.n_impr);
+      const int h2 = p.hist_offsets[nxt], c2 = p.cand_offsets[nxt];  // consumed at the end of this iteration
+      const int H = h1 - h0, C = c1 - c0;
+      if (C > p.max_cand || C <= 0 || H < 0) {
+        warp_flags |= MB200_FLAG_CAND_OVERFLOW;
+        if (p.per_impr)
+          for (int t = lane; t < W * MB200_NUM_METRICS; t += 32)
+            p.per_impr[((size_t)(t / MB200_NUM_METRICS) * p.n_impr + i) * MB200_NUM_METRICS + t % MB200_NUM_METRICS] = 0.f;
+      } else {
+        StreamSrc src;
+        src.hist_ids = p.hist_ids + h0, src.cand_ids = p.cand_ids + c0;
+        src.H = H, src.Hp = (H + R - 1) / R * R, src.C = C, src.n_slots = src.Hp + C;
+        src.n_news = p.n_news;
+        src.slot_of = (HOT && n_hot > 0) ? p.slot_of : nullptr;
+        const int ref_first = stream_fetch_refs(src, 0, warp_flags);  // the same ids serve every module
+        __syncwarp();
+        for (int j = lane; j < C; j += 32) sm.lab[j] = p.labels[c0 + j];
+        int slot = 0;
+        for (int m = 0; m < p.n_modules; ++m) {
+          if (!((p.active_mask >> m) & 1)) continue;
+          float* s_m = sm.sc + (size_t)slot * p.cpad;
+          warp_flags |= stream_pool_score<T, NV, R>(reinterpret_cast<const T*>(p.tables[m]), smem + (size_t)slot * p.hot_cap * kRowBytes, src,
+                                                    ref_first, s_m);
+          __syncwarp();
+          if (p.zscore) {
+            zscore_inplace(s_m, C, lane);
+            __syncwarp();
+          }
+          ++slot;
+        }
+        warp_flags |= rank_and_metrics(p, sm, i, h0, H, c0, C);
+      }
+      h0 = h1, c0 = c1, h1 = h2, c1 = c2;
+    }
+  }
+
+  __syncwarp();
+  for (int t = lane; t < W * MB200_NUM_METRICS; t += 32) {
+    const int w = t / MB200_NUM_METRICS, k = t % MB200_NUM_METRICS;
+    p.partials[(size_t)gw * W * MB200_NUM_METRICS + t] = k < p.acc_stride ? sm.acc[w * p.acc_stride + k] : 0.0;
+  }
+  warp_flags = __reduce_or_sync(kFull, warp_flags);
+  if (lane == 0 && warp_flags && p.flags) atomicOr(p.flags, warp_flags);
+}
+
+// ---- hot-row directory: which rows does this behaviour set gather most often? -------------------------------------
+// counts[id] += 1 for the ids of every `stride`-th block of 1024 consecutive hist / cand ids (an unbiased sample: the
+// impressions are exchangeable); REDs on distinct ids run in parallel in the L2, the hottest id serialises ~n/stride/B of them.
+__global__ void __launch_bounds__(256) hot_count_kernel(const int32_t* __restrict__ hist_offsets, const int32_t* __restrict__ hist_ids,
+                                                        const int32_t* __restrict__ cand_offsets, const int32_t* __restrict__ cand_ids, int n_impr,
+                                                        long long n_news, int32_t* __restrict__ counts) {
+  const long long n_hist = hist_offsets[n_impr], n_cand = cand_offsets[n_impr];
+  const long long hist_blocks = (n_hist + 1023) / 1024, blocks = hist_blocks + (n_cand + 1023) / 1024;
+  const long long stride = max(1ll, (blocks * 1024 + (1ll << 21) - 1) >> 21);  // sample <= 2^21 ids: counts stay below 2^22
+  for (long long blk = (long long)blockIdx.x * stride; blk < blocks; blk += (long long)gridDim.x * stride) {
+    const int32_t* ids = hist_ids;
+    long long n = n_hist, first = blk * 1024;
+    if (blk >= hist_blocks) ids = cand_ids, n = n_cand, first = (blk - hist_blocks) * 1024;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const long long t = first + k * 256 + threadIdx.x;
+      if (t < n) {
+        const int id = ids[t];
+        if ((unsigned long long)(long long)id < (unsigned long long)n_news) atomicAdd(&counts[id], 1);
+      }
+    }
+  }
+}
+
+// The `cap` most frequently counted ids get cache slots (two-level radix select on the counts, one CTA), every other id
+// kHotCold; the cache is switched off (n_hot = 0) when the selected rows cover less than 1/32 of the sampled reads.
+__global__ void __launch_bounds__(1024) hot_select_kernel(const int32_t* __restrict__ counts, int n_news, int cap, HotDir* __restrict__ dir,
+                                                          int32_t* __restrict__ hot_ids, uint8_t* __restrict__ slot_of) {
+  __shared__ int hist[2048];
+  __shared__ int s_bin, s_above, s_next, s_ties_left, s_total, s_covered;
+  const int t = threadIdx.x;
+  // level 1: counts >> 11 (counts < 2^22: the sample is at most 2^21 ids)
+  for (int b = t; b < 2048; b += 1024) hist[b] = 0;
+  if (t == 0) s_total = 0, s_covered = 0, s_next = 0;
+  __syncthreads();
+  int local_total = 0;
+  for (int i = t; i < n_news; i += 1024) {
+    const int c = counts[i];
+    local_total += c;
+    if (c > 0) atomicAdd(&hist[min(c >> 11, 2047)], 1);
+  }
+  local_total = __reduce_add_sync(kFull, local_total);
+  if ((t & 31) == 0 && local_total) atomicAdd(&s_total, local_total);
+  __syncthreads();
+  if (t == 0) {
+    int above = 0, b = 2047;
+    for (; b > 0 && above + hist[b] < cap; --b) above += hist[b];
+    s_bin = b, s_above = above;  // the cap-th largest count lies in bin b (or there are fewer than cap non-zero counts: b = 0)
+  }
+  __syncthreads();
+  const int bin1 = s_bin, above1 = s_above;
+  __syncthreads();
+  // level 2: low 11 bits of the counts in bin1
+  for (int b = t; b < 2048; b += 1024) hist[b] = 0;
+  __syncthreads();
+  for (int i = t; i < n_news; i += 1024) {
+    const int c = counts[i];
+    if (c > 0 && min(c >> 11, 2047) == bin1) atomicAdd(&hist[c & 2047], 1);
+  }
+  __syncthreads();
+  if (t == 0) {
+    int above = above1, b = 2047;
+    for (; b > 0 && above + hist[b] < cap; --b) above += hist[b];
+    s_bin = b, s_above = above;
+    s_ties_left = cap - above;  // slots left for ids whose count equals the threshold
+  }
+  __syncthreads();
+  const int thresh = (bin1 << 11) | s_bin;  // ids with count > thresh are hot, ties fill what is left; 0 never is
+  for (int i = t; i < n_news; i += 1024) {
+    const int c = counts[i];
+    int slot = kHotCold;
+    if (c > 0 && c >= thresh) {
+      bool take = c > thresh;
+      if (!take) take = atomicSub(&s_ties_left, 1) > 0;
+      if (take) {
+        slot = atomicAdd(&s_next, 1);
+        if (slot < cap) hot_ids[slot] = i, atomicAdd(&s_covered, c);
+        else slot = kHotCold;
+      }
+    }
+    slot_of[i] = (uint8_t)slot;
+  }
+  __syncthreads();
+  if (t == 0) {
+    const int n = min(s_next, cap);
+    dir->total = s_total, dir->covered = s_covered;
+    dir->n_hot = ((long long)s_covered * 32 >= (long long)s_total && s_total > 0) ? n : 0;
+    dir->reserved = n;
+  }
+}
+
 // mb200_rank_metrics: the ranking / metrics half of the fused kernel on predictions that already exist (one warp per
 // impression, same shared-memory layout, rank_and_metrics unchanged).
 __global__ void __launch_bounds__(kThreads) rank_metrics_kernel(const __grid_constant__ EvalParams p) {
@@ -939,6 +1290,7 @@ __global__ void __launch_bounds__(256) reduce_partials_kernel(const double* __re
 
 struct LaunchPlan {
   int grid = 0;
+  int warps_per_cta = kWarpsPerCta;
   int total_warps = 0;
   int n_chunks = 0;
   int cpad = 0;
@@ -947,26 +1299,58 @@ struct LaunchPlan {
   int smem_per_warp = 0;
   size_t smem_per_cta = 0;
   size_t bounds_bytes = 0, partials_bytes = 0;
+  // streaming kernel only
+  int has_aspects = 1, comb_alias = 0;
+  int hot_cap = 0, hot_bytes = 0;
 };
 
 static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
-static int make_plan(const mb200_eval_desc* d, int sm_count, int ctas, LaunchPlan* plan) {
+constexpr size_t kMaxSmemPerCta = 227 * 1024;
+
+static size_t hot_region_bytes(long long n_news) {
+  // HotDir, hot_ids[256], counts[n_news], slot_of[n_news]
+  return 256 + 1024 + align_up((size_t)n_news * sizeof(int32_t), 256) + align_up((size_t)n_news, 256);
+}
+
+// `stream`: plan for score_eval_stream_kernel (one CTA of kStreamWarps warps per SM; per-warp area trimmed to what the call
+// uses; the rest of the shared memory becomes the hot-row cache, `row_bytes` per row and active module).
+static int make_plan(const mb200_eval_desc* d, int sm_count, int ctas, LaunchPlan* plan, bool stream = false, int row_bytes = 0, bool hot = false) {
   const int n_active = __builtin_popcount((unsigned)d->active_modules_mask);
   plan->cpad = (int)align_up((size_t)(d->max_cand > 0 ? d->max_cand : 1), 32);
   // the aspect-weight sweep (lane per weighting: rank_and_metrics -> sweep_weightings) fills only the first kSweepSlots slots
   const bool sweep = d->weights != nullptr && d->n_weightings >= kSweepMinWeightings && d->news_category == nullptr;
   plan->acc_stride = sweep ? kSweepSlots : MB200_NUM_METRICS;
   plan->acc_bytes = (int)align_up((size_t)d->n_weightings * plan->acc_stride * sizeof(double), 16);
-  size_t per_warp = (size_t)plan->acc_bytes + (size_t)(n_active + 1) * plan->cpad * sizeof(float) + 3 * (size_t)plan->cpad +
-                    2 * MB200_MAX_CLASSES * sizeof(int) + 64;
+  plan->warps_per_cta = stream ? kStreamWarps : kWarpsPerCta;
+  size_t per_warp;
+  if (stream) {
+    plan->has_aspects = d->news_category != nullptr;
+    plan->comb_alias = d->n_weightings == 1;
+    per_warp = (size_t)plan->acc_bytes + (size_t)(n_active + (plan->comb_alias ? 0 : 1)) * plan->cpad * sizeof(float) + (size_t)plan->cpad;
+    if (plan->has_aspects) per_warp += 2 * (size_t)plan->cpad + 2 * MB200_MAX_CLASSES * sizeof(int) + 64;
+    ctas = 1;
+  } else {
+    per_warp = (size_t)plan->acc_bytes + (size_t)(n_active + 1) * plan->cpad * sizeof(float) + 3 * (size_t)plan->cpad +
+               2 * MB200_MAX_CLASSES * sizeof(int) + 64;
+  }
   per_warp = align_up(per_warp, 16);
   plan->smem_per_warp = (int)per_warp;
-  plan->smem_per_cta = per_warp * kWarpsPerCta;
-  if (plan->smem_per_cta > 227 * 1024) return MB200_ERR_UNSUPPORTED;
+  plan->smem_per_cta = per_warp * plan->warps_per_cta;
+  if (plan->smem_per_cta > kMaxSmemPerCta) return MB200_ERR_UNSUPPORTED;
+  plan->hot_cap = plan->hot_bytes = 0;
+  if (stream && hot) {
+    long long cap = (long long)(kMaxSmemPerCta - plan->smem_per_cta) / ((long long)n_active * row_bytes);
+    if (cap > kHotMaxSlots) cap = kHotMaxSlots;
+    if (cap >= 8) {
+      plan->hot_cap = (int)cap;
+      plan->hot_bytes = (int)(cap * n_active * row_bytes);
+      plan->smem_per_cta += plan->hot_bytes;
+    }
+  }
   if (ctas < 1) ctas = 1;
   plan->grid = sm_count * ctas;
-  plan->total_warps = plan->grid * kWarpsPerCta;
+  plan->total_warps = plan->grid * plan->warps_per_cta;
   long long chunks = (long long)plan->total_warps * (tuning().chunks_per_warp > 0 ? tuning().chunks_per_warp : 1);
   if (chunks > d->n_impressions) chunks = d->n_impressions;
   if (chunks < 1) chunks = 1;
@@ -1096,8 +1480,16 @@ size_t eval_workspace_bytes(const mb200_eval_desc* d) {
   if (validate(d) != MB200_OK) return 0;
   LaunchPlan plan;
   // the SM count is not known without a device; size for the largest part this library targets (148 SMs, <= 160)
-  if (make_plan(d, 160, 8, &plan) != MB200_OK) return 0;  // upper bound: 160 SMs x 8 CTAs
-  return plan.bounds_bytes + plan.partials_bytes + 256;
+  if (make_plan(d, 160, 8, &plan) != MB200_OK) return 0;  // upper bound: 160 SMs x 8 CTAs (the streaming kernel runs 16 warps per SM: less)
+  return plan.bounds_bytes + plan.partials_bytes + 256 + hot_region_bytes(d->n_news);
+}
+
+template <typename T>
+static KernelFn select_stream_kernel(bool hot) {
+  constexpr int kRefNV = 768 / Elem<T>::E / 32;  // 6 (fp32) or 3 (bf16)
+  constexpr int R = (kRefNV == 6) ? 3 : 6;       // rows in flight per warp: 72 registers of landing buffers either way
+  if (hot) return score_eval_stream_kernel<T, kRefNV, R, true>;
+  return score_eval_stream_kernel<T, kRefNV, R, false>;
 }
 
 int score_eval(const mb200_eval_desc* d, cudaStream_t stream) {
@@ -1110,28 +1502,46 @@ int score_eval(const mb200_eval_desc* d, cudaStream_t stream) {
   st = sm_count_of(device, &sms);
   if (st != MB200_OK) return st;
   if (sms > 160) return MB200_ERR_UNSUPPORTED;
-  const int vec_per_row = d->dim * (d->dtype == MB200_F32 ? 4 : 2) / 16;
+  const int esz = d->dtype == MB200_F32 ? 4 : 2;
+  const int vec_per_row = d->dim * esz / 16;
   bool attn = false;
   for (int m = 0; m < d->n_modules; ++m) attn |= ((d->active_modules_mask >> m) & 1) && d->attn_logits[m] != nullptr;
   const bool sharded = d->n_table_shards > 1;
-  KernelFn kern = (d->dtype == MB200_F32) ? select_kernel<float>(vec_per_row, attn, sharded) : select_kernel<__nv_bfloat16>(vec_per_row, attn, sharded);
-  if (kern == nullptr) return MB200_ERR_UNSUPPORTED;  // row-sharded tables: reference width, late fusion only
+
+  // The streaming kernel (hot-row cache in shared memory + rotating row pipeline) is the default for the reference width with
+  // late fusion and replicated tables; tuning variant 7 = streaming without the cache, 8 = with it, 0..6 = the register-batch kernels.
+  const int variant = tuning().variant;
   LaunchPlan plan;
-  st = make_plan(d, sms, 1, &plan);  // shared-memory sizes first: they decide how many CTAs fit
-  if (st != MB200_OK) return st;
-  if (plan.smem_per_cta > 48 * 1024) {
+  KernelFn kern = nullptr;
+  bool stream_path = d->dim == 768 && d->row_stride == 768 && !attn && !sharded && (variant < 0 || variant == 7 || variant == 8) && d->n_news < (1ll << 31);
+  bool hot = false;
+  if (stream_path) {
+    if (make_plan(d, sms, 1, &plan, true, vec_per_row * 16, variant != 7) != MB200_OK) stream_path = false;  // per-warp areas too large for 16 warps
+  }
+  if (stream_path) {
+    hot = plan.hot_cap > 0;
+    kern = (d->dtype == MB200_F32) ? select_stream_kernel<float>(hot) : select_stream_kernel<__nv_bfloat16>(hot);
     st = cuda_status(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem_per_cta), "cudaFuncSetAttribute");
     if (st != MB200_OK) return st;
+  } else {
+    kern = (d->dtype == MB200_F32) ? select_kernel<float>(vec_per_row, attn, sharded) : select_kernel<__nv_bfloat16>(vec_per_row, attn, sharded);
+    if (kern == nullptr) return MB200_ERR_UNSUPPORTED;  // row-sharded tables: reference width, late fusion only
+    st = make_plan(d, sms, 1, &plan);  // shared-memory sizes first: they decide how many CTAs fit
+    if (st != MB200_OK) return st;
+    if (plan.smem_per_cta > 48 * 1024) {
+      st = cuda_status(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem_per_cta), "cudaFuncSetAttribute");
+      if (st != MB200_OK) return st;
+    }
+    // persistent grid: exactly as many CTAs as are resident at once (registers and shared memory decide)
+    int resident = 0;
+    st = cuda_status(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, kern, kThreads, plan.smem_per_cta), "cudaOccupancyMaxActiveBlocksPerMultiprocessor");
+    if (st != MB200_OK) return st;
+    if (resident < 1) return MB200_ERR_UNSUPPORTED;
+    const int want = tuning().ctas_per_sm > 0 ? tuning().ctas_per_sm : resident;
+    st = make_plan(d, sms, want < resident ? want : resident, &plan);
+    if (st != MB200_OK) return st;
   }
-  // persistent grid: exactly as many CTAs as are resident at once (registers and shared memory decide)
-  int resident = 0;
-  st = cuda_status(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, kern, kThreads, plan.smem_per_cta), "cudaOccupancyMaxActiveBlocksPerMultiprocessor");
-  if (st != MB200_OK) return st;
-  if (resident < 1) return MB200_ERR_UNSUPPORTED;
-  const int want = tuning().ctas_per_sm > 0 ? tuning().ctas_per_sm : resident;
-  st = make_plan(d, sms, want < resident ? want : resident, &plan);
-  if (st != MB200_OK) return st;
-  const size_t need = plan.bounds_bytes + plan.partials_bytes;
+  const size_t need = plan.bounds_bytes + plan.partials_bytes + (hot ? hot_region_bytes(d->n_news) : 0);
   if (d->workspace == nullptr || ((uintptr_t)d->workspace & 255) || d->workspace_bytes < need) return MB200_ERR_WORKSPACE;
 
   EvalParams p{};
@@ -1145,8 +1555,9 @@ int score_eval(const mb200_eval_desc* d, cudaStream_t stream) {
   p.labels = d->labels, p.weights = d->weights;
   p.news_category = d->news_category, p.news_sentiment = d->news_sentiment;
   p.scores = d->scores, p.per_impr = d->per_impression, p.flags = d->flags;
-  p.bounds = reinterpret_cast<int32_t*>(d->workspace);
-  p.partials = reinterpret_cast<double*>(reinterpret_cast<unsigned char*>(d->workspace) + plan.bounds_bytes);
+  unsigned char* ws = reinterpret_cast<unsigned char*>(d->workspace);
+  p.bounds = reinterpret_cast<int32_t*>(ws);
+  p.partials = reinterpret_cast<double*>(ws + plan.bounds_bytes);
   p.n_news = d->n_news, p.row_stride = d->row_stride;
   p.n_impr = (int)d->n_impressions, p.n_modules = d->n_modules, p.active_mask = d->active_modules_mask;
   p.vec_per_row = vec_per_row;
@@ -1157,14 +1568,33 @@ int score_eval(const mb200_eval_desc* d, cudaStream_t stream) {
   for (int m = 0; m < MB200_MAX_MODULES; ++m) p.attn_logits[m] = (m < d->n_modules) ? d->attn_logits[m] : nullptr;
   p.hist_pad = d->hist_pad, p.cand_pad = d->cand_pad, p.loss_per_impr = d->loss_per_impression;
   p.loss_kind = d->loss_kind, p.loss_temperature = d->loss_temperature;
+  p.has_aspects = plan.has_aspects, p.comb_alias = plan.comb_alias;
+  p.hot_cap = plan.hot_cap, p.hot_bytes = plan.hot_bytes;
 
+  KernelTimer* timer = tuning().time_kernel ? timer_for(device) : nullptr;
+  int launches = 3;
+  if (hot && d->n_impressions > 0) {
+    // hot-row directory of this behaviour set: sampled id histogram -> the hot_cap most gathered rows -> id -> slot map
+    unsigned char* hr = ws + plan.bounds_bytes + plan.partials_bytes;
+    HotDir* dir = reinterpret_cast<HotDir*>(hr);
+    int32_t* hot_ids = reinterpret_cast<int32_t*>(hr + 256);
+    int32_t* counts = reinterpret_cast<int32_t*>(hr + 256 + 1024);
+    uint8_t* slot_of = hr + 256 + 1024 + align_up((size_t)d->n_news * sizeof(int32_t), 256);
+    st = cuda_status(cudaMemsetAsync(counts, 0, (size_t)d->n_news * sizeof(int32_t), stream), "cudaMemsetAsync(hot counts)");
+    if (st != MB200_OK) return st;
+    hot_count_kernel<<<sms * 8, 256, 0, stream>>>(d->hist_offsets, d->hist_ids, d->cand_offsets, d->cand_ids, p.n_impr, d->n_news, counts);
+    if ((st = cuda_status(cudaGetLastError(), "hot_count_kernel")) != MB200_OK) return st;
+    hot_select_kernel<<<1, 1024, 0, stream>>>(counts, (int)d->n_news, plan.hot_cap, dir, hot_ids, slot_of);
+    if ((st = cuda_status(cudaGetLastError(), "hot_select_kernel")) != MB200_OK) return st;
+    p.hot_dir = dir, p.hot_ids = hot_ids, p.slot_of = slot_of;
+    launches += 2;
+  }
   partition_kernel<<<(plan.n_chunks + 1 + 255) / 256, 256, 0, stream>>>(d->hist_offsets, d->cand_offsets, p.n_impr, plan.n_chunks,
                                                                        reinterpret_cast<int32_t*>(d->workspace));
   st = cuda_status(cudaGetLastError(), "partition_kernel");
   if (st != MB200_OK) return st;
-  KernelTimer* timer = tuning().time_kernel ? timer_for(device) : nullptr;
   if (timer) cudaEventRecord(timer->begin, stream);
-  kern<<<plan.grid, kThreads, plan.smem_per_cta, stream>>>(p);
+  kern<<<plan.grid, plan.warps_per_cta * 32, plan.smem_per_cta, stream>>>(p);
   cudaError_t e = cudaGetLastError();
   if (timer) cudaEventRecord(timer->end, stream), timer->armed = true, g_last_timer = timer;
   st = cuda_status(e, "score_eval_kernel");
@@ -1173,7 +1603,7 @@ int score_eval(const mb200_eval_desc* d, cudaStream_t stream) {
                                                               d->pack_payload);
   st = cuda_status(cudaGetLastError(), "reduce_partials_kernel");
   if (st != MB200_OK) return st;
-  note_launch(3);
+  note_launch(launches);
   return MB200_OK;
 }
 

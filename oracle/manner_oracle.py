@@ -492,6 +492,78 @@ def pooled_auc_exact(preds: np.ndarray, labels: np.ndarray, sigmoid: Optional[bo
     return float((lo + hi).sum() / (2.0 * pos.size * neg.size))
 
 
+# ----------------------------------------------------------------------------------------------
+# full-size score check: the same arithmetic in fp64, vectorised over impressions (no per-step padding -- the
+# padded cells of the reference's dense batches contribute exact zeros to every sum it takes)
+# ----------------------------------------------------------------------------------------------
+
+
+def ensemble_truth_f64(tables: Sequence[Tensor], weights: Sequence[float], bhv: Behaviours, zscore_modules: bool = True,
+                       rtol: float = 1e-5, chunk: int = 4096) -> Tuple[np.ndarray, np.ndarray]:
+    """(scores fp64 [sum C], tol fp64 [sum C]): cr_module.py:105-131 / ensemble_module.py:95-151 evaluated in fp64, and the
+    tolerance of the stated parity bar: raw dot products |ds| <= rtol * sum_i |u_i c_i| (condition-aware, SURVEY 7);
+    z-scored module scores 2 rtol (1 + |z|); the weighting adds them up.  An fp32 evaluation in any summation order (the
+    reference's bmm, this library's warp reduction) must lie within ``tol`` of these scores."""
+    ho, co = bhv.hist_offsets.astype(np.int64), bhv.cand_offsets.astype(np.int64)
+    n_impr = ho.shape[0] - 1
+    out = np.zeros(int(co[-1]), dtype=np.float64)
+    tol = np.zeros(int(co[-1]), dtype=np.float64)
+    for lo in range(0, n_impr, chunk):
+        hi = min(lo + chunk, n_impr)
+        hids = torch.from_numpy(bhv.hist_ids[ho[lo]:ho[hi]].astype(np.int64))
+        cids = torch.from_numpy(bhv.cand_ids[co[lo]:co[hi]].astype(np.int64))
+        hseg = torch.from_numpy(np.repeat(np.arange(hi - lo), np.diff(ho[lo:hi + 1])))
+        cseg = torch.from_numpy(np.repeat(np.arange(hi - lo), np.diff(co[lo:hi + 1])))
+        hlen = torch.from_numpy(np.diff(ho[lo:hi + 1]).astype(np.float64))
+        clen = torch.from_numpy(np.diff(co[lo:hi + 1]).astype(np.float64))
+        total = torch.zeros(cids.shape[0], dtype=torch.float64)
+        total_tol = torch.zeros(cids.shape[0], dtype=torch.float64)
+        for m, (table, w) in enumerate(zip(tables, weights)):
+            if m > 0 and w == 0:
+                continue
+            t = table.float()
+            hrows = t[hids].double()
+            u = torch.zeros(hi - lo, t.shape[1], dtype=torch.float64).index_add_(0, hseg, hrows) / hlen[:, None]
+            ua = torch.zeros(hi - lo, t.shape[1], dtype=torch.float64).index_add_(0, hseg, hrows.abs()) / hlen[:, None]
+            crows = t[cids].double()
+            sc = (crows * u[cseg]).sum(1)
+            st = rtol * (crows.abs() * ua[cseg]).sum(1) + 1e-30
+            if zscore_modules:
+                mean = torch.zeros(hi - lo, dtype=torch.float64).index_add_(0, cseg, sc) / clen
+                var = torch.zeros(hi - lo, dtype=torch.float64).index_add_(0, cseg, (sc - mean[cseg]) ** 2) / (clen - 1)
+                std = var.sqrt()
+                z = (sc - mean[cseg]) / std[cseg]
+                st = 2.0 * rtol * (1.0 + z.abs())  # z-scores are O(1): the stated 1e-5 relative bar on each side (the propagated bound is ~100x looser)
+                sc = z
+            total += float(w) * sc if m > 0 else (sc if w == 1 else float(w) * sc)
+            total_tol += abs(float(w)) * st
+        out[co[lo]:co[hi]] = total.numpy()
+        tol[co[lo]:co[hi]] = total_tol.numpy()
+    return out, tol
+
+
+def unexplained_rank_flips(got: np.ndarray, ref: np.ndarray, slack: np.ndarray, offsets: np.ndarray) -> Tuple[int, int, float]:
+    """Candidates ranked differently under ``got`` and ``ref`` scores: (flips, unexplained, largest gap among the explained).
+    A flip of candidate j is *explained* when another candidate of its impression lies within slack_j + slack_k of it in
+    ``ref`` -- a near-tie that two correct fp32 evaluations may order differently; anything else is a real ranking error."""
+    ra, rb = stable_ranks(got, offsets), stable_ranks(ref, offsets)
+    bad = np.nonzero(ra != rb)[0]
+    if bad.size == 0:
+        return 0, 0, 0.0
+    seg = np.searchsorted(offsets.astype(np.int64), bad, side="right") - 1
+    unexplained, worst = 0, 0.0
+    for j, i in zip(bad.tolist(), seg.tolist()):
+        lo, hi = int(offsets[i]), int(offsets[i + 1])
+        gap = np.abs(ref[lo:hi] - ref[j]) - (slack[lo:hi] + slack[j])
+        gap[j - lo] = np.inf
+        k = int(np.argmin(gap))
+        if gap[k] <= 0:
+            worst = max(worst, float(abs(ref[lo + k] - ref[j])))
+        else:
+            unexplained += 1
+    return int(bad.size), unexplained, worst
+
+
 # ---- full-catalogue retrieval (BASELINE.json configs[4]; no reference counterpart) -----------------------
 
 
