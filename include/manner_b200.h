@@ -35,7 +35,7 @@ extern "C" {
 #define MB200_API
 #endif
 
-#define MB200_ABI_VERSION 2
+#define MB200_ABI_VERSION 3
 #define MB200_MAX_MODULES 4 /* CR-Module + up to 3 A-Modules (reference: CR, category, sentiment) */
 #define MB200_MAX_K 31      /* largest ranking cut-off k for nDCG / diversity / personalization */
 #define MB200_MAX_CLASSES 64
@@ -53,6 +53,8 @@ extern "C" {
 #define MB200_FLAG_CAND_OVERFLOW 2   /* an impression had more than max_cand candidates: skipped      */
 #define MB200_FLAG_OUTSIDE_UNIT 4    /* some materialised score was not in [0,1] (AUROC sigmoid rule) */
 #define MB200_FLAG_BAD_ASPECT 8      /* an aspect label was outside [0, num_classes)                  */
+#define MB200_FLAG_EXCHANGE_TIMEOUT 16 /* mb200_exchange_finish: a peer GPU's stores did not arrive within 4 s     */
+#define MB200_FLAG_POS_OVERFLOW 32   /* mb200_exchange_finish: a rank had more positives than pos_capacity: AUROC invalid */
 
 /* ---- embedding table element types ----------------------------------------------------------------- */
 #define MB200_F32 0
@@ -313,6 +315,51 @@ MB200_API int mb200_pool_users(const void* table, int dtype, int dim, int64_t ro
 MB200_API int mb200_merge_topk(const float* scores, const int64_t* ids, int shards, int64_t n_users, int k, float* out_scores,
                                int64_t* out_ids, void* stream);
 
+/*
+ * Fused multi-GPU exchange of one evaluation (the reference is single-device, configs/trainer/default.yaml:9, so
+ * the contract is "same numbers as one GPU").  Replaces the NCCL all-reduce of the metric payload, the all-gather of the
+ * positive keys and the all-reduce of the AUROC statistics: `mb200_exchange_post` STORES this rank's payload (the packed `sums` of
+ * mb200_score_eval with pack_payload) and the raw keys of its positives into slot `my_rank` of EVERY rank's mailbox over
+ * NVLink / NVSwitch peer memory; `mb200_exchange_finish` (same stream, after it) waits for all ranks' stores, sums the payloads
+ * in rank order into `out_payload` (bit-identical on every rank), ranks all ranks' positives against this rank's sorted
+ * negatives, exchanges the three additive integers the same way and writes their sums to `out_stats` = {sum2, P, N}
+ * (auc = sum2 / (2 P N)).  mailbox[r] = rank r's mailbox as mapped in THIS process (mb200_ipc_open; own = local memory),
+ * mb200_exchange_mailbox_bytes() bytes each, zero-filled once before the first exchange.  `epoch` = 1, 2, 3, ... must advance by
+ * one per exchange on every rank.  Keys: mb200_auc_build_keys with sigmoid_mode 0 + mb200_auc_sort_keys (raw score order); the
+ * sigmoid rule of torchmetrics' AUROC is applied inside the rank search from the reduced payload (entry `outside_index` > 0 on
+ * any rank), which is valid because the fp32 sigmoid is monotone.  Waits are bounded (4 s -> MB200_FLAG_EXCHANGE_TIMEOUT).
+ * One process per GPU: the two kernels of different ranks run on different GPUs.
+ */
+typedef struct mb200_exchange_desc {
+  uint32_t struct_size; /* = sizeof(mb200_exchange_desc) */
+  int32_t n_ranks;      /* 1..MB200_MAX_TABLE_SHARDS */
+  int32_t my_rank;
+  uint32_t epoch;       /* >= 1 */
+  int32_t n_payload;    /* doubles in the payload */
+  int32_t outside_index; /* payload entry that is > 0 when a score of that rank was outside [0,1]; -1 = never apply the sigmoid */
+  int64_t pos_capacity; /* positive keys a mailbox slot can hold (same on every rank) */
+  void* mailbox[MB200_MAX_TABLE_SHARDS];
+  const double* payload;      /* [n_payload] this rank's */
+  const uint32_t* pos_keys;   /* this rank's positive keys (mb200_auc_build_keys, sigmoid_mode 0) */
+  const int64_t* n_pos;       /* device: how many */
+  const uint32_t* sorted_neg; /* [n_rows] mb200_auc_sort_keys output: negatives in [0, n_rows - *n_pos) */
+  int64_t n_rows;
+  double* out_payload;        /* [n_payload] sums over ranks */
+  int64_t* out_stats;         /* [3] */
+  int32_t* flags;             /* optional: TWO int32 (an int64 slot), zeroed by _post, then OR-ed with MB200_FLAG_EXCHANGE_TIMEOUT /
+                                 MB200_FLAG_POS_OVERFLOW by _finish */
+} mb200_exchange_desc;
+
+MB200_API size_t mb200_exchange_mailbox_bytes(int n_ranks, int n_payload, int64_t pos_capacity);
+MB200_API int mb200_exchange_post(const mb200_exchange_desc* desc, void* stream);
+MB200_API int mb200_exchange_finish(const mb200_exchange_desc* desc, void* stream);
+
+/* Read-bandwidth probe for the roofline denominators bench.py reports: every warp streams 3 KB rows of `buf` (the access shape
+ * of the row gather: six 16-byte loads per lane and row, four rows in flight) for `repeats` passes.  A buffer that fits the
+ * 126 MB L2 measures the L2 -> SM read bandwidth a gather can reach at best; a larger one the HBM read bandwidth.  The caller
+ * times it with events.  `sink`: 4 bytes of device memory. */
+MB200_API int mb200_read_probe(const void* buf, size_t bytes, int repeats, void* sink, void* stream);
+
 /* Lets kernels running on `device` load from memory that lives on `peer` (cudaDeviceEnablePeerAccess; "already enabled" is
  * not an error): needed once per pair of GPUs before row-sharded tables (mb200_eval_desc.table_shards) are used. */
 MB200_API int mb200_enable_peer_access(int device, int peer);
@@ -333,8 +380,10 @@ MB200_API float mb200_dcg_discount(int rank);
 MB200_API int64_t mb200_launch_count(void);
 MB200_API int64_t mb200_library_launch_count(void);
 /* tuning knobs; returns the previous value.  key 0 = impression chunks per warp; 1 = variant of the reference-width fused
- * kernel (-1 = by table type [default], 0/2/3/5/6 = rows in flight x resident CTAs per SM: 4x3, 3x4, 2x5, 3x6, 2x7 for fp32
- * rows, twice the rows for bf16; 1 = 4x3 with L1::no_allocate loads); 2 = cap on CTAs per SM; 3 = time the fused kernel with
+ * kernel (-1 = default: one 16-warp CTA per SM with the hot-row cache in shared memory [= 9]; 10 = that CTA shape without the
+ * cache; 7 / 8 = rotating row pipeline without / with the cache; 0/2/3/5/6 = the round-1 4-warp kernels, rows in flight x
+ * resident CTAs per SM: 4x3, 3x4, 2x5, 3x6, 2x7 for fp32 rows, twice the rows for bf16; 1 = 4x3 with L1::no_allocate loads);
+ * 2 = cap on CTAs per SM; 3 = time the fused kernel with
  * CUDA events; 4 = retrieval diagnostics (1, 2: parts of the epilogue disabled, RESULTS INVALID; 4: cycle counters in the
  * workspace header, results valid); 5 = retrieval pipeline (1 = CTA pairs / tcgen05 cta_group::2 [default], 0 = one CTA per tile) */
 MB200_API int mb200_set_tuning(int key, int value);

@@ -12,7 +12,7 @@ from typing import Optional
 
 LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libmanner_b200.so")
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 MAX_MODULES = 4
 MAX_TABLE_SHARDS = 8
 MAX_K = 31
@@ -22,6 +22,7 @@ PAYLOAD_TAIL = 5
 
 OK, ERR_INVALID_ARG, ERR_UNSUPPORTED, ERR_CUDA, ERR_WORKSPACE = 0, 1, 2, 3, 4
 FLAG_BAD_ID, FLAG_CAND_OVERFLOW, FLAG_OUTSIDE_UNIT, FLAG_BAD_ASPECT = 1, 2, 4, 8
+FLAG_EXCHANGE_TIMEOUT, FLAG_POS_OVERFLOW = 16, 32
 F32, BF16 = 0, 1
 
 # metric slots
@@ -133,6 +134,29 @@ class RetrievalDesc(Structure):
     ]
 
 
+class ExchangeDesc(Structure):
+    """mb200_exchange_desc, field for field."""
+
+    _fields_ = [
+        ("struct_size", c_uint32),
+        ("n_ranks", c_int32),
+        ("my_rank", c_int32),
+        ("epoch", c_uint32),
+        ("n_payload", c_int32),
+        ("outside_index", c_int32),
+        ("pos_capacity", c_int64),
+        ("mailbox", c_void_p * MAX_TABLE_SHARDS),
+        ("payload", c_void_p),
+        ("pos_keys", c_void_p),
+        ("n_pos", c_void_p),
+        ("sorted_neg", c_void_p),
+        ("n_rows", c_int64),
+        ("out_payload", c_void_p),
+        ("out_stats", c_void_p),
+        ("flags", c_void_p),
+    ]
+
+
 # every symbol include/manner_b200.h declares: (restype, argtypes)
 SIGNATURES = {
     "mb200_abi_version": (c_int, []),
@@ -154,6 +178,10 @@ SIGNATURES = {
     "mb200_step_loss": (c_int, [c_void_p, c_int64, c_int, c_int, c_void_p, c_void_p]),
     "mb200_metrics_workspace_bytes": (c_size_t, [POINTER(MetricsDesc)]),
     "mb200_rank_metrics": (c_int, [POINTER(MetricsDesc), c_void_p]),
+    "mb200_exchange_mailbox_bytes": (c_size_t, [c_int, c_int, c_int64]),
+    "mb200_exchange_post": (c_int, [POINTER(ExchangeDesc), c_void_p]),
+    "mb200_exchange_finish": (c_int, [POINTER(ExchangeDesc), c_void_p]),
+    "mb200_read_probe": (c_int, [c_void_p, c_size_t, c_int, c_void_p, c_void_p]),
     "mb200_enable_peer_access": (c_int, [c_int, c_int]),
     "mb200_ipc_export": (c_int, [c_void_p, c_char_p, POINTER(c_int64)]),
     "mb200_ipc_open": (c_int, [c_char_p, c_int64, c_int, POINTER(c_void_p)]),

@@ -59,6 +59,10 @@ int pool_users(const void*, int, int, long long, long long, const int32_t*, cons
 int merge_topk(const float*, const long long*, int, long long, int, float*, long long*, cudaStream_t);
 int attention_logits(const void*, int, int, long long, long long, const float*, const float*, const float*, int, float*, cudaStream_t);
 int step_loss(const float*, long long, int, int, double*, cudaStream_t);
+size_t exchange_mailbox_bytes(int n_ranks, int n_payload, long long pos_capacity);
+int exchange_post(const mb200_exchange_desc* d, cudaStream_t stream);
+int exchange_finish(const mb200_exchange_desc* d, cudaStream_t stream);
+int read_probe(const void* buf, size_t bytes, int repeats, void* sink, cudaStream_t stream);
 size_t metrics_workspace_bytes(const mb200_metrics_desc* d);
 int rank_metrics(const mb200_metrics_desc* d, cudaStream_t stream);
 
@@ -157,6 +161,16 @@ int mb200_step_loss(const float* loss_per_impression, int64_t n_impressions, int
 size_t mb200_metrics_workspace_bytes(const mb200_metrics_desc* desc) { return metrics_workspace_bytes(desc); }
 
 int mb200_rank_metrics(const mb200_metrics_desc* desc, void* stream) { return rank_metrics(desc, static_cast<cudaStream_t>(stream)); }
+
+size_t mb200_exchange_mailbox_bytes(int n_ranks, int n_payload, int64_t pos_capacity) { return exchange_mailbox_bytes(n_ranks, n_payload, pos_capacity); }
+
+int mb200_exchange_post(const mb200_exchange_desc* desc, void* stream) { return exchange_post(desc, static_cast<cudaStream_t>(stream)); }
+
+int mb200_exchange_finish(const mb200_exchange_desc* desc, void* stream) { return exchange_finish(desc, static_cast<cudaStream_t>(stream)); }
+
+int mb200_read_probe(const void* buf, size_t bytes, int repeats, void* sink, void* stream) {
+  return read_probe(buf, bytes, repeats, sink, static_cast<cudaStream_t>(stream));
+}
 
 int mb200_enable_peer_access(int device, int peer) {
   int can = 0;

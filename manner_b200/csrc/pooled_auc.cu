@@ -184,4 +184,292 @@ int pooled_auc(const float* preds, const uint8_t* labels, long long n, int sigmo
   return cuda_status(cudaGetLastError(), "auc_finalize_kernel");
 }
 
+
+// ------------------------------------------------------------------------------------------------------
+// Fused multi-GPU exchange: everything an evaluation has to tell the other GPUs -- the fp64 metric payload
+// and the raw keys of its (few) positives -- is STORED straight into every peer's mailbox over NVLink / NVSwitch peer memory
+// by one kernel; a second kernel waits for the peers' stores, reduces the payloads in rank order, ranks ALL ranks' positives
+// against the local sorted negatives, posts the three additive integers and sums the peers'.  No NCCL call on the path: it
+// replaces all_reduce(sums) + all_gather(positive keys) + all_reduce(stats) + one rank-sum launch per rank.
+//
+// The negatives are sorted by their RAW score keys before anything is exchanged; whether torchmetrics' AUROC would apply the
+// sigmoid is only known globally (any score outside [0,1] on any rank), so the rank search compares sigmoid(key) when the
+// reduced payload says so -- fp32 sigmoid is monotone, hence the raw order is a valid order for it (ties only merge).
+//
+// Mailbox of a rank = 2 (epoch parity) x n_ranks slots; slot = [256 B header][payload doubles][positive keys].
+// ------------------------------------------------------------------------------------------------------
+
+struct ExchangeHeader {
+  uint32_t flag1;  // epoch once payload + positives of this slot are complete
+  uint32_t flag2;  // epoch once the statistics below are complete
+  long long n_pos;
+  unsigned long long sum2;
+  long long pos_total, neg_total;
+  // local scratch of the OWNER of the mailbox (only used in its own slot [parity][my_rank])
+  unsigned int ticket;
+  unsigned int pad;
+  unsigned long long acc;
+};
+static_assert(sizeof(ExchangeHeader) <= 256, "mailbox header");
+
+struct ExchangeParams {
+  unsigned char* mailbox[MB200_MAX_TABLE_SHARDS];
+  int n_ranks, my_rank;
+  uint32_t epoch;
+  int n_payload;
+  int outside_index;  // payload entry that is > 0 when some score of that rank was outside [0,1] (-1: never)
+  long long pos_capacity;
+  size_t slot_bytes, payload_off, keys_off;
+  const double* payload;
+  const uint32_t* pos_keys;
+  const long long* n_pos;
+  const uint32_t* sorted_neg;
+  long long n_rows;
+  double* out_payload;
+  long long* out_stats;
+  int32_t* flags;
+};
+
+__device__ __forceinline__ unsigned char* slot_of_mailbox(const ExchangeParams& p, int owner, int src) {
+  return p.mailbox[owner] + ((size_t)(p.epoch & 1u) * p.n_ranks + src) * p.slot_bytes;
+}
+
+__device__ __forceinline__ void st_release_sys(uint32_t* addr, uint32_t v) { asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(addr), "r"(v) : "memory"); }
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* addr) {
+  uint32_t v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+
+// waits until *flag == epoch (bounded: 4 s, then reports instead of hanging the GPU)
+__device__ bool wait_flag(const uint32_t* flag, uint32_t epoch) {
+  const unsigned long long t0 = global_timer_ns();
+  while (ld_acquire_sys(flag) != epoch) {
+    __nanosleep(200);
+    if (global_timer_ns() - t0 > 4000000000ull) return false;
+  }
+  return true;
+}
+
+__global__ void __launch_bounds__(256) exchange_post_kernel(const ExchangeParams p) {
+  const long long n_pos = min(*p.n_pos, p.pos_capacity);
+  const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x, nthreads = (long long)gridDim.x * blockDim.x;
+  if (tid == 0 && p.flags) *p.flags = 0, p.flags[1] = 0;  // the exchange's own flag word (an int64 slot of the result): set by the finish kernel only
+  for (int r = 0; r < p.n_ranks; ++r) {
+    unsigned char* slot = slot_of_mailbox(p, r, p.my_rank);
+    double* pay = reinterpret_cast<double*>(slot + p.payload_off);
+    for (long long i = tid; i < p.n_payload; i += nthreads) pay[i] = p.payload[i];
+    uint32_t* keys = reinterpret_cast<uint32_t*>(slot + p.keys_off);
+    for (long long i = tid; i < n_pos; i += nthreads) keys[i] = p.pos_keys[i];
+    if (tid == 0) reinterpret_cast<ExchangeHeader*>(slot)->n_pos = *p.n_pos;  // the true count: the receiver reports an overflow
+  }
+  ExchangeHeader* own = reinterpret_cast<ExchangeHeader*>(slot_of_mailbox(p, p.my_rank, p.my_rank));
+  __threadfence_system();
+  __syncthreads();
+  __shared__ bool last;
+  if (threadIdx.x == 0) last = atomicAdd(&own->ticket, 1u) == gridDim.x - 1;
+  __syncthreads();
+  if (last) {
+    if (threadIdx.x == 0) own->ticket = 0, own->acc = 0;
+    __threadfence_system();
+    __syncthreads();
+    if ((int)threadIdx.x < p.n_ranks) st_release_sys(&reinterpret_cast<ExchangeHeader*>(slot_of_mailbox(p, threadIdx.x, p.my_rank))->flag1, p.epoch);
+  }
+}
+
+__device__ __forceinline__ float key_to_float(uint32_t k) { return __uint_as_float((k & 0x80000000u) ? (k ^ 0x80000000u) : ~k); }
+
+__global__ void __launch_bounds__(256) exchange_finish_kernel(const ExchangeParams p) {
+  __shared__ bool ok, sig, last;
+  __shared__ unsigned long long sh[8];
+  if (threadIdx.x == 0) {
+    bool good = true, outside = false;
+    for (int r = 0; r < p.n_ranks; ++r) {
+      unsigned char* slot = slot_of_mailbox(p, p.my_rank, r);
+      good = good && wait_flag(&reinterpret_cast<ExchangeHeader*>(slot)->flag1, p.epoch);
+      if (good && p.outside_index >= 0) outside |= reinterpret_cast<const double*>(slot + p.payload_off)[p.outside_index] > 0.0;
+    }
+    ok = good, sig = outside;
+  }
+  __syncthreads();
+  if (!ok) {
+    if (blockIdx.x == 0 && threadIdx.x == 0 && p.flags) atomicOr(p.flags, MB200_FLAG_EXCHANGE_TIMEOUT);
+    return;
+  }
+  // metric payload: fixed rank order, every rank computes the same doubles
+  if (blockIdx.x == 0) {
+    for (int i = threadIdx.x; i < p.n_payload; i += blockDim.x) {
+      double a = 0.0;
+      for (int r = 0; r < p.n_ranks; ++r) a += reinterpret_cast<const double*>(slot_of_mailbox(p, p.my_rank, r) + p.payload_off)[i];
+      p.out_payload[i] = a;
+    }
+  }
+  // every rank's positives against MY sorted negatives
+  const long long my_pos = *p.n_pos;
+  const long long n_neg = p.n_rows - my_pos;
+  const bool use_sig = sig;
+  unsigned long long local = 0;
+  bool overflow = false;
+  for (int r = 0; r < p.n_ranks; ++r) {
+    const unsigned char* slot = slot_of_mailbox(p, p.my_rank, r);
+    long long cnt = reinterpret_cast<const ExchangeHeader*>(slot)->n_pos;
+    if (cnt > p.pos_capacity) cnt = p.pos_capacity, overflow = true;
+    const uint32_t* keys = reinterpret_cast<const uint32_t*>(slot + p.keys_off);
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < cnt; i += (long long)gridDim.x * blockDim.x) {
+      uint32_t key = keys[i];
+      if (use_sig) key = orderable_key(sigmoid_f32(key_to_float(key)));
+      long long lo = 0, hi = n_neg;  // lower_bound: first negative whose (sigmoid) key is >= key
+      while (lo < hi) {
+        const long long mid = (lo + hi) >> 1;
+        uint32_t km = p.sorted_neg[mid];
+        if (use_sig) km = orderable_key(sigmoid_f32(key_to_float(km)));
+        if (km < key) lo = mid + 1; else hi = mid;
+      }
+      const long long lb = lo;
+      hi = n_neg;
+      while (lo < hi) {
+        const long long mid = (lo + hi) >> 1;
+        uint32_t km = p.sorted_neg[mid];
+        if (use_sig) km = orderable_key(sigmoid_f32(key_to_float(km)));
+        if (km <= key) lo = mid + 1; else hi = mid;
+      }
+      local += (unsigned long long)(lb + lo);
+    }
+  }
+  if (overflow && blockIdx.x == 0 && threadIdx.x == 0 && p.flags) atomicOr(p.flags, MB200_FLAG_POS_OVERFLOW);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) local += __shfl_xor_sync(kFull, local, o);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = local;
+  __syncthreads();
+  ExchangeHeader* own = reinterpret_cast<ExchangeHeader*>(slot_of_mailbox(p, p.my_rank, p.my_rank));
+  if (threadIdx.x == 0) {
+    unsigned long long t = 0;
+    for (int w = 0; w < 8; ++w) t += sh[w];
+    if (t) atomicAdd(&own->acc, t);
+    __threadfence();
+    last = atomicAdd(&own->ticket, 1u) == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (!last) return;
+  // the last block posts this rank's three additive integers to every peer, then sums what the peers posted
+  if (threadIdx.x == 0) {
+    __threadfence();
+    const unsigned long long sum2 = atomicAdd(&own->acc, 0ull);
+    own->ticket = 0;
+    for (int r = 0; r < p.n_ranks; ++r) {
+      ExchangeHeader* h = reinterpret_cast<ExchangeHeader*>(slot_of_mailbox(p, r, p.my_rank));
+      h->sum2 = sum2, h->pos_total = my_pos, h->neg_total = n_neg;
+    }
+    __threadfence_system();
+    for (int r = 0; r < p.n_ranks; ++r) st_release_sys(&reinterpret_cast<ExchangeHeader*>(slot_of_mailbox(p, r, p.my_rank))->flag2, p.epoch);
+    unsigned long long s2 = 0;
+    long long P = 0, N = 0;
+    bool good = true;
+    for (int r = 0; r < p.n_ranks; ++r) {
+      const ExchangeHeader* h = reinterpret_cast<const ExchangeHeader*>(slot_of_mailbox(p, p.my_rank, r));
+      good = good && wait_flag(&h->flag2, p.epoch);
+      s2 += *reinterpret_cast<const volatile unsigned long long*>(&h->sum2);
+      P += *reinterpret_cast<const volatile long long*>(&h->pos_total);
+      N += *reinterpret_cast<const volatile long long*>(&h->neg_total);
+    }
+    if (!good && p.flags) atomicOr(p.flags, MB200_FLAG_EXCHANGE_TIMEOUT);
+    p.out_stats[0] = (long long)s2, p.out_stats[1] = P, p.out_stats[2] = N;
+  }
+}
+
+static size_t exchange_layout(int n_payload, long long pos_capacity, size_t* payload_off, size_t* keys_off) {
+  const size_t po = 256, ko = po + al256((size_t)n_payload * sizeof(double));
+  if (payload_off) *payload_off = po;
+  if (keys_off) *keys_off = ko;
+  return ko + al256((size_t)pos_capacity * sizeof(uint32_t));
+}
+
+size_t exchange_mailbox_bytes(int n_ranks, int n_payload, long long pos_capacity) {
+  if (n_ranks < 1 || n_ranks > MB200_MAX_TABLE_SHARDS || n_payload < 0 || pos_capacity < 0) return 0;
+  return 2 * (size_t)n_ranks * exchange_layout(n_payload, pos_capacity, nullptr, nullptr);
+}
+
+static int exchange_params(const mb200_exchange_desc* d, ExchangeParams* p) {
+  if (d == nullptr || d->struct_size != sizeof(mb200_exchange_desc)) return MB200_ERR_INVALID_ARG;
+  if (d->n_ranks < 1 || d->n_ranks > MB200_MAX_TABLE_SHARDS || d->my_rank < 0 || d->my_rank >= d->n_ranks) return MB200_ERR_INVALID_ARG;
+  if (d->n_payload < 0 || d->pos_capacity < 0 || d->n_rows < 0 || d->epoch == 0) return MB200_ERR_INVALID_ARG;
+  if (d->outside_index >= d->n_payload) return MB200_ERR_INVALID_ARG;
+  if (!d->n_pos || !d->out_payload || !d->out_stats || (d->n_payload > 0 && !d->payload)) return MB200_ERR_INVALID_ARG;
+  if (d->n_rows > 0 && (!d->sorted_neg || !d->pos_keys)) return MB200_ERR_INVALID_ARG;
+  for (int r = 0; r < d->n_ranks; ++r)
+    if (d->mailbox[r] == nullptr || ((uintptr_t)d->mailbox[r] & 255)) return MB200_ERR_INVALID_ARG;
+  for (int r = 0; r < d->n_ranks; ++r) p->mailbox[r] = reinterpret_cast<unsigned char*>(d->mailbox[r]);
+  p->n_ranks = d->n_ranks, p->my_rank = d->my_rank, p->epoch = d->epoch, p->n_payload = d->n_payload, p->outside_index = d->outside_index;
+  p->pos_capacity = d->pos_capacity;
+  p->slot_bytes = exchange_layout(d->n_payload, d->pos_capacity, &p->payload_off, &p->keys_off);
+  p->payload = d->payload, p->pos_keys = d->pos_keys, p->n_pos = reinterpret_cast<const long long*>(d->n_pos);
+  p->sorted_neg = d->sorted_neg, p->n_rows = d->n_rows;
+  p->out_payload = d->out_payload, p->out_stats = reinterpret_cast<long long*>(d->out_stats), p->flags = d->flags;
+  return MB200_OK;
+}
+
+int exchange_post(const mb200_exchange_desc* d, cudaStream_t stream) {
+  ExchangeParams p{};
+  int st = exchange_params(d, &p);
+  if (st != MB200_OK) return st;
+  if ((st = use_device_of(d->out_payload, nullptr)) != MB200_OK) return st;
+  exchange_post_kernel<<<32, 256, 0, stream>>>(p);
+  note_launch(1);
+  return cuda_status(cudaGetLastError(), "exchange_post_kernel");
+}
+
+int exchange_finish(const mb200_exchange_desc* d, cudaStream_t stream) {
+  ExchangeParams p{};
+  int st = exchange_params(d, &p);
+  if (st != MB200_OK) return st;
+  if ((st = use_device_of(d->out_payload, nullptr)) != MB200_OK) return st;
+  exchange_finish_kernel<<<148 * 2, 256, 0, stream>>>(p);
+  note_launch(1);
+  return cuda_status(cudaGetLastError(), "exchange_finish_kernel");
+}
+
+// ---- read-bandwidth probe (bench.py's L2 roofline denominator) ----------------------------------------------------------
+// Every warp streams 3 KB rows (the gather's access shape: 6 x LDG.E.128 per lane and row, 4 rows in flight) of a buffer, `repeats`
+// passes; with a buffer that fits the 126 MB L2 this measures the L2 -> SM read bandwidth a row gather can reach at best, with
+// a larger one the HBM read bandwidth.
+__global__ void __launch_bounds__(512, 1) read_probe_kernel(const uint4* __restrict__ buf, long long n_rows, int repeats, unsigned int* __restrict__ sink) {
+  const int lane = threadIdx.x & 31;
+  const long long gw = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = ((long long)gridDim.x * blockDim.x) >> 5;
+  unsigned int acc = 0;
+  for (int it = 0; it < repeats; ++it) {
+    for (long long r0 = gw * 4; r0 < n_rows; r0 += nw * 4) {
+      uint4 v[4][6];
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        // rows of one batch are far apart (like gathered rows), not neighbours
+        const long long row = (r0 + r < n_rows) ? ((r0 + r) * 2654435761ll + it) % n_rows : 0;
+        const uint4* src = buf + row * 192 + lane;
+#pragma unroll
+        for (int k = 0; k < 6; ++k) v[r][k] = __ldg(src + 32 * k);
+      }
+#pragma unroll
+      for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int k = 0; k < 6; ++k) acc ^= v[r][k].x ^ v[r][k].y ^ v[r][k].z ^ v[r][k].w;
+    }
+  }
+  if (acc == 0x9e3779b9u) *sink = acc;  // keeps the loads alive
+}
+
+int read_probe(const void* buf, size_t bytes, int repeats, void* sink, cudaStream_t stream) {
+  if (buf == nullptr || sink == nullptr || bytes < 3072 || repeats < 1 || ((uintptr_t)buf & 15)) return MB200_ERR_INVALID_ARG;
+  int device = 0, sms = 0;
+  int st = use_device_of(buf, &device);
+  if (st != MB200_OK) return st;
+  if ((st = cuda_status(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device), "cudaDeviceGetAttribute")) != MB200_OK) return st;
+  read_probe_kernel<<<sms, 512, 0, stream>>>(reinterpret_cast<const uint4*>(buf), (long long)(bytes / 3072), repeats, reinterpret_cast<unsigned int*>(sink));
+  note_launch(1);
+  return cuda_status(cudaGetLastError(), "read_probe_kernel");
+}
+
 }  // namespace mb200

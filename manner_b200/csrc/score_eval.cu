@@ -252,12 +252,17 @@ __device__ __noinline__ float personalization_value(const uint8_t* top, int kk, 
 // ATTN (early fusion, cr_module.py:124-125): when `logits` is given the history rows are combined with the
 // additive-attention weights softmax(logits of the H history rows and of n_pad zero rows) instead of 1/H
 // (attention.py:20-27; the reference's softmax runs over the PADDED history, so the pad rows take mass).
-template <typename T, int NV, int R, bool EXACT, int POLICY, bool ATTN>
+//
+// HOT: rows whose id has a slot in the CTA's shared-memory hot-row cache (`slot_of[id] != kHotCold`; see score_eval_stream_kernel)
+// are read from there with LDS.128 instead of through the L2 -> SM crossbar; the arithmetic is the same either way.
+template <typename T, int NV, int R, bool EXACT, int POLICY, bool ATTN, bool HOT = false>
 __device__ __forceinline__ int gather_pool_score(const T* __restrict__ table, long long row_stride, int vec_per_row, long long n_news,
                                                  const int32_t* __restrict__ hist_ids, int H, const int32_t* __restrict__ cand_ids, int C,
                                                  float* __restrict__ s_out, const float* __restrict__ logits, int n_pad,
-                                                 const void* const* __restrict__ shard_base, int shard_shift) {
+                                                 const void* const* __restrict__ shard_base, int shard_shift,
+                                                 const unsigned char* hot_rows = nullptr, const uint8_t* __restrict__ slot_of = nullptr) {
   constexpr int E = Elem<T>::E;
+  constexpr int kRowBytes = NV * 32 * 16;
   const int lane = threadIdx.x & 31;
   int flags = 0;
   // per-lane vector slots: slot v covers 16-byte vector lane + 32 v of the row; for widths that do not
@@ -308,6 +313,10 @@ __device__ __forceinline__ int gather_pool_score(const T* __restrict__ table, lo
     if ((unsigned long long)(long long)my_id >= (unsigned long long)n_news) my_id = 0, flags |= MB200_FLAG_BAD_ID;
     float my_w = 1.0f;  // weight of this lane's history row: softmax weight (early fusion) or 1 (late fusion divides by H below)
     if (ATTN && attn) my_w = __fdiv_rn(expf(logits[my_id] - att_max), att_sum);
+    if (HOT && slot_of != nullptr) {
+      const int sl = slot_of[my_id];
+      if (sl != kHotCold) my_id = ~sl;  // negative: slot of the hot-row cache
+    }
 #pragma unroll 1
     for (int r0 = 0; r0 < cnt; r0 += R) {
       uint4 buf[R][NV];
@@ -315,6 +324,12 @@ __device__ __forceinline__ int gather_pool_score(const T* __restrict__ table, lo
       for (int r = 0; r < R; ++r) {
         const int src = (r0 + r < cnt) ? (r0 + r) : 0;
         const int id = __shfl_sync(kFull, my_id, src);
+        if (HOT && id < 0) {
+          const uint4* hrow = reinterpret_cast<const uint4*>(hot_rows + (unsigned)(~id) * (unsigned)kRowBytes) + lane;
+#pragma unroll
+          for (int v = 0; v < NV; ++v) buf[r][v] = hrow[32 * v];
+          continue;
+        }
         // POLICY 3: the table is row-sharded over the GPUs of the box; the row is read where it lives -- a plain load from the
         // owner's memory over NVLink / NVSwitch peer access when it is not this GPU's shard
         const T* tbase = POLICY == 3 ? reinterpret_cast<const T*>(shard_base[id >> shard_shift]) : table;
@@ -363,6 +378,10 @@ __device__ __forceinline__ int gather_pool_score(const T* __restrict__ table, lo
     const int cnt = min(32, C - b0);
     int my_id = cand_ids[b0 + ((lane < cnt) ? lane : 0)];
     if ((unsigned long long)(long long)my_id >= (unsigned long long)n_news) my_id = 0, flags |= MB200_FLAG_BAD_ID;
+    if (HOT && slot_of != nullptr) {
+      const int sl = slot_of[my_id];
+      if (sl != kHotCold) my_id = ~sl;
+    }
 #pragma unroll 1
     for (int r0 = 0; r0 < cnt; r0 += R) {
       uint4 buf[R][NV];
@@ -370,6 +389,12 @@ __device__ __forceinline__ int gather_pool_score(const T* __restrict__ table, lo
       for (int r = 0; r < R; ++r) {
         const int src = (r0 + r < cnt) ? (r0 + r) : 0;
         const int id = __shfl_sync(kFull, my_id, src);
+        if (HOT && id < 0) {
+          const uint4* hrow = reinterpret_cast<const uint4*>(hot_rows + (unsigned)(~id) * (unsigned)kRowBytes) + lane;
+#pragma unroll
+          for (int v = 0; v < NV; ++v) buf[r][v] = hrow[32 * v];
+          continue;
+        }
         // POLICY 3: the table is row-sharded over the GPUs of the box; the row is read where it lives -- a plain load from the
         // owner's memory over NVLink / NVSwitch peer access when it is not this GPU's shard
         const T* tbase = POLICY == 3 ? reinterpret_cast<const T*>(shard_base[id >> shard_shift]) : table;
@@ -1003,7 +1028,10 @@ __device__ __forceinline__ WarpSmem warp_smem_of(unsigned char* base, const Eval
   return sm;
 }
 
-template <typename T, int NV, int R, bool HOT>
+// PIPE 0: register batches (gather_pool_score: R rows issued, then consumed) -- the shipped path; PIPE 1: rotating row pipeline
+// (stream_pool_score) -- measured slower (profiles/r2_stream_experiment.md: per-row refills defeat the load scoreboards), kept
+// selectable for the record.
+template <typename T, int NV, int R, bool HOT, int PIPE>
 __global__ void __launch_bounds__(kStreamWarps * 32, 1) score_eval_stream_kernel(const __grid_constant__ EvalParams p) {
   extern __shared__ __align__(16) unsigned char smem[];
   constexpr int kVecPerRow = NV * 32;
@@ -1057,19 +1085,28 @@ __global__ void __launch_bounds__(kStreamWarps * 32, 1) score_eval_stream_kernel
             p.per_impr[((size_t)(t / MB200_NUM_METRICS) * p.n_impr + i) * MB200_NUM_METRICS + t % MB200_NUM_METRICS] = 0.f;
       } else {
         StreamSrc src;
-        src.hist_ids = p.hist_ids + h0, src.cand_ids = p.cand_ids + c0;
-        src.H = H, src.Hp = (H + R - 1) / R * R, src.C = C, src.n_slots = src.Hp + C;
-        src.n_news = p.n_news;
-        src.slot_of = (HOT && n_hot > 0) ? p.slot_of : nullptr;
-        const int ref_first = stream_fetch_refs(src, 0, warp_flags);  // the same ids serve every module
+        int ref_first = 0;
+        if (PIPE == 1) {
+          src.hist_ids = p.hist_ids + h0, src.cand_ids = p.cand_ids + c0;
+          src.H = H, src.Hp = (H + R - 1) / R * R, src.C = C, src.n_slots = src.Hp + C;
+          src.n_news = p.n_news;
+          src.slot_of = (HOT && n_hot > 0) ? p.slot_of : nullptr;
+          ref_first = stream_fetch_refs(src, 0, warp_flags);  // the same ids serve every module
+        }
         __syncwarp();
         for (int j = lane; j < C; j += 32) sm.lab[j] = p.labels[c0 + j];
         int slot = 0;
         for (int m = 0; m < p.n_modules; ++m) {
           if (!((p.active_mask >> m) & 1)) continue;
           float* s_m = sm.sc + (size_t)slot * p.cpad;
-          warp_flags |= stream_pool_score<T, NV, R>(reinterpret_cast<const T*>(p.tables[m]), smem + (size_t)slot * p.hot_cap * kRowBytes, src,
-                                                    ref_first, s_m);
+          if (PIPE == 1)
+            warp_flags |= stream_pool_score<T, NV, R>(reinterpret_cast<const T*>(p.tables[m]), smem + (size_t)slot * p.hot_cap * kRowBytes, src,
+                                                      ref_first, s_m);
+          else
+            warp_flags |= gather_pool_score<T, NV, R, true, 0, false, HOT>(reinterpret_cast<const T*>(p.tables[m]), p.row_stride, p.vec_per_row, p.n_news,
+                                                                           p.hist_ids + h0, H, p.cand_ids + c0, C, s_m, nullptr, 0, nullptr, 0,
+                                                                           smem + (size_t)slot * p.hot_cap * kRowBytes,
+                                                                           (HOT && n_hot > 0) ? p.slot_of : nullptr);
           __syncwarp();
           if (p.zscore) {
             zscore_inplace(s_m, C, lane);
@@ -1485,11 +1522,11 @@ size_t eval_workspace_bytes(const mb200_eval_desc* d) {
 }
 
 template <typename T>
-static KernelFn select_stream_kernel(bool hot) {
+static KernelFn select_stream_kernel(bool hot, bool rotating) {
   constexpr int kRefNV = 768 / Elem<T>::E / 32;  // 6 (fp32) or 3 (bf16)
   constexpr int R = (kRefNV == 6) ? 3 : 6;       // rows in flight per warp: 72 registers of landing buffers either way
-  if (hot) return score_eval_stream_kernel<T, kRefNV, R, true>;
-  return score_eval_stream_kernel<T, kRefNV, R, false>;
+  if (rotating) return hot ? score_eval_stream_kernel<T, kRefNV, R, true, 1> : score_eval_stream_kernel<T, kRefNV, R, false, 1>;
+  return hot ? score_eval_stream_kernel<T, kRefNV, R, true, 0> : score_eval_stream_kernel<T, kRefNV, R, false, 0>;
 }
 
 int score_eval(const mb200_eval_desc* d, cudaStream_t stream) {
@@ -1508,19 +1545,21 @@ int score_eval(const mb200_eval_desc* d, cudaStream_t stream) {
   for (int m = 0; m < d->n_modules; ++m) attn |= ((d->active_modules_mask >> m) & 1) && d->attn_logits[m] != nullptr;
   const bool sharded = d->n_table_shards > 1;
 
-  // The streaming kernel (hot-row cache in shared memory + rotating row pipeline) is the default for the reference width with
-  // late fusion and replicated tables; tuning variant 7 = streaming without the cache, 8 = with it, 0..6 = the register-batch kernels.
+  // One 16-warp CTA per SM with the hot-row cache in shared memory is the default for the reference width with late fusion and
+  // replicated tables (tuning variant 9; 10 = the same CTA shape without the cache).  Variants 7 / 8 = rotating row pipeline
+  // without / with the cache (measured slower), 0..6 = the round-1 register-batch kernels (4-warp CTAs, no cache).
   const int variant = tuning().variant;
   LaunchPlan plan;
   KernelFn kern = nullptr;
-  bool stream_path = d->dim == 768 && d->row_stride == 768 && !attn && !sharded && (variant < 0 || variant == 7 || variant == 8) && d->n_news < (1ll << 31);
+  bool stream_path = d->dim == 768 && d->row_stride == 768 && !attn && !sharded && (variant < 0 || (variant >= 7 && variant <= 10)) && d->n_news < (1ll << 31);
   bool hot = false;
   if (stream_path) {
-    if (make_plan(d, sms, 1, &plan, true, vec_per_row * 16, variant != 7) != MB200_OK) stream_path = false;  // per-warp areas too large for 16 warps
+    if (make_plan(d, sms, 1, &plan, true, vec_per_row * 16, variant != 7 && variant != 10) != MB200_OK) stream_path = false;  // per-warp areas too large for 16 warps
   }
   if (stream_path) {
     hot = plan.hot_cap > 0;
-    kern = (d->dtype == MB200_F32) ? select_stream_kernel<float>(hot) : select_stream_kernel<__nv_bfloat16>(hot);
+    const bool rotating = variant == 7 || variant == 8;
+    kern = (d->dtype == MB200_F32) ? select_stream_kernel<float>(hot, rotating) : select_stream_kernel<__nv_bfloat16>(hot, rotating);
     st = cuda_status(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem_per_cta), "cudaFuncSetAttribute");
     if (st != MB200_OK) return st;
   } else {

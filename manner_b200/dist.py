@@ -40,7 +40,7 @@ class _PeerMemory:
     """A peer GPU's memory mapped into this process, presented to torch through the CUDA array interface (zero copy)."""
 
     def __init__(self, ptr: int, shape, dtype: torch.dtype) -> None:
-        typestr = {torch.float32: "<f4", torch.bfloat16: "<u2", torch.float16: "<f2", torch.int64: "<i8", torch.int32: "<i4"}[dtype]
+        typestr = {torch.float32: "<f4", torch.bfloat16: "<u2", torch.float16: "<f2", torch.int64: "<i8", torch.int32: "<i4", torch.uint8: "|u1"}[dtype]
         self.__cuda_array_interface__ = {"data": (int(ptr), False), "shape": tuple(shape), "typestr": typestr, "version": 2, "strides": None}
 
 
@@ -81,6 +81,67 @@ def share_table_shards(local_shard: Tensor, group: Optional[dist.ProcessGroup] =
     torch.cuda.synchronize(local_shard.device)
     dist.barrier(group=group)
     return shards
+
+
+class P2PExchange:
+    """The fused exchange of one evaluation (mb200_exchange_post / mb200_exchange_finish): every rank's metric payload and
+    positive keys are stored straight into every other rank's mailbox over NVLink peer memory, the AUROC statistics follow
+    the same way -- no NCCL call on the evaluation path.  Construction is collective (the mailboxes are mapped into every
+    process with CUDA IPC); ``run`` must then be called by all ranks in the same order.  ``n_payload`` doubles per payload,
+    ``pos_cap`` = agreed upper bound on any rank's positives (``agree_pos_cap``)."""
+
+    def __init__(self, device: torch.device, n_payload: int, pos_cap: int, group: Optional[dist.ProcessGroup] = None) -> None:
+        from . import _native as nat
+
+        lib = nat.lib()
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.n_payload, self.pos_cap = int(n_payload), max(int(pos_cap), 1)
+        nbytes = int(lib.mb200_exchange_mailbox_bytes(self.world, self.n_payload, self.pos_cap))
+        if nbytes == 0:
+            raise ValueError("unsupported exchange shape (1..8 ranks of one NVSwitch box)")
+        self.mailbox = torch.zeros(nbytes, dtype=torch.uint8, device=device)
+        self.peers = share_table_shards(self.mailbox, group) if self.world > 1 else [self.mailbox]
+        self.epoch = 0
+        self._empty_i32 = torch.zeros(2, dtype=torch.int32, device=device)
+        self._zero_i64 = torch.zeros(1, dtype=torch.int64, device=device)
+
+    def fits(self, n_payload: int, pos_cap: int) -> bool:
+        return int(n_payload) == self.n_payload and int(pos_cap) <= self.pos_cap
+
+    def run(self, payload: Tensor, outside_index: int, sorted_keys: Optional[Tensor] = None, pos_keys: Optional[Tensor] = None,
+            n_pos: Optional[Tensor] = None) -> Tensor:
+        """Enqueues both kernels on the current stream.  Returns fp64 [n_payload + 4]: the payload summed over the ranks, then
+        (as int64 bit patterns) sum2, P, N of the pooled AUROC and the exchange's flag word."""
+        import ctypes
+
+        from . import _native as nat
+
+        lib = nat.lib()
+        dev = payload.device
+        if payload.dtype != torch.float64 or payload.numel() != self.n_payload or not payload.is_contiguous():
+            raise ValueError("payload must be the contiguous fp64 vector this exchange was sized for")
+        self.epoch += 1
+        out = torch.empty(self.n_payload + 4, dtype=torch.float64, device=dev)
+        tail = out[self.n_payload:].view(torch.int64)
+        d = nat.ExchangeDesc()
+        d.struct_size = ctypes.sizeof(nat.ExchangeDesc)
+        d.n_ranks, d.my_rank, d.epoch = self.world, self.rank, self.epoch
+        d.n_payload, d.outside_index, d.pos_capacity = self.n_payload, int(outside_index), self.pos_cap
+        for r, t in enumerate(self.peers):
+            d.mailbox[r] = t.data_ptr()
+        d.payload = payload.data_ptr()
+        if sorted_keys is not None:
+            d.pos_keys, d.n_pos, d.sorted_neg, d.n_rows = pos_keys.data_ptr(), n_pos.data_ptr(), sorted_keys.data_ptr(), sorted_keys.numel()
+        else:  # no pooled AUROC wanted: an empty key set
+            d.pos_keys, d.n_pos, d.sorted_neg, d.n_rows = self._empty_i32.data_ptr(), self._zero_i64.data_ptr(), self._empty_i32.data_ptr(), 0
+        d.out_payload, d.out_stats, d.flags = out.data_ptr(), tail.data_ptr(), tail[3:].data_ptr()
+        with torch.cuda.device(dev):
+            stream = torch.cuda.current_stream(dev).cuda_stream
+            nat.check(lib.mb200_exchange_post(ctypes.byref(d), stream), "mb200_exchange_post")
+            nat.check(lib.mb200_exchange_finish(ctypes.byref(d), stream), "mb200_exchange_finish")
+        return out
 
 
 def pack_metric_payload(sums: Tensor, flags: Tensor, n_impressions: int) -> Tensor:
@@ -182,9 +243,9 @@ def agree_pos_cap(n_pos_local: int, device: torch.device, group: Optional[dist.P
     return int(t.item())
 
 
-def init_from_env(backend: str = "nccl") -> Tuple[int, int, int]:
+def init_from_env(backend: str = "nccl", always: bool = False) -> Tuple[int, int, int]:
     """(rank, local_rank, world_size) from torchrun's environment; initialises the default group when
-    WORLD_SIZE > 1 and binds this process to its GPU."""
+    WORLD_SIZE > 1 (or ``always``, under torchrun) and binds this process to its GPU."""
     import os
 
     rank = int(os.environ.get("RANK", "0"))
@@ -192,7 +253,7 @@ def init_from_env(backend: str = "nccl") -> Tuple[int, int, int]:
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if torch.cuda.is_available():
         torch.cuda.set_device(local_rank)
-    if world > 1 and not dist.is_initialized():
+    if (world > 1 or (always and "MASTER_ADDR" in os.environ)) and not dist.is_initialized():
         kwargs = {}
         if backend == "nccl" and torch.cuda.is_available():
             kwargs["device_id"] = torch.device(f"cuda:{local_rank}")

@@ -110,6 +110,8 @@ class PendingEval:
     scores: Optional[Tensor]
     per_impression: Optional[Tensor]
     loss_stats: Optional[Tensor] = None  # fp64 [2]: sum of step losses, number of steps (all ranks)
+    fused: bool = False  # distributed through the fused exchange: `sums` = [payload, sum2, P, N, exchange flags] (one buffer, one read)
+    has_auc: bool = False
 
 
 class ScoreEvaluator:
@@ -131,12 +133,17 @@ class ScoreEvaluator:
         attention: Optional[Sequence[Optional[Tuple[Tensor, Tensor, Tensor]]]] = None,
         table_shards: Optional[Sequence[Sequence[Tensor]]] = None,
         n_news: Optional[int] = None,
+        exchange: str = "p2p",
     ) -> None:
         """``table_shards`` (instead of ``tables``): row-sharded tables for catalogues too large to replicate --
         ``table_shards[m]`` = the R shards of module m, each [2**s, dim] on ITS OWN GPU (this rank's shard plus the peers'
         opened with ``dist.share_table_shards``), ``n_news`` the catalogue size; row n lives in shard n >> s.  The kernel
         reads remote rows over NVLink.  Late fusion, reference width."""
         nat.lib()  # fail now, loudly, if the CUDA library is not built
+        if exchange not in ("p2p", "nccl"):
+            raise ValueError("exchange must be 'p2p' (fused: stores into the peers' mailboxes over NVLink) or 'nccl' (three collectives)")
+        self.exchange = exchange  # how a distributed evaluation meets the other ranks (dist.P2PExchange / dist.pooled_auc_distributed)
+        self._p2p: Optional[mdist.P2PExchange] = None
         if not torch.cuda.is_available():
             raise RuntimeError("manner_b200.ScoreEvaluator needs a CUDA device; there is no CPU path")
         self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
@@ -188,6 +195,8 @@ class ScoreEvaluator:
         ``dist.agree_pos_cap`` when the caller already has it.  ``step_batch`` (the reference's eval batch size)
         additionally uploads the per-impression pad counts early fusion and the cross-entropy loss need."""
         src = pinned if pinned is not None else self.pin(bhv, step_batch)
+        if pos_cap is not None and pos_cap < src["n_pos"]:
+            raise ValueError(f"pos_cap {pos_cap} is below this shard's {src['n_pos']} positives: the pooled AUROC would silently drop keys (dist.agree_pos_cap)")
         dev = {k: v.to(self.device, non_blocking=True) for k, v in src.items() if isinstance(v, Tensor)}
         nbytes = sum(v.numel() * v.element_size() for v in src.values() if isinstance(v, Tensor))
         return DeviceBehaviours(
@@ -266,7 +275,22 @@ class ScoreEvaluator:
                 torch.distributed.all_reduce(loss_stats, op=torch.distributed.ReduceOp.SUM, group=group)
         n_w = 1 if w_dev is None else w_dev.shape[0]
         auc_stats: Optional[Tensor] = None
-        if distributed:
+        fused = False
+        if distributed and self.exchange == "p2p" and (group is None or torch.distributed.get_backend(group) == "nccl"):
+            # fused exchange: payload + positive keys stored into every rank's mailbox over NVLink, AUROC statistics likewise;
+            # two kernels, no collective.  Creating / growing the mailboxes is collective and happens outside the hot loop
+            # (every rank sees the same n_payload and the agreed pos_cap, so all ranks do it in the same call).
+            cap = bhv.pos_cap if bhv.pos_cap is not None else mdist.agree_pos_cap(bhv.n_pos, self.device, group)
+            if self._p2p is None or not self._p2p.fits(sums.numel(), cap):
+                self._p2p = mdist.P2PExchange(self.device, sums.numel(), max(cap, 1), group)
+            outside = n_w * nat.NUM_METRICS + 1 + 2  # tail entry of the MB200_FLAG_OUTSIDE_UNIT bit
+            if pooled_auc:
+                sorted_keys, pos_keys, n_pos = ops.auc_build_and_sort(scores, bhv.labels, 0, None)  # raw score order; the sigmoid rule is applied after the exchange
+                sums = self._p2p.run(sums, outside, sorted_keys, pos_keys, n_pos)
+            else:
+                sums = self._p2p.run(sums, -1)
+            fused = True
+        elif distributed:
             # `sums` is the packed payload [W*NUM_METRICS sums, impression count, 4 flag bits]: one NCCL all-reduce
             torch.distributed.all_reduce(sums, op=torch.distributed.ReduceOp.SUM, group=group)
             if pooled_auc:
@@ -276,28 +300,43 @@ class ScoreEvaluator:
         elif pooled_auc:
             auc_stats = torch.ops.manner_b200.pooled_auc(scores, bhv.labels, 2, flags)
         return PendingEval(sums, flags, n_w, bhv.n_impressions, distributed, auc_stats,
-                           scores if want_scores else None, per_impr if want_per_impression else None, loss_stats)
+                           scores if want_scores else None, per_impr if want_per_impression else None, loss_stats, fused, pooled_auc)
 
     def finish(self, pending: "PendingEval") -> EvalResult:
         """The one device -> host read of a pass: metric sums, flag word, AUC statistics."""
         n_block = pending.n_weightings * nat.NUM_METRICS
-        if pending.distributed:
+        auc = counts = None
+        if pending.fused:
+            raw = pending.sums.cpu()  # the ONE device -> host read: reduced payload + AUROC integers + exchange flags
+            packed, tail = raw[: n_block + nat.PAYLOAD_TAIL].numpy(), raw[n_block + nat.PAYLOAD_TAIL :].view(torch.int64).tolist()
+            d2h = raw.numel() * 8
+            if tail[3] & nat.FLAG_EXCHANGE_TIMEOUT:
+                raise nat.NativeError("fused multi-GPU exchange: a peer GPU's stores did not arrive within 4 s (a rank died or skipped the call)")
+            if tail[3] & nat.FLAG_POS_OVERFLOW:
+                raise nat.NativeError("fused multi-GPU exchange: a rank had more positives than the agreed pos_cap (dist.agree_pos_cap)")
+            sums_h, n_total = packed[:n_block].reshape(pending.n_weightings, nat.NUM_METRICS), int(round(packed[n_block]))
+            flags_h = sum((1 << b) for b in range(mdist.N_FLAG_BITS) if packed[n_block + 1 + b] > 0)
+            if pending.has_auc:
+                s2, p, n = tail[0], tail[1], tail[2]
+                auc, counts = (s2 / (2.0 * p * n) if p > 0 and n > 0 else 0.0), (p, n)
+        elif pending.distributed:
             packed = pending.sums.cpu().numpy()
             sums_h, n_total = packed[:n_block].reshape(pending.n_weightings, nat.NUM_METRICS), int(round(packed[n_block]))
             flags_h = sum((1 << b) for b in range(mdist.N_FLAG_BITS) if packed[n_block + 1 + b] > 0)
-        else:
-            packed = torch.cat([pending.sums.reshape(-1), pending.flags.to(torch.float64)]).cpu().numpy()
-            sums_h, flags_h, n_total = packed[:-1].reshape(pending.n_weightings, nat.NUM_METRICS), int(packed[-1]), pending.n_impressions
-        d2h = packed.size * 8
-        auc = counts = None
-        if pending.auc_stats is not None:
-            if pending.distributed:
+            d2h = packed.size * 8
+            if pending.auc_stats is not None:
                 auc, p, n = mdist.auc_from_stats(pending.auc_stats)
                 counts = (p, n)
                 d2h += 24
-            else:
-                a = pending.auc_stats.cpu().numpy()
-                d2h += a.size * 8
+        else:
+            parts = [pending.sums.reshape(-1), pending.flags.to(torch.float64)]
+            if pending.auc_stats is not None:
+                parts.append(pending.auc_stats)
+            packed = torch.cat(parts).cpu().numpy()  # one read: sums, flag word, AUROC statistics
+            sums_h, flags_h, n_total = packed[:n_block].reshape(pending.n_weightings, nat.NUM_METRICS), int(packed[n_block]), pending.n_impressions
+            d2h = packed.size * 8
+            if pending.auc_stats is not None:
+                a = packed[n_block + 1 :]
                 auc, counts = float(a[0]), (int(a[1]), int(a[2]))
         loss_value = None
         if pending.loss_stats is not None:

@@ -317,6 +317,28 @@ def auc_rank_sum(sorted_keys: Tensor, n_pos_local: Tensor, pos_keys: Tensor, n_p
         )
 
 
+def read_bandwidth_probe(device: torch.device, buffer_bytes: int, repeats: int, rounds: int = 5) -> float:
+    """GB/s a warp-per-row gather of 3 KB rows can read from a ``buffer_bytes`` buffer on ``device`` (mb200_read_probe, best of
+    ``rounds``, CUDA events).  48 MiB stays in the 126 MB L2 after the first pass: the L2 -> SM roof of the scoring kernel on
+    Zipf-shaped ids; a buffer several times the L2 measures the HBM roof with the same access shape."""
+    lib = nat.lib()
+    rows = max(int(buffer_bytes) // 3072, 1)
+    with torch.cuda.device(device):
+        buf = torch.randint(0, 2**31 - 1, (rows * 768,), dtype=torch.int32, device=device)
+        sink = torch.zeros(1, dtype=torch.int32, device=device)
+        stream = torch.cuda.current_stream(device).cuda_stream
+        nat.check(lib.mb200_read_probe(buf.data_ptr(), rows * 3072, 1, sink.data_ptr(), stream), "mb200_read_probe")  # warm: fills the L2
+        best = 0.0
+        for _ in range(rounds):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            nat.check(lib.mb200_read_probe(buf.data_ptr(), rows * 3072, repeats, sink.data_ptr(), stream), "mb200_read_probe")
+            e1.record()
+            e1.synchronize()
+            best = max(best, rows * 3072 * repeats / (e0.elapsed_time(e1) * 1e-3) / 1e9)
+    return best
+
+
 def launch_counts() -> Tuple[int, int]:
     """(kernels of this library launched so far, CUB sort invocations so far) in this process."""
     lib = nat.lib()

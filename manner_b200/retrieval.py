@@ -217,6 +217,7 @@ class CatalogRetriever:
         self.distributed, self.group, self.exchange = bool(distributed), group, exchange
         self.user_block = int(user_block)
         self._gather = None  # exchange == "p2p": two sets of gather buffers shared over CUDA IPC (double buffered over user blocks)
+        self._blk = 0  # blocks exchanged so far, over ALL retrieve() calls: consecutive blocks must alternate buffers across calls too
 
     def _p2p_buffers(self):
         import torch.distributed as dist
@@ -253,9 +254,13 @@ class CatalogRetriever:
 
             rank = dist.get_rank(self.group)
             bufs = self._p2p_buffers()
-            for b, lo in enumerate(range(0, users.shape[0], self.user_block)):
+            for lo in range(0, users.shape[0], self.user_block):
                 blk = users[lo : lo + self.user_block]
-                gs, gi = bufs[b % 2]
+                # the buffer index persists across calls: a peer may still be merging the previous call's LAST block (its token
+                # all-reduce only proves it enqueued that merge), so this call's first block must go to the other buffer; the
+                # buffer written two blocks ago is safe because the all-reduce in between is ordered after that merge on every rank
+                gs, gi = bufs[self._blk % 2]
+                self._blk += 1
                 retrieve_topk_p2p(blk, self.catalog, self.k, self.offset, gs, gi, rank)
                 dist.all_reduce(self._token, group=self.group)
                 n = blk.shape[0]

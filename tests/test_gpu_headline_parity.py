@@ -135,8 +135,9 @@ def test_large_shape_sample(evaluator_cls):
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 def test_stream_kernel_bit_identical_to_register_batch_kernels(evaluator_cls, dtype):
-    """Tuning variant 2 = the round-1 register-batch kernel, 7 = streaming kernel without the hot-row cache, 8 / default =
-    with it: where a row is read from (HBM, L2, shared memory) must not change a single bit of any output."""
+    """Tuning variant 2 = the round-1 register-batch kernel (4-warp CTAs); 9 / default = one 16-warp CTA per SM with the
+    hot-row cache in shared memory, 10 = that shape without the cache; 7 / 8 = the rotating-pipeline experiment without / with
+    the cache: where a row is read from (HBM, L2, shared memory) must not change a single bit of any output."""
     n_news = 4096
     tables = [mdata.synth_table(n_news, 768, s, dtype) for s in mdata.TABLE_SEEDS]
     aspects = mdata.synth_aspects(n_news)
@@ -144,7 +145,7 @@ def test_stream_kernel_bit_identical_to_register_batch_kernels(evaluator_cls, dt
     grid = [[1.0, a / 4.0, b / 4.0] for a in range(5) for b in range(5)]
     outs = {}
     try:
-        for variant in (2, 7, 8, -1):
+        for variant in (2, 7, 8, 9, 10, -1):
             ops.set_tuning(variant=variant)
             runs = []
             ev = evaluator_cls(tables[:2])
@@ -160,7 +161,7 @@ def test_stream_kernel_bit_identical_to_register_batch_kernels(evaluator_cls, dt
     finally:
         ops.set_tuning(variant=-1)
     base = outs[2]
-    for variant in (7, 8, -1):
+    for variant in (7, 8, 9, 10, -1):
         for a, b in zip(base, outs[variant]):
             np.testing.assert_array_equal(a.scores.cpu().numpy().view(np.uint32), b.scores.cpu().numpy().view(np.uint32))
             np.testing.assert_array_equal(a.per_impression.cpu().numpy().view(np.uint32), b.per_impression.cpu().numpy().view(np.uint32))
@@ -184,16 +185,16 @@ def test_stream_kernel_edge_shapes(evaluator_cls):
     ev = evaluator_cls([table])
     outs = {}
     try:
-        for variant in (2, 7, 8):
+        for variant in (2, 7, 8, 9, 10):
             ops.set_tuning(variant=variant)
             outs[variant] = ev.evaluate(ev.upload(bhv), pooled_auc=True, want_scores=True, want_per_impression=True)
     finally:
         ops.set_tuning(variant=-1)
-    for variant in (7, 8):
+    for variant in (7, 8, 9, 10):
         np.testing.assert_array_equal(outs[2].scores.cpu().numpy().view(np.uint32), outs[variant].scores.cpu().numpy().view(np.uint32))
         np.testing.assert_array_equal(outs[2].per_impression.cpu().numpy(), outs[variant].per_impression.cpu().numpy())
     ref = mo.cr_eval_epoch(table, _ob(bhv))
-    got = outs[8].scores.cpu().numpy()
+    got = outs[9].scores.cpu().numpy()
     truth, tol = mo.ensemble_truth_f64([table], [1.0], bhv, zscore_modules=False)
     _check_scores_and_flips(got, truth, tol, bhv.cand_offsets, "edge shapes")
     assert np.allclose(got, ref["scores"], rtol=2e-5, atol=2e-6)

@@ -22,7 +22,7 @@ from manner_b200.evaluator import ScoreEvaluator
 
 
 def main() -> None:
-    rank, local_rank, world = mdist.init_from_env("nccl")
+    rank, local_rank, world = mdist.init_from_env("nccl", always=True)
     dev = torch.device(f"cuda:{local_rank}")
     n_news, dim = 5000, 768
     bhv = mdata.synth_behaviours(n_news, 20011, seed=3, cand_window=1500)
@@ -38,15 +38,26 @@ def main() -> None:
         "late_fusion_ce": (dict(tables=tables[:1]), dict(pooled_auc=True, loss="ce")),
     }
     for name, (ctor, kw) in cases.items():
-        ev = ScoreEvaluator(ctor["tables"], dev, attention=ctor.get("attention"))
-        one = ev.evaluate(ev.upload(bhv, step_batch=8), **kw)  # the whole set on this GPU
-        many = ev.evaluate(ev.upload(shard, pos_cap=pos_cap, step_batch=8), distributed=True, **kw)
-        ok = many.n_impressions == one.n_impressions and np.allclose(many.sums, one.sums, rtol=1e-12, atol=1e-9) and many.auc == one.auc
-        if one.loss is not None:
-            ok = ok and abs(many.loss - one.loss) <= 1e-12 * abs(one.loss)
-        t = torch.tensor([int(ok)], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MIN)
-        out[name] = bool(t.item())
+        for exchange in ("p2p", "nccl"):  # fused stores into the peers' mailboxes (default) / the three NCCL collectives
+            ev = ScoreEvaluator(ctor["tables"], dev, attention=ctor.get("attention"), exchange=exchange)
+            one = ev.evaluate(ev.upload(bhv, step_batch=8), **kw)  # the whole set on this GPU
+            dev_shard = ev.upload(shard, pos_cap=pos_cap, step_batch=8)
+            ok = True
+            for rep in range(3):  # three passes: both mailbox parities are reused
+                many = ev.evaluate(dev_shard, distributed=True, **kw)
+                ok = ok and many.n_impressions == one.n_impressions and np.allclose(many.sums, one.sums, rtol=1e-12, atol=1e-9) and many.auc == one.auc
+                ok = ok and many.auc_counts == one.auc_counts
+                if one.loss is not None:
+                    ok = ok and abs(many.loss - one.loss) <= 1e-12 * abs(one.loss)
+            # scores in the unit interval: AUROC without the sigmoid (the rule is decided over ALL ranks' scores)
+            if name == "ensemble":
+                unit = ScoreEvaluator([t * 0.02 + 0.03 for t in tables[:1]], dev, exchange=exchange)
+                u_one = unit.evaluate(unit.upload(bhv), pooled_auc=True)
+                u_many = unit.evaluate(unit.upload(shard, pos_cap=pos_cap), pooled_auc=True, distributed=True)
+                ok = ok and u_many.auc == u_one.auc and not (u_one.flags & 4) and np.allclose(u_many.sums, u_one.sums, rtol=1e-12, atol=1e-9)
+            t = torch.tensor([int(ok)], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MIN)
+            out[f"{name}_{exchange}"] = bool(t.item())
         out[name + "_metrics"] = {k: round(v, 6) for k, v in many.metrics().items()}
     if rank == 0:
         print(json.dumps(out))

@@ -40,6 +40,14 @@ def main() -> None:
         else:
             idx = torch.tensor(rt.CatalogRetriever.user_slice(n_users, 2048, rank, world), device=dev)
             ok = bool(torch.equal(i, ref_i[idx]) and torch.equal(s, ref_s[idx]))
+        if exchange == "p2p":
+            # consecutive single-block calls with DIFFERENT users (the double buffer must alternate across calls, or a
+            # fast rank's next call overwrites the gather buffer a slow rank is still merging)
+            single = rt.CatalogRetriever(shard, k=k, catalog_id_offset=lo, distributed=True, exchange="p2p", user_block=2048)
+            for rep in range(6):
+                sl = slice(rep * 700, rep * 700 + 1500 + 37 * rep)
+                s2, i2 = single.retrieve(users[sl])
+                ok = ok and bool(torch.equal(i2, ref_i[sl]) and torch.equal(s2, ref_s[sl]))
         t = torch.tensor([int(ok)], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MIN)
         out[exchange] = bool(t.item())

@@ -38,11 +38,18 @@ def main() -> None:
     ap.add_argument("--variants", default="2,7,8")
     ap.add_argument("--chunks-per-warp", default="1")
     ap.add_argument("--shape", default="small")
+    ap.add_argument("--probe", action="store_true", help="also run the read-bandwidth probe (L2-resident and HBM-sized buffers)")
     args = ap.parse_args()
     dev = torch.device("cuda:0")
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     ops.set_tuning(time_kernel=1)
     out = []
+    if args.probe:
+        for mib in (24, 48, 96, 1024, 4096):
+            gbs = ops.read_bandwidth_probe(dev, mib << 20, max(1, (8192 // mib)))
+            rec = {"probe_buffer_MiB": mib, "read_GBps": round(gbs, 1)}
+            print(json.dumps(rec), flush=True)
+            out.append(rec)
     for case in args.cases.split(","):
         n_mod, uniform, dtype = CASES[case]
         tables, bhv = mdata.synth_workload(args.shape, n_modules=n_mod, uniform_ids=uniform, dtype=dtype)
