@@ -355,10 +355,11 @@ MB200_API int mb200_exchange_post(const mb200_exchange_desc* desc, void* stream)
 MB200_API int mb200_exchange_finish(const mb200_exchange_desc* desc, void* stream);
 
 /* Read-bandwidth probe for the roofline denominators bench.py reports: every warp streams 3 KB rows of `buf` (the access shape
- * of the row gather: six 16-byte loads per lane and row, four rows in flight) for `repeats` passes.  A buffer that fits the
- * 126 MB L2 measures the L2 -> SM read bandwidth a gather can reach at best; a larger one the HBM read bandwidth.  The caller
- * times it with events.  `sink`: 4 bytes of device memory. */
-MB200_API int mb200_read_probe(const void* buf, size_t bytes, int repeats, void* sink, void* stream);
+ * of the row gather: six 16-byte loads per lane and row; rows of a batch far apart) for `repeats` passes.  bytes / 3072 must be
+ * a power of two.  A buffer that fits the 126 MB L2 measures the L2 -> SM read bandwidth a gather can reach at best; a larger
+ * one the HBM read bandwidth.  mode 0 / 1 / 2 = 16 warps x 4 rows in flight / 32 x 2 / 64 x 1 per SM; the caller times it with
+ * events and takes the best.  `sink`: 4 bytes of device memory. */
+MB200_API int mb200_read_probe(const void* buf, size_t bytes, int repeats, int mode, void* sink, void* stream);
 
 /* Lets kernels running on `device` load from memory that lives on `peer` (cudaDeviceEnablePeerAccess; "already enabled" is
  * not an error): needed once per pair of GPUs before row-sharded tables (mb200_eval_desc.table_shards) are used. */
@@ -385,12 +386,19 @@ MB200_API int64_t mb200_library_launch_count(void);
  * resident CTAs per SM: 4x3, 3x4, 2x5, 3x6, 2x7 for fp32 rows, twice the rows for bf16; 1 = 4x3 with L1::no_allocate loads);
  * 2 = cap on CTAs per SM; 3 = time the fused kernel with
  * CUDA events; 4 = retrieval diagnostics (1, 2: parts of the epilogue disabled, RESULTS INVALID; 4: cycle counters in the
- * workspace header, results valid); 5 = retrieval pipeline (1 = CTA pairs / tcgen05 cta_group::2 [default], 0 = one CTA per tile) */
+ * workspace header, results valid); 5 = retrieval pipeline (1 = CTA pairs / tcgen05 cta_group::2 [default], 0 = one CTA per tile); 6 = cap in KB on the
+ * hot-row cache of variants 8 / 9 (0 = no cap) */
 MB200_API int mb200_set_tuning(int key, int value);
 
 /* duration in ms of the most recent fused score/eval kernel launched while tuning key 3 was on
  * (synchronises on its end event; -1 if none).  This is the kernel bench.py reports a roofline for. */
 MB200_API float mb200_last_score_kernel_ms(void);
+
+/* Hot-row cache of the most recent mb200_score_eval launch in this process (HOST int32 out[4]; synchronises the device):
+ * {rows cached per module (0 = cache off for that behaviour set), sampled row reads, sampled row reads that hit the cached rows,
+ * slots per module the launch had room for}.  covered / sampled = the fraction of the gather served from shared memory
+ * instead of the L2 -- bench.py reports it beside the roofline. */
+MB200_API int mb200_last_hot_stats(int32_t out[4]);
 
 #ifdef __cplusplus
 }

@@ -181,7 +181,7 @@ SIGNATURES = {
     "mb200_exchange_mailbox_bytes": (c_size_t, [c_int, c_int, c_int64]),
     "mb200_exchange_post": (c_int, [POINTER(ExchangeDesc), c_void_p]),
     "mb200_exchange_finish": (c_int, [POINTER(ExchangeDesc), c_void_p]),
-    "mb200_read_probe": (c_int, [c_void_p, c_size_t, c_int, c_void_p, c_void_p]),
+    "mb200_read_probe": (c_int, [c_void_p, c_size_t, c_int, c_int, c_void_p, c_void_p]),
     "mb200_enable_peer_access": (c_int, [c_int, c_int]),
     "mb200_ipc_export": (c_int, [c_void_p, c_char_p, POINTER(c_int64)]),
     "mb200_ipc_open": (c_int, [c_char_p, c_int64, c_int, POINTER(c_void_p)]),
@@ -190,6 +190,7 @@ SIGNATURES = {
     "mb200_library_launch_count": (c_int64, []),
     "mb200_set_tuning": (c_int, [c_int, c_int]),
     "mb200_last_score_kernel_ms": (c_float, []),
+    "mb200_last_hot_stats": (c_int, [POINTER(c_int32)]),
 }
 
 _lib: Optional[ctypes.CDLL] = None

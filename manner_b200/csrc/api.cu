@@ -45,6 +45,7 @@ int use_device_of(const void* ptr, int* device_out) {
 // implemented in score_eval.cu / pooled_auc.cu
 float host_dcg_discount(int rank);
 float last_score_kernel_ms();
+int last_hot_stats(int32_t out[4]);
 size_t eval_workspace_bytes(const mb200_eval_desc* d);
 int score_eval(const mb200_eval_desc* d, cudaStream_t stream);
 int auc_build_keys(const float*, const uint8_t*, long long, int, const int32_t*, uint32_t*, uint32_t*, long long*, cudaStream_t);
@@ -62,7 +63,7 @@ int step_loss(const float*, long long, int, int, double*, cudaStream_t);
 size_t exchange_mailbox_bytes(int n_ranks, int n_payload, long long pos_capacity);
 int exchange_post(const mb200_exchange_desc* d, cudaStream_t stream);
 int exchange_finish(const mb200_exchange_desc* d, cudaStream_t stream);
-int read_probe(const void* buf, size_t bytes, int repeats, void* sink, cudaStream_t stream);
+int read_probe(const void* buf, size_t bytes, int repeats, int mode, void* sink, cudaStream_t stream);
 size_t metrics_workspace_bytes(const mb200_metrics_desc* d);
 int rank_metrics(const mb200_metrics_desc* d, cudaStream_t stream);
 
@@ -168,8 +169,8 @@ int mb200_exchange_post(const mb200_exchange_desc* desc, void* stream) { return 
 
 int mb200_exchange_finish(const mb200_exchange_desc* desc, void* stream) { return exchange_finish(desc, static_cast<cudaStream_t>(stream)); }
 
-int mb200_read_probe(const void* buf, size_t bytes, int repeats, void* sink, void* stream) {
-  return read_probe(buf, bytes, repeats, sink, static_cast<cudaStream_t>(stream));
+int mb200_read_probe(const void* buf, size_t bytes, int repeats, int mode, void* sink, void* stream) {
+  return read_probe(buf, bytes, repeats, mode, sink, static_cast<cudaStream_t>(stream));
 }
 
 int mb200_enable_peer_access(int device, int peer) {
@@ -232,6 +233,8 @@ int64_t mb200_library_launch_count(void) { return g_library_launches.load(); }
 
 float mb200_last_score_kernel_ms(void) { return last_score_kernel_ms(); }
 
+int mb200_last_hot_stats(int32_t out[4]) { return out ? last_hot_stats(out) : MB200_ERR_INVALID_ARG; }
+
 int mb200_set_tuning(int key, int value) {
   int prev = -1;
   switch (key) {
@@ -241,6 +244,7 @@ int mb200_set_tuning(int key, int value) {
     case 3: prev = tuning().time_kernel, tuning().time_kernel = value; break;
     case 4: prev = tuning().retrieval_diag, tuning().retrieval_diag = value; break;
     case 5: prev = tuning().retrieval_pair, tuning().retrieval_pair = value; break;
+    case 6: prev = tuning().hot_kb_cap, tuning().hot_kb_cap = value; break;
   }
   return prev;
 }

@@ -434,40 +434,59 @@ int exchange_finish(const mb200_exchange_desc* d, cudaStream_t stream) {
 }
 
 // ---- read-bandwidth probe (bench.py's L2 roofline denominator) ----------------------------------------------------------
-// Every warp streams 3 KB rows (the gather's access shape: 6 x LDG.E.128 per lane and row, 4 rows in flight) of a buffer, `repeats`
-// passes; with a buffer that fits the 126 MB L2 this measures the L2 -> SM read bandwidth a row gather can reach at best, with
-// a larger one the HBM read bandwidth.
-__global__ void __launch_bounds__(512, 1) read_probe_kernel(const uint4* __restrict__ buf, long long n_rows, int repeats, unsigned int* __restrict__ sink) {
+// Every warp streams 3 KB rows (the gather's access shape: 6 x LDG.E.128 per lane and row, K rows in flight) of a buffer of
+// 2^k rows, `repeats` passes; rows of one batch are far apart like gathered rows.  With a buffer that fits the 126 MB L2 this
+// measures the L2 -> SM read bandwidth a row gather can reach at best, with a larger one the HBM read bandwidth.  Three shapes
+// of the same bytes in flight per SM (mode 0: 16 warps x 4 rows, 1: 32 x 2, 2: 64 x 1); the caller takes the best.
+template <int K>
+__device__ __forceinline__ void read_probe_body(const uint4* __restrict__ buf, unsigned row_mask, int repeats, unsigned int* __restrict__ sink) {
   const int lane = threadIdx.x & 31;
-  const long long gw = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = ((long long)gridDim.x * blockDim.x) >> 5;
+  const unsigned gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
+  const unsigned n_rows = row_mask + 1;
   unsigned int acc = 0;
   for (int it = 0; it < repeats; ++it) {
-    for (long long r0 = gw * 4; r0 < n_rows; r0 += nw * 4) {
-      uint4 v[4][6];
+    for (unsigned r0 = gw * K; r0 < n_rows; r0 += nw * K) {
+      uint4 v[K][6];
 #pragma unroll
-      for (int r = 0; r < 4; ++r) {
-        // rows of one batch are far apart (like gathered rows), not neighbours
-        const long long row = (r0 + r < n_rows) ? ((r0 + r) * 2654435761ll + it) % n_rows : 0;
-        const uint4* src = buf + row * 192 + lane;
+      for (int r = 0; r < K; ++r) {
+        const unsigned row = ((r0 + r) * 2654435761u + (unsigned)it * 40503u) & row_mask;  // odd multiplier: a permutation of the rows
+        const uint4* src = buf + (size_t)row * 192 + lane;
 #pragma unroll
         for (int k = 0; k < 6; ++k) v[r][k] = __ldg(src + 32 * k);
       }
 #pragma unroll
-      for (int r = 0; r < 4; ++r)
+      for (int r = 0; r < K; ++r)
 #pragma unroll
         for (int k = 0; k < 6; ++k) acc ^= v[r][k].x ^ v[r][k].y ^ v[r][k].z ^ v[r][k].w;
     }
   }
   if (acc == 0x9e3779b9u) *sink = acc;  // keeps the loads alive
 }
+__global__ void __launch_bounds__(512, 1) read_probe_kernel4(const uint4* __restrict__ buf, unsigned row_mask, int repeats, unsigned int* __restrict__ sink) {
+  read_probe_body<4>(buf, row_mask, repeats, sink);
+}
+__global__ void __launch_bounds__(1024, 1) read_probe_kernel2(const uint4* __restrict__ buf, unsigned row_mask, int repeats, unsigned int* __restrict__ sink) {
+  read_probe_body<2>(buf, row_mask, repeats, sink);
+}
+__global__ void __launch_bounds__(1024, 2) read_probe_kernel1(const uint4* __restrict__ buf, unsigned row_mask, int repeats, unsigned int* __restrict__ sink) {
+  read_probe_body<1>(buf, row_mask, repeats, sink);
+}
 
-int read_probe(const void* buf, size_t bytes, int repeats, void* sink, cudaStream_t stream) {
-  if (buf == nullptr || sink == nullptr || bytes < 3072 || repeats < 1 || ((uintptr_t)buf & 15)) return MB200_ERR_INVALID_ARG;
+int read_probe(const void* buf, size_t bytes, int repeats, int mode, void* sink, cudaStream_t stream) {
+  if (buf == nullptr || sink == nullptr || bytes < 3072 || repeats < 1 || ((uintptr_t)buf & 15) || mode < 0 || mode > 2) return MB200_ERR_INVALID_ARG;
+  size_t rows = bytes / 3072;
+  if (rows & (rows - 1)) return MB200_ERR_INVALID_ARG;  // power of two
+  if (rows > (1ull << 31)) return MB200_ERR_UNSUPPORTED;
   int device = 0, sms = 0;
   int st = use_device_of(buf, &device);
   if (st != MB200_OK) return st;
   if ((st = cuda_status(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device), "cudaDeviceGetAttribute")) != MB200_OK) return st;
-  read_probe_kernel<<<sms, 512, 0, stream>>>(reinterpret_cast<const uint4*>(buf), (long long)(bytes / 3072), repeats, reinterpret_cast<unsigned int*>(sink));
+  const uint4* b = reinterpret_cast<const uint4*>(buf);
+  unsigned int* sk = reinterpret_cast<unsigned int*>(sink);
+  const unsigned mask = (unsigned)(rows - 1);
+  if (mode == 0) read_probe_kernel4<<<sms, 512, 0, stream>>>(b, mask, repeats, sk);
+  else if (mode == 1) read_probe_kernel2<<<sms, 1024, 0, stream>>>(b, mask, repeats, sk);
+  else read_probe_kernel1<<<sms * 2, 1024, 0, stream>>>(b, mask, repeats, sk);
   note_launch(1);
   return cuda_status(cudaGetLastError(), "read_probe_kernel");
 }

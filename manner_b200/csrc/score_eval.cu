@@ -1379,7 +1379,11 @@ static int make_plan(const mb200_eval_desc* d, int sm_count, int ctas, LaunchPla
   if (stream && hot) {
     long long cap = (long long)(kMaxSmemPerCta - plan->smem_per_cta) / ((long long)n_active * row_bytes);
     if (cap > kHotMaxSlots) cap = kHotMaxSlots;
-    if (cap >= 8) {
+    if (tuning().hot_kb_cap > 0) {
+      const long long lim = (long long)tuning().hot_kb_cap * 1024 / ((long long)n_active * row_bytes);
+      if (cap > lim) cap = lim;
+    }
+    if (cap >= 4) {
       plan->hot_cap = (int)cap;
       plan->hot_bytes = (int)(cap * n_active * row_bytes);
       plan->smem_per_cta += plan->hot_bytes;
@@ -1505,6 +1509,20 @@ static KernelTimer* timer_for(int device) {
   return t;
 }
 
+// introspection for bench.py: the hot-row directory of the most recent launch that used the cache
+static const HotDir* g_last_hot_dir = nullptr;
+static int g_last_hot_cap = 0;
+
+int last_hot_stats(int32_t out[4]) {
+  out[0] = out[1] = out[2] = out[3] = 0;
+  if (g_last_hot_dir == nullptr) return MB200_OK;
+  HotDir h;
+  int st = cuda_status(cudaMemcpy(&h, g_last_hot_dir, sizeof(h), cudaMemcpyDeviceToHost), "cudaMemcpy(hot dir)");  // synchronises
+  if (st != MB200_OK) return st;
+  out[0] = h.n_hot, out[1] = h.total, out[2] = h.covered, out[3] = g_last_hot_cap;
+  return MB200_OK;
+}
+
 float last_score_kernel_ms() {
   KernelTimer* t = g_last_timer;
   if (t == nullptr || !t->armed) return -1.0f;
@@ -1545,13 +1563,15 @@ int score_eval(const mb200_eval_desc* d, cudaStream_t stream) {
   for (int m = 0; m < d->n_modules; ++m) attn |= ((d->active_modules_mask >> m) & 1) && d->attn_logits[m] != nullptr;
   const bool sharded = d->n_table_shards > 1;
 
-  // One 16-warp CTA per SM with the hot-row cache in shared memory is the default for the reference width with late fusion and
-  // replicated tables (tuning variant 9; 10 = the same CTA shape without the cache).  Variants 7 / 8 = rotating row pipeline
-  // without / with the cache (measured slower), 0..6 = the round-1 register-batch kernels (4-warp CTAs, no cache).
+  // Round-2 experiments for the reference width with late fusion and replicated tables, selectable but NOT the default
+  // (profiles/r2_stream_experiment.md): tuning variant 9 = one 16-warp CTA per SM with the hot-row cache in shared memory (key 6
+  // caps its size), 10 = that CTA shape without the cache, 7 / 8 = rotating row pipeline without / with the cache.  Default and
+  // 0..6 = the register-batch kernels (4-warp CTAs): the L1 is the landing buffer of the gathers in flight, and every KB of
+  // shared memory the cache takes from it costs more bandwidth than the cache's hits return.
   const int variant = tuning().variant;
   LaunchPlan plan;
   KernelFn kern = nullptr;
-  bool stream_path = d->dim == 768 && d->row_stride == 768 && !attn && !sharded && (variant < 0 || (variant >= 7 && variant <= 10)) && d->n_news < (1ll << 31);
+  bool stream_path = d->dim == 768 && d->row_stride == 768 && !attn && !sharded && (variant >= 7 && variant <= 10) && d->n_news < (1ll << 31);
   bool hot = false;
   if (stream_path) {
     if (make_plan(d, sms, 1, &plan, true, vec_per_row * 16, variant != 7 && variant != 10) != MB200_OK) stream_path = false;  // per-warp areas too large for 16 warps
@@ -1612,6 +1632,7 @@ int score_eval(const mb200_eval_desc* d, cudaStream_t stream) {
 
   KernelTimer* timer = tuning().time_kernel ? timer_for(device) : nullptr;
   int launches = 3;
+  if (!hot) g_last_hot_dir = nullptr;
   if (hot && d->n_impressions > 0) {
     // hot-row directory of this behaviour set: sampled id histogram -> the hot_cap most gathered rows -> id -> slot map
     unsigned char* hr = ws + plan.bounds_bytes + plan.partials_bytes;
@@ -1626,6 +1647,7 @@ int score_eval(const mb200_eval_desc* d, cudaStream_t stream) {
     hot_select_kernel<<<1, 1024, 0, stream>>>(counts, (int)d->n_news, plan.hot_cap, dir, hot_ids, slot_of);
     if ((st = cuda_status(cudaGetLastError(), "hot_select_kernel")) != MB200_OK) return st;
     p.hot_dir = dir, p.hot_ids = hot_ids, p.slot_of = slot_of;
+    g_last_hot_dir = dir, g_last_hot_cap = plan.hot_cap;
     launches += 2;
   }
   partition_kernel<<<(plan.n_chunks + 1 + 255) / 256, 256, 0, stream>>>(d->hist_offsets, d->cand_offsets, p.n_impr, plan.n_chunks,

@@ -317,26 +317,30 @@ def auc_rank_sum(sorted_keys: Tensor, n_pos_local: Tensor, pos_keys: Tensor, n_p
         )
 
 
-def read_bandwidth_probe(device: torch.device, buffer_bytes: int, repeats: int, rounds: int = 5) -> float:
-    """GB/s a warp-per-row gather of 3 KB rows can read from a ``buffer_bytes`` buffer on ``device`` (mb200_read_probe, best of
-    ``rounds``, CUDA events).  48 MiB stays in the 126 MB L2 after the first pass: the L2 -> SM roof of the scoring kernel on
-    Zipf-shaped ids; a buffer several times the L2 measures the HBM roof with the same access shape."""
+def read_bandwidth_probe(device: torch.device, buffer_bytes: int, repeats: int, rounds: int = 3) -> dict:
+    """GB/s a warp-per-row gather of 3 KB rows can read from a buffer of about ``buffer_bytes`` on ``device`` (mb200_read_probe,
+    best of ``rounds`` per launch shape, CUDA events).  48 MiB stays in the 126 MB L2 after the first pass: the L2 -> SM roof
+    of the scoring kernel on Zipf-shaped ids; a buffer several times the L2 measures the HBM roof with the same access shape.
+    Returns {"GBps": best, "by_mode": [...], "buffer_bytes": actual}."""
     lib = nat.lib()
-    rows = max(int(buffer_bytes) // 3072, 1)
+    rows = 1 << max(int(buffer_bytes) // 3072, 1).bit_length() - 1  # power of two
     with torch.cuda.device(device):
         buf = torch.randint(0, 2**31 - 1, (rows * 768,), dtype=torch.int32, device=device)
         sink = torch.zeros(1, dtype=torch.int32, device=device)
         stream = torch.cuda.current_stream(device).cuda_stream
-        nat.check(lib.mb200_read_probe(buf.data_ptr(), rows * 3072, 1, sink.data_ptr(), stream), "mb200_read_probe")  # warm: fills the L2
-        best = 0.0
-        for _ in range(rounds):
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            nat.check(lib.mb200_read_probe(buf.data_ptr(), rows * 3072, repeats, sink.data_ptr(), stream), "mb200_read_probe")
-            e1.record()
-            e1.synchronize()
-            best = max(best, rows * 3072 * repeats / (e0.elapsed_time(e1) * 1e-3) / 1e9)
-    return best
+        by_mode = []
+        for mode in (0, 1, 2):
+            nat.check(lib.mb200_read_probe(buf.data_ptr(), rows * 3072, 1, mode, sink.data_ptr(), stream), "mb200_read_probe")  # warm: fills the L2
+            best = 0.0
+            for _ in range(rounds):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                nat.check(lib.mb200_read_probe(buf.data_ptr(), rows * 3072, repeats, mode, sink.data_ptr(), stream), "mb200_read_probe")
+                e1.record()
+                e1.synchronize()
+                best = max(best, rows * 3072 * repeats / (e0.elapsed_time(e1) * 1e-3) / 1e9)
+            by_mode.append(round(best, 1))
+    return {"GBps": max(by_mode), "by_mode": by_mode, "buffer_bytes": rows * 3072}
 
 
 def launch_counts() -> Tuple[int, int]:
@@ -350,9 +354,20 @@ def last_score_kernel_ms() -> float:
     return float(nat.lib().mb200_last_score_kernel_ms())
 
 
+def last_hot_stats() -> dict:
+    """Hot-row cache of the most recent fused launch: slots used / available per module and the sampled fraction of row reads
+    it serves from shared memory (mb200_last_hot_stats; synchronises)."""
+    out = (ctypes.c_int32 * 4)()
+    nat.check(nat.lib().mb200_last_hot_stats(out), "mb200_last_hot_stats")
+    n_hot, total, covered, cap = (int(v) for v in out)
+    return {"rows_cached_per_module": n_hot, "slots_per_module": cap, "sampled_row_reads": total,
+            "hit_fraction": (covered / total) if (total > 0 and n_hot > 0) else 0.0}
+
+
 def set_tuning(chunks_per_warp: Optional[int] = None, variant: Optional[int] = None, ctas_per_sm: Optional[int] = None,
-               time_kernel: Optional[int] = None, retrieval_diag: Optional[int] = None, retrieval_pair: Optional[int] = None) -> None:
+               time_kernel: Optional[int] = None, retrieval_diag: Optional[int] = None, retrieval_pair: Optional[int] = None,
+               hot_kb_cap: Optional[int] = None) -> None:
     lib = nat.lib()
-    for key, val in ((0, chunks_per_warp), (1, variant), (2, ctas_per_sm), (3, time_kernel), (4, retrieval_diag), (5, retrieval_pair)):
+    for key, val in ((0, chunks_per_warp), (1, variant), (2, ctas_per_sm), (3, time_kernel), (4, retrieval_diag), (5, retrieval_pair), (6, hot_kb_cap)):
         if val is not None:
             lib.mb200_set_tuning(key, int(val))

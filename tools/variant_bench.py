@@ -37,6 +37,7 @@ def main() -> None:
     ap.add_argument("--cases", default="zipf,uniform,bf16,m1")
     ap.add_argument("--variants", default="2,7,8")
     ap.add_argument("--chunks-per-warp", default="1")
+    ap.add_argument("--hot-kb", default="0", help="comma list of hot-row cache caps in KB (variants 8 / 9)")
     ap.add_argument("--shape", default="small")
     ap.add_argument("--probe", action="store_true", help="also run the read-bandwidth probe (L2-resident and HBM-sized buffers)")
     args = ap.parse_args()
@@ -46,8 +47,8 @@ def main() -> None:
     out = []
     if args.probe:
         for mib in (24, 48, 96, 1024, 4096):
-            gbs = ops.read_bandwidth_probe(dev, mib << 20, max(1, (8192 // mib)))
-            rec = {"probe_buffer_MiB": mib, "read_GBps": round(gbs, 1)}
+            pr = ops.read_bandwidth_probe(dev, mib << 20, max(1, (8192 // mib)))
+            rec = {"probe_buffer_MiB": pr["buffer_bytes"] >> 20, "read_GBps": pr["GBps"], "by_mode": pr["by_mode"]}
             print(json.dumps(rec), flush=True)
             out.append(rec)
     for case in args.cases.split(","):
@@ -59,8 +60,8 @@ def main() -> None:
         algo = bhv.algorithmic_bytes(n_mod, 768, tables[0].element_size(), True)
         ref_sums = None
         for variant in [int(v) for v in args.variants.split(",")]:
-            for cpw in [int(c) for c in args.chunks_per_warp.split(",")]:
-                ops.set_tuning(variant=variant, chunks_per_warp=cpw)
+            for cpw, hot_kb in [(int(c), int(h)) for c in args.chunks_per_warp.split(",") for h in (args.hot_kb.split(",") if variant in (8, 9) else ["0"])]:
+                ops.set_tuning(variant=variant, chunks_per_warp=cpw, hot_kb_cap=hot_kb)
                 for _ in range(3):
                     res = ev.evaluate(d, weights=w, zscore=True, pooled_auc=True)
                 step_ms, kern_ms = [], []
@@ -78,14 +79,14 @@ def main() -> None:
                     ref_sums = res.sums.copy()
                 same = bool(abs(res.sums - ref_sums).max() <= 1e-9 * max(1.0, abs(ref_sums).max()))
                 k = sum(kern_ms) / len(kern_ms)
-                rec = {"case": case, "variant": variant, "chunks_per_warp": cpw, "kernel_ms": round(k, 4), "kernel_ms_min": round(min(kern_ms), 4),
+                rec = {"case": case, "variant": variant, "chunks_per_warp": cpw, "hot_kb": hot_kb, "hot": ops.last_hot_stats() if variant in (8, 9) else None, "kernel_ms": round(k, 4), "kernel_ms_min": round(min(kern_ms), 4),
                        "step_ms": round(sum(step_ms) / len(step_ms), 4), "algo_TBps": round(algo / k / 1e9, 2), "sums_match_first_variant": same,
                        "ndcg10": round(res.metrics()["test/ndcg@10"], 6)}
                 print(json.dumps(rec), flush=True)
                 out.append(rec)
         del ev, d, tables
         torch.cuda.empty_cache()
-    ops.set_tuning(variant=-1, chunks_per_warp=1)
+    ops.set_tuning(variant=-1, chunks_per_warp=1, hot_kb_cap=0)
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     with open(os.path.join(ROOT, "gpurun_out", "variant_bench.json"), "w") as f:
         json.dump(out, f, indent=1)
