@@ -124,8 +124,9 @@ class ClockSampler:
         }
 
 
-def cpu_reference_pass(tables, bhv, n_sample: int, threads: int) -> tuple:
-    """Times the oracle port of the reference's CPU path on the first ``n_sample`` impressions."""
+def cpu_reference_pass(tables, bhv, n_sample: int, threads: int, keep: bool = False) -> tuple:
+    """Times the oracle port of the reference's CPU path on the first ``n_sample`` impressions.  ``keep`` also returns what it
+    computed (flat scores + logged metrics) so the GPU arm can be checked against it on the same prefix."""
     from oracle import manner_oracle as mo
 
     torch.set_num_threads(threads)
@@ -133,9 +134,85 @@ def cpu_reference_pass(tables, bhv, n_sample: int, threads: int) -> tuple:
     ob = mo.Behaviours(head.hist_offsets, head.hist_ids, head.cand_offsets, head.cand_ids, head.labels)
     weights = [1.0, CATEG_WEIGHT] + [0.0] * (len(tables) - 2)
     t0 = time.perf_counter()
-    mo.ensemble_eval_epoch([t.float() for t in tables], weights[: len(tables)], ob, double_compute=True, reference_only=True)
+    out = mo.ensemble_eval_epoch([t.float() for t in tables], weights[: len(tables)], ob, double_compute=True, reference_only=True)
     dt = time.perf_counter() - t0
-    return head.n_impressions / dt, dt, head.n_impressions
+    return head.n_impressions / dt, dt, head.n_impressions, (out if keep else None)
+
+
+def parity_vs_cpu_prefix(ev, bhv, n: int, kw: dict, cpu_out: dict) -> dict:
+    """The GPU path on the SAME impression prefix the CPU leg just evaluated: scores within 2e-5 (z-scores
+    are O(1): the 1e-5-relative bar on either side), nDCG@5/10 within 1e-6 -- plus 1/B for every rank flip, and every flip
+    must be a near-tie inside the score tolerance.  Raises when the parity bar is missed."""
+    import numpy as np
+
+    from oracle import manner_oracle as mo
+
+    head = bhv.slice(0, n)
+    kw = dict(kw, distributed=False, want_scores=True)
+    res = ev.evaluate(ev.upload(head), **kw)
+    got, ref = res.scores.cpu().numpy().astype(np.float64), cpu_out["scores"].astype(np.float64)
+    slack = 2e-5 * np.maximum(1.0, np.abs(ref))
+    err = np.abs(got - ref)
+    flips, unexplained, gap = mo.unexplained_rank_flips(got, ref, slack, head.cand_offsets)
+    m = res.metrics()
+    deltas = {k: abs(m["test/" + k] - cpu_out["metrics"]["test/" + k]) for k in ("ndcg@5", "ndcg@10")}
+    ok = bool(np.all(err <= slack)) and unexplained == 0 and all(d <= 1e-6 + flips / head.n_impressions for d in deltas.values())
+    rec = {"parity_vs_cpu_prefix": ok, "prefix_impressions": head.n_impressions, "max_abs_score_diff": float(err.max()),
+           "rank_flips": flips, "rank_flips_not_near_ties": unexplained, "widest_flipped_gap": gap,
+           "ndcg_abs_diff": {k: float(v) for k, v in deltas.items()}}
+    if not ok:
+        raise SystemExit("bench.py: GPU result does not match the CPU reference leg on the same prefix: " + json.dumps(rec))
+    return rec
+
+
+def shard_invariance_probe(ev, kw: dict, rank: int, world: int, dev) -> dict:
+    """A FIXED probe set (the first 8 192 impressions of the seed-42 MIND-small-shaped behaviours) evaluated whole on every rank
+    and sharded ``world`` ways through the distributed path: the reduced sums must agree to 1e-12 and the pooled AUROC exactly
+    (VERDICT r1 item 2).  With one rank the probe is split three ways and the parts are added up."""
+    import numpy as np
+
+    from manner_b200 import data as mdata
+    from manner_b200 import dist as mdist
+
+    n_news = mdata.SHAPES["small"][0]
+    probe = mdata.synth_behaviours(n_news, 8192, 42)
+    kw = {k: v for k, v in kw.items() if k != "distributed"}
+    one = ev.evaluate(ev.upload(probe), **kw)
+    if world > 1:
+        shard = mdist.shard_for_rank(probe, rank, world)
+        cap = mdist.agree_pos_cap(int(shard.labels.sum()), dev)
+        many = ev.evaluate(ev.upload(shard, pos_cap=cap), distributed=True, **kw)
+        sums, auc, n = many.sums, many.auc, many.n_impressions
+    else:
+        bounds = mdata.balanced_shard_bounds(probe, 3)
+        parts = [ev.evaluate(ev.upload(probe.slice(int(bounds[r]), int(bounds[r + 1]))), **{k: v for k, v in kw.items() if k != "pooled_auc"}) for r in range(3)]
+        sums, auc, n = sum(p.sums for p in parts), one.auc, sum(p.n_impressions for p in parts)
+    ok = n == one.n_impressions and bool(np.allclose(sums, one.sums, rtol=1e-12, atol=1e-9)) and auc == one.auc
+    t = torch.tensor([int(ok)], device=dev)
+    if world > 1:
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MIN)
+    return {"shard_invariant": bool(t.item()), "probe_impressions": probe.n_impressions, "ways": max(world, 3),
+            "probe_ndcg@10": round(one.metrics()["test/ndcg@10"], 9), "probe_auc": one.auc}
+
+
+def timed_passes(ev, dev_bhv, kw: dict, steps: int, flush, rank: int = 0) -> tuple:
+    """(mean device-timed ms per pass, mean fused-kernel ms) over ``steps`` passes after 3 warm-up passes, L2 flushed between."""
+    from manner_b200 import ops
+
+    for _ in range(3):
+        ev.finish(ev.launch(dev_bhv, **kw))
+    step_ms, kernel_ms = [], []
+    for _ in range(steps):
+        flush.fill_(rank + 1)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        pending = ev.launch(dev_bhv, **kw)
+        e1.record()
+        kernel_ms.append(ops.last_score_kernel_ms())
+        torch.cuda.synchronize()
+        step_ms.append(e0.elapsed_time(e1))
+    ev.finish(pending)
+    return sum(step_ms) / len(step_ms), sum(kernel_ms) / len(kernel_ms)
 
 
 def run_reference_arm(args) -> None:
@@ -153,7 +230,7 @@ def run_reference_arm(args) -> None:
         cpu_reference_pass(tables, bhv, max(64, n_sample // 16), threads)
     rates, times = [], []
     for _ in range(args.steps):
-        r, dt, n = cpu_reference_pass(tables, bhv, n_sample, threads)
+        r, dt, n, _ = cpu_reference_pass(tables, bhv, n_sample, threads)
         rates.append(r), times.append(dt)
     value = n_sample * len(times) / sum(times)
     line = {
@@ -179,7 +256,7 @@ def run_gpu_arm(args) -> None:
     from manner_b200 import ops
     from manner_b200.evaluator import ScoreEvaluator
 
-    os.environ["NCCL_DEBUG"] = os.environ.get("MB200_NCCL_DEBUG", "WARN")  # keep stdout to the one JSON line
+    os.environ.setdefault("NCCL_DEBUG", "WARN")  # a driver that sets NCCL_DEBUG=INFO keeps it; the JSON line is printed last
     rank, local_rank, world = mdist.init_from_env("nccl")
     if world != args.gpus and world > 1:
         raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
@@ -300,6 +377,11 @@ def run_gpu_arm(args) -> None:
         dist.all_reduce(n_impr_total, op=dist.ReduceOp.SUM)
     n_impr_total = float(n_impr_total.item())
 
+    # multi-GPU: a fixed probe set sharded `world` ways must reproduce the single-GPU numbers (all ranks take part)
+    shard_check = None
+    if args.mode == "eval" and not args.sweep and not args.loss and not args.early_fusion and not args.no_checks:
+        shard_check = shard_invariance_probe(ev, kw, rank, world, dev)
+
     if rank != 0:
         if distributed:
             dist.barrier()
@@ -317,20 +399,51 @@ def run_gpu_arm(args) -> None:
             entries = json.load(f).get("entries", [])
         for t in entries:  # ncu captures of this exact workload (fp32 tables, default kernel)
             if (t.get("shape") == args.workload and t.get("n_modules") == args.modules and bool(t.get("uniform_ids")) == args.uniform_ids
-                    and args.table_dtype == "f32" and not args.sweep and not args.early_fusion):
+                    and t.get("table_dtype", "f32") == args.table_dtype and not args.sweep and not args.early_fusion):
                 traffic = t.get("dram_bytes_per_launch")
                 l2_note = t.get("l2")
 
-    cpu = None
+    # The roof that binds.  Zipf-shaped ids: ~83 % of the gathered sectors hit the 126 MB L2, the rows come
+    # over the L2 -> SM crossbar, so the denominator is the L2-resident read bandwidth of the same access shape, measured here
+    # (mb200_read_probe on a 48 MiB buffer).  Uniform ids: HBM (MEASURED_PEAKS.json copy bandwidth; the read-only probe on a
+    # 6 GiB buffer is reported beside it).
+    l2_probe = ops.read_bandwidth_probe(dev, 48 << 20, 160)
+    hbm_probe = ops.read_bandwidth_probe(dev, 6 << 30, 2)
+    bound = "hbm" if args.uniform_ids else "l2"
+    peak = hbm_peak if bound == "hbm" else l2_probe["GBps"]
+    roofline = {
+        "bound": bound, "kernel": "score_eval_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+        "peak_kind": (peak_kind + " HBM copy bandwidth (MEASURED_PEAKS.json)") if bound == "hbm" else
+                     "measured in this run: L2-resident row-gather read bandwidth (mb200_read_probe, 48 MiB buffer, best of 3 launch shapes)",
+        "traffic": traffic, "algorithmic_bytes_per_launch": algo_bytes, "kernel_ms": k_ms,
+        "kernel_share_of_step": k_ms * args.steps / total_ms if total_ms > 0 else None,
+        "l2_read_probe": l2_probe, "hbm_read_probe": hbm_probe, "hbm_copy_peak": hbm_peak, "l2": l2_note,
+        # what actually crossed the HBM interface per second (ncu DRAM bytes of the same launch / live kernel time)
+        "dram_achieved": (traffic / (k_ms * 1e-3) / 1e9) if traffic else None,
+        "dram_frac": (traffic / (k_ms * 1e-3) / 1e9 / hbm_peak) if traffic else None,
+    }
+
+    cpu, parity = None, None
     if world == 1 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
-        rate, dt, n = cpu_reference_pass(tables, bhv, args.cpu_sample, threads)
+        rate, dt, n, cpu_out = cpu_reference_pass(tables, bhv, args.cpu_sample, threads, keep=True)
         cpu = {
             "value": rate, "unit": UNIT, "cores": threads, "kind": "port",
             "sample": f"first {n} impressions of the workload ({dt:.1f} s); oracle port of EnsembleModule.test_step (batches of 8, per-row loops) "
                       "+ torchmetrics-style nDCG@5/10 group loop run twice",
         }
+        if not args.sweep and not args.loss and not args.early_fusion and not args.no_checks:
+            parity = parity_vs_cpu_prefix(ev, bhv, n, kw, cpu_out)  # raises when the GPU result misses the parity bar
 
+    extra = None
+    if world == 1 and args.extra and not (args.sweep or args.loss or args.early_fusion or args.uniform_ids or args.table_dtype != "f32" or args.shard):
+        extra = extra_results(args, ev, tables, bhv, dev, flush, hbm_peak, l2_probe["GBps"])
+
+    check = {k: round(v, 6) for k, v in res.metrics().items()}
+    if shard_check:
+        check.update(shard_check)
+    if parity:
+        check.update(parity)
     line = {
         "metric": METRIC, "value": n_impr_total * args.steps / (total_ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "strong" if args.shard else "weak",
@@ -342,27 +455,100 @@ def run_gpu_arm(args) -> None:
         },
         "gpu_launches": launches1[0] - launches0[0],
         "library_launches": launches1[1] - launches0[1],
-        "roofline": {
-            "bound": "hbm", "kernel": "score_eval_kernel", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-            "peak_kind": peak_kind, "traffic": traffic, "algorithmic_bytes_per_launch": algo_bytes, "kernel_ms": k_ms,
-            "kernel_share_of_step": k_ms * args.steps / total_ms if total_ms > 0 else None,
-            # zipf-shaped ids: ~83 % of the gathered sectors hit the 126 MB L2, so `achieved` (algorithmic bytes / time) exceeds the
-            # HBM copy peak and the binding resource is L2 -> SM bandwidth; --uniform-ids is the HBM-bound case
-            "l2": l2_note,
-            # what actually crossed the HBM interface per second (ncu DRAM bytes of the same launch / live kernel time)
-            "dram_achieved": (traffic / (k_ms * 1e-3) / 1e9) if traffic else None,
-            "dram_frac": (traffic / (k_ms * 1e-3) / 1e9 / hbm_peak) if traffic else None,
-        },
+        "exchange": ev.exchange if distributed else "none",
+        "roofline": roofline,
         "cpu_baseline": cpu,
         "clocks": clocks,
         "wall_s_timed_region": wall,
         "impressions_per_rank": n_impr_rank,
-        "check": {k: round(v, 6) for k, v in res.metrics().items()},
+        "check": check,
+        "extra": extra,
     }
-    print(json.dumps(line))
     if distributed:
         dist.barrier()
         dist.destroy_process_group()
+    sys.stdout.flush()
+    print(json.dumps(line), flush=True)  # last line of stdout, after NCCL has said whatever NCCL_DEBUG asked it to say
+
+
+def extra_results(args, ev, tables, bhv, dev, flush, hbm_peak: float, l2_peak: float) -> dict:
+    """Compact records of the other BASELINE.json configurations in the default line, a few hundred ms of GPU
+    time each: the HBM-bound id distribution, bf16 tables, the 121-weighting sweep over three modules, full-catalogue retrieval."""
+    from manner_b200 import data as mdata
+    from manner_b200.evaluator import ScoreEvaluator
+
+    steps = max(5, min(args.steps, 10))
+    n_news = tables[0].shape[0]
+    w2 = torch.tensor([[1.0, CATEG_WEIGHT]], dtype=torch.float32, device=dev)
+    out = {}
+
+    def record(name, evaluator, behaviours, kw, n_mod, elem, peak, bound, extra_fields=None):
+        d = evaluator.upload(behaviours)
+        step_ms, k_ms = timed_passes(evaluator, d, kw, steps, flush)
+        algo = behaviours.algorithmic_bytes(n_mod, 768, elem, scores_written=True)
+        rec = {"impressions_per_s": behaviours.n_impressions / (step_ms * 1e-3), "ms_per_step": step_ms, "kernel_ms": k_ms,
+               "roofline": {"bound": bound, "achieved": algo / (k_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s", "frac": algo / (k_ms * 1e-3) / 1e9 / peak}}
+        rec.update(extra_fields or {})
+        out[name] = rec
+        del d
+
+    # (a) uniform ids: nothing to reuse in the L2, the gather runs at HBM speed -- the HBM-bound leg of the roofline
+    uni = mdata.synth_behaviours(n_news, bhv.n_impressions, mdata.SHAPES[args.workload][2], uniform_ids=True)
+    record("uniform_ids", ev, uni, dict(weights=w2, zscore=True, pooled_auc=True), 2, 4, hbm_peak, "hbm")
+    # (b) bf16 tables (fp32 arithmetic): half the row bytes
+    ev16 = ScoreEvaluator([t.to(torch.bfloat16) for t in tables], dev)
+    record("bf16_tables", ev16, bhv, dict(weights=w2, zscore=True, pooled_auc=True), 2, 2, l2_peak, "l2")
+    record("bf16_tables_uniform_ids", ev16, uni, dict(weights=w2, zscore=True, pooled_auc=True), 2, 2, hbm_peak, "hbm")
+    del ev16, uni
+    # (c) BASELINE.json configs[3]: CR + category + sentiment, 121 weightings re-scored from one gather
+    t3 = list(tables) + [mdata.synth_table(n_news, 768, mdata.TABLE_SEEDS[2])]
+    ev3 = ScoreEvaluator(t3, dev)
+    grid = torch.tensor([[1.0, a / 10.0, b / 10.0] for a in range(11) for b in range(11)], dtype=torch.float32, device=dev)
+    record("sweep121_m3", ev3, bhv, dict(weights=grid, zscore=True, pooled_auc=False), 3, 4, l2_peak, "l2",
+           {"weightings": 121, "weighting_impressions_per_s": None})
+    out["sweep121_m3"]["weighting_impressions_per_s"] = 121 * out["sweep121_m3"]["impressions_per_s"]
+    del ev3, t3
+    torch.cuda.empty_cache()
+    # (d) BASELINE.json configs[4] on one GPU: 37 888 users x 1.25 M news (1/8 of the 10 M catalogue), top-100
+    out["retrieval"] = retrieval_extra(dev, flush, steps=3)
+    return out
+
+
+def retrieval_extra(dev, flush, steps: int, n_users: int = 37888, n_shard: int = 1_250_000) -> dict:
+    from manner_b200 import retrieval as rt
+
+    dim, k = 768, 100
+    g = torch.Generator(device=dev).manual_seed(4321)
+    catalog = (torch.randn(n_shard, dim, generator=g, device=dev) * dim ** -0.5).to(torch.bfloat16)
+    users = (torch.randn(n_users, dim, generator=g, device=dev) * dim ** -0.5).to(torch.bfloat16)
+    r = rt.CatalogRetriever(catalog, k=k)
+    for _ in range(3):
+        r.local_topk(users)
+    torch.cuda.synchronize(dev)
+    sampler = ClockSampler(dev.index or 0)
+    events = []
+    for _ in range(steps):
+        flush.fill_(1)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        r.local_topk(users)
+        e1.record()
+        events.append((e0, e1))
+    torch.cuda.synchronize(dev)
+    clocks = sampler.stop()
+    ms = sum(a.elapsed_time(b) for a, b in events) / steps
+    burst, sustained, kind = FALLBACK_BF16_TFLOPS, FALLBACK_BF16_TFLOPS_SUSTAINED, "fallback"
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            mp = json.load(f)
+        burst, sustained, kind = float(mp["bf16_tflops"]), float(mp.get("bf16_tflops_sustained", mp["bf16_tflops"])), "measured"
+    tf = 2.0 * n_users * n_shard * dim / (ms * 1e-3) / 1e12
+    return {"users_per_s": n_users / (ms * 1e-3), "ms_per_step": ms, "users": n_users, "catalog_rows": n_shard, "k": k, "dtype": "bf16",
+            "roofline": {"bound": "tensor", "kernel": "retrieve_topk_kernel", "achieved": tf, "peak": sustained, "unit": "TFLOP/s", "frac": tf / sustained,
+                         "peak_kind": kind + " sustained cuBLAS bf16 (a ~55 ms kernel launched back to back under the power cap)",
+                         "peak_burst": burst, "frac_of_burst": tf / burst},
+            "clocks": clocks}
 
 
 def run_retrieval_arm(args) -> None:
@@ -375,7 +561,7 @@ def run_retrieval_arm(args) -> None:
     from manner_b200 import ops
     from manner_b200 import retrieval as rt
 
-    os.environ["NCCL_DEBUG"] = os.environ.get("MB200_NCCL_DEBUG", "WARN")
+    os.environ.setdefault("NCCL_DEBUG", "WARN")
     rank, local_rank, world = mdist.init_from_env("nccl")
     dev = torch.device(f"cuda:{local_rank}")
     distributed = world > 1
@@ -511,6 +697,8 @@ def main() -> None:
     ap.add_argument("--uniform-ids", action="store_true", help="draw ids uniformly over the catalogue (no L2-friendly head)")
     ap.add_argument("--cpu-sample", type=int, default=24576, help="impressions of the workload the CPU baseline is timed on (~12 s on 16 cores)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-checks", action="store_true", help="skip the in-bench parity / shard-invariance assertions (kernel tuning runs)")
+    ap.add_argument("--no-extra", dest="extra", action="store_false", help="skip the compact sub-results of the other configurations (uniform ids, bf16, sweep, retrieval)")
     ap.add_argument("--mode", default="eval", choices=["eval", "retrieval"], help="retrieval: BASELINE.json configs[4] (tcgen05 GEMM + fused top-100)")
     ap.add_argument("--users", type=int, default=37888, help="retrieval mode: users per step (37 888 = 2 full waves of 148 CTAs x 128 rows)")
     ap.add_argument("--catalog-per-gpu", type=int, default=1_250_000, help="retrieval mode: catalogue rows per GPU (10 M over 8)")

@@ -198,10 +198,14 @@ MB200_API int mb200_attention_logits(const void* table, int dtype, int dim, int6
 /*
  * The reference logs `test/loss` / `val/loss` as a MeanMetric over its steps (cr_module.py:214-225,253-259): every step of
  * `step` consecutive impressions contributes one value -- the mean of its impressions' losses (cross entropy), or the mean
- * of the losses that are > 0 (SupCon, AvgNonZeroReducer).  out (device, 2 doubles) = {sum of the step values, number of
- * steps}: both additive over ranks when every rank's shard starts on a step boundary.
+ * of the losses that are > 0 (SupCon, AvgNonZeroReducer).  SupCon additionally has two STEP-level guards
+ * (components/losses.py:15-16 `all(len(x) <= 1 for x in indices_tuple)` and :22 `pos_mask.any() and neg_mask.any()`): a step
+ * with at most one positive and at most one negative candidate in total, or without any positive or any negative, is worth 0;
+ * they need `cand_offsets` [n_impressions + 1] and `labels` (both NULL: guards skipped).  out (device, 2 doubles) = {sum of the
+ * step values, number of steps}: both additive over ranks when every rank's shard starts on a step boundary.
  */
-MB200_API int mb200_step_loss(const float* loss_per_impression, int64_t n_impressions, int step, int loss_kind, double* out, void* stream);
+MB200_API int mb200_step_loss(const float* loss_per_impression, int64_t n_impressions, int step, int loss_kind, const int32_t* cand_offsets,
+                              const uint8_t* labels, double* out, void* stream);
 
 /*
  * Ranking metrics on scores that already exist: the seam of torchmetrics' `update(preds, target, indexes)` / `compute()` that

@@ -175,7 +175,7 @@ SIGNATURES = {
     "mb200_pool_users": (c_int, [c_void_p, c_int, c_int, c_int64, c_int64, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
     "mb200_merge_topk": (c_int, [c_void_p, c_void_p, c_int, c_int64, c_int, c_void_p, c_void_p, c_void_p]),
     "mb200_attention_logits": (c_int, [c_void_p, c_int, c_int, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
-    "mb200_step_loss": (c_int, [c_void_p, c_int64, c_int, c_int, c_void_p, c_void_p]),
+    "mb200_step_loss": (c_int, [c_void_p, c_int64, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "mb200_metrics_workspace_bytes": (c_size_t, [POINTER(MetricsDesc)]),
     "mb200_rank_metrics": (c_int, [POINTER(MetricsDesc), c_void_p]),
     "mb200_exchange_mailbox_bytes": (c_size_t, [c_int, c_int, c_int64]),

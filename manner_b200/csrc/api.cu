@@ -59,7 +59,7 @@ int retrieve_topk(const mb200_retrieval_desc* d, cudaStream_t stream);
 int pool_users(const void*, int, int, long long, long long, const int32_t*, const int32_t*, long long, void*, int32_t*, cudaStream_t);
 int merge_topk(const float*, const long long*, int, long long, int, float*, long long*, cudaStream_t);
 int attention_logits(const void*, int, int, long long, long long, const float*, const float*, const float*, int, float*, cudaStream_t);
-int step_loss(const float*, long long, int, int, double*, cudaStream_t);
+int step_loss(const float*, long long, int, int, const int32_t*, const uint8_t*, double*, cudaStream_t);
 size_t exchange_mailbox_bytes(int n_ranks, int n_payload, long long pos_capacity);
 int exchange_post(const mb200_exchange_desc* d, cudaStream_t stream);
 int exchange_finish(const mb200_exchange_desc* d, cudaStream_t stream);
@@ -155,8 +155,9 @@ int mb200_attention_logits(const void* table, int dtype, int dim, int64_t row_st
   return attention_logits(table, dtype, dim, row_stride, n_rows, weight, bias, query, q_dim, out, static_cast<cudaStream_t>(stream));
 }
 
-int mb200_step_loss(const float* loss_per_impression, int64_t n_impressions, int step, int loss_kind, double* out, void* stream) {
-  return step_loss(loss_per_impression, n_impressions, step, loss_kind, out, static_cast<cudaStream_t>(stream));
+int mb200_step_loss(const float* loss_per_impression, int64_t n_impressions, int step, int loss_kind, const int32_t* cand_offsets,
+                    const uint8_t* labels, double* out, void* stream) {
+  return step_loss(loss_per_impression, n_impressions, step, loss_kind, cand_offsets, labels, out, static_cast<cudaStream_t>(stream));
 }
 
 size_t mb200_metrics_workspace_bytes(const mb200_metrics_desc* desc) { return metrics_workspace_bytes(desc); }

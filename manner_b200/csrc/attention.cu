@@ -112,7 +112,11 @@ __global__ void __launch_bounds__(att::WARPS * 32) attention_logits_kernel(const
 }
 
 // out[0] = sum over steps of the step's loss value, out[1] = number of steps (one block, fixed order).
+// SupCon with `cand_offsets` / `labels`: the two step-level guards of components/losses.py -- `all(len(x) <= 1 for x in indices_tuple)`
+// (:15-16: at most one positive AND at most one negative pair in the whole step) and `pos_mask.any() and neg_mask.any()` (:22) --
+// turn the step's value into 0 before the non-zero average is taken.
 __global__ void __launch_bounds__(256) step_loss_kernel(const float* __restrict__ loss, long long n_impr, int step, int kind,
+                                                        const int32_t* __restrict__ cand_offsets, const uint8_t* __restrict__ labels,
                                                         double* __restrict__ out) {
   __shared__ double sh[256];
   const long long n_steps = (n_impr + step - 1) / step;
@@ -121,6 +125,13 @@ __global__ void __launch_bounds__(256) step_loss_kernel(const float* __restrict_
     const long long lo = s * step, hi = min(n_impr, lo + step);
     double sum = 0.0;
     int cnt = 0;
+    if (kind == MB200_LOSS_SUPCON && cand_offsets != nullptr && labels != nullptr) {
+      const int c0 = cand_offsets[lo], c1 = cand_offsets[hi];
+      int pos = 0;
+      for (int j = c0; j < c1; ++j) pos += labels[j] != 0;
+      const int neg = (c1 - c0) - pos;
+      if ((pos <= 1 && neg <= 1) || pos == 0 || neg == 0) continue;  // zero_losses(): the step contributes 0 to the MeanMetric
+    }
     for (long long i = lo; i < hi; ++i) {
       const float l = loss[i];
       if (kind == MB200_LOSS_SUPCON) {
@@ -164,11 +175,13 @@ int attention_logits(const void* table, int dtype, int dim, long long row_stride
   return cuda_status(cudaGetLastError(), "attention_logits_kernel");
 }
 
-int step_loss(const float* loss, long long n_impr, int step, int kind, double* out, cudaStream_t stream) {
+int step_loss(const float* loss, long long n_impr, int step, int kind, const int32_t* cand_offsets, const uint8_t* labels, double* out,
+              cudaStream_t stream) {
   if (!loss || !out || n_impr < 0 || step < 1 || (kind != MB200_LOSS_CE && kind != MB200_LOSS_SUPCON)) return MB200_ERR_INVALID_ARG;
+  if ((cand_offsets == nullptr) != (labels == nullptr)) return MB200_ERR_INVALID_ARG;
   int st = use_device_of(out, nullptr);
   if (st != MB200_OK) return st;
-  step_loss_kernel<<<1, 256, 0, stream>>>(loss, n_impr, step, kind, out);
+  step_loss_kernel<<<1, 256, 0, stream>>>(loss, n_impr, step, kind, cand_offsets, labels, out);
   note_launch(1);
   return cuda_status(cudaGetLastError(), "step_loss_kernel");
 }

@@ -566,7 +566,9 @@ __device__ __noinline__ float impression_loss(const EvalParams& p, const float* 
   __builtin_assume(__isShared(s));
   __builtin_assume(__isShared(lab));
   const bool ce = p.loss_kind == MB200_LOSS_CE;
-  const int n_pad = (ce && p.cand_pad) ? p.cand_pad[i] : 0;
+  // zero columns the step's dense batch appends: part of the cross entropy's softmax; for SupCon only of the row maximum that
+  // is subtracted for stability (losses.py:24-25 takes mat.max over the dense row, the log-sum-exp keeps pos + neg only)
+  const int n_pad = p.cand_pad ? p.cand_pad[i] : 0;
   const float T = ce ? 1.0f : p.loss_temperature;
   float mx = n_pad > 0 ? 0.f : -INFINITY;
 #pragma unroll 1
@@ -583,7 +585,7 @@ __device__ __noinline__ float impression_loss(const EvalParams& p, const float* 
   }
   se = warp_sum(se), sp = warp_sum(sp);
   n_pos = __reduce_add_sync(kFull, n_pos);
-  if (n_pad > 0) se += (double)n_pad * (double)expf(-mx);
+  if (ce && n_pad > 0) se += (double)n_pad * (double)expf(-mx);
   float loss = 0.f;
   if (n_pos > 0) {
     const double lse = (double)logf((float)se);

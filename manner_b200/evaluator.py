@@ -239,8 +239,8 @@ class ScoreEvaluator:
         them.  ``weights`` may be a device fp32 tensor [W, n_modules] (then every module is gathered).
         ``loss`` = "ce" | "supcon" adds the reference's test/loss (cr_module.py:140-171,253-259; ``temperature`` for
         SupCon); it and early fusion need ``upload(..., step_batch=...)``."""
-        if (loss == "ce" or self.attn_logits is not None) and bhv.hist_pad is None:
-            raise ValueError("early fusion / the cross-entropy loss depend on the reference's step padding: upload(..., step_batch=8)")
+        if (loss is not None or self.attn_logits is not None) and bhv.hist_pad is None:
+            raise ValueError("early fusion / the losses depend on the reference's step structure: upload(..., step_batch=8)")
         n_mod = self.n_modules
         w_dev: Optional[Tensor] = None
         active = (1 << n_mod) - 1
@@ -265,12 +265,12 @@ class ScoreEvaluator:
             self.news_category, self.news_sentiment, self.num_categ_classes, self.num_sent_classes,
             self.attn_logits if self.attn_logits is not None else [], distributed,
             bhv.hist_pad if self.attn_logits is not None else None, loss_kind, float(temperature),
-            bhv.cand_pad if loss == "ce" else None, self.n_table_shards, self.table_shard_shift, self.n_news,
+            bhv.cand_pad if loss is not None else None, self.n_table_shards, self.table_shard_shift, self.n_news,
         )
         loss_stats: Optional[Tensor] = None
         if loss is not None:
             # MeanMetric over the reference's steps (cr_module.py:253-259): (sum of step losses, number of steps)
-            loss_stats = ops.step_loss(loss_per_impr, bhv.step_batch, loss_kind)
+            loss_stats = ops.step_loss(loss_per_impr, bhv.step_batch, loss_kind, bhv.cand_offsets, bhv.labels)
             if distributed:
                 torch.distributed.all_reduce(loss_stats, op=torch.distributed.ReduceOp.SUM, group=group)
         n_w = 1 if w_dev is None else w_dev.shape[0]

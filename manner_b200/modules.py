@@ -95,15 +95,18 @@ class StepScorer:
         dev = cand_vecs[0].device
         batch_hist, batch_cand = batch["batch_hist"].to(dev), batch["batch_cand"].to(dev)
         n_hist, n_cand = hist_vecs[0].shape[0], cand_vecs[0].shape[0]
-        # B = batch.max() + 1 as to_dense_batch derives it (the one host read of the step)
-        n_impr = int(torch.maximum(batch_hist.max(), batch_cand.max()).item()) + 1
+        # B = batch.max() + 1 as to_dense_batch derives it, and the longest candidate list (it sizes the kernel's per-warp shared
+        # memory: the step's TOTAL candidate count would cap eval batches at ~3 000 candidates) -- the one host read of the step
+        n_impr, max_cand = (int(v) for v in torch.stack([torch.maximum(batch_hist.max(), batch_cand.max()) + 1, torch.bincount(batch_cand).max()]).tolist())
         hist_off, cand_off = _segment_offsets(batch_hist, n_impr), _segment_offsets(batch_cand, n_impr)
         # the step's table is [history rows; candidate rows]: ids are just positions
         tables = [torch.cat([h, c]).float().contiguous() for h, c in zip(hist_vecs, cand_vecs)]
         hist_ids = torch.arange(n_hist, dtype=torch.int32, device=dev)
         cand_ids = torch.arange(n_hist, n_hist + n_cand, dtype=torch.int32, device=dev)
         labels = (batch["labels"].to(dev) != 0).to(torch.uint8)
-        w_dev = None if weights is None else torch.tensor([list(weights)], dtype=torch.float32, device=dev)
+        w_dev = None
+        if weights is not None:  # one weighting [n_modules] or a sweep [[...], ...] re-scored from the one gather
+            w_dev = torch.tensor(weights, dtype=torch.float32, device=dev).reshape(-1, len(tables))
         active = (1 << len(tables)) - 1
         cat = sent = None
         if "category" in batch["x_cand"] and "sentiment" in batch["x_cand"] and self.zscore:
@@ -116,19 +119,19 @@ class StepScorer:
             from . import ops
 
             attn_logits = [None if a is None else ops.attention_logits(t, *a) for t, a in zip(tables, attention)]
-        if attn_logits or self.loss_kind == nat.LOSS_CE:
+        if attn_logits or self.loss_kind != nat.LOSS_NONE:
             # the step IS the reference's dense batch: every impression is padded to the step's longest (to_dense_batch)
             h_len, c_len = hist_off[1:] - hist_off[:-1], cand_off[1:] - cand_off[:-1]
             hist_pad, cand_pad = (h_len.max() - h_len).to(torch.int32), (c_len.max() - c_len).to(torch.int32)
         scores, _, sums, flags, loss_per_impr = torch.ops.manner_b200.score_eval(
-            tables, hist_off, hist_ids, cand_off, cand_ids, labels, w_dev, self.zscore, max(n_cand, 1), active,
+            tables, hist_off, hist_ids, cand_off, cand_ids, labels, w_dev, self.zscore, max(max_cand, 1), active,
             self.ks[0], self.ks[1], True, 0, False, cat, sent, self.num_categ_classes, self.num_sent_classes, attn_logits,
-            False, hist_pad if attn_logits else None, self.loss_kind, self.temperature, cand_pad if self.loss_kind == nat.LOSS_CE else None,
+            False, hist_pad if attn_logits else None, self.loss_kind, self.temperature, cand_pad if self.loss_kind != nat.LOSS_NONE else None,
         )
         if self.loss_kind != nat.LOSS_NONE:
             from . import ops
 
-            st = ops.step_loss(loss_per_impr, n_impr, self.loss_kind)  # this step's value for the MeanMetric (cr_module.py:255-259)
+            st = ops.step_loss(loss_per_impr, n_impr, self.loss_kind, cand_off, labels)  # this step's value for the MeanMetric (cr_module.py:255-259)
             self.loss_stats = st if self.loss_stats is None else self.loss_stats + st
         self.sums = sums if self.sums is None else self.sums + sums
         self.flags = flags if self.flags is None else self.flags | flags
@@ -146,16 +149,20 @@ class StepScorer:
         if self.with_auc and self.preds:
             # AUROC's any-outside-[0,1] sigmoid rule is decided over the whole epoch (cr_module.py:273)
             auc_stats = torch.ops.manner_b200.pooled_auc(torch.cat(self.preds), torch.cat(self.targets), 2, self.flags)
-        s = self.sums[0].cpu().numpy()
+        sums = self.sums.cpu().numpy()
         flags = int(self.flags.cpu().item())
         if flags & (nat.FLAG_BAD_ID | nat.FLAG_CAND_OVERFLOW | nat.FLAG_BAD_ASPECT):
             raise nat.NativeError(f"manner_b200 kernels flagged bad input (flags={flags})")
         n = max(self.n_impressions, 1)
-        for slot, key in SLOT_KEYS.items():
-            if slot >= nat.M_CATEG_DIV_K0 and not self.has_aspects:
-                continue
-            out[prefix + key.format(k0=self.ks[0], k1=self.ks[1])] = float(s[slot] / n)
-        out[prefix + "gauc"] = float(s[nat.M_GAUC] / s[nat.M_GAUC_VALID]) if s[nat.M_GAUC_VALID] > 0 else 0.0
+        for w in range(sums.shape[0]):
+            # one weighting: the reference's keys; a sweep (EnsembleModuleB200(aspect_weights=...)): `<key>/w<i>` per weighting
+            suffix = "" if sums.shape[0] == 1 else f"/w{w}"
+            s = sums[w]
+            for slot, key in SLOT_KEYS.items():
+                if slot >= nat.M_CATEG_DIV_K0 and not self.has_aspects:
+                    continue
+                out[prefix + key.format(k0=self.ks[0], k1=self.ks[1]) + suffix] = float(s[slot] / n)
+            out[prefix + "gauc" + suffix] = float(s[nat.M_GAUC] / s[nat.M_GAUC_VALID]) if s[nat.M_GAUC_VALID] > 0 else 0.0
         if auc_stats is not None:
             out[prefix + "auc"] = float(auc_stats.cpu()[0])
         if self.loss_stats is not None:
@@ -258,12 +265,18 @@ class B200EvalMixin:
         ev = ScoreEvaluator(tables, device, attention=self._b200_attention(), **aspects)
         weights = self._b200_weights()
         hp = getattr(self, "hparams", {})
+        sweep = weights is not None and len(weights) > 0 and isinstance(weights[0], (list, tuple))
         res = ev.evaluate(
-            ev.upload(bhv, step_batch=step), weights=None if weights is None else [weights], zscore=self._b200_zscore,
+            ev.upload(bhv, step_batch=step), weights=None if weights is None else (weights if sweep else [weights]), zscore=self._b200_zscore,
             pooled_auc=self._b200_with_auc, loss=None if self._b200_zscore else self._b200_loss(),
             temperature=float(hp.get("temperature", 0.1)) if hasattr(hp, "get") else 0.1,
         )
-        return res.metrics(prefix=stage + "/")
+        if not sweep:
+            return res.metrics(prefix=stage + "/")
+        values: Dict[str, float] = {}
+        for w in range(len(weights)):
+            values.update({k + f"/w{w}": v for k, v in res.metrics(weighting=w, prefix=stage + "/").items()})
+        return values
 
     def on_test_start(self) -> None:
         if self._b200_cached:
@@ -354,22 +367,54 @@ class CRModuleB200(B200EvalMixin, _RefCRModule):
 
 class EnsembleModuleB200(B200EvalMixin, _RefEnsembleModule):
     """EnsembleModule (CR + category / sentiment A-Modules, z-score, aspect weights) with the B200 test
-    path.  Logs the reference's keys (ndcg, *_div, *_pers) plus mrr / gauc."""
+    path.  Logs the reference's keys (ndcg, *_div, *_pers) plus mrr / gauc.
+
+    Extra keywords (defaulted, so the reference's YAMLs and `load_from_checkpoint` work unchanged):
+      ``scorer``         "b200" (per step) | "b200_cached" (tables built once, one call per epoch)
+      ``aspect_weights`` ``[[categ_weight, sent_weight], ...]`` (YAML key ``model.aspect_weights``): an aspect-weight SWEEP --
+                         every weighting is re-scored from ONE gather of the step / epoch (BASELINE.json configs[3]) instead of
+                         one `python manner/train.py ... model.categ_weight=...` run per weighting; metrics are logged as
+                         ``test/<metric>/w<i>``.  A-Modules a weighting needs are loaded even when ``categ_weight`` /
+                         ``sent_weight`` are 0 (ensemble_module.py:37-46 loads them only for non-zero weights)."""
 
     _b200_zscore = True
     _b200_with_auc = False  # the reference's EnsembleModule has no AUROC (ensemble_module.py:50-55)
 
-    def __init__(self, *args: Any, scorer: str = "b200", **kwargs: Any) -> None:
+    def __init__(self, *args: Any, scorer: str = "b200", aspect_weights: Optional[Sequence[Sequence[float]]] = None, **kwargs: Any) -> None:
         super().__init__(*args, **kwargs)
         if scorer not in ("b200", "b200_cached"):
             raise ValueError("scorer must be 'b200' (per step) or 'b200_cached' (tables built once, one call per epoch)")
         self._b200_cached = scorer == "b200_cached"
+        self._b200_aspect_weights: Optional[List[List[float]]] = None
+        if aspect_weights is not None:
+            grid = [[float(w) for w in pair] for pair in aspect_weights]
+            if not grid or any(len(pair) != 2 for pair in grid):
+                raise ValueError("aspect_weights must be a non-empty list of [categ_weight, sent_weight] pairs")
+            self._b200_aspect_weights = grid
+            # the sub-modules the sweep needs, loaded exactly as ensemble_module.py:37-46 loads them
+            if any(wc != 0 for wc, _ in grid) and not hasattr(self, "a_module_categ"):
+                from manner.models.a_module import AModule  # type: ignore
+
+                assert isinstance(self.hparams.a_module_categ_ckpt, str), "aspect_weights with a category weight needs a_module_categ_ckpt"
+                self.a_module_categ = AModule.load_from_checkpoint(checkpoint_path=self.hparams.a_module_categ_ckpt)
+            if any(ws != 0 for _, ws in grid) and not hasattr(self, "a_module_sent"):
+                from manner.models.a_module import AModule  # type: ignore
+
+                assert isinstance(self.hparams.a_module_sent_ckpt, str), "aspect_weights with a sentiment weight needs a_module_sent_ckpt"
+                self.a_module_sent = AModule.load_from_checkpoint(checkpoint_path=self.hparams.a_module_sent_ckpt)
+
+    def _b200_use(self) -> tuple:
+        """(category A-Module takes part, sentiment A-Module takes part)"""
+        if self._b200_aspect_weights is not None:
+            return any(wc != 0 for wc, _ in self._b200_aspect_weights), any(ws != 0 for _, ws in self._b200_aspect_weights)
+        return self.hparams.categ_weight != 0, self.hparams.sent_weight != 0
 
     def _b200_encoders(self) -> List[torch.nn.Module]:
+        use_c, use_s = self._b200_use()
         encs = [self.cr_module.news_encoder]
-        if self.hparams.categ_weight != 0:
+        if use_c:
             encs.append(self.a_module_categ.news_encoder)
-        if self.hparams.sent_weight != 0:
+        if use_s:
             encs.append(self.a_module_sent.news_encoder)
         return encs
 
@@ -379,10 +424,51 @@ class EnsembleModuleB200(B200EvalMixin, _RefEnsembleModule):
     def on_validation_epoch_end(self) -> None:
         pass
 
-    def _b200_weights(self) -> Optional[List[float]]:
+    def _b200_weights(self):
+        use_c, use_s = self._b200_use()
+        if self._b200_aspect_weights is not None:
+            return [[1.0] + ([wc] if use_c else []) + ([ws] if use_s else []) for wc, ws in self._b200_aspect_weights]
         w = [1.0]
-        if self.hparams.categ_weight != 0:
+        if use_c:
             w.append(float(self.hparams.categ_weight))
-        if self.hparams.sent_weight != 0:
+        if use_s:
             w.append(float(self.hparams.sent_weight))
         return w
+
+
+class B200MetricsMixin:
+    """Epoch-end metrics of the reference's nine BASELINE recommenders (manner/models/baselines/*_module.py) on the B200 kernels.
+
+    The baselines keep their own model code; what they share with CRModule / EnsembleModule is the epoch end: `test_step`
+    collects `preds`, `targets`, `cand_news_size`, `hist_news_size` and the aspect labels in `self.test_step_outputs`, and
+    `on_test_epoch_end` feeds five torchmetrics collections (nrms_plm_module.py:275-313): auc / mrr / ndcg@5/10,
+    categ_div / sent_div @5/10, categ_pers / sent_pers @5/10.  Mixed in BEFORE the baseline class
+
+        class NRMSModuleB200(B200MetricsMixin, NRMSModule): pass
+
+    this replaces only `on_test_epoch_end`: one `mb200_rank_metrics` launch + `mb200_pooled_auc` instead of torchmetrics'
+    Python loop over every impression, same log keys (plus ``test/gauc``)."""
+
+    def on_test_epoch_end(self) -> None:
+        from .metrics import RetrievalMetricsB200
+
+        outs = self.test_step_outputs
+        cat = lambda key: torch.cat([o for o in outs[key]])  # noqa: E731  (nrms_plm_module.py:276-286)
+        preds, targets = cat("preds"), cat("targets")
+        cand_news_size, hist_news_size = cat("cand_news_size"), cat("hist_news_size")
+        dev = preds.device
+        if not preds.is_cuda:
+            raise RuntimeError("B200MetricsMixin needs the module on a CUDA device (there is no CPU path)")
+        cand_indexes = torch.arange(cand_news_size.shape[0], device=dev).repeat_interleave(cand_news_size.to(dev))
+        hist_indexes = torch.arange(hist_news_size.shape[0], device=dev).repeat_interleave(hist_news_size.to(dev))
+        hp = getattr(self, "hparams", {})
+        metrics = RetrievalMetricsB200(
+            prefix="test/",
+            num_categ_classes=int(hp.get("num_categ_classes", 19)) if hasattr(hp, "get") else 19,
+            num_sent_classes=int(hp.get("num_sent_classes", 4)) if hasattr(hp, "get") else 4,
+        )
+        metrics.update(preds, targets, indexes=cand_indexes, target_categories=cat("target_categories"), target_sentiments=cat("target_sentiments"),
+                       hist_categories=cat("hist_categories"), hist_sentiments=cat("hist_sentiments"), hist_indexes=hist_indexes)
+        self.log_dict(metrics.compute(), on_step=False, on_epoch=True, prog_bar=True, logger=True)
+        for key in self.keys:  # clean memory for the next epoch (nrms_plm_module.py:311-313)
+            outs[key].clear()

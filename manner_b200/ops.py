@@ -235,17 +235,23 @@ def attention_logits(table: Tensor, weight: Tensor, bias: Tensor, query: Tensor)
     return out
 
 
-def step_loss(loss_per_impression: Tensor, step: int, loss_kind: int) -> Tensor:
+def step_loss(loss_per_impression: Tensor, step: int, loss_kind: int, cand_offsets: Optional[Tensor] = None, labels: Optional[Tensor] = None) -> Tensor:
     """fp64 [2] = (sum over the reference's steps of the step loss, number of steps): what MeanMetric averages into
-    test/loss (cr_module.py:253-259); mb200_step_loss."""
+    test/loss (cr_module.py:253-259); mb200_step_loss.  ``cand_offsets`` / ``labels`` enable SupCon's step-level guards
+    (components/losses.py:15-16,22)."""
     lib = nat.lib()
     _require_cuda("loss_per_impression", loss_per_impression, torch.float32)
+    if (cand_offsets is None) != (labels is None):
+        raise ValueError("give cand_offsets and labels together")
+    if cand_offsets is not None:
+        _require_cuda("cand_offsets", cand_offsets, torch.int32)
+        _require_cuda("labels", labels, torch.uint8)
     dev = loss_per_impression.device
     with torch.cuda.device(dev):
         stream = torch.cuda.current_stream(dev).cuda_stream
         out = torch.empty(2, dtype=torch.float64, device=dev)
-        nat.check(lib.mb200_step_loss(loss_per_impression.data_ptr(), loss_per_impression.numel(), int(step), int(loss_kind), out.data_ptr(), stream),
-                  "mb200_step_loss")
+        nat.check(lib.mb200_step_loss(loss_per_impression.data_ptr(), loss_per_impression.numel(), int(step), int(loss_kind),
+                                      _ptr(cand_offsets), _ptr(labels), out.data_ptr(), stream), "mb200_step_loss")
     return out
 
 

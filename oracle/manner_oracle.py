@@ -142,19 +142,21 @@ def ce_step_loss(scores: Tensor, batch: Dict) -> Tensor:
 
 
 def supcon_step_loss(scores: Tensor, batch: Dict, temperature: float) -> Tensor:
-    """PARITY UNPINNED restatement of cr_module.py:144-169 + components/losses.py:6-40 on top of
-    pytorch_metric_learning 2.1.1's SupConLoss (absent here): per impression with >= 1 positive,
-    -mean over positives of (s_p / T - logsumexp over the impression's real candidates of s / T);
-    AvgNonZeroReducer (the SupConLoss default) averages the impressions whose loss is > 0; a step without any
-    positive or without any negative gives 0."""
+    """cr_module.py:144-169 + components/losses.py:6-40 on pytorch_metric_learning 2.1.1's SupConLoss: per impression with
+    >= 1 positive, -mean over positives of (s_p / T - logsumexp over the impression's real candidates of s / T) (the row
+    maximum that is subtracted first runs over the DENSE row, pads included); AvgNonZeroReducer averages the impressions whose
+    loss is > 0.  Step-level guards: at most one positive and at most one negative pair in the whole step
+    (`all(len(x) <= 1 for x in indices_tuple)`, losses.py:15-16), or no positive / no negative anywhere (:22), give 0.
+    Pinned on tests/golden/cr_supcon_*.npz, which the reference's own SupConLoss produced (oracle/ref_stubs.py)."""
     y_true, mask_cand = tp.to_dense_batch(batch["labels"], batch["batch_cand"])
     pos = (y_true > 0) & mask_cand
     neg = (y_true == 0) & mask_cand
-    if not bool(pos.any()) or not bool(neg.any()):
+    n_pos, n_neg = int(pos.sum()), int(neg.sum())
+    if (n_pos <= 1 and n_neg <= 1) or n_pos == 0 or n_neg == 0:
         return torch.zeros(())
     mat = scores / temperature
     mat = mat - mat.max(dim=1, keepdim=True)[0]
-    denom = torch.logsumexp(mat.masked_fill(~mask_cand, float("-inf")), dim=1, keepdim=True)
+    denom = torch.logsumexp(mat.masked_fill(~mask_cand, torch.finfo(mat.dtype).min), dim=1, keepdim=True)
     log_prob = mat - denom
     mean_log_prob_pos = (pos * log_prob).sum(dim=1) / (pos.sum(dim=1) + torch.finfo(torch.float32).tiny)
     losses = -mean_log_prob_pos

@@ -8,7 +8,9 @@ them in ``sys.modules``:
 
 * the arithmetic the hot path needs from them (``to_dense_batch``, the torchmetrics metric classes
   and helpers) comes from the restatement in oracle/thirdparty.py;
-* everything off the path (losses, tSNE, plotting) is an inert placeholder.
+* pytorch_metric_learning: the base class and helpers the reference's own SupConLoss (components/losses.py) builds on are
+  restated from the published 2.1.1 sources, so `val/loss` / `test/loss` with supcon_loss=True come from the reference's code;
+* everything off the path (tSNE, plotting) is an inert placeholder.
 
 With the shims in place tests/golden/make_golden.py runs the reference's unmodified
 ``CRModule.forward/model_step/test_step/on_test_epoch_end``, ``EnsembleModule.*``, ``DotProduct``,
@@ -87,6 +89,56 @@ class _Inert:
         pass
 
 
+# ---- pytorch_metric_learning 2.1.1 (pinned `>=2.1.1`, requirements.txt): the pieces the reference's own SupConLoss subclass
+# (manner/models/components/losses.py:6-40) inherits or calls, restated from the published 2.1.1 sources so that the reference's
+# OWN compute_loss / _compute_loss run unmodified on top of them.  TEST INFRASTRUCTURE (golden generation only).
+
+
+class PmlSupConLossBase(torch.nn.Module):
+    """losses.SupConLoss as the reference subclasses it: BaseMetricLossFunction.forward (compute_loss -> reducer),
+    GenericPairLoss.mat_based_loss (pos / neg masks from the index tuple), zero_losses, and the class default reducer
+    AvgNonZeroReducer (mean of the element losses that are > 0, else 0)."""
+
+    def __init__(self, temperature: float = 0.1, **kwargs: Any) -> None:
+        super().__init__()
+        self.temperature = temperature
+
+    def add_to_recordable_attributes(self, *args: Any, **kwargs: Any) -> None:
+        pass
+
+    def zero_losses(self) -> Dict[str, Any]:
+        return {"loss": {"losses": 0, "indices": None, "reduction_type": "already_reduced"}}
+
+    def loss_method(self, mat: torch.Tensor, indices_tuple) -> Dict[str, Any]:  # GenericPairLoss.mat_based_loss
+        a1, p, a2, n = indices_tuple
+        pos_mask, neg_mask = torch.zeros_like(mat), torch.zeros_like(mat)
+        pos_mask[a1, p] = 1
+        neg_mask[a2, n] = 1
+        return self._compute_loss(mat, pos_mask, neg_mask)
+
+    def forward(self, embeddings, labels=None, indices_tuple=None, ref_emb=None, ref_labels=None) -> torch.Tensor:
+        loss_dict = self.compute_loss(embeddings, labels, indices_tuple, ref_emb, ref_labels)
+        item = loss_dict["loss"]
+        if item["reduction_type"] == "already_reduced" or not torch.is_tensor(item["losses"]):
+            return torch.sum(embeddings * 0)  # BaseReducer.zero_loss
+        losses = item["losses"]
+        keep = losses > 0  # AvgNonZeroReducer = ThresholdReducer(low=0)
+        return torch.mean(losses[keep]) if bool(keep.any()) else torch.sum(embeddings * 0)
+
+
+def _pml_logsumexp(x: torch.Tensor, keep_mask=None, add_one: bool = True, dim: int = 1) -> torch.Tensor:
+    """loss_and_miner_utils.logsumexp."""
+    if keep_mask is not None:
+        x = x.masked_fill(~keep_mask, torch.finfo(x.dtype).min)
+    if add_one:
+        zeros = torch.zeros(x.size(dim - 1), dtype=x.dtype, device=x.device).unsqueeze(dim)
+        x = torch.cat([x, zeros], dim=dim)
+    output = torch.logsumexp(x, dim=dim, keepdim=True)
+    if keep_mask is not None:
+        output = output.masked_fill(~torch.any(keep_mask, dim=dim, keepdim=True), 0)
+    return output
+
+
 def install(reference_root: str = "/root/reference") -> None:
     """Register the shims and put the reference on sys.path (idempotent)."""
     if reference_root not in sys.path:
@@ -120,11 +172,15 @@ def install(reference_root: str = "/root/reference") -> None:
     )
 
     pml = _module("pytorch_metric_learning")
-    pml.losses = _module("pytorch_metric_learning.losses", SupConLoss=_Inert)
+    pml.losses = _module("pytorch_metric_learning.losses", SupConLoss=PmlSupConLossBase)
     pml.distances = _module("pytorch_metric_learning.distances", DotProductSimilarity=_Inert)
     pml.utils = _module("pytorch_metric_learning.utils")
-    pml.utils.common_functions = _module("pytorch_metric_learning.utils.common_functions")
-    pml.utils.loss_and_miner_utils = _module("pytorch_metric_learning.utils.loss_and_miner_utils")
+    pml.utils.common_functions = _module(
+        "pytorch_metric_learning.utils.common_functions",
+        small_val=lambda dtype: torch.finfo(dtype).tiny,
+        torch_arange_from_size=lambda t, size_dim=0: torch.arange(t.size(size_dim), device=t.device),
+    )
+    pml.utils.loss_and_miner_utils = _module("pytorch_metric_learning.utils.loss_and_miner_utils", logsumexp=_pml_logsumexp)
     _module("MulticoreTSNE", MulticoreTSNE=_Inert)
     _module("seaborn")
     _module("colorcet")

@@ -117,10 +117,11 @@ def table(n_news: int, dim: int, seed: int) -> torch.Tensor:
     return torch.randn(n_news, dim, generator=g) * (2.0 / dim**0.5)
 
 
-def run_reference_cr(tab: torch.Tensor, bhv: mo.Behaviours, step: int = 8, late_fusion: bool = True, query_vector_dim: int = 200) -> Dict[str, np.ndarray]:
+def run_reference_cr(tab: torch.Tensor, bhv: mo.Behaviours, step: int = 8, late_fusion: bool = True, query_vector_dim: int = 200,
+                     supcon_loss: bool = False, temperature: float = 0.1) -> Dict[str, np.ndarray]:
     ref_cr.MannerNewsEncoder = TableEncoder  # the only substitution inside CRModule.__init__
     model = ref_cr.CRModule(
-        supcon_loss=False, late_fusion=late_fusion, temperature=0.1, plm_model="", frozen_layers=[], dropout_probability=0.2,
+        supcon_loss=supcon_loss, late_fusion=late_fusion, temperature=temperature, plm_model="", frozen_layers=[], dropout_probability=0.2,
         use_entities=False, pretrained_entity_embeddings_path="", entity_embedding_dim=100, num_attention_heads=10,
         query_vector_dim=query_vector_dim, text_embedding_dim=tab.shape[1], optimizer=None,
     )
@@ -165,6 +166,39 @@ def run_reference_ensemble(tabs: List[torch.Tensor], wc: float, ws: float, bhv: 
     for k, v in model.logged.items():
         out[k] = np.float32(float(v))
     return out
+
+
+def run_reference_baseline_epoch_end(bhv: mo.Behaviours, preds: np.ndarray, aspects: Dict[str, np.ndarray], step: int = 8) -> Dict[str, np.ndarray]:
+    """The epoch end every BASELINE recommender of the reference shares (nrms_plm_module.py:275-313), run on the reference's own
+    NRMSPLMModule: `test_step_outputs` is filled per step exactly as its test_step does (:258-272) from given flat predictions,
+    then the unmodified on_test_epoch_end feeds the five metric collections."""
+    import manner.models.baselines.nrms_plm_module as ref_nrms
+
+    class _Inert(torch.nn.Module):
+        def __init__(self, *args, **kwargs):
+            super().__init__()
+
+    ref_nrms.NewsEncoder = _Inert
+    ref_nrms.UserEncoder = _Inert
+    model = ref_nrms.NRMSPLMModule(plm_model="", frozen_layers=[], dropout_probability=0.2, text_embedding_dim=16, num_attention_heads=2,
+                                   query_vector_dim=8, num_categ_classes=19, num_sent_classes=4, optimizer=None)
+    ho, co = bhv.hist_offsets, bhv.cand_offsets
+    for lo in range(0, bhv.n_impressions, step):
+        hi = min(lo + step, bhv.n_impressions)
+        c_ids, h_ids = bhv.cand_ids[co[lo]:co[hi]], bhv.hist_ids[ho[lo]:ho[hi]]
+        out = model.test_step_outputs
+        out["preds"].append(torch.from_numpy(preds[co[lo]:co[hi]]))
+        out["targets"].append(torch.from_numpy(bhv.labels[co[lo]:co[hi]].astype(np.int64)))
+        out["cand_news_size"].append(torch.from_numpy(np.diff(co[lo:hi + 1]).astype(np.int64)))
+        out["hist_news_size"].append(torch.from_numpy(np.diff(ho[lo:hi + 1]).astype(np.int64)))
+        out["target_categories"].append(torch.from_numpy(aspects["category"][c_ids].astype(np.int64)))
+        out["target_sentiments"].append(torch.from_numpy(aspects["sentiment"][c_ids].astype(np.int64)))
+        out["hist_categories"].append(torch.from_numpy(aspects["category"][h_ids].astype(np.int64)))
+        out["hist_sentiments"].append(torch.from_numpy(aspects["sentiment"][h_ids].astype(np.int64)))
+    with torch.no_grad():
+        model.on_test_epoch_end()
+    assert all(len(v) == 0 for v in model.test_step_outputs.values())  # the reference clears its buffers
+    return {k: np.float32(float(v)) for k, v in model.logged.items()}
 
 
 def save(name: str, **arrays) -> None:
@@ -225,6 +259,24 @@ def main() -> None:
             ref = run_reference_cr(tab, bhv, late_fusion=False, query_vector_dim=qdim)
         save(name, table=tab.numpy(), **bhv_arrays(bhv), **{k.replace("/", "_"): v for k, v in ref.items()})
 
+    # ---- CR eval with the reference's OWN SupConLoss (supcon_loss=True, the reference default; components/losses.py on the
+    #      pytorch_metric_learning base restated in oracle/ref_stubs.py), late and early fusion; the last step of the first set
+    #      is a single impression with one positive and one negative -> the `all(len(x) <= 1 ...)` guard (losses.py:15-16) ----
+    for name, dim, late, n_news, b, seed, T in (("cr_supcon_d128", 128, True, 256, 41, 2031, 0.36), ("cr_supcon_ef_d768", 768, False, 96, 22, 2032, 0.1)):
+        rng = np.random.default_rng(seed)
+        hs, cs, ps = ragged_sizes(rng, b, cmax=40)
+        if name == "cr_supcon_d128":
+            cs[-1], ps[-1] = 2, 1  # the 41st impression is alone in its step
+            cs[8:16] = [3] * 8  # a step without any positive -> `pos_mask.any()` guard (losses.py:22)
+            ps[8:16] = [0] * 8
+        bhv = make_behaviours(rng, n_news, hs, cs, ps)
+        tab = table(n_news, dim, 1234)
+        torch.manual_seed(seed)
+        with stable_argsort():
+            ref = run_reference_cr(tab, bhv, late_fusion=late, supcon_loss=True, temperature=T)
+        assert ref["step_losses"][-1] == 0.0 or name != "cr_supcon_d128"
+        save(name, table=tab.numpy(), temperature=np.float32(T), **bhv_arrays(bhv), **{k.replace("/", "_"): v for k, v in ref.items()})
+
     # ---- ensemble: CR + category + sentiment A-Modules, 4 weightings, with aspects ------------------
     rng = np.random.default_rng(2027)
     n_news, dim = 200, 128
@@ -271,6 +323,20 @@ def main() -> None:
         for k, v in ref.items():
             fixture[f"w{w}_" + k.replace("/", "_")] = v
     save("ensemble_d768", **fixture)
+
+    # ---- the baselines' shared epoch end (nrms_plm_module.py:275-313) on the reference's own NRMSPLMModule --------------------
+    rng = np.random.default_rng(2033)
+    n_news = 300
+    hs, cs, ps = ragged_sizes(rng, 48, cmax=45)
+    bhv = make_behaviours(rng, n_news, hs, cs, ps)
+    aspects = {"category": rng.integers(1, 19, n_news).astype(np.int32), "sentiment": rng.integers(1, 4, n_news).astype(np.int32)}
+    c0, c1 = bhv.cand_offsets[11], bhv.cand_offsets[12]
+    aspects["sentiment"][bhv.cand_ids[c0:c1]] = 0  # an impression whose sentiment labels sum to 0 -> the "neg" branch (base.py:114-122)
+    preds = rng.standard_normal(int(bhv.cand_offsets[-1])).astype(np.float32)  # a baseline's click scores: any real numbers
+    with stable_argsort():
+        ref = run_reference_baseline_epoch_end(bhv, preds, aspects)
+    save("baseline_epoch_end", preds=preds, category=aspects["category"], sentiment=aspects["sentiment"], **bhv_arrays(bhv),
+         **{k.replace("/", "_"): v for k, v in ref.items()})
 
     # ---- functional level ------------------------------------------------------------------------------
     g = torch.Generator().manual_seed(5)

@@ -78,6 +78,45 @@ encs = ens._b200_encoders()
 assert len(encs) == 2 and encs[0] is ens.cr_module.news_encoder and encs[1] is ens.a_module_categ.news_encoder  # sent_weight 0: not loaded
 assert ens._b200_weights() == [1.0, 0.3] and ens._b200_zscore and not ens._b200_with_auc and ens._b200_loss() is None
 assert modules.EnsembleModuleB200(**dict(EKW, sent_weight=0.5), scorer="b200_cached")._b200_weights() == [1.0, 0.3, 0.5]
+# ---- model.aspect_weights: a sweep through the reference's real EnsembleModule constructor --------------------------------
+sweep = modules.EnsembleModuleB200(**dict(EKW, categ_weight=0, sent_weight=0), aspect_weights=[[0, 0], [0.2, 0], [0.4, 0.1]])
+assert isinstance(sweep, ref_ens.EnsembleModule) and sweep.hparams["categ_weight"] == 0  # the reference's own hparams are untouched
+assert hasattr(sweep, "a_module_categ") and hasattr(sweep, "a_module_sent")  # loaded for the sweep although the scalar weights are 0
+assert sweep.a_module_categ.tag == "categ" and sweep.a_module_sent.tag == "sent"
+assert sweep._b200_weights() == [[1.0, 0.0, 0.0], [1.0, 0.2, 0.0], [1.0, 0.4, 0.1]] and len(sweep._b200_encoders()) == 3
+only_c = modules.EnsembleModuleB200(**dict(EKW, categ_weight=0, sent_weight=0), aspect_weights=[[0.1, 0], [0.3, 0]])
+assert not hasattr(only_c, "a_module_sent") and only_c._b200_weights() == [[1.0, 0.1], [1.0, 0.3]]
+try:
+    modules.EnsembleModuleB200(**EKW, aspect_weights=[[0.1, 0.2, 0.3]])
+    raise SystemExit("a malformed aspect_weights was accepted")
+except ValueError:
+    pass
+
+# ---- B200MetricsMixin on a real baseline of the reference (nrms_plm_module.py) ---------------------------------------------
+import manner.models.baselines.nrms_plm_module as ref_nrms
+
+ref_nrms.NewsEncoder = TinyEncoder
+ref_nrms.UserEncoder = TinyEncoder
+
+
+class NRMSModuleB200(modules.B200MetricsMixin, ref_nrms.NRMSPLMModule):
+    pass
+
+
+nrms = NRMSModuleB200(plm_model="", frozen_layers=[], dropout_probability=0.2, text_embedding_dim=16, num_attention_heads=2, query_vector_dim=8,
+                      num_categ_classes=19, num_sent_classes=4, optimizer=None)
+mro = [c.__name__ for c in type(nrms).__mro__]
+assert mro.index("B200MetricsMixin") < mro.index("NRMSPLMModule")
+assert type(nrms).on_test_epoch_end is modules.B200MetricsMixin.on_test_epoch_end and type(nrms).test_step is ref_nrms.NRMSPLMModule.test_step
+assert set(nrms.keys) == set(nrms.test_step_outputs) and "hist_sentiments" in nrms.keys  # the buffers the mixin reads
+nrms.test_step_outputs["preds"].append(torch.zeros(3))
+try:
+    for k in nrms.keys[1:]:
+        nrms.test_step_outputs[k].append(torch.zeros(3, dtype=torch.long))
+    nrms.on_test_epoch_end()
+    raise SystemExit("the mixin computed on CPU tensors")
+except RuntimeError as e:
+    assert "no CPU path" in str(e)
 print("dropin ok")
 '''
 

@@ -131,8 +131,34 @@ def test_cross_entropy_loss_matches_reference_golden(golden_dir, evaluator_cls, 
     np.testing.assert_array_equal(res.sums[0][:5], base.sums[0][:5])
 
 
-def test_supcon_loss_matches_restatement(evaluator_cls):
-    """PARITY UNPINNED (pytorch_metric_learning absent): against oracle.supcon_step_loss."""
+@pytest.mark.parametrize("name", ["cr_supcon_d128", "cr_supcon_ef_d768"])
+def test_supcon_loss_matches_reference_golden(golden_dir, evaluator_cls, name):
+    """test/loss with supcon_loss=True (the reference default, what ModelCheckpoint(monitor="val/loss") watches): against the
+    per-step values of the reference's OWN SupConLoss (components/losses.py:6-40 run on the pytorch_metric_learning base
+    restated in oracle/ref_stubs.py), late fusion and early fusion, including both step-level guards."""
+    z = np.load(os.path.join(golden_dir, name + ".npz"))
+    table, bhv, T = torch.from_numpy(z["table"]), _bhv(z), float(z["temperature"])
+    att = [(torch.from_numpy(z["att_weight"]), torch.from_numpy(z["att_bias"]), torch.from_numpy(z["att_query"]))] if "att_weight" in z else None
+    ev = evaluator_cls([table], attention=att)
+    res = ev.evaluate(ev.upload(bhv, step_batch=8), loss="supcon", temperature=T, want_per_impression=True, want_scores=True)
+    want = float(z["test_loss"])
+    assert abs(res.loss - want) <= 1e-5 * abs(want), (res.loss, want)
+    # per step: mean of the non-zero per-impression losses == the reference's step losses, 0 where a step-level guard fired
+    per = res.per_impression.cpu().numpy()[0][:, nat.M_LOSS].astype(np.float64)
+    lab, off = bhv.labels, bhv.cand_offsets
+    for s_i, lo in enumerate(range(0, bhv.n_impressions, 8)):
+        hi = min(lo + 8, bhv.n_impressions)
+        pos = int(lab[off[lo]:off[hi]].sum())
+        neg = int(off[hi] - off[lo]) - pos
+        guard = (pos <= 1 and neg <= 1) or pos == 0 or neg == 0
+        nz = per[lo:hi][per[lo:hi] > 0]
+        mine = 0.0 if (guard or nz.size == 0) else nz.mean()
+        assert abs(mine - float(z["step_losses"][s_i])) <= 1e-5 * max(1.0, abs(float(z["step_losses"][s_i]))), (s_i, mine, float(z["step_losses"][s_i]))
+    np.testing.assert_allclose(res.scores.cpu().numpy(), z["preds"], rtol=2e-5, atol=2e-6)
+
+
+def test_supcon_loss_larger_set_against_oracle(evaluator_cls):
+    """A larger behaviour set against the oracle (itself pinned on the reference's SupConLoss by tests/test_oracle.py)."""
     n_news, dim = 300, 128
     bhv = mdata.synth_behaviours(n_news, 83, seed=21, cand_window=200)
     table = mdata.synth_table(n_news, dim, 5)
@@ -155,3 +181,11 @@ def test_step_loss_kernel_known_answers():
     assert sc[1] == 3 and sc[0] == 9.0
     z = ops.step_loss(torch.zeros(4, device="cuda"), 2, nat.LOSS_SUPCON).cpu().numpy()
     assert z[0] == 0.0 and z[1] == 2
+    # step-level guards of components/losses.py:15-16,22 (need the labels): steps of 2 impressions
+    off = torch.tensor([0, 1, 2, 5, 8, 10, 12, 13], dtype=torch.int32, device="cuda")
+    lab = torch.tensor([1, 0,  1, 0, 0, 1, 0, 0,  1, 1, 1, 1,  1], dtype=torch.uint8, device="cuda")
+    g = ops.step_loss(loss, 2, nat.LOSS_SUPCON, off, lab).cpu().numpy()
+    # step 0: one positive + one negative in total -> 0; step 1: (3 + 0 nonzero -> 3)... values [1,3][0,2][0,0][5]
+    # step 0 = impressions 0,1 (labels [1],[0]) -> guard 1; step 1 = impressions 2,3 -> mean of {2} = 2; step 2 = impressions 4,5 all
+    # positive -> no negative -> 0; step 3 = impression 6, a single positive -> 0
+    assert g[1] == 4 and g[0] == 2.0, g

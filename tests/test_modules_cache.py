@@ -210,6 +210,88 @@ def test_ensemble_step_mode_dropin_logs_the_reference_values(golden_dir):
 
 
 @pytest.mark.gpu
+def test_ensemble_aspect_weight_sweep_logs_every_weighting(golden_dir):
+    """`model.aspect_weights` (EnsembleModuleB200(aspect_weights=[[wc, ws], ...])): all weightings of the golden from ONE pass per
+    step, logged as test/<metric>/w<i> -- each equal to what the reference's EnsembleModule logged when it was run with that
+    (categ_weight, sent_weight) pair."""
+    from manner_b200.modules import B200EvalMixin
+
+    class FakeSweep(B200EvalMixin, torch.nn.Module):
+        _b200_zscore = True
+        _b200_with_auc = False
+
+        def __init__(self, tables, grid):
+            super().__init__()
+            self.encs = torch.nn.ModuleList([TableEncoder(t) for t in tables])
+            self.grid, self.logged = grid, {}
+
+        def _b200_encoders(self):
+            return list(self.encs)
+
+        def _b200_weights(self):
+            return [[1.0, wc, ws] for wc, ws in self.grid]  # what EnsembleModuleB200._b200_weights returns for a sweep
+
+        def log_dict(self, values, **kw):
+            self.logged.update(values)
+
+    z = np.load(os.path.join(golden_dir, "ensemble_d128.npz"))
+    bhv = _bhv(z)
+    aspects = {"category": z["category"], "sentiment": z["sentiment"]}
+    tabs = [torch.from_numpy(z[f"table{m}"]) for m in range(3)]
+    grid = z["weightings"].tolist()
+    model = FakeSweep(tabs, grid).cuda()
+    for i, lo in enumerate(range(0, bhv.n_impressions, 8)):
+        model.test_step(mo.step_batch(bhv, lo, min(lo + 8, bhv.n_impressions), aspects), i)
+    model.on_test_epoch_end()
+    for w in range(len(grid)):
+        for k in ("ndcg@5", "ndcg@10", "categ_div@5", "categ_div@10", "sent_div@5", "sent_div@10",
+                  "categ_pers@5", "categ_pers@10", "sent_pers@5", "sent_pers@10"):
+            assert abs(model.logged[f"test/{k}/w{w}"] - float(z[f"w{w}_test_{k}"])) <= 1e-6, (w, k)
+    assert "test/ndcg@5" not in model.logged  # a sweep logs per-weighting keys only
+
+
+@pytest.mark.gpu
+def test_baseline_metrics_mixin_logs_what_the_reference_baseline_logged(golden_dir):
+    """B200MetricsMixin on the epoch-end seam of the reference's nine baselines: the golden holds what the reference's own
+    NRMSPLMModule.on_test_epoch_end (nrms_plm_module.py:275-313) logged for these step outputs."""
+    from manner_b200.modules import B200MetricsMixin
+
+    class FakeBaseline(B200MetricsMixin, torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.keys = ["preds", "targets", "cand_news_size", "hist_news_size", "target_categories", "target_sentiments",
+                         "hist_categories", "hist_sentiments"]  # nrms_plm_module.py:105-111
+            self.test_step_outputs = {k: [] for k in self.keys}
+            self.hparams = {"num_categ_classes": 19, "num_sent_classes": 4}
+            self.logged = {}
+
+        def log_dict(self, values, **kw):
+            self.logged.update(values)
+
+    z = np.load(os.path.join(golden_dir, "baseline_epoch_end.npz"))
+    bhv = _bhv(z)
+    model = FakeBaseline()
+    ho, co = bhv.hist_offsets, bhv.cand_offsets
+    for lo in range(0, bhv.n_impressions, 8):  # what the baseline's test_step appends (:258-272): preds on the device, sizes on the host
+        hi = min(lo + 8, bhv.n_impressions)
+        c_ids, h_ids = bhv.cand_ids[co[lo]:co[hi]], bhv.hist_ids[ho[lo]:ho[hi]]
+        out = model.test_step_outputs
+        out["preds"].append(torch.from_numpy(z["preds"][co[lo]:co[hi]]).cuda())
+        out["targets"].append(torch.from_numpy(bhv.labels[co[lo]:co[hi]].astype(np.int64)).cuda())
+        out["cand_news_size"].append(torch.from_numpy(np.diff(co[lo:hi + 1]).astype(np.int64)))
+        out["hist_news_size"].append(torch.from_numpy(np.diff(ho[lo:hi + 1]).astype(np.int64)))
+        out["target_categories"].append(torch.from_numpy(z["category"][c_ids].astype(np.int64)).cuda())
+        out["target_sentiments"].append(torch.from_numpy(z["sentiment"][c_ids].astype(np.int64)).cuda())
+        out["hist_categories"].append(torch.from_numpy(z["category"][h_ids].astype(np.int64)).cuda())
+        out["hist_sentiments"].append(torch.from_numpy(z["sentiment"][h_ids].astype(np.int64)).cuda())
+    model.on_test_epoch_end()
+    for k in ("auc", "mrr", "ndcg@5", "ndcg@10", "categ_div@5", "categ_div@10", "sent_div@5", "sent_div@10",
+              "categ_pers@5", "categ_pers@10", "sent_pers@5", "sent_pers@10"):
+        assert abs(model.logged["test/" + k] - float(z["test_" + k])) <= 1e-6, (k, model.logged["test/" + k], float(z["test_" + k]))
+    assert all(len(v) == 0 for v in model.test_step_outputs.values())  # buffers cleared like the reference does
+
+
+@pytest.mark.gpu
 def test_cached_mode_table_builder_feeds_the_evaluator(golden_dir):
     from manner_b200.evaluator import ScoreEvaluator
 

@@ -60,8 +60,23 @@ def test_early_fusion_epoch_matches_reference_golden(golden_dir, name):
         np.testing.assert_allclose((table[cids] @ user).numpy(), z["preds"][bhv.cand_offsets[i] : bhv.cand_offsets[i + 1]], rtol=2e-5, atol=2e-6)
 
 
+@pytest.mark.parametrize("name", ["cr_supcon_d128", "cr_supcon_ef_d768"])
+def test_supcon_loss_matches_reference_golden(golden_dir, name):
+    """supcon_loss=True (the reference default): the goldens hold what the reference's OWN SupConLoss.compute_loss / _compute_loss
+    (components/losses.py:6-40) returned per step, including a step without any positive (losses.py:22) and a one-impression
+    step with one positive and one negative (the `all(len(x) <= 1 ...)` guard, :15-16)."""
+    z = np.load(os.path.join(golden_dir, name + ".npz"))
+    bhv = mo.Behaviours(z["hist_offsets"], z["hist_ids"], z["cand_offsets"], z["cand_ids"], z["labels"])
+    att = mo.Attention(torch.from_numpy(z["att_weight"]), torch.from_numpy(z["att_bias"]), torch.from_numpy(z["att_query"])) if "att_weight" in z else None
+    ref = mo.cr_eval_epoch(torch.from_numpy(z["table"]), bhv, attention=att, supcon_temperature=float(z["temperature"]))
+    np.testing.assert_allclose(ref["step_losses"], z["step_losses"], rtol=1e-6, atol=0)
+    assert ref["metrics"]["test/loss"] == pytest.approx(float(z["test_loss"]), rel=1e-6)
+    if name == "cr_supcon_d128":
+        assert z["step_losses"][1] == 0.0 and z["step_losses"][-1] == 0.0  # the two step-level guards fired in the reference
+
+
 def test_supcon_restatement_known_answers():
-    """PARITY UNPINNED (pytorch_metric_learning absent): hand-computed values of the restated SupCon step loss."""
+    """Hand-computed values of the SupCon step loss (the restatement is pinned on the reference's own loss by the goldens above)."""
     bhv = mo.Behaviours(np.array([0, 1, 2, 3], np.int32), np.zeros(3, np.int32), np.array([0, 3, 5, 7], np.int32), np.zeros(7, np.int32),
                         np.array([1, 0, 0, 1, 1, 0, 0], np.uint8))
     batch = mo.step_batch(bhv, 0, 3)
