@@ -293,7 +293,7 @@ def run_gpu_arm(args) -> None:
         attention = [(torch.randn(200, dim, generator=ga) * dim ** -0.5, torch.randn(200, generator=ga) * 0.1, torch.rand(200, generator=ga) * 0.2 - 0.1)]
         attention += [None] * (len(tables) - 1)
     step_batch = 8 if (args.early_fusion or args.loss) else None  # configs/data/mind_rec.yaml:51
-    ev = ScoreEvaluator(tables, dev, attention=attention)
+    ev = ScoreEvaluator(tables, dev, attention=attention, exchange=args.eval_exchange)
     pinned = ev.pin(bhv, step_batch)
     # multi-GPU pooled AUC: agree once (outside the timed loop) on the largest per-rank positive count
     pos_cap = mdist.agree_pos_cap(int(bhv.labels.sum()), dev) if distributed else None
@@ -714,6 +714,8 @@ def main() -> None:
     ap.add_argument("--users", type=int, default=37888, help="retrieval mode: users per step (37 888 = 2 full waves of 148 CTAs x 128 rows)")
     ap.add_argument("--catalog-per-gpu", type=int, default=1_250_000, help="retrieval mode: catalogue rows per GPU (10 M over 8)")
     ap.add_argument("--exchange", default="all_gather", choices=["all_gather", "all_to_all", "p2p"])
+    ap.add_argument("--eval-exchange", default="p2p", choices=["p2p", "nccl"],
+                    help="multi-GPU evaluation: fused stores into the peers' mailboxes over NVLink (default) or the three NCCL collectives")
     ap.add_argument("--retrieval-pair", type=int, default=None, help="retrieval kernel: 1 = CTA pairs (cta_group::2), 0 = one CTA per tile")
     ap.add_argument("--retrieval-diag", type=int, default=0, help="DIAGNOSTIC: 1/2 disable parts of the retrieval epilogue (results invalid)")
     ap.add_argument("--variant", type=int, default=None)

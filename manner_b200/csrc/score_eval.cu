@@ -78,6 +78,7 @@ struct EvalParams {
   const uint8_t* slot_of;         // [n_news] slot of a news id, kHotCold = not cached
   int hot_cap;                    // slots per module the launch reserved shared memory for
   int hot_bytes;                  // bytes of the cache at the front of the CTA's shared memory
+  int upart_off;                  // byte offset, in the per-warp area, of the three bf16 parts of the user vector (tensor-core path)
   int has_aspects;                // the per-warp area holds the aspect buffers
   int comb_alias;                 // one weighting: the combined scores overwrite module 0's (no separate buffer)
 };
@@ -255,12 +256,20 @@ __device__ __noinline__ float personalization_value(const uint8_t* top, int kk, 
 //
 // HOT: rows whose id has a slot in the CTA's shared-memory hot-row cache (`slot_of[id] != kHotCold`; see score_eval_stream_kernel)
 // are read from there with LDS.128 instead of through the L2 -> SM crossbar; the arithmetic is the same either way.
-template <typename T, int NV, int R, bool EXACT, int POLICY, bool ATTN, bool HOT = false>
+//
+// MMA (bf16 rows, reference width, contiguous rows): the candidate dot products run on the tensor cores (mma.sync m16n8k16,
+// fp32 accumulation) instead of 24 unpack + 24 FMA instructions per lane and row -- the bf16 kernel is issue-bound, not
+// bandwidth-bound (profiles/r2_score_eval_bf16_ncu.json: 65 % issue-active at 41 % of the L2 roof).  The fp32 user vector is
+// split exactly into three bf16 vectors u = hi + mid + lo (8 significand bits each) that occupy three of the eight MMA
+// columns; 16 candidate rows are the M dimension.  Products of bf16 pairs are exact in fp32, sums are fp32: the same
+// "bf16 storage, fp32 arithmetic" contract, in tensor-core summation order.
+template <typename T, int NV, int R, bool EXACT, int POLICY, bool ATTN, bool HOT = false, bool MMA = false>
 __device__ __forceinline__ int gather_pool_score(const T* __restrict__ table, long long row_stride, int vec_per_row, long long n_news,
                                                  const int32_t* __restrict__ hist_ids, int H, const int32_t* __restrict__ cand_ids, int C,
                                                  float* __restrict__ s_out, const float* __restrict__ logits, int n_pad,
                                                  const void* const* __restrict__ shard_base, int shard_shift,
-                                                 const unsigned char* hot_rows = nullptr, const uint8_t* __restrict__ slot_of = nullptr) {
+                                                 const unsigned char* hot_rows = nullptr, const uint8_t* __restrict__ slot_of = nullptr,
+                                                 unsigned char* upart = nullptr) {
   constexpr int E = Elem<T>::E;
   constexpr int kRowBytes = NV * 32 * 16;
   const int lane = threadIdx.x & 31;
@@ -371,6 +380,88 @@ __device__ __forceinline__ int gather_pool_score(const T* __restrict__ table, lo
     for (int v = 0; v < NV; ++v)
 #pragma unroll
       for (int e = 0; e < E; ++e) u[v * E + e] = (vmask[v] != 0.0f) ? u[v * E + e] : 0.0f;
+  }
+
+  if constexpr (MMA) {
+    static_assert(Elem<T>::E == 8 && NV == 3 && EXACT && POLICY == 0 && !HOT, "tensor-core candidate scoring: bf16 rows of the reference width");
+    __builtin_assume(__isShared(upart));
+    constexpr int kRow = 1536;  // bytes per row / per u part
+    // u = hi + mid + lo, each a bf16 vector in the rows' own memory layout
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+      uint4 part[3];
+      unsigned* w[3] = {&part[0].x, &part[1].x, &part[2].x};
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        unsigned packed[3] = {0u, 0u, 0u};
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          float x = u[v * 8 + 2 * q + h];
+#pragma unroll
+          for (int t = 0; t < 3; ++t) {
+            const __nv_bfloat16 b = __float2bfloat16_rn(x);
+            packed[t] |= (unsigned)__bfloat16_as_ushort(b) << (16 * h);
+            x = __fsub_rn(x, __bfloat162float(b));  // exact: the remainder has at most 16 significant bits
+          }
+        }
+#pragma unroll
+        for (int t = 0; t < 3; ++t) w[t][q] = packed[t];
+      }
+#pragma unroll
+      for (int t = 0; t < 3; ++t) *reinterpret_cast<uint4*>(upart + t * kRow + (256 * v + 8 * lane) * 2) = part[t];
+    }
+    __syncwarp();
+    const int g = lane >> 2, j = lane & 3;
+    const unsigned char* tbytes = reinterpret_cast<const unsigned char*>(table) + 16 * j;
+    const unsigned char* ub = upart + (g < 3 ? g : 0) * kRow + 16 * j;
+#pragma unroll 1
+    for (int b0 = 0; b0 < C; b0 += 32) {
+      const int cnt = min(32, C - b0);
+      int my_id = cand_ids[b0 + ((lane < cnt) ? lane : 0)];
+      if ((unsigned long long)(long long)my_id >= (unsigned long long)n_news) my_id = 0, flags |= MB200_FLAG_BAD_ID;
+#pragma unroll 1
+      for (int h0 = 0; h0 < cnt; h0 += 16) {
+        const int ra = h0 + g, rb = h0 + g + 8;  // MMA rows g and g + 8 of this lane
+        const int ida = __shfl_sync(kFull, my_id, ra < cnt ? ra : 0), idb = __shfl_sync(kFull, my_id, rb < cnt ? rb : 0);
+        const unsigned char* pa = tbytes + (unsigned long long)(unsigned)ida * kRow;
+        const unsigned char* pb = tbytes + (unsigned long long)(unsigned)idb * kRow;
+        float c[4] = {0.f, 0.f, 0.f, 0.f}, d[4] = {0.f, 0.f, 0.f, 0.f};
+        // 6 chunks of 4 blocks of 32 dims (64 B per row and block: lanes j = 0..3 of a row read consecutive 16 B), double buffered
+        uint4 xa[2][4], xb[2][4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) xa[0][k] = __ldg(reinterpret_cast<const uint4*>(pa + 64 * k)), xb[0][k] = __ldg(reinterpret_cast<const uint4*>(pb + 64 * k));
+#pragma unroll
+        for (int ch = 0; ch < 6; ++ch) {
+          if (ch + 1 < 6) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              xa[(ch + 1) & 1][k] = __ldg(reinterpret_cast<const uint4*>(pa + 256 * (ch + 1) + 64 * k));
+              xb[(ch + 1) & 1][k] = __ldg(reinterpret_cast<const uint4*>(pb + 256 * (ch + 1) + 64 * k));
+            }
+          }
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            uint4 uv = make_uint4(0u, 0u, 0u, 0u);
+            if (g < 3) uv = *reinterpret_cast<const uint4*>(ub + 256 * ch + 64 * k);  // columns 0..2 = hi, mid, lo; 3..7 = 0
+            const uint4 a = xa[ch & 1][k], b = xb[ch & 1][k];
+            asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                         : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3]) : "r"(a.x), "r"(b.x), "r"(a.y), "r"(b.y), "r"(uv.x), "r"(uv.y));
+            asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                         : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3]) : "r"(a.z), "r"(b.z), "r"(a.w), "r"(b.w), "r"(uv.z), "r"(uv.w));
+          }
+        }
+        // lane (g, j) holds columns 2j, 2j + 1 of rows g (c0, c1) and g + 8 (c2, c3): score = (hi + mid) + lo
+        float sa = __fadd_rn(__fadd_rn(c[0], d[0]), __fadd_rn(c[1], d[1]));
+        float sb = __fadd_rn(__fadd_rn(c[2], d[2]), __fadd_rn(c[3], d[3]));
+        sa = __fadd_rn(sa, __shfl_xor_sync(kFull, sa, 1));
+        sb = __fadd_rn(sb, __shfl_xor_sync(kFull, sb, 1));
+        if (j == 0) {
+          if (ra < cnt) s_out[b0 + ra] = sa;
+          if (rb < cnt) s_out[b0 + rb] = sb;
+        }
+      }
+    }
+    return flags;
   }
 
 #pragma unroll 1
@@ -806,7 +897,7 @@ __device__ __noinline__ int rank_and_metrics(const EvalParams& p, const WarpSmem
   return warp_flags;
 }
 
-template <typename T, int NV, int R, bool EXACT, int POLICY, int MINB, bool ATTN = false>
+template <typename T, int NV, int R, bool EXACT, int POLICY, int MINB, bool ATTN = false, bool MMA = false>
 __global__ void __launch_bounds__(kThreads, MINB) score_eval_kernel(const __grid_constant__ EvalParams p) {
   extern __shared__ __align__(16) unsigned char smem[];
   const int lane = threadIdx.x & 31;
@@ -853,10 +944,11 @@ __global__ void __launch_bounds__(kThreads, MINB) score_eval_kernel(const __grid
       for (int m = 0; m < p.n_modules; ++m) {
         if (!((p.active_mask >> m) & 1)) continue;
         float* s_m = sm.sc + (size_t)slot * p.cpad;
-        warp_flags |= gather_pool_score<T, NV, R, EXACT, POLICY, ATTN>(reinterpret_cast<const T*>(p.tables[m]), p.row_stride, p.vec_per_row,
-                                                                       p.n_news, p.hist_ids + h0, H, p.cand_ids + c0, C, s_m,
-                                                                       ATTN ? p.attn_logits[m] : nullptr,
-                                                                       (ATTN && p.hist_pad) ? p.hist_pad[i] : 0, p.shard_base[m], p.shard_shift);
+        warp_flags |= gather_pool_score<T, NV, R, EXACT, POLICY, ATTN, false, MMA>(reinterpret_cast<const T*>(p.tables[m]), p.row_stride, p.vec_per_row,
+                                                                                   p.n_news, p.hist_ids + h0, H, p.cand_ids + c0, C, s_m,
+                                                                                   ATTN ? p.attn_logits[m] : nullptr,
+                                                                                   (ATTN && p.hist_pad) ? p.hist_pad[i] : 0, p.shard_base[m], p.shard_shift,
+                                                                                   nullptr, nullptr, MMA ? base + p.upart_off : nullptr);
         __syncwarp();
         if (p.zscore) {
           zscore_inplace(s_m, C, lane);
@@ -1341,7 +1433,10 @@ struct LaunchPlan {
   // streaming kernel only
   int has_aspects = 1, comb_alias = 0;
   int hot_cap = 0, hot_bytes = 0;
+  int upart_off = 0;  // tensor-core bf16 path: where the per-warp area keeps u = hi + mid + lo
 };
+
+constexpr int kUpartBytes = 3 * 768 * 2;
 
 static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
@@ -1354,7 +1449,8 @@ static size_t hot_region_bytes(long long n_news) {
 
 // `stream`: plan for score_eval_stream_kernel (one CTA of kStreamWarps warps per SM; per-warp area trimmed to what the call
 // uses; the rest of the shared memory becomes the hot-row cache, `row_bytes` per row and active module).
-static int make_plan(const mb200_eval_desc* d, int sm_count, int ctas, LaunchPlan* plan, bool stream = false, int row_bytes = 0, bool hot = false) {
+static int make_plan(const mb200_eval_desc* d, int sm_count, int ctas, LaunchPlan* plan, bool stream = false, int row_bytes = 0, bool hot = false,
+                     bool mma = false) {
   const int n_active = __builtin_popcount((unsigned)d->active_modules_mask);
   plan->cpad = (int)align_up((size_t)(d->max_cand > 0 ? d->max_cand : 1), 32);
   // the aspect-weight sweep (lane per weighting: rank_and_metrics -> sweep_weightings) fills only the first kSweepSlots slots
@@ -1374,6 +1470,7 @@ static int make_plan(const mb200_eval_desc* d, int sm_count, int ctas, LaunchPla
                2 * MB200_MAX_CLASSES * sizeof(int) + 64;
   }
   per_warp = align_up(per_warp, 16);
+  if (mma) plan->upart_off = (int)per_warp, per_warp += kUpartBytes;
   plan->smem_per_warp = (int)per_warp;
   plan->smem_per_cta = per_warp * plan->warps_per_cta;
   if (plan->smem_per_cta > kMaxSmemPerCta) return MB200_ERR_UNSUPPORTED;
@@ -1574,7 +1671,7 @@ int score_eval(const mb200_eval_desc* d, cudaStream_t stream) {
   LaunchPlan plan;
   KernelFn kern = nullptr;
   bool stream_path = d->dim == 768 && d->row_stride == 768 && !attn && !sharded && (variant >= 7 && variant <= 10) && d->n_news < (1ll << 31);
-  bool hot = false;
+  bool hot = false, mma = false;
   if (stream_path) {
     if (make_plan(d, sms, 1, &plan, true, vec_per_row * 16, variant != 7 && variant != 10) != MB200_OK) stream_path = false;  // per-warp areas too large for 16 warps
   }
@@ -1585,9 +1682,13 @@ int score_eval(const mb200_eval_desc* d, cudaStream_t stream) {
     st = cuda_status(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem_per_cta), "cudaFuncSetAttribute");
     if (st != MB200_OK) return st;
   } else {
-    kern = (d->dtype == MB200_F32) ? select_kernel<float>(vec_per_row, attn, sharded) : select_kernel<__nv_bfloat16>(vec_per_row, attn, sharded);
+    // bf16 rows of the reference width: candidate dot products on the tensor cores (default; tuning variant 11 forces it, any other
+    // explicit variant selects the FMA kernels)
+    mma = d->dtype == MB200_BF16 && d->dim == 768 && d->row_stride == 768 && !attn && !sharded && (variant < 0 || variant == 11);
+    if (mma) kern = score_eval_kernel<__nv_bfloat16, 3, 4, true, 0, 5, false, true>;
+    else kern = (d->dtype == MB200_F32) ? select_kernel<float>(vec_per_row, attn, sharded) : select_kernel<__nv_bfloat16>(vec_per_row, attn, sharded);
     if (kern == nullptr) return MB200_ERR_UNSUPPORTED;  // row-sharded tables: reference width, late fusion only
-    st = make_plan(d, sms, 1, &plan);  // shared-memory sizes first: they decide how many CTAs fit
+    st = make_plan(d, sms, 1, &plan, false, 0, false, mma);  // shared-memory sizes first: they decide how many CTAs fit
     if (st != MB200_OK) return st;
     if (plan.smem_per_cta > 48 * 1024) {
       st = cuda_status(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem_per_cta), "cudaFuncSetAttribute");
@@ -1599,7 +1700,7 @@ int score_eval(const mb200_eval_desc* d, cudaStream_t stream) {
     if (st != MB200_OK) return st;
     if (resident < 1) return MB200_ERR_UNSUPPORTED;
     const int want = tuning().ctas_per_sm > 0 ? tuning().ctas_per_sm : resident;
-    st = make_plan(d, sms, want < resident ? want : resident, &plan);
+    st = make_plan(d, sms, want < resident ? want : resident, &plan, false, 0, false, mma);
     if (st != MB200_OK) return st;
   }
   const size_t need = plan.bounds_bytes + plan.partials_bytes + (hot ? hot_region_bytes(d->n_news) : 0);
@@ -1630,7 +1731,7 @@ int score_eval(const mb200_eval_desc* d, cudaStream_t stream) {
   p.hist_pad = d->hist_pad, p.cand_pad = d->cand_pad, p.loss_per_impr = d->loss_per_impression;
   p.loss_kind = d->loss_kind, p.loss_temperature = d->loss_temperature;
   p.has_aspects = plan.has_aspects, p.comb_alias = plan.comb_alias;
-  p.hot_cap = plan.hot_cap, p.hot_bytes = plan.hot_bytes;
+  p.hot_cap = plan.hot_cap, p.hot_bytes = plan.hot_bytes, p.upart_off = plan.upart_off;
 
   KernelTimer* timer = tuning().time_kernel ? timer_for(device) : nullptr;
   int launches = 3;

@@ -256,9 +256,10 @@ def step_loss(loss_per_impression: Tensor, step: int, loss_kind: int, cand_offse
 
 
 @torch.library.custom_op("manner_b200::pooled_auc", mutates_args=())
-def pooled_auc(preds: Tensor, labels: Tensor, sigmoid_mode: int, flags: Optional[Tensor]) -> Tensor:
+def pooled_auc(preds: Tensor, labels: Tensor, sigmoid_mode: int, flags: Optional[Tensor], max_positives: int = 0) -> Tensor:
     """Pooled AUROC of torchmetrics' ``AUROC(task="binary")`` (cr_module.py:81,273) on one device.
-    Returns fp64 [4] = (auc, P, N, sum2).  sigmoid_mode 0 never / 1 always / 2 from ``flags``."""
+    Returns fp64 [4] = (auc, P, N, sum2).  sigmoid_mode 0 never / 1 always / 2 from ``flags``.  ``max_positives``: an upper
+    bound on the label sum when the caller knows one (only the positives are sorted: it sizes that sort; 0 = unknown)."""
     lib = nat.lib()
     _require_cuda("preds", preds, torch.float32)
     _require_cuda("labels", labels, torch.uint8)
@@ -271,7 +272,7 @@ def pooled_auc(preds: Tensor, labels: Tensor, sigmoid_mode: int, flags: Optional
         out = torch.empty(4, dtype=torch.float64, device=dev)
         ws = _workspace(dev, stream, "auc", lib.mb200_pooled_auc_workspace_bytes(n))
         nat.check(
-            lib.mb200_pooled_auc(preds.data_ptr(), labels.data_ptr(), n, sigmoid_mode, _ptr(flags), ws.data_ptr(), ws.numel(),
+            lib.mb200_pooled_auc(preds.data_ptr(), labels.data_ptr(), n, sigmoid_mode, _ptr(flags), int(max_positives), ws.data_ptr(), ws.numel(),
                                  out.data_ptr(), stream),
             "mb200_pooled_auc",
         )
@@ -279,7 +280,7 @@ def pooled_auc(preds: Tensor, labels: Tensor, sigmoid_mode: int, flags: Optional
 
 
 @pooled_auc.register_fake
-def _(preds, labels, sigmoid_mode, flags):
+def _(preds, labels, sigmoid_mode, flags, max_positives=0):
     return torch.empty(4, dtype=torch.float64, device=preds.device)
 
 
@@ -307,6 +308,23 @@ def auc_build_and_sort(preds: Tensor, labels: Tensor, sigmoid_mode: int, flags: 
         ws = _workspace(dev, stream, "sort", lib.mb200_auc_sort_workspace_bytes(n))
         nat.check(lib.mb200_auc_sort_keys(keys.data_ptr(), sorted_keys.data_ptr(), n, ws.data_ptr(), ws.numel(), stream), "mb200_auc_sort_keys")
     return sorted_keys, pos_keys, n_pos
+
+
+def auc_build_keys(preds: Tensor, labels: Tensor, sigmoid_mode: int, flags: Optional[Tensor]) -> Tuple[Tensor, Tensor, Tensor]:
+    """Stage 1 alone: (keys uint32-as-int32 [n] with the positives marked, positive keys [n] with the first n_pos entries valid,
+    n_pos int64 [1]) -- what the fused multi-GPU exchange consumes (dist.P2PExchange)."""
+    lib = nat.lib()
+    _require_cuda("preds", preds, torch.float32)
+    _require_cuda("labels", labels, torch.uint8)
+    dev, n = preds.device, preds.numel()
+    with torch.cuda.device(dev):
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        keys = torch.empty(n, dtype=torch.int32, device=dev)
+        pos_keys = torch.empty(n, dtype=torch.int32, device=dev)
+        n_pos = torch.empty(1, dtype=torch.int64, device=dev)
+        nat.check(lib.mb200_auc_build_keys(preds.data_ptr(), labels.data_ptr(), n, sigmoid_mode, _ptr(flags), keys.data_ptr(), pos_keys.data_ptr(),
+                                           n_pos.data_ptr(), stream), "mb200_auc_build_keys")
+    return keys, pos_keys, n_pos
 
 
 def auc_rank_sum(sorted_keys: Tensor, n_pos_local: Tensor, pos_keys: Tensor, n_pos: Tensor, sum2: Tensor) -> None:
