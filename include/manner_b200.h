@@ -266,14 +266,11 @@ MB200_API int mb200_auc_rank_sum(const uint32_t* sorted_keys, int64_t n_sorted, 
                        const uint32_t* pos_keys, int64_t pos_capacity, const int64_t* n_pos /* device: entries of pos_keys to use */,
                        uint64_t* sum2 /* device, accumulated (caller zeroes) */, void* stream);
 
-/* Single-GPU convenience.  out (device, 4 doubles) = {auc, P, N, sum2}.  auc = 0 when P == 0 or N == 0 (torchmetrics returns 0
- * with a warning).  Evaluates the same statistic from the other side: only the POSITIVE keys are sorted and every negative
- * binary-searches that small list (sum2 = sum over negatives of 2 #(pos > n) + #(pos == n)).  `max_positives` = an upper bound
- * on the number of positives the caller knows (e.g. the label sum; it sizes the sort), 0 = unknown (the sort then covers n
- * keys).  More positives than the bound: auc = NaN. */
+/* Single-GPU convenience: the three stages + the division.  out (device, 4 doubles) = {auc, P, N, sum2}.
+ * auc = 0 when P == 0 or N == 0 (torchmetrics returns 0 with a warning). */
 MB200_API size_t mb200_pooled_auc_workspace_bytes(int64_t n);
-MB200_API int mb200_pooled_auc(const float* preds, const uint8_t* labels, int64_t n, int sigmoid_mode, const int32_t* flags,
-                               int64_t max_positives, void* workspace, size_t workspace_bytes, double* out, void* stream);
+MB200_API int mb200_pooled_auc(const float* preds, const uint8_t* labels, int64_t n, int sigmoid_mode,
+                     const int32_t* flags, void* workspace, size_t workspace_bytes, double* out, void* stream);
 
 /*
  * Full-catalog retrieval (BASELINE.json configs[4]; no reference counterpart -- the reference scores only an
@@ -327,15 +324,17 @@ MB200_API int mb200_merge_topk(const float* scores, const int64_t* ids, int shar
  * the contract is "same numbers as one GPU").  Replaces the NCCL all-reduce of the metric payload, the all-gather of the
  * positive keys and the all-reduce of the AUROC statistics: `mb200_exchange_post` STORES this rank's payload (the packed `sums` of
  * mb200_score_eval with pack_payload) and the raw keys of its positives into slot `my_rank` of EVERY rank's mailbox over
- * NVLink / NVSwitch peer memory; `mb200_exchange_finish` (same stream, after it) waits for all ranks' stores, sums the payloads
- * in rank order into `out_payload` (bit-identical on every rank), sorts ALL ranks' positives (a few % of the rows), streams this
- * rank's negatives against them, exchanges the three additive integers the same way and writes their sums to `out_stats` =
- * {sum2, P, N} (auc = sum2 / (2 P N)).  mailbox[r] = rank r's mailbox as mapped in THIS process (mb200_ipc_open; own = local
- * memory), mb200_exchange_mailbox_bytes() bytes each, zero-filled once before the first exchange.  `epoch` = 1, 2, 3, ... must
- * advance by one per exchange on every rank.  Keys: mb200_auc_build_keys with sigmoid_mode 0 (raw score keys, NOT sorted); the
- * sigmoid rule of torchmetrics' AUROC is decided from the reduced payload (entry `outside_index` > 0 on any rank) and applied to
- * both sides inside `_finish`.  Waits are bounded (4 s -> MB200_FLAG_EXCHANGE_TIMEOUT).  One process per GPU: the kernels of
- * different ranks run on different GPUs.
+ * NVLink / NVSwitch peer memory (and, while those stores fly, prepares the sigmoid keys of its sorted negatives);
+ * `mb200_exchange_finish` (same stream, after it) waits for all ranks' stores, sums the payloads in rank order into
+ * `out_payload` (bit-identical on every rank), ranks all ranks' positives against this rank's sorted negatives, exchanges the
+ * three additive integers the same way and writes their sums to `out_stats` = {sum2, P, N} (auc = sum2 / (2 P N)).
+ * mailbox[r] = rank r's mailbox as mapped in THIS process (mb200_ipc_open; own = local memory),
+ * mb200_exchange_mailbox_bytes() bytes each, zero-filled once before the first exchange.  `epoch` = 1, 2, 3, ... must advance by
+ * one per exchange on every rank.  Keys: mb200_auc_build_keys with sigmoid_mode 0 + mb200_auc_sort_keys (RAW score order: no
+ * dependency on the other ranks, so the sort overlaps their kernels); whether torchmetrics' AUROC applies the sigmoid is only
+ * known from the reduced payload (entry `outside_index` > 0 on any rank) -- the fp32 sigmoid is monotone, so the raw order is a
+ * valid order of the sigmoid keys too (ties only merge) and the search simply runs on the prepared sigmoid keys.
+ * Waits are bounded (4 s -> MB200_FLAG_EXCHANGE_TIMEOUT).  One process per GPU: the kernels of different ranks run on different GPUs.
  */
 typedef struct mb200_exchange_desc {
   uint32_t struct_size; /* = sizeof(mb200_exchange_desc) */
@@ -344,23 +343,23 @@ typedef struct mb200_exchange_desc {
   uint32_t epoch;       /* >= 1 */
   int32_t n_payload;    /* doubles in the payload */
   int32_t outside_index; /* payload entry that is > 0 when a score of that rank was outside [0,1]; -1 = never apply the sigmoid */
-  int64_t pos_capacity; /* >= 1: positive keys a mailbox slot can hold (same on every rank) */
+  int64_t pos_capacity; /* positive keys a mailbox slot can hold (same on every rank) */
   void* mailbox[MB200_MAX_TABLE_SHARDS];
   const double* payload;      /* [n_payload] this rank's */
   const uint32_t* pos_keys;   /* this rank's positive keys (mb200_auc_build_keys, sigmoid_mode 0) */
   const int64_t* n_pos;       /* device: how many */
-  const uint32_t* keys;       /* [n_rows] mb200_auc_build_keys' neg_keys: raw keys, positives marked */
-  int64_t n_rows;             /* 0 = no pooled AUROC wanted (keys / pos_keys unused) */
+  const uint32_t* sorted_neg; /* [n_rows] mb200_auc_sort_keys output: negatives in [0, n_rows - *n_pos) */
+  int64_t n_rows;             /* 0 = no pooled AUROC wanted */
   double* out_payload;        /* [n_payload] sums over ranks */
   int64_t* out_stats;         /* [3] */
   int32_t* flags;             /* optional: TWO int32 (an int64 slot), zeroed by _post, then OR-ed with MB200_FLAG_EXCHANGE_TIMEOUT /
                                  MB200_FLAG_POS_OVERFLOW by _finish */
-  void* workspace;            /* >= mb200_exchange_workspace_bytes(n_ranks, pos_capacity), 256-byte aligned, this rank's own */
+  void* workspace;            /* >= mb200_exchange_workspace_bytes(n_rows), 256-byte aligned, this rank's own */
   size_t workspace_bytes;
 } mb200_exchange_desc;
 
 MB200_API size_t mb200_exchange_mailbox_bytes(int n_ranks, int n_payload, int64_t pos_capacity);
-MB200_API size_t mb200_exchange_workspace_bytes(int n_ranks, int64_t pos_capacity);
+MB200_API size_t mb200_exchange_workspace_bytes(int64_t n_rows);
 MB200_API int mb200_exchange_post(const mb200_exchange_desc* desc, void* stream);
 MB200_API int mb200_exchange_finish(const mb200_exchange_desc* desc, void* stream);
 

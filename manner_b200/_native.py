@@ -149,7 +149,7 @@ class ExchangeDesc(Structure):
         ("payload", c_void_p),
         ("pos_keys", c_void_p),
         ("n_pos", c_void_p),
-        ("keys", c_void_p),
+        ("sorted_neg", c_void_p),
         ("n_rows", c_int64),
         ("out_payload", c_void_p),
         ("out_stats", c_void_p),
@@ -171,7 +171,7 @@ SIGNATURES = {
     "mb200_auc_sort_keys": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_size_t, c_void_p]),
     "mb200_auc_rank_sum": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
     "mb200_pooled_auc_workspace_bytes": (c_size_t, [c_int64]),
-    "mb200_pooled_auc": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_void_p, c_int64, c_void_p, c_size_t, c_void_p, c_void_p]),
+    "mb200_pooled_auc": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p, c_size_t, c_void_p, c_void_p]),
     "mb200_retrieval_workspace_bytes": (c_size_t, [POINTER(RetrievalDesc)]),
     "mb200_retrieve_topk": (c_int, [POINTER(RetrievalDesc), c_void_p]),
     "mb200_pool_users": (c_int, [c_void_p, c_int, c_int, c_int64, c_int64, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
@@ -181,7 +181,7 @@ SIGNATURES = {
     "mb200_metrics_workspace_bytes": (c_size_t, [POINTER(MetricsDesc)]),
     "mb200_rank_metrics": (c_int, [POINTER(MetricsDesc), c_void_p]),
     "mb200_exchange_mailbox_bytes": (c_size_t, [c_int, c_int, c_int64]),
-    "mb200_exchange_workspace_bytes": (c_size_t, [c_int, c_int64]),
+    "mb200_exchange_workspace_bytes": (c_size_t, [c_int64]),
     "mb200_exchange_post": (c_int, [POINTER(ExchangeDesc), c_void_p]),
     "mb200_exchange_finish": (c_int, [POINTER(ExchangeDesc), c_void_p]),
     "mb200_read_probe": (c_int, [c_void_p, c_size_t, c_int, c_int, c_void_p, c_void_p]),

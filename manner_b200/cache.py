@@ -167,3 +167,99 @@ def aspect_arrays(news_frame: Any, nid2row: Dict[str, int]) -> Tuple[np.ndarray,
     order = sorted(nid2row, key=nid2row.get)
     sub = news_frame.loc[order]
     return sub["category_label"].to_numpy().astype(np.int32), sub["sentiment_label"].to_numpy().astype(np.int32)
+
+
+# ---- persistence: tables + id map + CSR on disk, so cached mode does not re-encode per run ------------------
+# The reference writes its parsed frames once and reloads them (mind_dataframe.py:278-288,360-366: `parsed_behaviors.tsv`; the
+# news frame likewise); the embedding tables are the equivalent artefact of the accelerated path.  One directory per
+# (split, checkpoint): `tables.npy` [M, n_news, D] (np.save: memory-mappable, fp32 or bf16-as-uint16), `news_ids.txt` (row order =
+# the nid -> row map), `behaviours.npz` (CSR), optional `aspects.npz`, and `meta.json` with a fingerprint of whatever produced the
+# table (checkpoint path + mtime / size, dtype, max history) so a stale cache is refused rather than silently used.
+
+CACHE_FORMAT = 1
+
+
+def fingerprint(*sources: Any) -> str:
+    """A short stable digest of what the cached tables depend on: file paths are digested as (path, size, mtime), anything else by repr."""
+    import hashlib
+    import os
+
+    h = hashlib.sha256()
+    for s in sources:
+        if isinstance(s, str) and os.path.exists(s):
+            stt = os.stat(s)
+            h.update(f"{os.path.abspath(s)}:{stt.st_size}:{int(stt.st_mtime)}".encode())
+        else:
+            h.update(repr(s).encode())
+    return h.hexdigest()[:16]
+
+
+def save_cache(directory: str, tables: Sequence[Tensor], news_ids: Sequence[str], bhv: Behaviours, key: str,
+               aspects: Tuple[np.ndarray, np.ndarray] = None, max_history_length: int = MAX_HISTORY) -> None:
+    """Writes the cache directory atomically (temporary names, then rename): a reader never sees a half-written cache."""
+    import json
+    import os
+
+    os.makedirs(directory, exist_ok=True)
+    if len(news_ids) != tables[0].shape[0] or any(t.shape != tables[0].shape or t.dtype != tables[0].dtype for t in tables):
+        raise ValueError("tables must share shape / dtype and have one row per news id")
+    stack = torch.stack([t.detach().cpu() for t in tables])
+    is_bf16 = stack.dtype == torch.bfloat16
+    arr = stack.view(torch.int16).numpy().view(np.uint16) if is_bf16 else stack.float().numpy()
+    tmp = lambda name: os.path.join(directory, "." + name + ".tmp")
+    final = lambda name: os.path.join(directory, name)
+    with open(tmp("tables.npy"), "wb") as f:
+        np.save(f, arr)
+    with open(tmp("news_ids.txt"), "w") as f:
+        f.write("\n".join(news_ids) + "\n")
+    with open(tmp("behaviours.npz"), "wb") as f:
+        np.savez(f, hist_offsets=bhv.hist_offsets, hist_ids=bhv.hist_ids, cand_offsets=bhv.cand_offsets, cand_ids=bhv.cand_ids, labels=bhv.labels)
+    names = ["tables.npy", "news_ids.txt", "behaviours.npz"]
+    if aspects is not None:
+        with open(tmp("aspects.npz"), "wb") as f:
+            np.savez(f, category=np.asarray(aspects[0], dtype=np.int32), sentiment=np.asarray(aspects[1], dtype=np.int32))
+        names.append("aspects.npz")
+    meta = {"format": CACHE_FORMAT, "key": key, "n_modules": len(tables), "n_news": int(tables[0].shape[0]), "dim": int(tables[0].shape[1]),
+            "dtype": "bf16" if is_bf16 else "f32", "n_impressions": bhv.n_impressions, "max_history_length": int(max_history_length),
+            "has_aspects": aspects is not None}
+    for name in names:
+        os.replace(tmp(name), final(name))
+    with open(tmp("meta.json"), "w") as f:
+        json.dump(meta, f)
+    os.replace(tmp("meta.json"), final("meta.json"))  # last: its presence marks the cache complete
+
+
+def load_cache(directory: str, key: str, device: torch.device = None, mmap: bool = True):
+    """(tables [list of Tensor], news_ids, Behaviours, aspects or None) from ``save_cache``'s directory, or None when there is no
+    complete cache or it was built from something else (``key`` differs) -- the caller then rebuilds.  ``mmap`` maps the table
+    file instead of reading it through Python (a 161 k x 768 x 3 fp32 set is 1.5 GB); ``device`` uploads the tables."""
+    import json
+    import os
+
+    meta_path = os.path.join(directory, "meta.json")
+    if not os.path.exists(meta_path):
+        return None
+    with open(meta_path) as f:
+        meta = json.load(f)
+    if meta.get("format") != CACHE_FORMAT or meta.get("key") != key:
+        return None
+    arr = np.load(os.path.join(directory, "tables.npy"), mmap_mode="r" if mmap else None)
+    if arr.shape != (meta["n_modules"], meta["n_news"], meta["dim"]):
+        return None
+    tables = []
+    for m in range(arr.shape[0]):
+        t = torch.from_numpy(np.ascontiguousarray(arr[m]).view(np.int16) if meta["dtype"] == "bf16" else np.ascontiguousarray(arr[m]))
+        t = t.view(torch.bfloat16) if meta["dtype"] == "bf16" else t
+        tables.append(t.to(device) if device is not None else t)
+    with open(os.path.join(directory, "news_ids.txt")) as f:
+        news_ids = f.read().split("\n")[:-1]
+    z = np.load(os.path.join(directory, "behaviours.npz"))
+    bhv = Behaviours(z["hist_offsets"], z["hist_ids"], z["cand_offsets"], z["cand_ids"], z["labels"])
+    bhv.validate(meta["n_news"])
+    aspects = None
+    if meta.get("has_aspects"):
+        a = np.load(os.path.join(directory, "aspects.npz"))
+        aspects = (a["category"], a["sentiment"])
+    if len(news_ids) != meta["n_news"] or bhv.n_impressions != meta["n_impressions"]:
+        return None
+    return tables, news_ids, bhv, aspects

@@ -53,7 +53,7 @@ size_t auc_sort_workspace_bytes(long long n);
 int auc_sort_keys(const uint32_t*, uint32_t*, long long, void*, size_t, cudaStream_t);
 int auc_rank_sum(const uint32_t*, long long, const long long*, const uint32_t*, long long, const long long*, unsigned long long*, cudaStream_t);
 size_t pooled_auc_workspace_bytes(long long n);
-int pooled_auc(const float*, const uint8_t*, long long, int, const int32_t*, long long, void*, size_t, double*, cudaStream_t);
+int pooled_auc(const float*, const uint8_t*, long long, int, const int32_t*, void*, size_t, double*, cudaStream_t);
 size_t retrieval_workspace_bytes(const mb200_retrieval_desc* d);
 int retrieve_topk(const mb200_retrieval_desc* d, cudaStream_t stream);
 int pool_users(const void*, int, int, long long, long long, const int32_t*, const int32_t*, long long, void*, int32_t*, cudaStream_t);
@@ -61,7 +61,7 @@ int merge_topk(const float*, const long long*, int, long long, int, float*, long
 int attention_logits(const void*, int, int, long long, long long, const float*, const float*, const float*, int, float*, cudaStream_t);
 int step_loss(const float*, long long, int, int, const int32_t*, const uint8_t*, double*, cudaStream_t);
 size_t exchange_mailbox_bytes(int n_ranks, int n_payload, long long pos_capacity);
-size_t exchange_workspace_bytes(int n_ranks, long long pos_capacity);
+size_t exchange_workspace_bytes(long long n_rows);
 int exchange_post(const mb200_exchange_desc* d, cudaStream_t stream);
 int exchange_finish(const mb200_exchange_desc* d, cudaStream_t stream);
 int read_probe(const void* buf, size_t bytes, int repeats, int mode, void* sink, cudaStream_t stream);
@@ -127,13 +127,13 @@ int mb200_auc_rank_sum(const uint32_t* sorted_keys, int64_t n_sorted, const int6
 
 size_t mb200_pooled_auc_workspace_bytes(int64_t n) { return n < 0 ? 0 : pooled_auc_workspace_bytes(n); }
 
-int mb200_pooled_auc(const float* preds, const uint8_t* labels, int64_t n, int sigmoid_mode, const int32_t* flags, int64_t max_positives,
-                     void* workspace, size_t workspace_bytes, double* out, void* stream) {
-  if (n < 0 || max_positives < 0 || out == nullptr || (n > 0 && (!preds || !labels))) return MB200_ERR_INVALID_ARG;
+int mb200_pooled_auc(const float* preds, const uint8_t* labels, int64_t n, int sigmoid_mode, const int32_t* flags, void* workspace,
+                     size_t workspace_bytes, double* out, void* stream) {
+  if (n < 0 || out == nullptr || (n > 0 && (!preds || !labels))) return MB200_ERR_INVALID_ARG;
   if (sigmoid_mode < 0 || sigmoid_mode > 2 || (sigmoid_mode == 2 && flags == nullptr)) return MB200_ERR_INVALID_ARG;
   int st = use_device_of(out, nullptr);
   if (st != MB200_OK) return st;
-  return pooled_auc(preds, labels, n, sigmoid_mode, flags, max_positives, workspace, workspace_bytes, out, static_cast<cudaStream_t>(stream));
+  return pooled_auc(preds, labels, n, sigmoid_mode, flags, workspace, workspace_bytes, out, static_cast<cudaStream_t>(stream));
 }
 
 size_t mb200_retrieval_workspace_bytes(const mb200_retrieval_desc* desc) { return retrieval_workspace_bytes(desc); }
@@ -167,7 +167,7 @@ int mb200_rank_metrics(const mb200_metrics_desc* desc, void* stream) { return ra
 
 size_t mb200_exchange_mailbox_bytes(int n_ranks, int n_payload, int64_t pos_capacity) { return exchange_mailbox_bytes(n_ranks, n_payload, pos_capacity); }
 
-size_t mb200_exchange_workspace_bytes(int n_ranks, int64_t pos_capacity) { return exchange_workspace_bytes(n_ranks, pos_capacity); }
+size_t mb200_exchange_workspace_bytes(int64_t n_rows) { return exchange_workspace_bytes(n_rows); }
 
 int mb200_exchange_post(const mb200_exchange_desc* desc, void* stream) { return exchange_post(desc, static_cast<cudaStream_t>(stream)); }
 

@@ -6,16 +6,10 @@
 //
 // Stage 1 turns every prediction into an order-preserving uint32 key (fp32 sigmoid first when the
 // reference would apply it), leaves the negatives in place and appends the (few) positives to a side
-// list.  Two equivalent evaluations of the sum follow:
-//   (a) sort ALL keys, binary-search each positive in the sorted negatives (the staged entry points
-//       mb200_auc_sort_keys / mb200_auc_rank_sum; used by the NCCL fallback of manner_b200/dist.py);
-//   (b) sort only the POSITIVES (~4 % of the rows on MIND) and stream the negatives once, each one
-//       binary-searching the small sorted list (it stays in L1 / L2):
-//           sum2 = sum over negatives n of 2 * #(pos > n) + #(pos == n)
-//       -- mb200_pooled_auc with a `max_positives` hint and the fused multi-GPU exchange.  The radix sort of 2.7 M
-//       keys that (a) needs was ~6 % of an evaluation step; (b) sorts ~0.1 M.
-// Sorting is cub::DeviceRadixSort (library code, the one non-hand-written kernel family in this library).
-// Everything is additive over shards.
+// list.  Stage 2 radix-sorts the keys (cub::DeviceRadixSort -- library code, the one non-hand-written
+// kernel family in this library).  Stage 3 binary-searches each positive in the sorted negatives.
+// All three are additive over shards: a multi-GPU caller all-gathers only the positive keys and
+// all-reduces one uint64 (manner_b200/dist.py).
 
 #include <cub/device/device_radix_sort.cuh>
 
@@ -109,57 +103,10 @@ __global__ void __launch_bounds__(256) auc_rank_sum_kernel(const uint32_t* __res
   }
 }
 
-// (b): every negative key of `keys` (positives carry kPositiveSentinel) against the ascending `sorted_pos[0 .. *n_pos_total)`:
-// adds 2 * #(pos > key) + #(pos == key) into *sum2.  apply_sigmoid: 0 never, 1 always, 2 = iff *sig_flag != 0 -- the keys are
-// then RAW score keys and are mapped through the fp32 sigmoid here (multi-GPU: the rule is decided over all ranks' scores,
-// after the keys were built).
-__global__ void __launch_bounds__(256) auc_rank_negatives_kernel(const uint32_t* __restrict__ keys, long long n, const uint32_t* __restrict__ sorted_pos,
-                                                                 const long long* __restrict__ n_pos_total, long long pos_capacity, int apply_sigmoid,
-                                                                 const int32_t* __restrict__ sig_flag, unsigned long long* __restrict__ sum2) {
-  long long P = *n_pos_total;
-  if (P > pos_capacity) P = pos_capacity;
-  const bool sig = apply_sigmoid == 1 || (apply_sigmoid == 2 && sig_flag != nullptr && *sig_flag != 0);
-  unsigned long long local = 0;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-    uint32_t key = keys[i];
-    if (key == kPositiveSentinel) continue;
-    if (sig) key = orderable_key(sigmoid_f32(key_to_float(key)));
-    long long lo = 0, hi = P;  // lower_bound: first positive >= key
-    while (lo < hi) {
-      const long long mid = (lo + hi) >> 1;
-      if (sorted_pos[mid] < key) lo = mid + 1; else hi = mid;
-    }
-    const long long lb = lo;
-    hi = P;  // upper_bound continues from lb
-    while (lo < hi) {
-      const long long mid = (lo + hi) >> 1;
-      if (sorted_pos[mid] <= key) lo = mid + 1; else hi = mid;
-    }
-    local += (unsigned long long)(2 * (P - lo) + (lo - lb));
-  }
-  __shared__ unsigned long long sh[8];
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) local += __shfl_xor_sync(kFull, local, o);
-  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = local;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    unsigned long long t = 0;
-    for (int w = 0; w < 8; ++w) t += sh[w];
-    if (t) atomicAdd(sum2, t);
-  }
-}
-
-// pads pos_keys[*n_pos .. capacity) with the sentinel so that a fixed-size sort leaves the real keys in front
-__global__ void __launch_bounds__(256) auc_pad_positives_kernel(uint32_t* __restrict__ pos_keys, const long long* __restrict__ n_pos, long long capacity) {
-  const long long first = *n_pos < capacity ? *n_pos : capacity;
-  for (long long i = first + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < capacity; i += (long long)gridDim.x * blockDim.x) pos_keys[i] = kPositiveSentinel;
-}
-
 __global__ void auc_finalize_kernel(const unsigned long long* __restrict__ sum2, const long long* __restrict__ n_pos, long long n,
-                                    double* __restrict__ out, long long pos_capacity) {
+                                    double* __restrict__ out) {
   const double P = (double)*n_pos, N = (double)(n - *n_pos);
   out[0] = (P > 0 && N > 0) ? (double)*sum2 / (2.0 * P * N) : 0.0;
-  if (*n_pos > pos_capacity) out[0] = __longlong_as_double(0x7ff8000000000000ll);  // more positives than the caller's hint: refuse, loudly
   out[1] = P, out[2] = N, out[3] = (double)*sum2;
 }
 
@@ -212,34 +159,29 @@ size_t pooled_auc_workspace_bytes(long long n) {
   return 3 * al256((size_t)n * sizeof(uint32_t)) + 256 + auc_sort_workspace_bytes(n);
 }
 
-int pooled_auc(const float* preds, const uint8_t* labels, long long n, int sigmoid_mode, const int32_t* flags, long long max_positives,
-               void* workspace, size_t workspace_bytes, double* out, cudaStream_t stream) {
+int pooled_auc(const float* preds, const uint8_t* labels, long long n, int sigmoid_mode, const int32_t* flags, void* workspace,
+               size_t workspace_bytes, double* out, cudaStream_t stream) {
   if (workspace == nullptr || ((uintptr_t)workspace & 255) || workspace_bytes < pooled_auc_workspace_bytes(n)) return MB200_ERR_WORKSPACE;
   unsigned char* w = reinterpret_cast<unsigned char*>(workspace);
   const size_t keys_bytes = al256((size_t)n * sizeof(uint32_t));
   uint32_t* neg_keys = reinterpret_cast<uint32_t*>(w);
-  uint32_t* sorted_pos = reinterpret_cast<uint32_t*>(w + keys_bytes);
+  uint32_t* sorted = reinterpret_cast<uint32_t*>(w + keys_bytes);
   uint32_t* pos_keys = reinterpret_cast<uint32_t*>(w + 2 * keys_bytes);
   long long* n_pos = reinterpret_cast<long long*>(w + 3 * keys_bytes);
   unsigned long long* sum2 = reinterpret_cast<unsigned long long*>(w + 3 * keys_bytes + 8);
   void* cub_ws = w + 3 * keys_bytes + 256;
   const size_t cub_bytes = workspace_bytes - (3 * keys_bytes + 256);
-  // only the positives are sorted: `max_positives` (an upper bound the caller knows, e.g. the label sum) sizes that sort; without
-  // it the sort covers n keys (mostly padding) and costs what sorting everything cost
-  const long long cap = (max_positives > 0 && max_positives < n) ? max_positives : n;
 
   int st = cuda_status(cudaMemsetAsync(sum2, 0, sizeof(unsigned long long), stream), "cudaMemsetAsync(sum2)");
   if (st != MB200_OK) return st;
   if ((st = auc_build_keys(preds, labels, n, sigmoid_mode, flags, neg_keys, pos_keys, n_pos, stream)) != MB200_OK) return st;
-  if (n > 0) {
-    auc_pad_positives_kernel<<<grid_for(cap, 256, 148 * 4), 256, 0, stream>>>(pos_keys, n_pos, cap);
-    if ((st = cuda_status(cudaGetLastError(), "auc_pad_positives_kernel")) != MB200_OK) return st;
-    if ((st = auc_sort_keys(pos_keys, sorted_pos, cap, cub_ws, cub_bytes, stream)) != MB200_OK) return st;
-    auc_rank_negatives_kernel<<<grid_for(n, 256, 148 * 8), 256, 0, stream>>>(neg_keys, n, sorted_pos, n_pos, cap, 0, nullptr, sum2);
-    if ((st = cuda_status(cudaGetLastError(), "auc_rank_negatives_kernel")) != MB200_OK) return st;
-    note_launch(2);
+  if (n == 0) {
+    st = cuda_status(cudaMemsetAsync(n_pos, 0, sizeof(long long), stream), "cudaMemsetAsync");
+    if (st != MB200_OK) return st;
   }
-  auc_finalize_kernel<<<1, 1, 0, stream>>>(sum2, n_pos, n, out, cap);
+  if ((st = auc_sort_keys(neg_keys, sorted, n, cub_ws, cub_bytes, stream)) != MB200_OK) return st;
+  if ((st = auc_rank_sum(sorted, n, n_pos, pos_keys, n, n_pos, sum2, stream)) != MB200_OK) return st;
+  auc_finalize_kernel<<<1, 1, 0, stream>>>(sum2, n_pos, n, out);
   note_launch(1);
   return cuda_status(cudaGetLastError(), "auc_finalize_kernel");
 }
@@ -283,16 +225,12 @@ struct ExchangeParams {
   const double* payload;
   const uint32_t* pos_keys;
   const long long* n_pos;
-  const uint32_t* keys;  // this rank's raw keys, positives = sentinel (mb200_auc_build_keys, sigmoid_mode 0)
+  const uint32_t* sorted_neg;  // this rank's keys, sorted by RAW score key (negatives in front)
+  uint32_t* sorted_sig;        // workspace [n_rows]: the same negatives as sigmoid keys (still sorted: the fp32 sigmoid is monotone)
   long long n_rows;
   double* out_payload;
   long long* out_stats;
   int32_t* flags;
-  // workspace
-  uint32_t* all_pos;        // [n_ranks * pos_capacity] every rank's positives (sigmoid applied when the rule says so), sentinel padded
-  uint32_t* all_pos_sorted; // same size
-  long long* total_pos;     // [1]
-  int32_t* sig_flag;        // [1] != 0: AUROC's sigmoid applies (some score of some rank outside [0,1])
 };
 
 __device__ __forceinline__ unsigned char* slot_of_mailbox(const ExchangeParams& p, int owner, int src) {
@@ -321,11 +259,10 @@ __device__ bool wait_flag(const uint32_t* flag, uint32_t epoch) {
   return true;
 }
 
-// stage 1: this rank's payload + positive keys into slot `my_rank` of every rank's mailbox, then the arrival flags
 __global__ void __launch_bounds__(256) exchange_post_kernel(const ExchangeParams p) {
   const long long n_pos = min(*p.n_pos, p.pos_capacity);
   const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x, nthreads = (long long)gridDim.x * blockDim.x;
-  if (tid == 0 && p.flags) p.flags[0] = 0, p.flags[1] = 0;  // the exchange's own flag word (an int64 slot of the result): set by the later stages only
+  if (tid == 0 && p.flags) *p.flags = 0, p.flags[1] = 0;  // the exchange's own flag word (an int64 slot of the result): set by the finish kernel only
   for (int r = 0; r < p.n_ranks; ++r) {
     unsigned char* slot = slot_of_mailbox(p, r, p.my_rank);
     double* pay = reinterpret_cast<double*>(slot + p.payload_off);
@@ -348,10 +285,18 @@ __global__ void __launch_bounds__(256) exchange_post_kernel(const ExchangeParams
   }
 }
 
-// stage 2: wait for every rank's stage 1, reduce the payloads (fixed rank order: the same doubles on every rank), decide AUROC's
-// sigmoid rule over all ranks, and lay all positives out as one sentinel-padded array for the sort
-__global__ void __launch_bounds__(256) exchange_gather_kernel(const ExchangeParams p) {
-  __shared__ bool ok, sig;
+// sigmoid keys of this rank's sorted negatives, computed while the peers' stores are still arriving: the rank search after the
+// exchange then compares plain integers whichever way AUROC's sigmoid rule (known only once all payloads are in) turns out
+__global__ void __launch_bounds__(256) exchange_sigmoid_keys_kernel(const uint32_t* __restrict__ sorted_neg, long long n_rows, const long long* __restrict__ n_pos,
+                                                                    uint32_t* __restrict__ sorted_sig) {
+  const long long n_neg = n_rows - *n_pos;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_neg; i += (long long)gridDim.x * blockDim.x)
+    sorted_sig[i] = orderable_key(sigmoid_f32(key_to_float(sorted_neg[i])));
+}
+
+__global__ void __launch_bounds__(256) exchange_finish_kernel(const ExchangeParams p) {
+  __shared__ bool ok, sig, last;
+  __shared__ unsigned long long sh[8];
   if (threadIdx.x == 0) {
     bool good = true, outside = false;
     for (int r = 0; r < p.n_ranks; ++r) {
@@ -363,12 +308,10 @@ __global__ void __launch_bounds__(256) exchange_gather_kernel(const ExchangePara
   }
   __syncthreads();
   if (!ok) {
-    if (blockIdx.x == 0 && threadIdx.x == 0) {
-      if (p.flags) atomicOr(p.flags, MB200_FLAG_EXCHANGE_TIMEOUT);
-      *p.total_pos = 0, *p.sig_flag = 0;
-    }
+    if (blockIdx.x == 0 && threadIdx.x == 0 && p.flags) atomicOr(p.flags, MB200_FLAG_EXCHANGE_TIMEOUT);
     return;
   }
+  // metric payload: fixed rank order, every rank computes the same doubles
   if (blockIdx.x == 0) {
     for (int i = threadIdx.x; i < p.n_payload; i += blockDim.x) {
       double a = 0.0;
@@ -376,54 +319,74 @@ __global__ void __launch_bounds__(256) exchange_gather_kernel(const ExchangePara
       p.out_payload[i] = a;
     }
   }
+  // every rank's positives against MY sorted negatives
+  const long long my_pos = *p.n_pos;
+  const long long n_neg = p.n_rows - my_pos;
   const bool use_sig = sig;
-  const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x, nthreads = (long long)gridDim.x * blockDim.x;
-  long long off = 0;
+  const uint32_t* __restrict__ negs = use_sig ? p.sorted_sig : p.sorted_neg;
+  unsigned long long local = 0;
   bool overflow = false;
   for (int r = 0; r < p.n_ranks; ++r) {
     const unsigned char* slot = slot_of_mailbox(p, p.my_rank, r);
     long long cnt = reinterpret_cast<const ExchangeHeader*>(slot)->n_pos;
     if (cnt > p.pos_capacity) cnt = p.pos_capacity, overflow = true;
     const uint32_t* keys = reinterpret_cast<const uint32_t*>(slot + p.keys_off);
-    for (long long i = tid; i < cnt; i += nthreads) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < cnt; i += (long long)gridDim.x * blockDim.x) {
       uint32_t key = keys[i];
       if (use_sig) key = orderable_key(sigmoid_f32(key_to_float(key)));
-      p.all_pos[off + i] = key;
+      long long lo = 0, hi = n_neg;  // lower_bound: first negative whose (sigmoid) key is >= key
+      while (lo < hi) {
+        const long long mid = (lo + hi) >> 1;
+        if (negs[mid] < key) lo = mid + 1; else hi = mid;
+      }
+      const long long lb = lo;
+      hi = n_neg;
+      while (lo < hi) {
+        const long long mid = (lo + hi) >> 1;
+        if (negs[mid] <= key) lo = mid + 1; else hi = mid;
+      }
+      local += (unsigned long long)(lb + lo);
     }
-    off += cnt;
   }
-  for (long long i = off + tid; i < (long long)p.n_ranks * p.pos_capacity; i += nthreads) p.all_pos[i] = kPositiveSentinel;
-  if (tid == 0) {
-    *p.total_pos = off, *p.sig_flag = use_sig ? 1 : 0;
-    if (overflow && p.flags) atomicOr(p.flags, MB200_FLAG_POS_OVERFLOW);
-  }
-}
-
-// stage 4 (after the sort and auc_rank_negatives_kernel, which left this rank's part of the statistic in its header): post the three
-// additive integers to every rank, wait for theirs, add up
-__global__ void exchange_stats_kernel(const ExchangeParams p) {
-  if (threadIdx.x != 0) return;
+  if (overflow && blockIdx.x == 0 && threadIdx.x == 0 && p.flags) atomicOr(p.flags, MB200_FLAG_POS_OVERFLOW);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) local += __shfl_xor_sync(kFull, local, o);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = local;
+  __syncthreads();
   ExchangeHeader* own = reinterpret_cast<ExchangeHeader*>(slot_of_mailbox(p, p.my_rank, p.my_rank));
-  const unsigned long long sum2 = own->acc;
-  const long long my_pos = *p.n_pos, my_neg = p.n_rows - my_pos;
-  for (int r = 0; r < p.n_ranks; ++r) {
-    ExchangeHeader* h = reinterpret_cast<ExchangeHeader*>(slot_of_mailbox(p, r, p.my_rank));
-    h->sum2 = sum2, h->pos_total = my_pos, h->neg_total = my_neg;
+  if (threadIdx.x == 0) {
+    unsigned long long t = 0;
+    for (int w = 0; w < 8; ++w) t += sh[w];
+    if (t) atomicAdd(&own->acc, t);
+    __threadfence();
+    last = atomicAdd(&own->ticket, 1u) == gridDim.x - 1;
   }
-  __threadfence_system();
-  for (int r = 0; r < p.n_ranks; ++r) st_release_sys(&reinterpret_cast<ExchangeHeader*>(slot_of_mailbox(p, r, p.my_rank))->flag2, p.epoch);
-  unsigned long long s2 = 0;
-  long long P = 0, N = 0;
-  bool good = true;
-  for (int r = 0; r < p.n_ranks; ++r) {
-    const ExchangeHeader* h = reinterpret_cast<const ExchangeHeader*>(slot_of_mailbox(p, p.my_rank, r));
-    good = good && wait_flag(&h->flag2, p.epoch);
-    s2 += *reinterpret_cast<const volatile unsigned long long*>(&h->sum2);
-    P += *reinterpret_cast<const volatile long long*>(&h->pos_total);
-    N += *reinterpret_cast<const volatile long long*>(&h->neg_total);
+  __syncthreads();
+  if (!last) return;
+  // the last block posts this rank's three additive integers to every peer, then sums what the peers posted
+  if (threadIdx.x == 0) {
+    __threadfence();
+    const unsigned long long sum2 = atomicAdd(&own->acc, 0ull);
+    own->ticket = 0;
+    for (int r = 0; r < p.n_ranks; ++r) {
+      ExchangeHeader* h = reinterpret_cast<ExchangeHeader*>(slot_of_mailbox(p, r, p.my_rank));
+      h->sum2 = sum2, h->pos_total = my_pos, h->neg_total = n_neg;
+    }
+    __threadfence_system();
+    for (int r = 0; r < p.n_ranks; ++r) st_release_sys(&reinterpret_cast<ExchangeHeader*>(slot_of_mailbox(p, r, p.my_rank))->flag2, p.epoch);
+    unsigned long long s2 = 0;
+    long long P = 0, N = 0;
+    bool good = true;
+    for (int r = 0; r < p.n_ranks; ++r) {
+      const ExchangeHeader* h = reinterpret_cast<const ExchangeHeader*>(slot_of_mailbox(p, p.my_rank, r));
+      good = good && wait_flag(&h->flag2, p.epoch);
+      s2 += *reinterpret_cast<const volatile unsigned long long*>(&h->sum2);
+      P += *reinterpret_cast<const volatile long long*>(&h->pos_total);
+      N += *reinterpret_cast<const volatile long long*>(&h->neg_total);
+    }
+    if (!good && p.flags) atomicOr(p.flags, MB200_FLAG_EXCHANGE_TIMEOUT);
+    p.out_stats[0] = (long long)s2, p.out_stats[1] = P, p.out_stats[2] = N;
   }
-  if (!good && p.flags) atomicOr(p.flags, MB200_FLAG_EXCHANGE_TIMEOUT);
-  p.out_stats[0] = (long long)s2, p.out_stats[1] = P, p.out_stats[2] = N;
 }
 
 static size_t exchange_layout(int n_payload, long long pos_capacity, size_t* payload_off, size_t* keys_off) {
@@ -438,20 +401,16 @@ size_t exchange_mailbox_bytes(int n_ranks, int n_payload, long long pos_capacity
   return 2 * (size_t)n_ranks * exchange_layout(n_payload, pos_capacity, nullptr, nullptr);
 }
 
-size_t exchange_workspace_bytes(int n_ranks, long long pos_capacity) {
-  if (n_ranks < 1 || n_ranks > MB200_MAX_TABLE_SHARDS || pos_capacity < 0) return 0;
-  const long long items = (long long)n_ranks * (pos_capacity > 0 ? pos_capacity : 1);
-  return 256 + 2 * al256((size_t)items * sizeof(uint32_t)) + auc_sort_workspace_bytes(items);
-}
+size_t exchange_workspace_bytes(long long n_rows) { return n_rows < 0 ? 0 : al256((size_t)n_rows * sizeof(uint32_t)) + 256; }
 
 static int exchange_params(const mb200_exchange_desc* d, ExchangeParams* p) {
   if (d == nullptr || d->struct_size != sizeof(mb200_exchange_desc)) return MB200_ERR_INVALID_ARG;
   if (d->n_ranks < 1 || d->n_ranks > MB200_MAX_TABLE_SHARDS || d->my_rank < 0 || d->my_rank >= d->n_ranks) return MB200_ERR_INVALID_ARG;
-  if (d->n_payload < 0 || d->pos_capacity < 1 || d->n_rows < 0 || d->epoch == 0) return MB200_ERR_INVALID_ARG;
+  if (d->n_payload < 0 || d->pos_capacity < 0 || d->n_rows < 0 || d->epoch == 0) return MB200_ERR_INVALID_ARG;
   if (d->outside_index >= d->n_payload) return MB200_ERR_INVALID_ARG;
   if (!d->n_pos || !d->out_payload || !d->out_stats || (d->n_payload > 0 && !d->payload)) return MB200_ERR_INVALID_ARG;
-  if (d->n_rows > 0 && (!d->keys || !d->pos_keys)) return MB200_ERR_INVALID_ARG;
-  if (d->workspace == nullptr || ((uintptr_t)d->workspace & 255) || d->workspace_bytes < exchange_workspace_bytes(d->n_ranks, d->pos_capacity)) return MB200_ERR_WORKSPACE;
+  if (d->n_rows > 0 && (!d->sorted_neg || !d->pos_keys)) return MB200_ERR_INVALID_ARG;
+  if (d->workspace == nullptr || ((uintptr_t)d->workspace & 255) || d->workspace_bytes < exchange_workspace_bytes(d->n_rows)) return MB200_ERR_WORKSPACE;
   for (int r = 0; r < d->n_ranks; ++r)
     if (d->mailbox[r] == nullptr || ((uintptr_t)d->mailbox[r] & 255)) return MB200_ERR_INVALID_ARG;
   for (int r = 0; r < d->n_ranks; ++r) p->mailbox[r] = reinterpret_cast<unsigned char*>(d->mailbox[r]);
@@ -459,12 +418,8 @@ static int exchange_params(const mb200_exchange_desc* d, ExchangeParams* p) {
   p->pos_capacity = d->pos_capacity;
   p->slot_bytes = exchange_layout(d->n_payload, d->pos_capacity, &p->payload_off, &p->keys_off);
   p->payload = d->payload, p->pos_keys = d->pos_keys, p->n_pos = reinterpret_cast<const long long*>(d->n_pos);
-  p->keys = d->keys, p->n_rows = d->n_rows;
+  p->sorted_neg = d->sorted_neg, p->n_rows = d->n_rows, p->sorted_sig = reinterpret_cast<uint32_t*>(d->workspace);
   p->out_payload = d->out_payload, p->out_stats = reinterpret_cast<long long*>(d->out_stats), p->flags = d->flags;
-  unsigned char* w = reinterpret_cast<unsigned char*>(d->workspace);
-  const size_t items_bytes = al256((size_t)d->n_ranks * d->pos_capacity * sizeof(uint32_t));
-  p->total_pos = reinterpret_cast<long long*>(w), p->sig_flag = reinterpret_cast<int32_t*>(w + 8);
-  p->all_pos = reinterpret_cast<uint32_t*>(w + 256), p->all_pos_sorted = reinterpret_cast<uint32_t*>(w + 256 + items_bytes);
   return MB200_OK;
 }
 
@@ -474,8 +429,14 @@ int exchange_post(const mb200_exchange_desc* d, cudaStream_t stream) {
   if (st != MB200_OK) return st;
   if ((st = use_device_of(d->out_payload, nullptr)) != MB200_OK) return st;
   exchange_post_kernel<<<32, 256, 0, stream>>>(p);
+  if ((st = cuda_status(cudaGetLastError(), "exchange_post_kernel")) != MB200_OK) return st;
   note_launch(1);
-  return cuda_status(cudaGetLastError(), "exchange_post_kernel");
+  if (d->n_rows > 0 && d->outside_index >= 0) {  // overlaps the flight of the stores and the wait for the slowest rank
+    exchange_sigmoid_keys_kernel<<<grid_for(d->n_rows, 256, 148 * 8), 256, 0, stream>>>(p.sorted_neg, d->n_rows, p.n_pos, p.sorted_sig);
+    note_launch(1);
+    return cuda_status(cudaGetLastError(), "exchange_sigmoid_keys_kernel");
+  }
+  return MB200_OK;
 }
 
 int exchange_finish(const mb200_exchange_desc* d, cudaStream_t stream) {
@@ -483,23 +444,9 @@ int exchange_finish(const mb200_exchange_desc* d, cudaStream_t stream) {
   int st = exchange_params(d, &p);
   if (st != MB200_OK) return st;
   if ((st = use_device_of(d->out_payload, nullptr)) != MB200_OK) return st;
-  const long long items = (long long)d->n_ranks * d->pos_capacity;
-  exchange_gather_kernel<<<64, 256, 0, stream>>>(p);
-  if ((st = cuda_status(cudaGetLastError(), "exchange_gather_kernel")) != MB200_OK) return st;
+  exchange_finish_kernel<<<148 * 2, 256, 0, stream>>>(p);
   note_launch(1);
-  if (d->n_rows > 0) {
-    unsigned char* w = reinterpret_cast<unsigned char*>(d->workspace);
-    const size_t items_bytes = al256((size_t)items * sizeof(uint32_t));
-    void* cub_ws = w + 256 + 2 * items_bytes;
-    if ((st = auc_sort_keys(p.all_pos, p.all_pos_sorted, items, cub_ws, d->workspace_bytes - (256 + 2 * items_bytes), stream)) != MB200_OK) return st;
-    ExchangeHeader* own = reinterpret_cast<ExchangeHeader*>(p.mailbox[p.my_rank] + ((size_t)(p.epoch & 1u) * p.n_ranks + p.my_rank) * p.slot_bytes);
-    auc_rank_negatives_kernel<<<grid_for(d->n_rows, 256, 148 * 8), 256, 0, stream>>>(p.keys, d->n_rows, p.all_pos_sorted, p.total_pos, items, 2, p.sig_flag, &own->acc);
-    if ((st = cuda_status(cudaGetLastError(), "auc_rank_negatives_kernel")) != MB200_OK) return st;
-    note_launch(1);
-  }
-  exchange_stats_kernel<<<1, 32, 0, stream>>>(p);
-  note_launch(1);
-  return cuda_status(cudaGetLastError(), "exchange_stats_kernel");
+  return cuda_status(cudaGetLastError(), "exchange_finish_kernel");
 }
 
 // ---- read-bandwidth probe (bench.py's L2 roofline denominator) ----------------------------------------------------------

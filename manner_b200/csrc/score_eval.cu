@@ -1682,9 +1682,10 @@ int score_eval(const mb200_eval_desc* d, cudaStream_t stream) {
     st = cuda_status(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem_per_cta), "cudaFuncSetAttribute");
     if (st != MB200_OK) return st;
   } else {
-    // bf16 rows of the reference width: candidate dot products on the tensor cores (default; tuning variant 11 forces it, any other
-    // explicit variant selects the FMA kernels)
-    mma = d->dtype == MB200_BF16 && d->dim == 768 && d->row_stride == 768 && !attn && !sharded && (variant < 0 || variant == 11);
+    // bf16 rows of the reference width: tuning variant 11 runs the candidate dot products on the tensor cores (mma.sync).  Measured
+    // slower than the FMA kernel (1.36 vs 1.23 ms on Zipf ids, 2.64 vs 1.68 ms on uniform ids: the fragment layout makes every
+    // load instruction touch 8 rows x 64 B instead of 512 contiguous bytes of one row; profiles/r2_stream_experiment.md) -- not the default.
+    mma = d->dtype == MB200_BF16 && d->dim == 768 && d->row_stride == 768 && !attn && !sharded && variant == 11;
     if (mma) kern = score_eval_kernel<__nv_bfloat16, 3, 4, true, 0, 5, false, true>;
     else kern = (d->dtype == MB200_F32) ? select_kernel<float>(vec_per_row, attn, sharded) : select_kernel<__nv_bfloat16>(vec_per_row, attn, sharded);
     if (kern == nullptr) return MB200_ERR_UNSUPPORTED;  // row-sharded tables: reference width, late fusion only

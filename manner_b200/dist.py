@@ -103,7 +103,7 @@ class P2PExchange:
             raise ValueError("unsupported exchange shape (1..8 ranks of one NVSwitch box)")
         self.mailbox = torch.zeros(nbytes, dtype=torch.uint8, device=device)
         self.peers = share_table_shards(self.mailbox, group) if self.world > 1 else [self.mailbox]
-        self.workspace = torch.empty(int(lib.mb200_exchange_workspace_bytes(self.world, self.pos_cap)), dtype=torch.uint8, device=device)
+        self.workspace: Optional[Tensor] = None  # sigmoid keys of the sorted negatives, grown on demand
         self.epoch = 0
         self._empty_i32 = torch.zeros(2, dtype=torch.int32, device=device)
         self._zero_i64 = torch.zeros(1, dtype=torch.int64, device=device)
@@ -111,7 +111,7 @@ class P2PExchange:
     def fits(self, n_payload: int, pos_cap: int) -> bool:
         return int(n_payload) == self.n_payload and int(pos_cap) <= self.pos_cap
 
-    def run(self, payload: Tensor, outside_index: int, keys: Optional[Tensor] = None, pos_keys: Optional[Tensor] = None,
+    def run(self, payload: Tensor, outside_index: int, sorted_keys: Optional[Tensor] = None, pos_keys: Optional[Tensor] = None,
             n_pos: Optional[Tensor] = None) -> Tensor:
         """Enqueues both kernels on the current stream.  Returns fp64 [n_payload + 4]: the payload summed over the ranks, then
         (as int64 bit patterns) sum2, P, N of the pooled AUROC and the exchange's flag word."""
@@ -133,10 +133,13 @@ class P2PExchange:
         for r, t in enumerate(self.peers):
             d.mailbox[r] = t.data_ptr()
         d.payload = payload.data_ptr()
-        if keys is not None:
-            d.pos_keys, d.n_pos, d.keys, d.n_rows = pos_keys.data_ptr(), n_pos.data_ptr(), keys.data_ptr(), keys.numel()
+        if sorted_keys is not None:
+            d.pos_keys, d.n_pos, d.sorted_neg, d.n_rows = pos_keys.data_ptr(), n_pos.data_ptr(), sorted_keys.data_ptr(), sorted_keys.numel()
         else:  # no pooled AUROC wanted: an empty key set
-            d.pos_keys, d.n_pos, d.keys, d.n_rows = self._empty_i32.data_ptr(), self._zero_i64.data_ptr(), self._empty_i32.data_ptr(), 0
+            d.pos_keys, d.n_pos, d.sorted_neg, d.n_rows = self._empty_i32.data_ptr(), self._zero_i64.data_ptr(), self._empty_i32.data_ptr(), 0
+        need = int(lib.mb200_exchange_workspace_bytes(d.n_rows))
+        if self.workspace is None or self.workspace.numel() < need:
+            self.workspace = torch.empty(need, dtype=torch.uint8, device=dev)
         d.out_payload, d.out_stats, d.flags = out.data_ptr(), tail.data_ptr(), tail[3:].data_ptr()
         d.workspace, d.workspace_bytes = self.workspace.data_ptr(), self.workspace.numel()
         with torch.cuda.device(dev):

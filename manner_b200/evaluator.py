@@ -285,8 +285,8 @@ class ScoreEvaluator:
                 self._p2p = mdist.P2PExchange(self.device, sums.numel(), max(cap, 1), group)
             outside = n_w * nat.NUM_METRICS + 1 + 2  # tail entry of the MB200_FLAG_OUTSIDE_UNIT bit
             if pooled_auc:
-                keys, pos_keys, n_pos = ops.auc_build_keys(scores, bhv.labels, 0, None)  # raw score keys; the sigmoid rule is applied after the exchange
-                sums = self._p2p.run(sums, outside, keys, pos_keys, n_pos)
+                sorted_keys, pos_keys, n_pos = ops.auc_build_and_sort(scores, bhv.labels, 0, None)  # raw score order; the sigmoid rule is applied after the exchange
+                sums = self._p2p.run(sums, outside, sorted_keys, pos_keys, n_pos)
             else:
                 sums = self._p2p.run(sums, -1)
             fused = True
@@ -298,7 +298,7 @@ class ScoreEvaluator:
                 gflags = (sums[outside : outside + 1] > 0).to(torch.int32) * nat.FLAG_OUTSIDE_UNIT
                 auc_stats = mdist.pooled_auc_distributed(scores, bhv.labels, gflags, group, pos_cap=bhv.pos_cap)
         elif pooled_auc:
-            auc_stats = torch.ops.manner_b200.pooled_auc(scores, bhv.labels, 2, flags, bhv.n_pos)
+            auc_stats = torch.ops.manner_b200.pooled_auc(scores, bhv.labels, 2, flags)
         return PendingEval(sums, flags, n_w, bhv.n_impressions, distributed, auc_stats,
                            scores if want_scores else None, per_impr if want_per_impression else None, loss_stats, fused, pooled_auc)
 
@@ -337,8 +337,6 @@ class ScoreEvaluator:
             d2h = packed.size * 8
             if pending.auc_stats is not None:
                 a = packed[n_block + 1 :]
-                if a[0] != a[0]:
-                    raise nat.NativeError("pooled AUROC: more positives among the labels than DeviceBehaviours.n_pos says")
                 auc, counts = float(a[0]), (int(a[1]), int(a[2]))
         loss_value = None
         if pending.loss_stats is not None:

@@ -232,14 +232,22 @@ class B200EvalMixin:
         loader = dm.test_dataloader() if stage == "test" else dm.val_dataloader()
         ds, collate = loader.dataset, loader.collate_fn
         step = int(getattr(loader, "batch_size", 8) or 8)
-        news_ids = cache.unique_news_ids(ds.behaviors, ds.max_history_length)
-        nid2row = cache.news_row_map(news_ids)
         device = getattr(self, "device", None)  # LightningModule.device; plain modules: wherever their tensors live
         if not isinstance(device, torch.device):
             import itertools
 
             device = next(itertools.chain(self.parameters(), self.buffers())).device
         encoders = self._b200_encoders()
+        # on-disk cache of the tables / id map / CSR (test stage only: during training the encoder weights change between
+        # validations).  The key digests what the tables depend on; a cache built from other checkpoints is ignored.
+        cache_dir = getattr(self, "_b200_cache_dir", None) if stage == "test" else None
+        cache_key = cache.fingerprint(*self._b200_cache_sources(), len(ds.behaviors), ds.max_history_length, len(encoders)) if cache_dir else ""
+        cached = cache.load_cache(cache_dir, cache_key, device) if cache_dir else None
+        if cached is not None:
+            tables, news_ids, bhv, asp = cached
+            return self._b200_evaluate_tables(stage, tables, bhv, asp, step, device)
+        news_ids = cache.unique_news_ids(ds.behaviors, ds.max_history_length)
+        nid2row = cache.news_row_map(news_ids)
 
         def news_batches():
             for lo in range(0, len(news_ids), self._b200_news_batch):
@@ -255,11 +263,26 @@ class B200EvalMixin:
                 enc.train(was)
             tables.append(cache.build_embedding_table(enc, news_batches(), len(news_ids), dim, device))
         bhv = cache.behaviours_frame_to_csr(ds.behaviors, nid2row, ds.max_history_length)
-        aspects = {}
+        asp = None
         if self._b200_zscore and "category_label" in ds.news.columns and "sentiment_label" in ds.news.columns:
-            cat, sent = cache.aspect_arrays(ds.news, nid2row)
+            asp = cache.aspect_arrays(ds.news, nid2row)
+        if cache_dir:
+            cache.save_cache(cache_dir, tables, news_ids, bhv, cache_key, asp, ds.max_history_length)
+        return self._b200_evaluate_tables(stage, tables, bhv, asp, step, device)
+
+    def _b200_cache_sources(self) -> list:
+        """What the cached tables were computed from (digested into the cache key): checkpoint paths when the module has them."""
+        hp = getattr(self, "hparams", {})
+        get = hp.get if hasattr(hp, "get") else (lambda k, d=None: d)
+        return [get(k) for k in ("cr_module_module_ckpt", "a_module_categ_ckpt", "a_module_sent_ckpt", "plm_model")]
+
+    def _b200_evaluate_tables(self, stage: str, tables, bhv, asp, step: int, device) -> Dict[str, float]:
+        from .evaluator import ScoreEvaluator
+
+        aspects = {}
+        if asp is not None:
             hp = getattr(self, "hparams", {})
-            aspects = dict(news_category=cat, news_sentiment=sent,
+            aspects = dict(news_category=asp[0], news_sentiment=asp[1],
                            num_categ_classes=int(hp.get("num_categ_classes", 19)) if hasattr(hp, "get") else 19,
                            num_sent_classes=int(hp.get("num_sent_classes", 4)) if hasattr(hp, "get") else 4)
         ev = ScoreEvaluator(tables, device, attention=self._b200_attention(), **aspects)
@@ -324,12 +347,13 @@ class CRModuleB200(B200EvalMixin, _RefCRModule):
     """CRModule (late or early fusion, CE or SupCon loss) with the B200 test path.  Extra keyword: ``scorer``
     ("b200" | "reference") to fall back to the reference's own test path for A/B comparison."""
 
-    def __init__(self, *args: Any, scorer: str = "b200", **kwargs: Any) -> None:
+    def __init__(self, *args: Any, scorer: str = "b200", cache_dir: Optional[str] = None, **kwargs: Any) -> None:
         super().__init__(*args, **kwargs)
         if scorer not in ("b200", "b200_cached", "reference"):
             raise ValueError("scorer must be 'b200' (per step), 'b200_cached' (table built once, one call per epoch) or 'reference'")
         self._b200_enabled = scorer != "reference"
         self._b200_cached = scorer == "b200_cached"
+        self._b200_cache_dir = cache_dir  # cached mode: keep tables + nid -> row map + CSR on disk between runs
 
     def _b200_encoders(self) -> List[torch.nn.Module]:
         return [self.news_encoder]
@@ -380,11 +404,13 @@ class EnsembleModuleB200(B200EvalMixin, _RefEnsembleModule):
     _b200_zscore = True
     _b200_with_auc = False  # the reference's EnsembleModule has no AUROC (ensemble_module.py:50-55)
 
-    def __init__(self, *args: Any, scorer: str = "b200", aspect_weights: Optional[Sequence[Sequence[float]]] = None, **kwargs: Any) -> None:
+    def __init__(self, *args: Any, scorer: str = "b200", aspect_weights: Optional[Sequence[Sequence[float]]] = None,
+                 cache_dir: Optional[str] = None, **kwargs: Any) -> None:
         super().__init__(*args, **kwargs)
         if scorer not in ("b200", "b200_cached"):
             raise ValueError("scorer must be 'b200' (per step) or 'b200_cached' (tables built once, one call per epoch)")
         self._b200_cached = scorer == "b200_cached"
+        self._b200_cache_dir = cache_dir
         self._b200_aspect_weights: Optional[List[List[float]]] = None
         if aspect_weights is not None:
             grid = [[float(w) for w in pair] for pair in aspect_weights]

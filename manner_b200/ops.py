@@ -256,10 +256,9 @@ def step_loss(loss_per_impression: Tensor, step: int, loss_kind: int, cand_offse
 
 
 @torch.library.custom_op("manner_b200::pooled_auc", mutates_args=())
-def pooled_auc(preds: Tensor, labels: Tensor, sigmoid_mode: int, flags: Optional[Tensor], max_positives: int = 0) -> Tensor:
+def pooled_auc(preds: Tensor, labels: Tensor, sigmoid_mode: int, flags: Optional[Tensor]) -> Tensor:
     """Pooled AUROC of torchmetrics' ``AUROC(task="binary")`` (cr_module.py:81,273) on one device.
-    Returns fp64 [4] = (auc, P, N, sum2).  sigmoid_mode 0 never / 1 always / 2 from ``flags``.  ``max_positives``: an upper
-    bound on the label sum when the caller knows one (only the positives are sorted: it sizes that sort; 0 = unknown)."""
+    Returns fp64 [4] = (auc, P, N, sum2).  sigmoid_mode 0 never / 1 always / 2 from ``flags``."""
     lib = nat.lib()
     _require_cuda("preds", preds, torch.float32)
     _require_cuda("labels", labels, torch.uint8)
@@ -272,7 +271,7 @@ def pooled_auc(preds: Tensor, labels: Tensor, sigmoid_mode: int, flags: Optional
         out = torch.empty(4, dtype=torch.float64, device=dev)
         ws = _workspace(dev, stream, "auc", lib.mb200_pooled_auc_workspace_bytes(n))
         nat.check(
-            lib.mb200_pooled_auc(preds.data_ptr(), labels.data_ptr(), n, sigmoid_mode, _ptr(flags), int(max_positives), ws.data_ptr(), ws.numel(),
+            lib.mb200_pooled_auc(preds.data_ptr(), labels.data_ptr(), n, sigmoid_mode, _ptr(flags), ws.data_ptr(), ws.numel(),
                                  out.data_ptr(), stream),
             "mb200_pooled_auc",
         )
@@ -280,7 +279,7 @@ def pooled_auc(preds: Tensor, labels: Tensor, sigmoid_mode: int, flags: Optional
 
 
 @pooled_auc.register_fake
-def _(preds, labels, sigmoid_mode, flags, max_positives=0):
+def _(preds, labels, sigmoid_mode, flags):
     return torch.empty(4, dtype=torch.float64, device=preds.device)
 
 

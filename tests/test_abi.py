@@ -63,7 +63,7 @@ def test_descriptor_validation_without_a_gpu():
     assert lib.mb200_eval_workspace_bytes(ctypes.byref(d)) == 0  # struct_size unset -> invalid
     assert lib.mb200_score_eval(ctypes.byref(d), None) == nat.ERR_INVALID_ARG
     assert lib.mb200_score_eval(None, None) == nat.ERR_INVALID_ARG
-    assert lib.mb200_pooled_auc(None, None, -1, 0, None, 0, None, 0, None, None) == nat.ERR_INVALID_ARG
+    assert lib.mb200_pooled_auc(None, None, -1, 0, None, None, 0, None, None) == nat.ERR_INVALID_ARG
 
 
 def test_product_refuses_to_run_without_cuda():

@@ -161,8 +161,7 @@ def test_stream_kernel_bit_identical_to_register_batch_kernels(evaluator_cls, dt
     finally:
         ops.set_tuning(variant=-1)
     base = outs[2]
-    # bf16 rows: the default is the tensor-core path (another summation order, tests/test_gpu_parity.py) -- not part of this bit-identity
-    for variant in (7, 8, 9, 10) + ((-1,) if dtype == torch.float32 else ()):
+    for variant in (7, 8, 9, 10, -1):
         for a, b in zip(base, outs[variant]):
             np.testing.assert_array_equal(a.scores.cpu().numpy().view(np.uint32), b.scores.cpu().numpy().view(np.uint32))
             np.testing.assert_array_equal(a.per_impression.cpu().numpy().view(np.uint32), b.per_impression.cpu().numpy().view(np.uint32))

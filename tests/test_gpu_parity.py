@@ -149,10 +149,10 @@ def test_bf16_table_matches_oracle_on_rounded_table(golden_dir, evaluator_cls):
 
 
 def test_bf16_tensor_core_path_against_the_fma_kernels_and_the_oracle(evaluator_cls):
-    """bf16 rows of the reference width score their candidates on the tensor cores by default (mma.sync, u = hi + mid + lo split
-    exactly into three bf16 vectors, fp32 accumulation); tuning variant 3 is the FMA kernel.  Same contract -- bf16 storage,
-    fp32 arithmetic -- in another summation order: both within the condition-aware 1e-5 bar of the fp64 evaluation on the
-    rounded table, every rank flip between them a near-tie."""
+    """Tuning variant 11: bf16 rows of the reference width score their candidates on the tensor cores (mma.sync, u = hi + mid + lo
+    split exactly into three bf16 vectors, fp32 accumulation); variant 3 / default is the FMA kernel.  Same contract -- bf16
+    storage, fp32 arithmetic -- in another summation order: both within the condition-aware 1e-5 bar of the fp64 evaluation on
+    the rounded table, every rank flip between them a near-tie.  (Measured slower than the FMA kernel: kept as an experiment.)"""
     from manner_b200 import ops
 
     n_news = 3000
@@ -168,7 +168,7 @@ def test_bf16_tensor_core_path_against_the_fma_kernels_and_the_oracle(evaluator_
             res[(variant, "cr")] = ev1.evaluate(ev1.upload(bhv), pooled_auc=True, want_scores=True)
     finally:
         ops.set_tuning(variant=-1)
-    np.testing.assert_array_equal(res[11].scores.cpu().numpy(), res[-1].scores.cpu().numpy())  # the default IS the tensor-core path
+    np.testing.assert_array_equal(res[3].scores.cpu().numpy(), res[-1].scores.cpu().numpy())  # the default is the FMA kernel
     for tabs, w, zs, key in ((tables, [1.0, 0.4], True, None), (tables[:1], [1.0], False, "cr")):
         truth, tol = mo.ensemble_truth_f64([t.float() for t in tabs], w, bhv, zscore_modules=zs)
         for variant in (3, 11):
@@ -244,13 +244,6 @@ def test_pooled_auc_kernels_known_answers(evaluator_cls):
         want = float(tp.binary_auroc(torch.from_numpy(preds), torch.from_numpy(labels.astype(np.int64))))
         assert abs(out[0] - want) < METRIC_ATOL
         assert out[1] == labels.sum() and out[2] == labels.size - labels.sum()
-        # with an upper bound on the positives only that many keys are sorted: the statistic is the same integer
-        for hint in (int(labels.sum()), int(labels.sum()) + 1000):
-            hinted = torch.ops.manner_b200.pooled_auc(torch.from_numpy(preds).to(dev), torch.from_numpy(labels).to(dev), mode, None, hint).cpu().numpy()
-            np.testing.assert_array_equal(hinted, out)
-        if labels.sum() > 1:  # a bound below the true count is refused (NaN), never silently wrong
-            bad = torch.ops.manner_b200.pooled_auc(torch.from_numpy(preds).to(dev), torch.from_numpy(labels).to(dev), mode, None, int(labels.sum()) - 1).cpu().numpy()
-            assert np.isnan(bad[0])
     for labels in (np.zeros(100, np.uint8), np.ones(100, np.uint8)):
         out = torch.ops.manner_b200.pooled_auc(torch.rand(100, device=dev), torch.from_numpy(labels).to(dev), 0, None).cpu().numpy()
         assert out[0] == 0.0  # torchmetrics: no positive or no negative -> 0 (with a warning)
