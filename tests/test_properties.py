@@ -48,7 +48,7 @@ def test_oracle_padding_invariance(bhv, step_a, step_b):
     must not depend on which impressions share a step (cr_module.py:108-131 adds exact zeros)."""
     a = mo.cr_eval_epoch(TABLE, _ob(bhv), step=step_a)
     b = mo.cr_eval_epoch(TABLE, _ob(bhv), step=step_b)
-    np.testing.assert_allclose(a["scores"], b["scores"], rtol=1e-6, atol=1e-7)
+    np.testing.assert_allclose(a["scores"], b["scores"], rtol=2e-5, atol=2e-6)  # bmm may sum in another order for another padded shape
     for k in ("test/mrr", "test/ndcg@5", "test/ndcg@10"):
         if np.array_equal(mo.stable_ranks(a["scores"], bhv.cand_offsets), mo.stable_ranks(b["scores"], bhv.cand_offsets)):
             assert a["metrics"][k] == pytest.approx(b["metrics"][k], abs=1e-7)
