@@ -370,7 +370,8 @@ def run_gpu_arm(args) -> None:
         flush.fill_(rank + 1)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        step_bhv = ev.upload(bhv, pinned, pos_cap)
+        # pipelined: offsets first, the fused kernel starts on the first segment while the copy stream brings the rest
+        step_bhv = ev.upload(bhv, pinned, pos_cap, pipelined=args.upload_segments > 1, segments=args.upload_segments)
         r = ev.evaluate(step_bhv, **kw)  # includes the device -> host read of sums / AUC statistics
         e1.record()
         torch.cuda.synchronize(dev)
@@ -457,6 +458,8 @@ def run_gpu_arm(args) -> None:
             "value": n_impr_total / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": dev_bhv.h2d_bytes,
             "d2h_bytes_per_step": r.d2h_bytes, "ms_per_step": e2e_ms, "ms_per_step_median_rank0": e2e_median_ms, "steps": len(e2e_events),
             "ms_each_rank0": [round(x, 3) for x in e2e_events],
+            "upload": (f"pipelined: offsets, then {args.upload_segments} work-balanced segments on a copy stream overlapped with the fused kernel "
+                       "(mb200_upload_begin / _finish)") if args.upload_segments > 1 else "whole set copied in front of the pass",
         },
         "gpu_launches": launches1[0] - launches0[0],
         "library_launches": launches1[1] - launches0[1],
@@ -718,6 +721,8 @@ def main() -> None:
                     help="multi-GPU evaluation: fused stores into the peers' mailboxes over NVLink (default) or the three NCCL collectives")
     ap.add_argument("--retrieval-pair", type=int, default=None, help="retrieval kernel: 1 = CTA pairs (cta_group::2), 0 = one CTA per tile")
     ap.add_argument("--retrieval-diag", type=int, default=0, help="DIAGNOSTIC: 1/2 disable parts of the retrieval epilogue (results invalid)")
+    ap.add_argument("--upload-segments", type=int, default=8,
+                    help="end-to-end pass: segments of the pipelined host -> device upload (1 = copy everything in front of the pass)")
     ap.add_argument("--variant", type=int, default=None)
     ap.add_argument("--chunks-per-warp", type=int, default=None)
     ap.add_argument("--ctas-per-sm", type=int, default=None)

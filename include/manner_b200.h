@@ -35,11 +35,12 @@ extern "C" {
 #define MB200_API
 #endif
 
-#define MB200_ABI_VERSION 3
+#define MB200_ABI_VERSION 4
 #define MB200_MAX_MODULES 4 /* CR-Module + up to 3 A-Modules (reference: CR, category, sentiment) */
 #define MB200_MAX_K 31      /* largest ranking cut-off k for nDCG / diversity / personalization */
 #define MB200_MAX_CLASSES 64
 #define MB200_MAX_TABLE_SHARDS 8 /* GPUs of one NVSwitch box a row-sharded embedding table may be spread over */
+#define MB200_MAX_UPLOAD_SEGMENTS 32 /* segments of a pipelined behaviour upload (mb200_upload_begin) */
 
 /* ---- status codes ------------------------------------------------------------------------------ */
 #define MB200_OK 0
@@ -55,6 +56,7 @@ extern "C" {
 #define MB200_FLAG_BAD_ASPECT 8      /* an aspect label was outside [0, num_classes)                  */
 #define MB200_FLAG_EXCHANGE_TIMEOUT 16 /* mb200_exchange_finish: a peer GPU's stores did not arrive within 4 s     */
 #define MB200_FLAG_POS_OVERFLOW 32   /* mb200_exchange_finish: a rank had more positives than pos_capacity: AUROC invalid */
+#define MB200_FLAG_UPLOAD_TIMEOUT 64 /* mb200_score_eval with `ready`: a segment of the pipelined upload did not arrive within 4 s */
 
 /* ---- embedding table element types ----------------------------------------------------------------- */
 #define MB200_F32 0
@@ -78,7 +80,7 @@ extern "C" {
 #define MB200_M_LOSS 13         /* per-impression loss of `loss_kind` on the scores of `scores_weighting` (cr_module.py:140-171) */
 #define MB200_M_LOSS_NONZERO 14 /* 1 where that loss is > 0 (the AvgNonZero reduction of the SupCon loss)                       */
 #define MB200_NUM_METRICS 15
-#define MB200_PAYLOAD_TAIL 5
+#define MB200_PAYLOAD_TAIL 6
 
 /* ---- loss kinds (mb200_eval_desc.loss_kind) ---------------------------------------------------------- */
 #define MB200_LOSS_NONE 0
@@ -142,7 +144,7 @@ typedef struct mb200_eval_desc {
   float* scores;            /* [sum C] combined scores of weighting `scores_weighting` == the reference's flat `preds` */
   int32_t scores_weighting;
   int32_t pack_payload;     /* != 0: `sums` has MB200_PAYLOAD_TAIL more doubles behind the [W, MB200_NUM_METRICS] block:
-                               n_impressions, then one 0/1 double per MB200_FLAG_* bit (1, 2, 4, 8) -- everything
+                               n_impressions, then one 0/1 double per MB200_FLAG_* bit (1, 2, 4, 8, 64) -- everything
                                a multi-GPU caller sum-reduces, in one buffer, with no host-side packing */
   float* per_impression;    /* [W, n_impressions, MB200_NUM_METRICS] */
   double* sums;             /* [W, MB200_NUM_METRICS] sums over impressions (means = sums / n_impressions) */
@@ -175,6 +177,14 @@ typedef struct mb200_eval_desc {
   int32_t n_table_shards;
   int32_t table_shard_shift;
   const void* table_shards[MB200_MAX_MODULES][MB200_MAX_TABLE_SHARDS];
+
+  /* Pipelined upload (mb200_upload_begin / _finish): `ready` = DEVICE uint32 that the copy stream raises to the number of leading
+     impressions whose hist_ids / cand_ids / labels are resident; the offsets (and pads) are resident when the call is made.  The
+     persistent grid then walks `ready_segments` work-balanced chunks per warp, in upload order, and waits on `ready` before it
+     touches a chunk (bounded: 4 s -> MB200_FLAG_UPLOAD_TIMEOUT, remaining impressions skipped).  NULL = everything is resident. */
+  const uint32_t* ready;
+  int32_t ready_segments; /* 1..MB200_MAX_UPLOAD_SEGMENTS when `ready` is set */
+  int32_t reserved0;
 } mb200_eval_desc;
 
 MB200_API int mb200_abi_version(void);
@@ -183,6 +193,47 @@ MB200_API const char* mb200_last_cuda_error(void); /* HOST string, thread-local,
 
 MB200_API size_t mb200_eval_workspace_bytes(const mb200_eval_desc* desc);
 MB200_API int mb200_score_eval(const mb200_eval_desc* desc, void* stream);
+
+/*
+ * Pipelined host -> device upload of one behaviour set (the CSR arrays of mb200_eval_desc).  The reference moves each batch to
+ * the device in front of its forward pass (Lightning's batch transfer before cr_module.py:105 / ensemble_module.py:95); here a
+ * pass has ONE CSR set of ~20 MB, and the copy is overlapped with the fused kernel instead of preceding it:
+ *   mb200_upload_begin  (compute stream S, copy stream C != S):  S: ready = 0;  C waits for S, copies the two offset arrays (+ the
+ *                        optional pads), S waits for that;  C: the first `segments_first` segments of hist_ids / cand_ids /
+ *                        labels, each followed by a 4-byte copy that raises `ready` to the segment's last impression + 1
+ *   mb200_score_eval    on S with desc.ready / desc.ready_segments = n_segments: runs while the copies are still arriving
+ *   mb200_upload_finish  enqueues the remaining segments on C (call it right after mb200_score_eval returned; nothing that
+ *                        waits for S may come in between)
+ * Segment s ends where chunk group s of the persistent grid ends (same work measure: rows gathered + 4 per impression).  Copies
+ * cover disjoint 128-byte aligned ranges.  All HOST arrays must be page-locked and stay untouched until C has run the copies.
+ */
+typedef struct mb200_upload_desc {
+  uint32_t struct_size;   /* = sizeof(mb200_upload_desc) */
+  int32_t n_segments;     /* 1..MB200_MAX_UPLOAD_SEGMENTS */
+  int32_t segments_first; /* 1..n_segments: enqueued by _begin; the rest by _finish */
+  int32_t reserved;
+  int64_t n_impressions;  /* >= 1 */
+  const int32_t* h_hist_offsets; /* HOST [n_impressions + 1] */
+  const int32_t* h_hist_ids;     /* HOST */
+  const int32_t* h_cand_offsets; /* HOST [n_impressions + 1] */
+  const int32_t* h_cand_ids;     /* HOST */
+  const uint8_t* h_labels;       /* HOST */
+  int32_t* d_hist_offsets;
+  int32_t* d_hist_ids;  /* 128-byte aligned, like d_cand_ids and d_labels */
+  int32_t* d_cand_offsets;
+  int32_t* d_cand_ids;
+  uint8_t* d_labels;
+  const int32_t* h_hist_pad; /* optional HOST [n_impressions] (early fusion / cross entropy), with its destination */
+  int32_t* d_hist_pad;
+  const int32_t* h_cand_pad;
+  int32_t* d_cand_pad;
+  uint32_t* ready;   /* DEVICE, one uint32 */
+  uint32_t* h_marks; /* HOST page-locked scratch [n_segments], written by these calls */
+  void* copy_stream;
+} mb200_upload_desc;
+
+MB200_API int mb200_upload_begin(const mb200_upload_desc* desc, void* compute_stream);
+MB200_API int mb200_upload_finish(const mb200_upload_desc* desc);
 
 /*
  * Per-news additive-attention logits for early fusion: out[n] = query . tanh(weight x_n + bias) for the n_rows rows of
@@ -389,10 +440,13 @@ MB200_API float mb200_dcg_discount(int rank);
  * separately by mb200_library_launch_count). */
 MB200_API int64_t mb200_launch_count(void);
 MB200_API int64_t mb200_library_launch_count(void);
-/* tuning knobs; returns the previous value.  key 0 = impression chunks per warp; 1 = variant of the reference-width fused
- * kernel (-1 = default: one 16-warp CTA per SM with the hot-row cache in shared memory [= 9]; 10 = that CTA shape without the
- * cache; 7 / 8 = rotating row pipeline without / with the cache; 0/2/3/5/6 = the round-1 4-warp kernels, rows in flight x
- * resident CTAs per SM: 4x3, 3x4, 2x5, 3x6, 2x7 for fp32 rows, twice the rows for bf16; 1 = 4x3 with L1::no_allocate loads);
+/* tuning knobs; returns the previous value.  key 0 = impression chunks per resident warp of the fused kernel (0 = default: 1 when the
+ * behaviours are resident, 16 handed out dynamically in impression order under a pipelined upload; key 7 = 1 / 2 forces the
+ * static / dynamic schedule); 1 = variant of the reference-width fused
+ * kernel (-1 = default: 2 for fp32 rows, 3 for bf16 rows; 0/2/3/5/6 = 4-warp CTAs, rows in flight x resident CTAs per SM:
+ * 4x3, 3x4, 2x5, 3x6, 2x7 for fp32 rows, twice the rows for bf16; 1 = 4x3 with L1::no_allocate loads; measured and not shipped:
+ * 9 = one 16-warp CTA per SM with a hot-row cache in shared memory, 10 = that CTA shape without the cache, 7 / 8 = rotating row
+ * pipeline without / with the cache, 11 = bf16 candidates on mma.sync);
  * 2 = cap on CTAs per SM; 3 = time the fused kernel with
  * CUDA events; 4 = retrieval diagnostics (1, 2: parts of the epilogue disabled, RESULTS INVALID; 4: cycle counters in the
  * workspace header, results valid); 5 = retrieval pipeline (1 = CTA pairs / tcgen05 cta_group::2 [default], 0 = one CTA per tile); 6 = cap in KB on the

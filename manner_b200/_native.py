@@ -12,17 +12,20 @@ from typing import Optional
 
 LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libmanner_b200.so")
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 MAX_MODULES = 4
 MAX_TABLE_SHARDS = 8
+MAX_UPLOAD_SEGMENTS = 32
 MAX_K = 31
 MAX_CLASSES = 64
 NUM_METRICS = 15
-PAYLOAD_TAIL = 5
+PAYLOAD_TAIL = 6
 
 OK, ERR_INVALID_ARG, ERR_UNSUPPORTED, ERR_CUDA, ERR_WORKSPACE = 0, 1, 2, 3, 4
 FLAG_BAD_ID, FLAG_CAND_OVERFLOW, FLAG_OUTSIDE_UNIT, FLAG_BAD_ASPECT = 1, 2, 4, 8
-FLAG_EXCHANGE_TIMEOUT, FLAG_POS_OVERFLOW = 16, 32
+FLAG_EXCHANGE_TIMEOUT, FLAG_POS_OVERFLOW, FLAG_UPLOAD_TIMEOUT = 16, 32, 64
+# flag bits a packed payload carries behind the impression count (mb200_eval_desc.pack_payload), in this order
+PAYLOAD_FLAG_BITS = (1, 2, 4, 8, 64)
 F32, BF16 = 0, 1
 
 # metric slots
@@ -78,6 +81,38 @@ class EvalDesc(Structure):
         ("n_table_shards", c_int32),
         ("table_shard_shift", c_int32),
         ("table_shards", (c_void_p * MAX_TABLE_SHARDS) * MAX_MODULES),
+        ("ready", c_void_p),
+        ("ready_segments", c_int32),
+        ("reserved0", c_int32),
+    ]
+
+
+class UploadDesc(Structure):
+    """mb200_upload_desc, field for field."""
+
+    _fields_ = [
+        ("struct_size", c_uint32),
+        ("n_segments", c_int32),
+        ("segments_first", c_int32),
+        ("reserved", c_int32),
+        ("n_impressions", c_int64),
+        ("h_hist_offsets", c_void_p),
+        ("h_hist_ids", c_void_p),
+        ("h_cand_offsets", c_void_p),
+        ("h_cand_ids", c_void_p),
+        ("h_labels", c_void_p),
+        ("d_hist_offsets", c_void_p),
+        ("d_hist_ids", c_void_p),
+        ("d_cand_offsets", c_void_p),
+        ("d_cand_ids", c_void_p),
+        ("d_labels", c_void_p),
+        ("h_hist_pad", c_void_p),
+        ("d_hist_pad", c_void_p),
+        ("h_cand_pad", c_void_p),
+        ("d_cand_pad", c_void_p),
+        ("ready", c_void_p),
+        ("h_marks", c_void_p),
+        ("copy_stream", c_void_p),
     ]
 
 
@@ -166,6 +201,8 @@ SIGNATURES = {
     "mb200_last_cuda_error": (c_char_p, []),
     "mb200_eval_workspace_bytes": (c_size_t, [POINTER(EvalDesc)]),
     "mb200_score_eval": (c_int, [POINTER(EvalDesc), c_void_p]),
+    "mb200_upload_begin": (c_int, [POINTER(UploadDesc), c_void_p]),
+    "mb200_upload_finish": (c_int, [POINTER(UploadDesc)]),
     "mb200_auc_build_keys": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "mb200_auc_sort_workspace_bytes": (c_size_t, [c_int64]),
     "mb200_auc_sort_keys": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_size_t, c_void_p]),

@@ -18,7 +18,7 @@ CSRC = os.path.join(HERE, "csrc")
 BUILD = os.path.join(HERE, "build")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libmanner_b200.so")
-SOURCES = ["api.cu", "score_eval.cu", "pooled_auc.cu", "retrieval.cu", "attention.cu"]
+SOURCES = ["api.cu", "score_eval.cu", "pooled_auc.cu", "retrieval.cu", "attention.cu", "upload.cu"]
 HEADERS = [os.path.join(CSRC, "common.cuh"), os.path.join(os.path.dirname(HERE), "include", "manner_b200.h")]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

@@ -65,6 +65,8 @@ size_t exchange_workspace_bytes(long long n_rows);
 int exchange_post(const mb200_exchange_desc* d, cudaStream_t stream);
 int exchange_finish(const mb200_exchange_desc* d, cudaStream_t stream);
 int read_probe(const void* buf, size_t bytes, int repeats, int mode, void* sink, cudaStream_t stream);
+int upload_begin(const mb200_upload_desc* d, cudaStream_t compute);
+int upload_finish(const mb200_upload_desc* d);
 size_t metrics_workspace_bytes(const mb200_metrics_desc* d);
 int rank_metrics(const mb200_metrics_desc* d, cudaStream_t stream);
 
@@ -92,6 +94,10 @@ const char* mb200_last_cuda_error(void) { return g_cuda_err; }
 size_t mb200_eval_workspace_bytes(const mb200_eval_desc* desc) { return eval_workspace_bytes(desc); }
 
 int mb200_score_eval(const mb200_eval_desc* desc, void* stream) { return score_eval(desc, static_cast<cudaStream_t>(stream)); }
+
+int mb200_upload_begin(const mb200_upload_desc* desc, void* compute_stream) { return upload_begin(desc, static_cast<cudaStream_t>(compute_stream)); }
+
+int mb200_upload_finish(const mb200_upload_desc* desc) { return upload_finish(desc); }
 
 int mb200_auc_build_keys(const float* preds, const uint8_t* labels, int64_t n, int sigmoid_mode, const int32_t* flags, uint32_t* neg_keys,
                          uint32_t* pos_keys, int64_t* n_pos, void* stream) {
@@ -249,6 +255,7 @@ int mb200_set_tuning(int key, int value) {
     case 4: prev = tuning().retrieval_diag, tuning().retrieval_diag = value; break;
     case 5: prev = tuning().retrieval_pair, tuning().retrieval_pair = value; break;
     case 6: prev = tuning().hot_kb_cap, tuning().hot_kb_cap = value; break;
+    case 7: prev = tuning().static_chunks, tuning().static_chunks = value; break;
   }
   return prev;
 }

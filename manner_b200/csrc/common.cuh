@@ -24,7 +24,9 @@ constexpr unsigned kFull = 0xffffffffu;
       0x1.99999ap-3f, 0.0f
 
 struct Tuning {
-  int chunks_per_warp = 1;  // work-balanced impression chunks per resident warp (1: one contiguous range per warp)
+  int chunks_per_warp = 0;  // work-balanced impression chunks per resident warp of the fused kernel (0 = default: 1 static, 16 dynamic)
+  int static_chunks = 0;    // chunk schedule of the fused kernel: 0 = dynamic hand-out iff the behaviours come through a pipelined upload,
+                            // 1 = always static round-robin, 2 = always dynamic
   int variant = -1;         // reference-width kernel: -1 = by table type (fp32: 2, bf16: 3), 0 = 4 rows in flight / 3 CTAs per SM, 1 = same with L1::no_allocate loads,
                             // 2 = 3 rows / 4 CTAs (default: best on Zipf-shaped ids), 3 = 2 rows / 5 CTAs
   int ctas_per_sm = 0;      // CTAs (of kWarpsPerCta warps) per SM; 0 = as many as are resident (occupancy query)

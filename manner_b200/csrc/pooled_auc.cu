@@ -36,62 +36,177 @@ __device__ __forceinline__ float sigmoid_f32(float x) {
   return __fdiv_rn(1.0f, __fadd_rn(1.0f, e));
 }
 
+// One atomic per 2 048-row tile (not per warp: ~60 k same-address atomics serialised the first version at 46 us for 2.7 M rows):
+// every thread classifies 8 rows, the block scans the per-thread positive counts, thread 0 reserves the tile's slots.
+constexpr int kBuildItems = 8;
 __global__ void __launch_bounds__(256) auc_build_keys_kernel(const float* __restrict__ preds, const uint8_t* __restrict__ labels,
                                                              long long n, int sigmoid_mode, const int32_t* __restrict__ flags,
                                                              uint32_t* __restrict__ neg_keys, uint32_t* __restrict__ pos_keys,
                                                              unsigned long long* __restrict__ n_pos) {
   const bool sig = sigmoid_mode == 1 || (sigmoid_mode == 2 && flags != nullptr && (*flags & MB200_FLAG_OUTSIDE_UNIT));
-  const int lane = threadIdx.x & 31;
-  const long long stride = (long long)gridDim.x * blockDim.x;
-  const long long first = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  // every lane of a warp runs the same number of iterations so the ballots below are convergent
-  const long long warp_first = first - lane;
-  for (long long base = warp_first; base < n; base += stride) {
-    const long long i = base + lane;
-    bool pos = false;
-    uint32_t key = kPositiveSentinel;
-    if (i < n) {
-      float x = preds[i];
-      if (sig) x = sigmoid_f32(x);
-      key = orderable_key(x);
-      pos = labels[i] != 0;
-      neg_keys[i] = pos ? kPositiveSentinel : key;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  __shared__ unsigned int warp_count[8];
+  __shared__ unsigned long long tile_slot;
+  constexpr long long kTile = 256 * kBuildItems;
+  for (long long tile = (long long)blockIdx.x * kTile; tile < n; tile += (long long)gridDim.x * kTile) {
+    uint32_t key[kBuildItems];
+    unsigned pos_bits = 0;
+#pragma unroll
+    for (int u = 0; u < kBuildItems; ++u) {
+      const long long i = tile + u * 256 + threadIdx.x;
+      key[u] = kPositiveSentinel;
+      if (i < n) {
+        float x = preds[i];
+        if (sig) x = sigmoid_f32(x);
+        key[u] = orderable_key(x);
+        const bool pos = labels[i] != 0;
+        pos_bits |= (pos ? 1u : 0u) << u;
+        neg_keys[i] = pos ? kPositiveSentinel : key[u];
+      }
     }
-    const unsigned m = __ballot_sync(kFull, pos);
-    if (m) {
-      unsigned long long slot = 0;
-      if (lane == __ffs(m) - 1) slot = atomicAdd(n_pos, (unsigned long long)__popc(m));
-      slot = __shfl_sync(kFull, slot, __ffs(m) - 1);
-      if (pos) pos_keys[slot + __popc(m & ((1u << lane) - 1u))] = key;
+    // exclusive scan of the per-thread positive counts over the block
+    const unsigned mine = __popc(pos_bits);
+    unsigned incl = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const unsigned t = __shfl_up_sync(kFull, incl, o);
+      if (lane >= o) incl += t;
+    }
+    if (lane == 31) warp_count[warp] = incl;
+    __syncthreads();
+    unsigned before = 0, total = 0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) {
+      const unsigned c = warp_count[w];
+      before += (w < warp) ? c : 0u;
+      total += c;
+    }
+    if (threadIdx.x == 0 && total) tile_slot = atomicAdd(n_pos, (unsigned long long)total);
+    __syncthreads();
+    if (mine) {
+      unsigned long long slot = tile_slot + before + (incl - mine);
+#pragma unroll
+      for (int u = 0; u < kBuildItems; ++u)
+        if ((pos_bits >> u) & 1u) pos_keys[slot++] = key[u];
+    }
+    __syncthreads();  // tile_slot / warp_count are reused by the next tile
+  }
+}
+
+// ---- rank search: positives against the sorted negatives ---------------------------------------------------------------
+// lower_bound + upper_bound of every positive key.  A plain binary search is ~22 dependent L2 round trips per bound; with R ranks'
+// positives to rank (multi-GPU: every rank ranks ALL positives against its own negatives) that was the longest kernel after the
+// fused one.  Here the first 10 levels run on kSplitters evenly spaced keys staged in shared memory, the remaining levels are a
+// branch-free search over a window of uniform length (kSearchIlp keys per thread advance in lock step, so their loads are in flight
+// together), and the upper bound gallops from the lower bound (ties between fp32 scores are short runs unless the sigmoid saturates).
+constexpr int kSplitters = 1024;
+constexpr int kSearchIlp = 4;
+
+struct SortedNegatives {
+  const uint32_t* keys;
+  long long n;       // negatives (the positives' sentinels behind them are not searched)
+  long long window;  // uniform length of the second-level search
+  bool split;        // splitters staged (n large enough)
+};
+
+__device__ __forceinline__ long long splitter_pos(long long n, int j) { return (long long)(j + 1) * n / (kSplitters + 1); }
+
+// block-wide: stage the splitters of `keys[0, n)` into sh[kSplitters]
+__device__ __forceinline__ SortedNegatives stage_splitters(const uint32_t* __restrict__ keys, long long n, uint32_t* sh) {
+  SortedNegatives s;
+  s.keys = keys, s.n = n, s.split = n >= 4 * (kSplitters + 1);
+  s.window = s.split ? n / (kSplitters + 1) + 2 : n;
+  if (s.split)
+    for (int j = threadIdx.x; j < kSplitters; j += blockDim.x) sh[j] = __ldg(keys + splitter_pos(n, j));
+  __syncthreads();
+  return s;
+}
+
+__device__ __forceinline__ uint32_t neg_at(const SortedNegatives& s, long long idx) { return idx < s.n ? __ldg(s.keys + idx) : 0xffffffffu; }
+
+// sum over the kSearchIlp keys (the first `cnt` are real) of lower_bound + upper_bound
+__device__ __forceinline__ unsigned long long bounds_sum(const SortedNegatives& s, const uint32_t* sh, const uint32_t (&key)[kSearchIlp], int cnt) {
+  long long base[kSearchIlp];
+#pragma unroll
+  for (int k = 0; k < kSearchIlp; ++k) {
+    base[k] = 0;
+    if (s.split) {
+      int j = 0;  // first splitter >= key
+#pragma unroll
+      for (int half = kSplitters / 2; half > 0; half >>= 1) j += (sh[j + half - 1] < key[k]) ? half : 0;
+      j += (sh[j] < key[k]) ? 1 : 0;
+      base[k] = j ? splitter_pos(s.n, j - 1) + 1 : 0;
     }
   }
+  // the answer lies in [base, base + window]; slots beyond the array count as +inf
+  long long len = s.window;
+  while (len > 1) {
+    const long long half = len >> 1;
+    uint32_t v[kSearchIlp];
+#pragma unroll
+    for (int k = 0; k < kSearchIlp; ++k) v[k] = neg_at(s, base[k] + half - 1);
+#pragma unroll
+    for (int k = 0; k < kSearchIlp; ++k) base[k] += (v[k] < key[k]) ? half : 0;
+    len -= half;
+  }
+  unsigned long long sum = 0;
+#pragma unroll
+  for (int k = 0; k < kSearchIlp; ++k) {
+    if (k >= cnt) continue;
+    long long lb = base[k];
+    if (len == 1) lb += (neg_at(s, lb) < key[k]) ? 1 : 0;
+    // upper bound: gallop over the run of negatives equal to the key
+    long long ub = lb;
+    if (ub < s.n && __ldg(s.keys + ub) <= key[k]) {
+      long long step = 1;
+      while (ub + step < s.n && __ldg(s.keys + ub + step) <= key[k]) step <<= 1;
+      long long lo = ub + (step >> 1) + 1, hi = min(ub + step, s.n);  // first index with key above: in [lo, hi]
+      while (lo < hi) {
+        const long long mid = (lo + hi) >> 1;
+        if (__ldg(s.keys + mid) <= key[k]) lo = mid + 1; else hi = mid;
+      }
+      ub = lo;
+    }
+    sum += (unsigned long long)(lb + ub);
+  }
+  return sum;
+}
+
+// `count` keys of `pos_keys` (optionally mapped through the fp32 sigmoid first), strided over the grid
+template <bool SIGMOID>
+__device__ __forceinline__ unsigned long long rank_sum_span(const SortedNegatives& s, const uint32_t* sh, const uint32_t* pos_keys,
+                                                            long long count) {
+  unsigned long long local = 0;
+  const long long nthreads = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += nthreads * kSearchIlp) {
+    uint32_t key[kSearchIlp];
+    int cnt = 0;
+#pragma unroll
+    for (int k = 0; k < kSearchIlp; ++k) {
+      const long long ii = i + k * nthreads;
+      key[k] = 0u;
+      if (ii < count) {
+        key[k] = pos_keys[ii];
+        if (SIGMOID) key[k] = orderable_key(sigmoid_f32(key_to_float(key[k])));
+        cnt = k + 1;
+      }
+    }
+    local += bounds_sum(s, sh, key, cnt);
+  }
+  return local;
 }
 
 __global__ void __launch_bounds__(256) auc_rank_sum_kernel(const uint32_t* __restrict__ sorted, long long n_sorted,
                                                            const long long* __restrict__ n_pos_local, const uint32_t* __restrict__ pos_keys,
                                                            long long pos_capacity, const long long* __restrict__ n_pos,
                                                            unsigned long long* __restrict__ sum2) {
-  const long long n_neg = n_sorted - *n_pos_local;
+  __shared__ uint32_t sh_split[kSplitters];
+  __shared__ unsigned long long sh[8];
+  const SortedNegatives s = stage_splitters(sorted, n_sorted - *n_pos_local, sh_split);
   long long count = *n_pos;
   if (count > pos_capacity) count = pos_capacity;
-  unsigned long long local = 0;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (long long)gridDim.x * blockDim.x) {
-    const uint32_t key = pos_keys[i];
-    long long lo = 0, hi = n_neg;  // lower_bound: first index with sorted[idx] >= key
-    while (lo < hi) {
-      const long long mid = (lo + hi) >> 1;
-      if (sorted[mid] < key) lo = mid + 1; else hi = mid;
-    }
-    const long long lb = lo;
-    hi = n_neg;  // upper_bound continues from lb
-    while (lo < hi) {
-      const long long mid = (lo + hi) >> 1;
-      if (sorted[mid] <= key) lo = mid + 1; else hi = mid;
-    }
-    local += (unsigned long long)(lb + lo);
-  }
+  unsigned long long local = rank_sum_span<false>(s, sh_split, pos_keys, count);
   // block reduction, one atomic per block (integer: order-independent, deterministic)
-  __shared__ unsigned long long sh[8];
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) local += __shfl_xor_sync(kFull, local, o);
   if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = local;
@@ -121,7 +236,7 @@ int auc_build_keys(const float* preds, const uint8_t* labels, long long n, int s
                    uint32_t* pos_keys, long long* n_pos, cudaStream_t stream) {
   int st = cuda_status(cudaMemsetAsync(n_pos, 0, sizeof(long long), stream), "cudaMemsetAsync(n_pos)");
   if (st != MB200_OK || n == 0) return st;
-  auc_build_keys_kernel<<<grid_for(n, 256, 148 * 16), 256, 0, stream>>>(preds, labels, n, sigmoid_mode, flags, neg_keys, pos_keys,
+  auc_build_keys_kernel<<<grid_for(n, 256 * kBuildItems, 148 * 8), 256, 0, stream>>>(preds, labels, n, sigmoid_mode, flags, neg_keys, pos_keys,
                                                                        reinterpret_cast<unsigned long long*>(n_pos));
   note_launch(1);
   return cuda_status(cudaGetLastError(), "auc_build_keys_kernel");
@@ -146,7 +261,7 @@ int auc_sort_keys(const uint32_t* keys_in, uint32_t* keys_out, long long n, void
 int auc_rank_sum(const uint32_t* sorted, long long n_sorted, const long long* n_pos_local, const uint32_t* pos_keys, long long pos_capacity,
                  const long long* n_pos, unsigned long long* sum2, cudaStream_t stream) {
   if (pos_capacity <= 0) return MB200_OK;
-  auc_rank_sum_kernel<<<grid_for(pos_capacity, 256, 148 * 8), 256, 0, stream>>>(sorted, n_sorted, n_pos_local, pos_keys, pos_capacity, n_pos,
+  auc_rank_sum_kernel<<<grid_for(pos_capacity, 256, 148 * 4), 256, 0, stream>>>(sorted, n_sorted, n_pos_local, pos_keys, pos_capacity, n_pos,
                                                                                sum2);
   note_launch(1);
   return cuda_status(cudaGetLastError(), "auc_rank_sum_kernel");
@@ -297,6 +412,7 @@ __global__ void __launch_bounds__(256) exchange_sigmoid_keys_kernel(const uint32
 __global__ void __launch_bounds__(256) exchange_finish_kernel(const ExchangeParams p) {
   __shared__ bool ok, sig, last;
   __shared__ unsigned long long sh[8];
+  __shared__ uint32_t sh_split[kSplitters];
   if (threadIdx.x == 0) {
     bool good = true, outside = false;
     for (int r = 0; r < p.n_ranks; ++r) {
@@ -323,7 +439,7 @@ __global__ void __launch_bounds__(256) exchange_finish_kernel(const ExchangePara
   const long long my_pos = *p.n_pos;
   const long long n_neg = p.n_rows - my_pos;
   const bool use_sig = sig;
-  const uint32_t* __restrict__ negs = use_sig ? p.sorted_sig : p.sorted_neg;
+  const SortedNegatives negs = stage_splitters(use_sig ? p.sorted_sig : p.sorted_neg, n_neg, sh_split);
   unsigned long long local = 0;
   bool overflow = false;
   for (int r = 0; r < p.n_ranks; ++r) {
@@ -331,22 +447,7 @@ __global__ void __launch_bounds__(256) exchange_finish_kernel(const ExchangePara
     long long cnt = reinterpret_cast<const ExchangeHeader*>(slot)->n_pos;
     if (cnt > p.pos_capacity) cnt = p.pos_capacity, overflow = true;
     const uint32_t* keys = reinterpret_cast<const uint32_t*>(slot + p.keys_off);
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < cnt; i += (long long)gridDim.x * blockDim.x) {
-      uint32_t key = keys[i];
-      if (use_sig) key = orderable_key(sigmoid_f32(key_to_float(key)));
-      long long lo = 0, hi = n_neg;  // lower_bound: first negative whose (sigmoid) key is >= key
-      while (lo < hi) {
-        const long long mid = (lo + hi) >> 1;
-        if (negs[mid] < key) lo = mid + 1; else hi = mid;
-      }
-      const long long lb = lo;
-      hi = n_neg;
-      while (lo < hi) {
-        const long long mid = (lo + hi) >> 1;
-        if (negs[mid] <= key) lo = mid + 1; else hi = mid;
-      }
-      local += (unsigned long long)(lb + lo);
-    }
+    local += use_sig ? rank_sum_span<true>(negs, sh_split, keys, cnt) : rank_sum_span<false>(negs, sh_split, keys, cnt);
   }
   if (overflow && blockIdx.x == 0 && threadIdx.x == 0 && p.flags) atomicOr(p.flags, MB200_FLAG_POS_OVERFLOW);
 #pragma unroll
@@ -444,7 +545,7 @@ int exchange_finish(const mb200_exchange_desc* d, cudaStream_t stream) {
   int st = exchange_params(d, &p);
   if (st != MB200_OK) return st;
   if ((st = use_device_of(d->out_payload, nullptr)) != MB200_OK) return st;
-  exchange_finish_kernel<<<148 * 2, 256, 0, stream>>>(p);
+  exchange_finish_kernel<<<148 * 4, 256, 0, stream>>>(p);
   note_launch(1);
   return cuda_status(cudaGetLastError(), "exchange_finish_kernel");
 }

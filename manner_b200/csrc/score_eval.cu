@@ -49,8 +49,9 @@ struct EvalParams {
   float* loss_per_impr;
   float* scores;
   float* per_impr;
-  double* partials;  // [total_warps][W][MB200_NUM_METRICS]
+  double* partials;  // [n_chunks][W][MB200_NUM_METRICS] (score_eval_kernel: one slot per chunk) or [total_warps][...] (the other kernels)
   const int32_t* bounds;  // [n_chunks + 1] impression boundaries of the work-balanced chunks
+  int* chunk_counter;     // score_eval_kernel: next chunk to hand out (zeroed by partition_kernel); null = static round-robin
   int32_t* flags;
   long long n_news;
   long long row_stride;  // elements
@@ -81,6 +82,7 @@ struct EvalParams {
   int upart_off;                  // byte offset, in the per-warp area, of the three bf16 parts of the user vector (tensor-core path)
   int has_aspects;                // the per-warp area holds the aspect buffers
   int comb_alias;                 // one weighting: the combined scores overwrite module 0's (no separate buffer)
+  const unsigned int* ready;      // pipelined upload: leading impressions whose ids / labels are resident (null: all)
 };
 
 struct HotDir {
@@ -897,6 +899,29 @@ __device__ __noinline__ int rank_and_metrics(const EvalParams& p, const WarpSmem
   return warp_flags;
 }
 
+// Pipelined upload: wait (lane 0 polls, bounded to 4 s) until the copy stream has raised *ready to at least `need`; returns the
+// value seen.  The rows behind it were written by the copy engine before the word: system-scope acquire, then the warp re-converges.
+__device__ __noinline__ unsigned wait_ready(const unsigned int* ready, unsigned need) {
+  unsigned v = 0;
+  if ((threadIdx.x & 31) == 0) {
+    unsigned long long t0 = 0;
+    while (true) {
+      asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(ready) : "memory");
+      if (v >= need) break;
+      unsigned long long now;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+      if (t0 == 0) t0 = now;
+      if (now - t0 > 4000000000ull) break;
+      // thousands of warps may be waiting on this one word: poll slowly enough that they do not saturate its L2 slice
+      // (16 polling warps per SM at 400 ns stretched the copies themselves)
+      __nanosleep(now - t0 < 20000ull ? 1000 : 4000);
+    }
+  }
+  v = __shfl_sync(kFull, v, 0);
+  __syncwarp();
+  return v;
+}
+
 template <typename T, int NV, int R, bool EXACT, int POLICY, int MINB, bool ATTN = false, bool MMA = false>
 __global__ void __launch_bounds__(kThreads, MINB) score_eval_kernel(const __grid_constant__ EvalParams p) {
   extern __shared__ __align__(16) unsigned char smem[];
@@ -923,9 +948,30 @@ __global__ void __launch_bounds__(kThreads, MINB) score_eval_kernel(const __grid
   for (int t = lane; t < W * p.acc_stride; t += 32) sm.acc[t] = 0.0;
   __syncwarp();
 
+  // Chunks are contiguous impression ranges balanced by rows gathered (partition_kernel).  Behaviours resident: one chunk per
+  // warp.  Pipelined upload: 16 small chunks per warp handed out from a counter in impression order, so the grid consumes the
+  // set in the order its segments arrive and no warp sits on a late range.  Every chunk's sums go to the chunk's own slot of
+  // `partials`: the reduction order -- every bit of the fp64 sums -- does not depend on which warp ran which chunk.
   int warp_flags = 0;
-  for (int chunk = gw; chunk < p.n_chunks; chunk += total_warps) {
+  unsigned ready_seen = p.ready ? 0u : 0xffffffffu;
+  int chunk = gw - total_warps;
+  while (true) {
+    if (p.chunk_counter != nullptr) {
+      if (lane == 0) chunk = atomicAdd(p.chunk_counter, 1);
+      chunk = __shfl_sync(kFull, chunk, 0);
+    } else {
+      chunk += total_warps;  // static: chunk gw, gw + total_warps, ...
+    }
+    if (chunk >= p.n_chunks) break;
     const int i_begin = p.bounds[chunk], i_end = p.bounds[chunk + 1];
+    if (ready_seen < (unsigned)i_end) {
+      // pipelined upload: the ids / labels of this chunk may still be on their way (upload.cu)
+      ready_seen = wait_ready(p.ready, (unsigned)i_end);
+      if (ready_seen < (unsigned)i_end) {
+        warp_flags |= MB200_FLAG_UPLOAD_TIMEOUT;
+        break;
+      }
+    }
     for (int i = i_begin; i < i_end; ++i) {
       const int h0 = p.hist_offsets[i], h1 = p.hist_offsets[i + 1];
       const int c0 = p.cand_offsets[i], c1 = p.cand_offsets[i + 1];
@@ -958,13 +1004,16 @@ __global__ void __launch_bounds__(kThreads, MINB) score_eval_kernel(const __grid
       }
       warp_flags |= rank_and_metrics(p, sm, i, h0, H, c0, C);
     }
+    __syncwarp();
+    for (int t = lane; t < W * MB200_NUM_METRICS; t += 32) {
+      const int w = t / MB200_NUM_METRICS, k = t % MB200_NUM_METRICS;
+      p.partials[(size_t)chunk * W * MB200_NUM_METRICS + t] = k < p.acc_stride ? sm.acc[w * p.acc_stride + k] : 0.0;
+    }
+    __syncwarp();
+    for (int t = lane; t < W * p.acc_stride; t += 32) sm.acc[t] = 0.0;
+    __syncwarp();
   }
 
-  __syncwarp();
-  for (int t = lane; t < W * MB200_NUM_METRICS; t += 32) {
-    const int w = t / MB200_NUM_METRICS, k = t % MB200_NUM_METRICS;
-    p.partials[(size_t)gw * W * MB200_NUM_METRICS + t] = k < p.acc_stride ? sm.acc[w * p.acc_stride + k] : 0.0;
-  }
   warp_flags = __reduce_or_sync(kFull, warp_flags);
   if (lane == 0 && warp_flags && p.flags) atomicOr(p.flags, warp_flags);
 }
@@ -1369,6 +1418,7 @@ __global__ void partition_kernel(const int32_t* __restrict__ hist_offsets, const
   if (c > n_chunks) return;
   if (c == n_chunks) {
     bounds[c] = n_impr;
+    bounds[c + 1] = 0;  // the dynamic chunk counter of score_eval_kernel lives behind the bounds
     return;
   }
   const long long total = (long long)hist_offsets[n_impr] + cand_offsets[n_impr] + kPerImpression * n_impr;
@@ -1383,35 +1433,28 @@ __global__ void partition_kernel(const int32_t* __restrict__ hist_offsets, const
 }
 
 // Deterministic second stage: sums[w][k] = sum over warps of partials, fixed order (strided per thread,
-// then a fixed shared-memory tree).  One block per weighting.
+// then a fixed shared-memory tree).  One block per (weighting, metric slot): the slots reduce side by side
+// instead of one 256-thread block walking all of them (16 us of a 1.7 ms step).
 __global__ void __launch_bounds__(256) reduce_partials_kernel(const double* __restrict__ partials, int total_warps, int W,
                                                               double* __restrict__ sums, const int32_t* __restrict__ flags, int n_impr,
                                                               int pack_payload) {
-  __shared__ double sh[256][MB200_NUM_METRICS];
-  const int w = blockIdx.x, t = threadIdx.x;
-  double a[MB200_NUM_METRICS];
-#pragma unroll
-  for (int k = 0; k < MB200_NUM_METRICS; ++k) a[k] = 0.0;
-  for (int g = t; g < total_warps; g += 256) {
-    const double* src = partials + ((size_t)g * W + w) * MB200_NUM_METRICS;
-#pragma unroll
-    for (int k = 0; k < MB200_NUM_METRICS; ++k) a[k] += src[k];
-  }
-#pragma unroll
-  for (int k = 0; k < MB200_NUM_METRICS; ++k) sh[t][k] = a[k];
+  __shared__ double sh[256];
+  const int w = blockIdx.x, k = blockIdx.y, t = threadIdx.x;
+  double a = 0.0;
+  for (int g = t; g < total_warps; g += 256) a += partials[((size_t)g * W + w) * MB200_NUM_METRICS + k];
+  sh[t] = a;
   __syncthreads();
   for (int s = 128; s > 0; s >>= 1) {
-    if (t < s)
-#pragma unroll
-      for (int k = 0; k < MB200_NUM_METRICS; ++k) sh[t][k] += sh[t + s][k];
+    if (t < s) sh[t] += sh[t + s];
     __syncthreads();
   }
-  if (t < MB200_NUM_METRICS) sums[(size_t)w * MB200_NUM_METRICS + t] = sh[0][t];
-  if (pack_payload && w == 0 && t >= 32 && t < 32 + MB200_PAYLOAD_TAIL) {
+  if (t == 0) sums[(size_t)w * MB200_NUM_METRICS + k] = sh[0];
+  if (pack_payload && w == 0 && k == 0 && t >= 32 && t < 32 + MB200_PAYLOAD_TAIL) {
     // additive tail for a multi-GPU sum-reduction: impression count, then the flag word one bit per double
-    const int k = t - 32;
+    const int j = t - 32;
     const int f = flags ? *flags : 0;
-    sums[(size_t)W * MB200_NUM_METRICS + k] = (k == 0) ? (double)n_impr : (double)((f >> (k - 1)) & 1);
+    // bits 1, 2, 4, 8 and 64 (MB200_FLAG_UPLOAD_TIMEOUT); 16 / 32 belong to the exchange kernels
+    sums[(size_t)W * MB200_NUM_METRICS + j] = (j == 0) ? (double)n_impr : (double)((f >> (j == 5 ? 6 : j - 1)) & 1);
   }
 }
 
@@ -1430,6 +1473,7 @@ struct LaunchPlan {
   int smem_per_warp = 0;
   size_t smem_per_cta = 0;
   size_t bounds_bytes = 0, partials_bytes = 0;
+  int n_partials = 0;  // slots of `partials`: one per chunk (score_eval_kernel) or per warp (the other kernels)
   // streaming kernel only
   int has_aspects = 1, comb_alias = 0;
   int hot_cap = 0, hot_bytes = 0;
@@ -1442,6 +1486,12 @@ static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 constexpr size_t kMaxSmemPerCta = 227 * 1024;
 
+// tuning key 7: 0 = dynamic hand-out exactly when the behaviours arrive through a pipelined upload, 1 = always static, 2 = always dynamic
+static bool dynamic_schedule(const mb200_eval_desc* d) {
+  const int mode = tuning().static_chunks;
+  return mode == 2 || (mode == 0 && d->ready != nullptr);
+}
+
 static size_t hot_region_bytes(long long n_news) {
   // HotDir, hot_ids[256], counts[n_news], slot_of[n_news]
   return 256 + 1024 + align_up((size_t)n_news * sizeof(int32_t), 256) + align_up((size_t)n_news, 256);
@@ -1450,7 +1500,7 @@ static size_t hot_region_bytes(long long n_news) {
 // `stream`: plan for score_eval_stream_kernel (one CTA of kStreamWarps warps per SM; per-warp area trimmed to what the call
 // uses; the rest of the shared memory becomes the hot-row cache, `row_bytes` per row and active module).
 static int make_plan(const mb200_eval_desc* d, int sm_count, int ctas, LaunchPlan* plan, bool stream = false, int row_bytes = 0, bool hot = false,
-                     bool mma = false) {
+                     bool mma = false, bool per_chunk_slots = false) {
   const int n_active = __builtin_popcount((unsigned)d->active_modules_mask);
   plan->cpad = (int)align_up((size_t)(d->max_cand > 0 ? d->max_cand : 1), 32);
   // the aspect-weight sweep (lane per weighting: rank_and_metrics -> sweep_weightings) fills only the first kSweepSlots slots
@@ -1491,12 +1541,18 @@ static int make_plan(const mb200_eval_desc* d, int sm_count, int ctas, LaunchPla
   if (ctas < 1) ctas = 1;
   plan->grid = sm_count * ctas;
   plan->total_warps = plan->grid * plan->warps_per_cta;
-  long long chunks = (long long)plan->total_warps * (tuning().chunks_per_warp > 0 ? tuning().chunks_per_warp : 1);
+  // score_eval_kernel: resident behaviours -> one static chunk per warp (measured best: 1.484 ms against 1.505 ms for 16 dynamic
+  // chunks per warp, profiles/r2_i_schedule.log); pipelined upload -> 16 chunks per warp handed out in impression order, so the
+  // grid consumes the set in the order the segments arrive.  The other kernels walk one static chunk per warp.
+  const int cpw = tuning().chunks_per_warp;
+  const int per_warp_chunks = per_chunk_slots ? (cpw > 0 ? cpw : (dynamic_schedule(d) ? 16 : 1)) : 1;
+  long long chunks = (long long)plan->total_warps * per_warp_chunks;
   if (chunks > d->n_impressions) chunks = d->n_impressions;
   if (chunks < 1) chunks = 1;
   plan->n_chunks = (int)chunks;
-  plan->bounds_bytes = align_up((size_t)(plan->n_chunks + 1) * sizeof(int32_t), 256);
-  plan->partials_bytes = align_up((size_t)plan->total_warps * d->n_weightings * MB200_NUM_METRICS * sizeof(double), 256);
+  plan->n_partials = per_chunk_slots ? plan->n_chunks : plan->total_warps;
+  plan->bounds_bytes = align_up((size_t)(plan->n_chunks + 2) * sizeof(int32_t), 256);
+  plan->partials_bytes = align_up((size_t)plan->n_partials * d->n_weightings * MB200_NUM_METRICS * sizeof(double), 256);
   return MB200_OK;
 }
 
@@ -1523,6 +1579,7 @@ static int validate(const mb200_eval_desc* d) {
       for (int sh = 0; sh < d->n_table_shards; ++sh)
         if (((d->active_modules_mask >> m) & 1) && (d->table_shards[m][sh] == nullptr || ((uintptr_t)d->table_shards[m][sh] & 15))) return MB200_ERR_INVALID_ARG;
   }
+  if (d->ready != nullptr && (d->ready_segments < 1 || d->ready_segments > MB200_MAX_UPLOAD_SEGMENTS || ((uintptr_t)d->ready & 3))) return MB200_ERR_INVALID_ARG;
   if (d->loss_kind < MB200_LOSS_NONE || d->loss_kind > MB200_LOSS_SUPCON) return MB200_ERR_INVALID_ARG;
   if (d->loss_kind == MB200_LOSS_SUPCON && !(d->loss_temperature > 0.f)) return MB200_ERR_INVALID_ARG;
   if (d->loss_kind != MB200_LOSS_NONE && (d->scores_weighting < 0 || d->scores_weighting >= d->n_weightings)) return MB200_ERR_INVALID_ARG;
@@ -1634,7 +1691,7 @@ size_t eval_workspace_bytes(const mb200_eval_desc* d) {
   if (validate(d) != MB200_OK) return 0;
   LaunchPlan plan;
   // the SM count is not known without a device; size for the largest part this library targets (148 SMs, <= 160)
-  if (make_plan(d, 160, 8, &plan) != MB200_OK) return 0;  // upper bound: 160 SMs x 8 CTAs (the streaming kernel runs 16 warps per SM: less)
+  if (make_plan(d, 160, 8, &plan, false, 0, false, false, true) != MB200_OK) return 0;  // upper bound: 160 SMs x 8 CTAs, dynamic chunks (the streaming kernel runs 16 warps per SM: less)
   return plan.bounds_bytes + plan.partials_bytes + 256 + hot_region_bytes(d->n_news);
 }
 
@@ -1670,7 +1727,8 @@ int score_eval(const mb200_eval_desc* d, cudaStream_t stream) {
   const int variant = tuning().variant;
   LaunchPlan plan;
   KernelFn kern = nullptr;
-  bool stream_path = d->dim == 768 && d->row_stride == 768 && !attn && !sharded && (variant >= 7 && variant <= 10) && d->n_news < (1ll << 31);
+  bool stream_path = d->dim == 768 && d->row_stride == 768 && !attn && !sharded && (variant >= 7 && variant <= 10) && d->n_news < (1ll << 31) &&
+                     d->ready == nullptr;  // the experimental kernels do not gate on a pipelined upload
   bool hot = false, mma = false;
   if (stream_path) {
     if (make_plan(d, sms, 1, &plan, true, vec_per_row * 16, variant != 7 && variant != 10) != MB200_OK) stream_path = false;  // per-warp areas too large for 16 warps
@@ -1689,7 +1747,7 @@ int score_eval(const mb200_eval_desc* d, cudaStream_t stream) {
     if (mma) kern = score_eval_kernel<__nv_bfloat16, 3, 4, true, 0, 5, false, true>;
     else kern = (d->dtype == MB200_F32) ? select_kernel<float>(vec_per_row, attn, sharded) : select_kernel<__nv_bfloat16>(vec_per_row, attn, sharded);
     if (kern == nullptr) return MB200_ERR_UNSUPPORTED;  // row-sharded tables: reference width, late fusion only
-    st = make_plan(d, sms, 1, &plan, false, 0, false, mma);  // shared-memory sizes first: they decide how many CTAs fit
+    st = make_plan(d, sms, 1, &plan, false, 0, false, mma, true);  // shared-memory sizes first: they decide how many CTAs fit
     if (st != MB200_OK) return st;
     if (plan.smem_per_cta > 48 * 1024) {
       st = cuda_status(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem_per_cta), "cudaFuncSetAttribute");
@@ -1701,7 +1759,7 @@ int score_eval(const mb200_eval_desc* d, cudaStream_t stream) {
     if (st != MB200_OK) return st;
     if (resident < 1) return MB200_ERR_UNSUPPORTED;
     const int want = tuning().ctas_per_sm > 0 ? tuning().ctas_per_sm : resident;
-    st = make_plan(d, sms, want < resident ? want : resident, &plan, false, 0, false, mma);
+    st = make_plan(d, sms, want < resident ? want : resident, &plan, false, 0, false, mma, true);
     if (st != MB200_OK) return st;
   }
   const size_t need = plan.bounds_bytes + plan.partials_bytes + (hot ? hot_region_bytes(d->n_news) : 0);
@@ -1720,6 +1778,7 @@ int score_eval(const mb200_eval_desc* d, cudaStream_t stream) {
   p.scores = d->scores, p.per_impr = d->per_impression, p.flags = d->flags;
   unsigned char* ws = reinterpret_cast<unsigned char*>(d->workspace);
   p.bounds = reinterpret_cast<int32_t*>(ws);
+  p.chunk_counter = dynamic_schedule(d) ? reinterpret_cast<int*>(ws) + plan.n_chunks + 1 : nullptr;
   p.partials = reinterpret_cast<double*>(ws + plan.bounds_bytes);
   p.n_news = d->n_news, p.row_stride = d->row_stride;
   p.n_impr = (int)d->n_impressions, p.n_modules = d->n_modules, p.active_mask = d->active_modules_mask;
@@ -1733,6 +1792,7 @@ int score_eval(const mb200_eval_desc* d, cudaStream_t stream) {
   p.loss_kind = d->loss_kind, p.loss_temperature = d->loss_temperature;
   p.has_aspects = plan.has_aspects, p.comb_alias = plan.comb_alias;
   p.hot_cap = plan.hot_cap, p.hot_bytes = plan.hot_bytes, p.upart_off = plan.upart_off;
+  p.ready = d->ready;
 
   KernelTimer* timer = tuning().time_kernel ? timer_for(device) : nullptr;
   int launches = 3;
@@ -1764,7 +1824,7 @@ int score_eval(const mb200_eval_desc* d, cudaStream_t stream) {
   if (timer) cudaEventRecord(timer->end, stream), timer->armed = true, g_last_timer = timer;
   st = cuda_status(e, "score_eval_kernel");
   if (st != MB200_OK) return st;
-  reduce_partials_kernel<<<d->n_weightings, 256, 0, stream>>>(p.partials, plan.total_warps, d->n_weightings, d->sums, d->flags, p.n_impr,
+  reduce_partials_kernel<<<dim3(d->n_weightings, MB200_NUM_METRICS), 256, 0, stream>>>(p.partials, plan.n_partials, d->n_weightings, d->sums, d->flags, p.n_impr,
                                                               d->pack_payload);
   st = cuda_status(cudaGetLastError(), "reduce_partials_kernel");
   if (st != MB200_OK) return st;
@@ -1827,7 +1887,7 @@ int rank_metrics(const mb200_metrics_desc* d, cudaStream_t stream) {
   if ((st = cuda_status(cudaGetLastError(), "partition_kernel")) != MB200_OK) return st;
   rank_metrics_kernel<<<plan.grid, kThreads, plan.smem_per_cta, stream>>>(p);
   if ((st = cuda_status(cudaGetLastError(), "rank_metrics_kernel")) != MB200_OK) return st;
-  reduce_partials_kernel<<<1, 256, 0, stream>>>(p.partials, plan.total_warps, 1, d->sums, d->flags, p.n_impr, 0);
+  reduce_partials_kernel<<<dim3(1, MB200_NUM_METRICS), 256, 0, stream>>>(p.partials, plan.total_warps, 1, d->sums, d->flags, p.n_impr, 0);
   if ((st = cuda_status(cudaGetLastError(), "reduce_partials_kernel")) != MB200_OK) return st;
   note_launch(3);
   return MB200_OK;

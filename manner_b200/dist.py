@@ -22,7 +22,13 @@ from torch import Tensor
 
 from .data import Behaviours, balanced_shard_bounds
 
-N_FLAG_BITS = 4
+FLAG_BITS = (1, 2, 4, 8, 64)  # flag-word bits a packed payload carries, in order (_native.PAYLOAD_FLAG_BITS; MB200_PAYLOAD_TAIL - 1 of them)
+N_FLAG_BITS = len(FLAG_BITS)
+
+
+def flags_from_payload_tail(tail) -> int:
+    """Flag word from the 0 / >0 doubles behind the impression count of a (reduced) packed payload."""
+    return sum(bit for bit, v in zip(FLAG_BITS, tail) if v > 0)
 
 
 def shard_for_rank(bhv: Behaviours, rank: int, world_size: int, align: int = 1) -> Behaviours:
@@ -151,7 +157,8 @@ class P2PExchange:
 
 def pack_metric_payload(sums: Tensor, flags: Tensor, n_impressions: int) -> Tensor:
     """[W, NUM_METRICS] sums, the impression count and the flag word's bits as one fp64 vector (all additive)."""
-    bits = ((flags.to(torch.int64).reshape(1) >> torch.arange(N_FLAG_BITS, device=flags.device)) & 1).to(torch.float64)
+    shifts = torch.tensor([b.bit_length() - 1 for b in FLAG_BITS], device=flags.device)
+    bits = ((flags.to(torch.int64).reshape(1) >> shifts) & 1).to(torch.float64)
     count = torch.full((1,), float(n_impressions), dtype=torch.float64, device=sums.device)
     return torch.cat([sums.reshape(-1), count, bits])
 
@@ -160,7 +167,7 @@ def unpack_metric_payload(payload: Tensor, shape: torch.Size) -> Tuple[Tensor, T
     n = shape.numel()
     sums = payload[:n].reshape(shape)
     bits = (payload[n + 1 : n + 1 + N_FLAG_BITS] > 0).to(torch.int32)
-    flags = (bits << torch.arange(N_FLAG_BITS, device=payload.device, dtype=torch.int32)).sum().to(torch.int32).reshape(1)
+    flags = (bits * torch.tensor(FLAG_BITS, device=payload.device, dtype=torch.int32)).sum().to(torch.int32).reshape(1)
     return sums, flags, int(round(float(payload[n].item())))
 
 
@@ -168,7 +175,7 @@ def unpack_metric_payload_device(payload: Tensor, shape: torch.Size) -> Tuple[Te
     """Like ``unpack_metric_payload`` but without a host read: the count stays a device scalar."""
     n = shape.numel()
     bits = (payload[n + 1 : n + 1 + N_FLAG_BITS] > 0).to(torch.int32)
-    flags = (bits << torch.arange(N_FLAG_BITS, device=payload.device, dtype=torch.int32)).sum().to(torch.int32).reshape(1)
+    flags = (bits * torch.tensor(FLAG_BITS, device=payload.device, dtype=torch.int32)).sum().to(torch.int32).reshape(1)
     return payload[:n].reshape(shape), flags, payload[n]
 
 

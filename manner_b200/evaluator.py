@@ -64,6 +64,17 @@ class DeviceBehaviours:
     step_batch: int = 8
     hist_pad: Optional[Tensor] = None
     cand_pad: Optional[Tensor] = None
+    # pipelined upload (upload(..., pipelined=True)): the device word the copy stream raises as segments arrive, the number of
+    # segments, and the call that enqueues the segments still missing (made by launch() right behind the fused kernel)
+    ready: Optional[Tensor] = None
+    ready_segments: int = 0
+    _finish_upload: Optional[object] = None
+
+    def finish_upload(self) -> None:
+        """Enqueues what a pipelined upload has not enqueued yet (idempotent; launch() calls it)."""
+        if self._finish_upload is not None:
+            fin, self._finish_upload = self._finish_upload, None
+            fin()
 
 
 @dataclass
@@ -144,6 +155,7 @@ class ScoreEvaluator:
             raise ValueError("exchange must be 'p2p' (fused: stores into the peers' mailboxes over NVLink) or 'nccl' (three collectives)")
         self.exchange = exchange  # how a distributed evaluation meets the other ranks (dist.P2PExchange / dist.pooled_auc_distributed)
         self._p2p: Optional[mdist.P2PExchange] = None
+        self._copy_stream: Optional[torch.cuda.Stream] = None  # pipelined uploads run here
         if not torch.cuda.is_available():
             raise RuntimeError("manner_b200.ScoreEvaluator needs a CUDA device; there is no CPU path")
         self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
@@ -189,21 +201,68 @@ class ScoreEvaluator:
 
     # -- inputs ----------------------------------------------------------------------------------------------
     def upload(self, bhv: Behaviours, pinned: Optional[Dict[str, object]] = None, pos_cap: Optional[int] = None,
-               step_batch: Optional[int] = None) -> DeviceBehaviours:
+               step_batch: Optional[int] = None, pipelined: bool = False, segments: int = 8) -> DeviceBehaviours:
         """Host CSR -> device (asynchronous on the current stream).  ``pinned`` lets a caller reuse
         page-locked staging tensors (see ``pin``); ``pos_cap`` is the multi-GPU bound of
         ``dist.agree_pos_cap`` when the caller already has it.  ``step_batch`` (the reference's eval batch size)
-        additionally uploads the per-impression pad counts early fusion and the cross-entropy loss need."""
+        additionally uploads the per-impression pad counts early fusion and the cross-entropy loss need.
+
+        ``pipelined``: the copy overlaps the pass instead of preceding it (mb200_upload_begin / _finish): the offsets go first,
+        the id / label arrays follow in ``segments`` work-balanced segments on a copy stream, and the fused kernel -- launched
+        by the next ``launch`` / ``evaluate`` with the returned object -- starts on the first segment while the others are in
+        flight.  The returned arrays must not be read by anything else before that launch."""
         src = pinned if pinned is not None else self.pin(bhv, step_batch)
         if pos_cap is not None and pos_cap < src["n_pos"]:
             raise ValueError(f"pos_cap {pos_cap} is below this shard's {src['n_pos']} positives: the pooled AUROC would silently drop keys (dist.agree_pos_cap)")
-        dev = {k: v.to(self.device, non_blocking=True) for k, v in src.items() if isinstance(v, Tensor)}
-        nbytes = sum(v.numel() * v.element_size() for v in src.values() if isinstance(v, Tensor))
+        nbytes = sum(v.numel() * v.element_size() for k, v in src.items() if isinstance(v, Tensor) and k != "marks")
+        if pipelined and bhv.n_impressions >= 64 * segments and self.n_table_shards == 1:
+            return self._upload_pipelined(bhv, src, pos_cap, nbytes, int(segments))
+        dev = {k: v.to(self.device, non_blocking=True) for k, v in src.items() if isinstance(v, Tensor) and k != "marks"}
         return DeviceBehaviours(
             dev["hist_offsets"], dev["hist_ids"], dev["cand_offsets"], dev["cand_ids"], dev["labels"],
             bhv.n_impressions, src["max_cand"], nbytes, src["n_pos"], pos_cap,
             src.get("step_batch", 8), dev.get("hist_pad"), dev.get("cand_pad"),
         )
+
+    def _upload_pipelined(self, bhv: Behaviours, src: Dict[str, object], pos_cap: Optional[int], nbytes: int, segments: int) -> DeviceBehaviours:
+        import ctypes
+
+        lib = nat.lib()
+        segments = max(1, min(segments, nat.MAX_UPLOAD_SEGMENTS))
+        if "marks" not in src:
+            src["marks"] = torch.zeros(nat.MAX_UPLOAD_SEGMENTS, dtype=torch.int32).pin_memory()
+        with torch.cuda.device(self.device):
+            if self._copy_stream is None:
+                self._copy_stream = torch.cuda.Stream(self.device)
+            compute = torch.cuda.current_stream(self.device)
+            dev = {k: torch.empty(v.shape, dtype=v.dtype, device=self.device) for k, v in src.items() if isinstance(v, Tensor) and k != "marks"}
+            for t in dev.values():
+                t.record_stream(self._copy_stream)  # written there: the allocator must not recycle the block under the copies
+            ready = torch.empty(1, dtype=torch.int32, device=self.device)
+            d = nat.UploadDesc()
+            d.struct_size = ctypes.sizeof(nat.UploadDesc)
+            d.n_segments, d.segments_first, d.n_impressions = segments, 1, bhv.n_impressions
+            for name in ("hist_offsets", "hist_ids", "cand_offsets", "cand_ids", "labels"):
+                setattr(d, "h_" + name, src[name].data_ptr())
+                setattr(d, "d_" + name, dev[name].data_ptr())
+            for name in ("hist_pad", "cand_pad"):
+                if name in dev:
+                    setattr(d, "h_" + name, src[name].data_ptr())
+                    setattr(d, "d_" + name, dev[name].data_ptr())
+            d.ready, d.h_marks, d.copy_stream = ready.data_ptr(), src["marks"].data_ptr(), self._copy_stream.cuda_stream
+            nat.check(lib.mb200_upload_begin(ctypes.byref(d), compute.cuda_stream), "mb200_upload_begin")
+
+        def finish(d=d, keep=(src, dev, ready)) -> None:
+            nat.check(lib.mb200_upload_finish(ctypes.byref(d)), "mb200_upload_finish")
+
+        out = DeviceBehaviours(
+            dev["hist_offsets"], dev["hist_ids"], dev["cand_offsets"], dev["cand_ids"], dev["labels"],
+            bhv.n_impressions, src["max_cand"], nbytes, src["n_pos"], pos_cap,
+            src.get("step_batch", 8), dev.get("hist_pad"), dev.get("cand_pad"), ready, segments, finish,
+        )
+        if segments == 1:
+            out.finish_upload()
+        return out
 
     @staticmethod
     def pin(bhv: Behaviours, step_batch: Optional[int] = None) -> Dict[str, object]:
@@ -266,7 +325,9 @@ class ScoreEvaluator:
             self.attn_logits if self.attn_logits is not None else [], distributed,
             bhv.hist_pad if self.attn_logits is not None else None, loss_kind, float(temperature),
             bhv.cand_pad if loss is not None else None, self.n_table_shards, self.table_shard_shift, self.n_news,
+            bhv.ready, bhv.ready_segments,
         )
+        bhv.finish_upload()  # pipelined upload: the remaining segments follow the fused kernel into the queues
         loss_stats: Optional[Tensor] = None
         if loss is not None:
             # MeanMetric over the reference's steps (cr_module.py:253-259): (sum of step losses, number of steps)
@@ -315,14 +376,14 @@ class ScoreEvaluator:
             if tail[3] & nat.FLAG_POS_OVERFLOW:
                 raise nat.NativeError("fused multi-GPU exchange: a rank had more positives than the agreed pos_cap (dist.agree_pos_cap)")
             sums_h, n_total = packed[:n_block].reshape(pending.n_weightings, nat.NUM_METRICS), int(round(packed[n_block]))
-            flags_h = sum((1 << b) for b in range(mdist.N_FLAG_BITS) if packed[n_block + 1 + b] > 0)
+            flags_h = mdist.flags_from_payload_tail(packed[n_block + 1 : n_block + 1 + mdist.N_FLAG_BITS])
             if pending.has_auc:
                 s2, p, n = tail[0], tail[1], tail[2]
                 auc, counts = (s2 / (2.0 * p * n) if p > 0 and n > 0 else 0.0), (p, n)
         elif pending.distributed:
             packed = pending.sums.cpu().numpy()
             sums_h, n_total = packed[:n_block].reshape(pending.n_weightings, nat.NUM_METRICS), int(round(packed[n_block]))
-            flags_h = sum((1 << b) for b in range(mdist.N_FLAG_BITS) if packed[n_block + 1 + b] > 0)
+            flags_h = mdist.flags_from_payload_tail(packed[n_block + 1 : n_block + 1 + mdist.N_FLAG_BITS])
             d2h = packed.size * 8
             if pending.auc_stats is not None:
                 auc, p, n = mdist.auc_from_stats(pending.auc_stats)
@@ -343,6 +404,8 @@ class ScoreEvaluator:
             ls = pending.loss_stats.cpu().numpy()
             d2h += 16
             loss_value = float(ls[0] / ls[1]) if ls[1] > 0 else 0.0
+        if flags_h & nat.FLAG_UPLOAD_TIMEOUT:
+            raise nat.NativeError("pipelined upload: a segment of the behaviour set did not reach the device within 4 s (copy stream stalled?)")
         if flags_h & (nat.FLAG_BAD_ID | nat.FLAG_CAND_OVERFLOW | nat.FLAG_BAD_ASPECT):
             raise nat.NativeError(
                 f"manner_b200 kernels flagged bad input (flags={flags_h}): "

@@ -290,7 +290,7 @@ class B200EvalMixin:
         hp = getattr(self, "hparams", {})
         sweep = weights is not None and len(weights) > 0 and isinstance(weights[0], (list, tuple))
         res = ev.evaluate(
-            ev.upload(bhv, step_batch=step), weights=None if weights is None else (weights if sweep else [weights]), zscore=self._b200_zscore,
+            ev.upload(bhv, step_batch=step, pipelined=True), weights=None if weights is None else (weights if sweep else [weights]), zscore=self._b200_zscore,
             pooled_auc=self._b200_with_auc, loss=None if self._b200_zscore else self._b200_loss(),
             temperature=float(hp.get("temperature", 0.1)) if hasattr(hp, "get") else 0.1,
         )

@@ -71,6 +71,8 @@ def score_eval(
     n_table_shards: int = 1,
     table_shard_shift: int = 0,
     n_news: int = 0,
+    ready: Optional[Tensor] = None,
+    ready_segments: int = 0,
 ) -> Tuple[Tensor, Tensor, Tensor, Tensor, Tensor]:
     """Fused gather / pool / score / z-score / ensemble / per-impression metrics (include/manner_b200.h,
     mb200_score_eval).  Returns (scores fp32 [sum C] or empty, per_impression fp32 [W, B, NUM_METRICS] or empty,
@@ -85,7 +87,11 @@ def score_eval(
 
     Row-sharded tables (``n_table_shards`` = R > 1): ``tables`` then holds R tensors per module, module-major, each
     [1 << table_shard_shift, dim] -- this GPU's shard and the peers' shards opened over CUDA IPC (dist.share_table_shards);
-    ``n_news`` is the size of the whole catalogue.  The kernel reads remote rows directly over NVLink."""
+    ``n_news`` is the size of the whole catalogue.  The kernel reads remote rows directly over NVLink.
+
+    Pipelined upload (ScoreEvaluator.upload(pipelined=True) -> mb200_upload_begin): ``ready`` int32 [1] is the device word the
+    copy stream raises to the number of leading impressions whose ids / labels have arrived, ``ready_segments`` the number of
+    segments; the kernel starts on the first segment while the others are still being copied."""
     lib = nat.lib()
     n_modules = len(tables) // max(n_table_shards, 1)
     if n_table_shards > 1 and (n_table_shards > nat.MAX_TABLE_SHARDS or n_modules * n_table_shards != len(tables) or n_news <= 0):
@@ -181,6 +187,9 @@ def score_eval(
         d.per_impression = per_impr.data_ptr() if want_per_impression else None
         d.sums = sums.data_ptr()
         d.flags = flags.data_ptr()
+        if ready is not None:
+            _require_cuda("ready", ready, torch.int32)
+            d.ready, d.ready_segments = ready.data_ptr(), int(ready_segments)
         need = lib.mb200_eval_workspace_bytes(ctypes.byref(d))
         if need == 0:
             # the size query runs the same validation as the call: report the precise status
@@ -197,7 +206,7 @@ def score_eval(
 def _(tables, hist_offsets, hist_ids, cand_offsets, cand_ids, labels, weights, zscore, max_cand, active_mask, k0, k1,
       want_scores, scores_weighting, want_per_impression, news_category, news_sentiment, num_categ_classes, num_sent_classes,
       attn_logits, pack_payload=False, hist_pad=None, loss_kind=0, loss_temperature=1.0, cand_pad=None, n_table_shards=1,
-      table_shard_shift=0, n_news=0):
+      table_shard_shift=0, n_news=0, ready=None, ready_segments=0):
     dev = tables[0].device
     n_w = 1 if weights is None else weights.shape[0]
     n_impr = hist_offsets.numel() - 1
@@ -389,8 +398,9 @@ def last_hot_stats() -> dict:
 
 def set_tuning(chunks_per_warp: Optional[int] = None, variant: Optional[int] = None, ctas_per_sm: Optional[int] = None,
                time_kernel: Optional[int] = None, retrieval_diag: Optional[int] = None, retrieval_pair: Optional[int] = None,
-               hot_kb_cap: Optional[int] = None) -> None:
+               hot_kb_cap: Optional[int] = None, static_chunks: Optional[int] = None) -> None:
     lib = nat.lib()
-    for key, val in ((0, chunks_per_warp), (1, variant), (2, ctas_per_sm), (3, time_kernel), (4, retrieval_diag), (5, retrieval_pair), (6, hot_kb_cap)):
+    for key, val in ((0, chunks_per_warp), (1, variant), (2, ctas_per_sm), (3, time_kernel), (4, retrieval_diag), (5, retrieval_pair), (6, hot_kb_cap),
+                     (7, static_chunks)):
         if val is not None:
             lib.mb200_set_tuning(key, int(val))

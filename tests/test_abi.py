@@ -44,6 +44,28 @@ def test_struct_layout_matches_c(tmp_path):
     assert got == [ctypes.sizeof(E), E.tables.offset, E.weights.offset, E.scores.offset, E.workspace_bytes.offset]
 
 
+def test_upload_desc_layout_and_validation_without_a_gpu(tmp_path):
+    """mb200_upload_desc (pipelined host -> device upload) and the `ready` tail of mb200_eval_desc."""
+    src = tmp_path / "su.c"
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "manner_b200.h"\nint main(){printf("%zu %zu %zu %zu %zu %zu %d",'
+                   "sizeof(mb200_upload_desc),offsetof(mb200_upload_desc,n_impressions),offsetof(mb200_upload_desc,d_hist_offsets),"
+                   "offsetof(mb200_upload_desc,ready),offsetof(mb200_upload_desc,copy_stream),offsetof(mb200_eval_desc,ready),"
+                   "MB200_PAYLOAD_TAIL);return 0;}\n")
+    exe = tmp_path / "su"
+    subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    got = [int(x) for x in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()]
+    U = nat.UploadDesc
+    assert got == [ctypes.sizeof(U), U.n_impressions.offset, U.d_hist_offsets.offset, U.ready.offset, U.copy_stream.offset,
+                   nat.EvalDesc.ready.offset, nat.PAYLOAD_TAIL]
+    assert nat.PAYLOAD_TAIL == 1 + len(nat.PAYLOAD_FLAG_BITS)
+    lib = nat.lib()
+    d = U()
+    assert lib.mb200_upload_begin(ctypes.byref(d), None) == nat.ERR_INVALID_ARG  # struct_size unset
+    assert lib.mb200_upload_finish(None) == nat.ERR_INVALID_ARG
+    d.struct_size, d.n_segments, d.segments_first, d.n_impressions = ctypes.sizeof(U), 99, 1, 10
+    assert lib.mb200_upload_begin(ctypes.byref(d), None) == nat.ERR_INVALID_ARG  # more than MB200_MAX_UPLOAD_SEGMENTS
+
+
 def test_host_only_entry_points():
     lib = nat.lib()
     assert lib.mb200_abi_version() == nat.ABI_VERSION
