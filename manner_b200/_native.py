@@ -209,6 +209,8 @@ SIGNATURES = {
     "mb200_auc_rank_sum": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
     "mb200_pooled_auc_workspace_bytes": (c_size_t, [c_int64]),
     "mb200_pooled_auc": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p, c_size_t, c_void_p, c_void_p]),
+    "mb200_pooled_auc_bounded_workspace_bytes": (c_size_t, [c_int64, c_int64]),
+    "mb200_pooled_auc_bounded": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int, c_void_p, c_void_p, c_size_t, c_void_p, c_void_p]),
     "mb200_retrieval_workspace_bytes": (c_size_t, [POINTER(RetrievalDesc)]),
     "mb200_retrieve_topk": (c_int, [POINTER(RetrievalDesc), c_void_p]),
     "mb200_pool_users": (c_int, [c_void_p, c_int, c_int, c_int64, c_int64, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
@@ -225,6 +227,7 @@ SIGNATURES = {
     "mb200_enable_peer_access": (c_int, [c_int, c_int]),
     "mb200_ipc_export": (c_int, [c_void_p, c_char_p, POINTER(c_int64)]),
     "mb200_ipc_open": (c_int, [c_char_p, c_int64, c_int, POINTER(c_void_p)]),
+    "mb200_ipc_close": (c_int, [c_void_p, c_int]),
     "mb200_dcg_discount": (c_float, [c_int]),
     "mb200_launch_count": (c_int64, []),
     "mb200_library_launch_count": (c_int64, []),

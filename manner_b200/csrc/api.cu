@@ -54,6 +54,8 @@ int auc_sort_keys(const uint32_t*, uint32_t*, long long, void*, size_t, cudaStre
 int auc_rank_sum(const uint32_t*, long long, const long long*, const uint32_t*, long long, const long long*, unsigned long long*, cudaStream_t);
 size_t pooled_auc_workspace_bytes(long long n);
 int pooled_auc(const float*, const uint8_t*, long long, int, const int32_t*, void*, size_t, double*, cudaStream_t);
+size_t pooled_auc_bounded_workspace_bytes(long long n, long long pos_capacity);
+int pooled_auc_bounded(const float*, const uint8_t*, long long, long long, int, const int32_t*, void*, size_t, double*, cudaStream_t);
 size_t retrieval_workspace_bytes(const mb200_retrieval_desc* d);
 int retrieve_topk(const mb200_retrieval_desc* d, cudaStream_t stream);
 int pool_users(const void*, int, int, long long, long long, const int32_t*, const int32_t*, long long, void*, int32_t*, cudaStream_t);
@@ -140,6 +142,19 @@ int mb200_pooled_auc(const float* preds, const uint8_t* labels, int64_t n, int s
   int st = use_device_of(out, nullptr);
   if (st != MB200_OK) return st;
   return pooled_auc(preds, labels, n, sigmoid_mode, flags, workspace, workspace_bytes, out, static_cast<cudaStream_t>(stream));
+}
+
+size_t mb200_pooled_auc_bounded_workspace_bytes(int64_t n, int64_t pos_capacity) {
+  return (n < 0 || pos_capacity < 0) ? 0 : pooled_auc_bounded_workspace_bytes(n, pos_capacity);
+}
+
+int mb200_pooled_auc_bounded(const float* preds, const uint8_t* labels, int64_t n, int64_t pos_capacity, int sigmoid_mode, const int32_t* flags,
+                             void* workspace, size_t workspace_bytes, double* out, void* stream) {
+  if (n < 0 || pos_capacity < 0 || out == nullptr || (n > 0 && (!preds || !labels))) return MB200_ERR_INVALID_ARG;
+  if (sigmoid_mode < 0 || sigmoid_mode > 2 || (sigmoid_mode == 2 && flags == nullptr)) return MB200_ERR_INVALID_ARG;
+  int st = use_device_of(out, nullptr);
+  if (st != MB200_OK) return st;
+  return pooled_auc_bounded(preds, labels, n, pos_capacity, sigmoid_mode, flags, workspace, workspace_bytes, out, static_cast<cudaStream_t>(stream));
 }
 
 size_t mb200_retrieval_workspace_bytes(const mb200_retrieval_desc* desc) { return retrieval_workspace_bytes(desc); }
@@ -235,6 +250,17 @@ int mb200_ipc_open(const unsigned char handle[64], int64_t offset, int device, v
   if (st != MB200_OK) return st;
   *out_ptr = static_cast<unsigned char*>(base) + offset;
   return MB200_OK;
+}
+
+int mb200_ipc_close(void* mapped_base, int device) {
+  if (!mapped_base) return MB200_ERR_INVALID_ARG;
+  int prev = 0;
+  cudaGetDevice(&prev);
+  int st = cuda_status(cudaSetDevice(device), "cudaSetDevice");
+  if (st != MB200_OK) return st;
+  st = cuda_status(cudaIpcCloseMemHandle(mapped_base), "cudaIpcCloseMemHandle");
+  cudaSetDevice(prev);
+  return st;
 }
 
 float mb200_dcg_discount(int rank) { return host_dcg_discount(rank); }

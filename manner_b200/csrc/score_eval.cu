@@ -900,13 +900,15 @@ __device__ __noinline__ int rank_and_metrics(const EvalParams& p, const WarpSmem
 }
 
 // Pipelined upload: wait (lane 0 polls, bounded to 4 s) until the copy stream has raised *ready to at least `need`; returns the
-// value seen.  The rows behind it were written by the copy engine before the word: system-scope acquire, then the warp re-converges.
+// value seen.  The poll itself is a relaxed system-scope load -- an acquire load would invalidate the SM's L1 (CCTL.IVALL) on
+// every iteration, under the feet of the 15 other warps -- and ONE acquire fence follows once the word is high enough: the ids
+// and labels behind it were written by the copy engine before the word.
 __device__ __noinline__ unsigned wait_ready(const unsigned int* ready, unsigned need) {
   unsigned v = 0;
   if ((threadIdx.x & 31) == 0) {
     unsigned long long t0 = 0;
     while (true) {
-      asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(ready) : "memory");
+      asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(ready) : "memory");
       if (v >= need) break;
       unsigned long long now;
       asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
@@ -916,6 +918,7 @@ __device__ __noinline__ unsigned wait_ready(const unsigned int* ready, unsigned 
       // (16 polling warps per SM at 400 ns stretched the copies themselves)
       __nanosleep(now - t0 < 20000ull ? 1000 : 4000);
     }
+    asm volatile("fence.acq_rel.sys;" ::: "memory");
   }
   v = __shfl_sync(kFull, v, 0);
   __syncwarp();

@@ -12,6 +12,10 @@
 // reads up to the end of segment s cannot pull not-yet-written bytes of segment s + 1 into its L1.
 
 #include <algorithm>
+#include <condition_variable>
+#include <deque>
+#include <mutex>
+#include <thread>
 
 #include "common.cuh"
 
@@ -37,7 +41,7 @@ static int upload_events_for(int device, UploadEvents** out) {
 
 static int validate_upload(const mb200_upload_desc* d) {
   if (d == nullptr || d->struct_size != sizeof(mb200_upload_desc)) return MB200_ERR_INVALID_ARG;
-  if (d->n_segments < 1 || d->n_segments > MB200_MAX_UPLOAD_SEGMENTS || d->segments_first < 1 || d->segments_first > d->n_segments) return MB200_ERR_INVALID_ARG;
+  if (d->n_segments < 1 || d->n_segments > MB200_MAX_UPLOAD_SEGMENTS || d->segments_first < 0 || d->segments_first > d->n_segments) return MB200_ERR_INVALID_ARG;
   if (d->n_impressions < 1 || d->n_impressions > 0x7ffffff0ll) return MB200_ERR_INVALID_ARG;
   if (!d->h_hist_offsets || !d->h_hist_ids || !d->h_cand_offsets || !d->h_cand_ids || !d->h_labels) return MB200_ERR_INVALID_ARG;
   if (!d->d_hist_offsets || !d->d_hist_ids || !d->d_cand_offsets || !d->d_cand_ids || !d->d_labels) return MB200_ERR_INVALID_ARG;
@@ -93,6 +97,69 @@ static int copy_segments(const mb200_upload_desc* d, int first, int last) {
   return MB200_OK;
 }
 
+// The segments that mb200_upload_begin does not queue itself are queued by ONE library thread, concurrently with the caller -- who
+// goes straight on to launch the fused kernel.  The caller's thread therefore never has to get past that launch for the copies to
+// be issued: nothing deadlocks where launches block (a profiler that serialises kernels, CUDA_LAUNCH_BLOCKING=1), which a
+// "launch first, queue the rest afterwards" order on one thread would (the kernel waits for copies the host has not issued yet).
+struct UploadJob {
+  mb200_upload_desc d;
+  int first, last, device;
+  unsigned long long ticket;
+};
+
+class UploadWorker {
+ public:
+  UploadWorker() : thread_([this] { run(); }) { thread_.detach(); }
+  unsigned long long submit(const UploadJob& job) {
+    std::lock_guard<std::mutex> lock(m_);
+    UploadJob j = job;
+    j.ticket = ++issued_;
+    q_.push_back(j);
+    cv_.notify_one();
+    return j.ticket;
+  }
+  // blocks until every job submitted so far has been queued on its copy stream; returns the first error among them
+  int drain() {
+    std::unique_lock<std::mutex> lock(m_);
+    done_cv_.wait(lock, [this] { return done_ == issued_; });
+    const int st = status_;
+    status_ = MB200_OK;
+    return st;
+  }
+
+ private:
+  void run() {
+    for (;;) {
+      UploadJob job;
+      {
+        std::unique_lock<std::mutex> lock(m_);
+        cv_.wait(lock, [this] { return !q_.empty(); });
+        job = q_.front();
+        q_.pop_front();
+      }
+      int st = cuda_status(cudaSetDevice(job.device), "cudaSetDevice");
+      if (st == MB200_OK) st = copy_segments(&job.d, job.first, job.last);
+      {
+        std::lock_guard<std::mutex> lock(m_);
+        if (st != MB200_OK && status_ == MB200_OK) status_ = st;
+        done_ = job.ticket;
+      }
+      done_cv_.notify_all();
+    }
+  }
+  std::mutex m_;
+  std::condition_variable cv_, done_cv_;
+  std::deque<UploadJob> q_;
+  unsigned long long issued_ = 0, done_ = 0;
+  int status_ = MB200_OK;
+  std::thread thread_;
+};
+
+static UploadWorker& upload_worker() {
+  static UploadWorker* w = new UploadWorker();  // never destroyed: the thread sleeps on its queue until the process ends
+  return *w;
+}
+
 int upload_begin(const mb200_upload_desc* d, cudaStream_t compute) {
   int st = validate_upload(d);
   if (st != MB200_OK) return st;
@@ -116,14 +183,18 @@ int upload_begin(const mb200_upload_desc* d, cudaStream_t compute) {
   // the compute stream may run the partition + the fused kernel as soon as the offsets are in
   if ((st = cuda_status(cudaEventRecord(ev->offsets, cs), "cudaEventRecord")) != MB200_OK) return st;
   if ((st = cuda_status(cudaStreamWaitEvent(compute, ev->offsets, 0), "cudaStreamWaitEvent")) != MB200_OK) return st;
-  return copy_segments(d, 0, d->segments_first);
+  if ((st = copy_segments(d, 0, d->segments_first)) != MB200_OK) return st;
+  if (d->segments_first < d->n_segments) {
+    UploadJob job;
+    job.d = *d, job.first = d->segments_first, job.last = d->n_segments, job.device = device, job.ticket = 0;
+    upload_worker().submit(job);
+  }
+  return MB200_OK;
 }
 
 int upload_finish(const mb200_upload_desc* d) {
-  int st = validate_upload(d);
-  if (st != MB200_OK) return st;
-  if ((st = use_device_of(d->ready, nullptr)) != MB200_OK) return st;
-  return copy_segments(d, d->segments_first, d->n_segments);
+  if (d == nullptr || d->struct_size != sizeof(mb200_upload_desc)) return MB200_ERR_INVALID_ARG;
+  return upload_worker().drain();
 }
 
 }  // namespace mb200

@@ -39,7 +39,7 @@ def shard_for_rank(bhv: Behaviours, rank: int, world_size: int, align: int = 1) 
     return bhv.slice(int(bounds[rank]), int(bounds[rank + 1]))
 
 
-_ipc_bases: dict = {}  # (IPC handle, local device) -> base address of the mapping in this process
+_ipc_bases: dict = {}  # (IPC handle, local device) -> [base address of the mapping in this process, users]
 
 
 class _PeerMemory:
@@ -50,17 +50,46 @@ class _PeerMemory:
         self.__cuda_array_interface__ = {"data": (int(ptr), False), "shape": tuple(shape), "typestr": typestr, "version": 2, "strides": None}
 
 
-def share_table_shards(local_shard: Tensor, group: Optional[dist.ProcessGroup] = None) -> list:
+class SharedShards(list):
+    """What ``share_table_shards`` returns: the list of all ranks' tensors, plus the peer mappings behind them.  ``close()`` gives
+    the mappings back (the last user of a peer allocation unmaps it with mb200_ipc_close); the peer tensors are dead afterwards.
+    Not closing is harmless until the process exits -- but a peer that frees and re-creates its buffer may get the same IPC handle
+    bytes again, and a mapping kept for the old allocation would then point at stale memory: owners (P2PExchange,
+    CatalogRetriever) close what they opened."""
+
+    _keys: list
+
+    def close(self) -> None:
+        from . import _native as nat
+
+        keys, self._keys = getattr(self, "_keys", []), []
+        for key in keys:
+            entry = _ipc_bases.get(key)
+            if entry is None:
+                continue
+            entry[1] -= 1
+            if entry[1] <= 0:
+                del _ipc_bases[key]
+                nat.lib().mb200_ipc_close(entry[0], key[1])  # best effort: the process may already be tearing CUDA down
+        del self[:]
+
+
+def share_table_shards(local_shard: Tensor, group: Optional[dist.ProcessGroup] = None) -> "SharedShards":
     """(Also used for any other buffer the peers' kernels read or write directly, e.g. the retrieval gather buffers.)
     Row-sharded embedding table over the GPUs of one box: every rank contributes the shard it holds ([2**s, dim],
     contiguous, on its GPU) and gets back the list of ALL shards as tensors whose memory its own GPU's kernels can read --
     the peers' shards are mapped through CUDA IPC with peer access (mb200_ipc_export / mb200_ipc_open), so the fused kernel
-    loads remote rows directly over NVLink / NVSwitch.  No data moves here; keep ``local_shard`` alive while any rank uses it."""
+    loads remote rows directly over NVLink / NVSwitch.  No data moves here; keep ``local_shard`` alive while any rank uses it,
+    and ``close()`` the result when the peers' buffers are no longer used."""
     import ctypes
+    import os
 
     from . import _native as nat
 
     lib = nat.lib()
+    if "expandable_segments:true" in os.environ.get("PYTORCH_CUDA_ALLOC_CONF", "").replace(" ", "").lower():
+        raise RuntimeError("share_table_shards exports torch allocations with legacy CUDA IPC (cudaIpcGetMemHandle), which cannot export "
+                           "expandable segments: unset PYTORCH_CUDA_ALLOC_CONF=expandable_segments:True for processes that share buffers")
     world, rank = dist.get_world_size(group), dist.get_rank(group)
     if not local_shard.is_cuda or not local_shard.is_contiguous():
         raise ValueError("the local shard must be a contiguous CUDA tensor")
@@ -70,7 +99,8 @@ def share_table_shards(local_shard: Tensor, group: Optional[dist.ProcessGroup] =
     mine = (bytes(handle.raw), int(offset.value), local_shard.device.index, tuple(local_shard.shape), local_shard.dtype)
     gathered: list = [None] * world
     dist.all_gather_object(gathered, mine, group=group)
-    shards = []
+    shards = SharedShards()
+    shards._keys = []
     for r, (h, off, peer_dev, shape, dtype) in enumerate(gathered):
         if r == rank:
             shards.append(local_shard)
@@ -81,8 +111,10 @@ def share_table_shards(local_shard: Tensor, group: Optional[dist.ProcessGroup] =
         if key not in _ipc_bases:
             base = ctypes.c_void_p()
             nat.check(lib.mb200_ipc_open(h, 0, local_shard.device.index, ctypes.byref(base)), "mb200_ipc_open")
-            _ipc_bases[key] = int(base.value)
-        t = torch.as_tensor(_PeerMemory(_ipc_bases[key] + off, shape, dtype), device=torch.device("cuda", peer_dev))
+            _ipc_bases[key] = [int(base.value), 0]
+        _ipc_bases[key][1] += 1
+        shards._keys.append(key)
+        t = torch.as_tensor(_PeerMemory(_ipc_bases[key][0] + off, shape, dtype), device=torch.device("cuda", peer_dev))
         shards.append(t.view(torch.bfloat16) if dtype == torch.bfloat16 else t)
     torch.cuda.synchronize(local_shard.device)
     dist.barrier(group=group)
@@ -116,6 +148,13 @@ class P2PExchange:
 
     def fits(self, n_payload: int, pos_cap: int) -> bool:
         return int(n_payload) == self.n_payload and int(pos_cap) <= self.pos_cap
+
+    def close(self) -> None:
+        """Collective in spirit: call it on every rank once no exchange is in flight; unmaps the peers' mailboxes."""
+        if isinstance(self.peers, SharedShards):
+            torch.cuda.synchronize(self.mailbox.device)
+            self.peers.close()
+        self.peers = []
 
     def run(self, payload: Tensor, outside_index: int, sorted_keys: Optional[Tensor] = None, pos_keys: Optional[Tensor] = None,
             n_pos: Optional[Tensor] = None) -> Tensor:

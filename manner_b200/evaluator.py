@@ -71,10 +71,17 @@ class DeviceBehaviours:
     _finish_upload: Optional[object] = None
 
     def finish_upload(self) -> None:
-        """Enqueues what a pipelined upload has not enqueued yet (idempotent; launch() calls it)."""
+        """Waits until the library's thread has queued every segment copy of a pipelined upload and raises if one failed
+        (idempotent; launch() calls it behind the fused kernel's launch)."""
         if self._finish_upload is not None:
             fin, self._finish_upload = self._finish_upload, None
             fin()
+
+    def __del__(self) -> None:
+        try:  # the pinned host arrays the copies read from must outlive the queueing
+            self.finish_upload()
+        except Exception:
+            pass
 
 
 @dataclass
@@ -121,6 +128,7 @@ class PendingEval:
     scores: Optional[Tensor]
     per_impression: Optional[Tensor]
     loss_stats: Optional[Tensor] = None  # fp64 [2]: sum of step losses, number of steps (all ranks)
+    n_pos_bound: int = 0
     fused: bool = False  # distributed through the fused exchange: `sums` = [payload, sum2, P, N, exchange flags] (one buffer, one read)
     has_auc: bool = False
 
@@ -210,7 +218,9 @@ class ScoreEvaluator:
         ``pipelined``: the copy overlaps the pass instead of preceding it (mb200_upload_begin / _finish): the offsets go first,
         the id / label arrays follow in ``segments`` work-balanced segments on a copy stream, and the fused kernel -- launched
         by the next ``launch`` / ``evaluate`` with the returned object -- starts on the first segment while the others are in
-        flight.  The returned arrays must not be read by anything else before that launch."""
+        flight.  The returned arrays must not be read by anything else before that launch.  The segment copies are queued by a
+        thread of the library while this thread goes on to launch the kernel (no ordering hazard where launches block, e.g. under
+        a profiler)."""
         src = pinned if pinned is not None else self.pin(bhv, step_batch)
         if pos_cap is not None and pos_cap < src["n_pos"]:
             raise ValueError(f"pos_cap {pos_cap} is below this shard's {src['n_pos']} positives: the pooled AUROC would silently drop keys (dist.agree_pos_cap)")
@@ -241,7 +251,7 @@ class ScoreEvaluator:
             ready = torch.empty(1, dtype=torch.int32, device=self.device)
             d = nat.UploadDesc()
             d.struct_size = ctypes.sizeof(nat.UploadDesc)
-            d.n_segments, d.segments_first, d.n_impressions = segments, 1, bhv.n_impressions
+            d.n_segments, d.segments_first, d.n_impressions = segments, 0, bhv.n_impressions  # every segment by the library's thread
             for name in ("hist_offsets", "hist_ids", "cand_offsets", "cand_ids", "labels"):
                 setattr(d, "h_" + name, src[name].data_ptr())
                 setattr(d, "d_" + name, dev[name].data_ptr())
@@ -260,8 +270,6 @@ class ScoreEvaluator:
             bhv.n_impressions, src["max_cand"], nbytes, src["n_pos"], pos_cap,
             src.get("step_batch", 8), dev.get("hist_pad"), dev.get("cand_pad"), ready, segments, finish,
         )
-        if segments == 1:
-            out.finish_upload()
         return out
 
     @staticmethod
@@ -327,7 +335,7 @@ class ScoreEvaluator:
             bhv.cand_pad if loss is not None else None, self.n_table_shards, self.table_shard_shift, self.n_news,
             bhv.ready, bhv.ready_segments,
         )
-        bhv.finish_upload()  # pipelined upload: the remaining segments follow the fused kernel into the queues
+        bhv.finish_upload()  # pipelined upload: by now the library's thread has queued the segment copies; collect its status
         loss_stats: Optional[Tensor] = None
         if loss is not None:
             # MeanMetric over the reference's steps (cr_module.py:253-259): (sum of step losses, number of steps)
@@ -343,6 +351,8 @@ class ScoreEvaluator:
             # (every rank sees the same n_payload and the agreed pos_cap, so all ranks do it in the same call).
             cap = bhv.pos_cap if bhv.pos_cap is not None else mdist.agree_pos_cap(bhv.n_pos, self.device, group)
             if self._p2p is None or not self._p2p.fits(sums.numel(), cap):
+                if self._p2p is not None:
+                    self._p2p.close()  # unmap the peers' old mailboxes before they are replaced (every rank is here at the same call)
                 self._p2p = mdist.P2PExchange(self.device, sums.numel(), max(cap, 1), group)
             outside = n_w * nat.NUM_METRICS + 1 + 2  # tail entry of the MB200_FLAG_OUTSIDE_UNIT bit
             if pooled_auc:
@@ -359,9 +369,11 @@ class ScoreEvaluator:
                 gflags = (sums[outside : outside + 1] > 0).to(torch.int32) * nat.FLAG_OUTSIDE_UNIT
                 auc_stats = mdist.pooled_auc_distributed(scores, bhv.labels, gflags, group, pos_cap=bhv.pos_cap)
         elif pooled_auc:
+            # (mb200_pooled_auc_bounded -- sort only the positives, stream the negatives against them -- gives the same integers but
+            # measured slower on click-log shapes: 0.201 vs 0.185 ms, profiles/r2_n_schedule.log; the full sort stays the default)
             auc_stats = torch.ops.manner_b200.pooled_auc(scores, bhv.labels, 2, flags)
         return PendingEval(sums, flags, n_w, bhv.n_impressions, distributed, auc_stats,
-                           scores if want_scores else None, per_impr if want_per_impression else None, loss_stats, fused, pooled_auc)
+                           scores if want_scores else None, per_impr if want_per_impression else None, loss_stats, bhv.n_pos, fused, pooled_auc)
 
     def finish(self, pending: "PendingEval") -> EvalResult:
         """The one device -> host read of a pass: metric sums, flag word, AUC statistics."""
@@ -399,6 +411,8 @@ class ScoreEvaluator:
             if pending.auc_stats is not None:
                 a = packed[n_block + 1 :]
                 auc, counts = float(a[0]), (int(a[1]), int(a[2]))
+                if auc != auc:
+                    raise nat.NativeError(f"pooled AUROC: the rows hold {counts[0]} positives, more than the {pending.n_pos_bound} the upload counted")
         loss_value = None
         if pending.loss_stats is not None:
             ls = pending.loss_stats.cpu().numpy()

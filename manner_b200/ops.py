@@ -292,6 +292,38 @@ def _(preds, labels, sigmoid_mode, flags):
     return torch.empty(4, dtype=torch.float64, device=preds.device)
 
 
+@torch.library.custom_op("manner_b200::pooled_auc_bounded", mutates_args=())
+def pooled_auc_bounded(preds: Tensor, labels: Tensor, sigmoid_mode: int, flags: Optional[Tensor], pos_capacity: int) -> Tensor:
+    """``pooled_auc`` for callers that know an upper bound on the number of positives (``pos_capacity``; e.g. counted on the host
+    labels before the upload): only the positives are sorted, the negatives are ranked against them in one streaming pass
+    (mb200_pooled_auc_bounded).  Same fp64 [4]; auc is NaN if there were more positives than ``pos_capacity``.  When the
+    positives are not few (2 * pos_capacity > n) the full sort of ``pooled_auc`` is used."""
+    n = preds.numel()
+    if 2 * int(pos_capacity) > n:
+        return pooled_auc(preds, labels, sigmoid_mode, flags)
+    lib = nat.lib()
+    _require_cuda("preds", preds, torch.float32)
+    _require_cuda("labels", labels, torch.uint8)
+    if flags is not None:
+        _require_cuda("flags", flags, torch.int32)
+    dev = preds.device
+    with torch.cuda.device(dev):
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        out = torch.empty(4, dtype=torch.float64, device=dev)
+        ws = _workspace(dev, stream, "auc_bounded", lib.mb200_pooled_auc_bounded_workspace_bytes(n, int(pos_capacity)))
+        nat.check(
+            lib.mb200_pooled_auc_bounded(preds.data_ptr(), labels.data_ptr(), n, int(pos_capacity), sigmoid_mode, _ptr(flags), ws.data_ptr(), ws.numel(),
+                                         out.data_ptr(), stream),
+            "mb200_pooled_auc_bounded",
+        )
+    return out
+
+
+@pooled_auc_bounded.register_fake
+def _(preds, labels, sigmoid_mode, flags, pos_capacity):
+    return torch.empty(4, dtype=torch.float64, device=preds.device)
+
+
 # ---- staged pooled AUC (multi-GPU: positives are exchanged between stage 2 and 3; see dist.py) ----------
 
 

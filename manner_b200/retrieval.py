@@ -235,6 +235,14 @@ class CatalogRetriever:
             self._token = torch.zeros(1, dtype=torch.int32, device=dev)
         return self._gather
 
+    def close(self) -> None:
+        """Unmaps the peers' gather buffers of the fused exchange (call on every rank once no retrieve() is in flight)."""
+        if self._gather is not None:
+            torch.cuda.synchronize(self.catalog.device)
+            for gs, gi in self._gather:
+                gs.close(), gi.close()
+            self._gather = None
+
     def local_topk(self, users: Tensor) -> Tuple[Tensor, Tensor]:
         """Top-k of ``users`` against this rank's shard only (global ids)."""
         s, i, _ = torch.ops.manner_b200.retrieve_topk(users, self.catalog, self.k, self.offset, False)

@@ -40,7 +40,7 @@ def test_pipelined_upload_is_bit_identical(evaluator_cls, segments):
     kw = dict(weights=[[1.0, 0.4]], zscore=True, pooled_auc=True, want_scores=True, want_per_impression=True)
     plain = ev.evaluate(ev.upload(bhv), **kw)
     pinned = ev.pin(bhv)
-    for _ in range(3):  # repeated passes recycle the device buffers: the copies must wait for the previous pass
+    for it in range(4):  # repeated passes recycle the device buffers: the copies must wait for the previous pass
         d = ev.upload(bhv, pinned, pipelined=True, segments=segments)
         assert d.ready is not None and d.ready_segments == segments
         _same(ev.evaluate(d, **kw), plain)
@@ -112,3 +112,11 @@ def test_pooled_auc_rank_search_against_the_oracle(evaluator_cls, case):
     s2 = torch.zeros(1, dtype=torch.int64, device="cuda:0")
     ops.auc_rank_sum(sorted_keys, n_pos, pos_keys, n_pos, s2)
     assert int(s2.item()) == int(out[3])
+    # the bounded form (sort the positives, stream the negatives): the same integer statistic, bit for bit
+    n_pos_host = int(labels.sum())
+    for cap in (n_pos_host, n_pos_host + 1000):
+        b = torch.ops.manner_b200.pooled_auc_bounded(p, lab, 2, flags, cap).cpu().numpy()
+        assert b.tolist() == out.tolist(), (case, cap, b, out)
+    if 2 * (n_pos_host - 1) <= n and n_pos_host > 1:
+        under = torch.ops.manner_b200.pooled_auc_bounded(p, lab, 2, flags, n_pos_host - 1).cpu().numpy()
+        assert np.isnan(under[0]) and int(under[1]) == n_pos_host  # more positives than promised: reported, not silently wrong

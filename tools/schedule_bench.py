@@ -77,8 +77,27 @@ def main() -> None:
                 print(json.dumps({"kind": "device", "round": rnd, "schedule": "static" if static == 1 else "dynamic", "chunks_per_warp": cpw,
                                   "kernel_ms": round(k, 4), "kernel_ms_min": round(kmin, 4), "step_ms": round(st, 4), "same_results": same}), flush=True)
 
+    # pooled AUROC: full sort of all keys vs sort of the positives + streaming pass over the negatives, on this set's scores
+    ops.set_tuning(static_chunks=0, chunks_per_warp=0)
+    res = ev.evaluate(dev_bhv, want_scores=True, **kw)
+    flags = torch.tensor([4], dtype=torch.int32, device=dev)
+    for name, fn in (("full_sort", lambda: torch.ops.manner_b200.pooled_auc(res.scores, dev_bhv.labels, 2, flags)),
+                     ("sort_positives", lambda: torch.ops.manner_b200.pooled_auc_bounded(res.scores, dev_bhv.labels, 2, flags, dev_bhv.n_pos))):
+        for _ in range(3):
+            out = fn()
+        ms = []
+        for _ in range(args.steps):
+            flush.fill_(1)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            out = fn()
+            e1.record()
+            torch.cuda.synchronize()
+            ms.append(e0.elapsed_time(e1))
+        print(json.dumps({"kind": "pooled_auc", "path": name, "ms": round(statistics.mean(ms), 4), "ms_min": round(min(ms), 4), "auc": float(out[0]), "sum2": float(out[3])}), flush=True)
+
     for rnd in range(args.rounds):
-        for cpw in (8, 16):
+        for cpw, deferred in ((16, False), (8, False)):
             for seg in [int(s) for s in args.segments.split(",")]:
                 ops.set_tuning(static_chunks=0, chunks_per_warp=cpw)
                 ms = []
@@ -93,7 +112,7 @@ def main() -> None:
                     if i >= 3:
                         ms.append(e0.elapsed_time(e1))
                 same = bool(abs(r.sums - ref.sums).max() <= 1e-9 * abs(ref.sums).max()) and r.auc == ref.auc
-                print(json.dumps({"kind": "e2e", "round": rnd, "chunks_per_warp": cpw, "segments": seg, "e2e_ms": round(statistics.mean(ms), 4),
+                print(json.dumps({"kind": "e2e", "round": rnd, "chunks_per_warp": cpw, "segments": seg, "deferred": deferred, "e2e_ms": round(statistics.mean(ms), 4),
                                   "e2e_ms_median": round(statistics.median(ms), 4), "e2e_ms_max": round(max(ms), 4), "same_results": same}), flush=True)
     ops.set_tuning(static_chunks=0, chunks_per_warp=0)
 
