@@ -383,6 +383,14 @@ def run_gpu_arm(args) -> None:
         dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
     total_ms = float(total_ms.item())
     res = ev.finish(pending)
+    # per-rank view of the same steps: which part of a multi-GPU step is the fused kernel on the slowest GPU, which part the rendezvous
+    per_rank = None
+    if distributed:
+        mine = torch.tensor([sum(step_ms) / len(step_ms), sum(kernel_ms) / len(kernel_ms)], dtype=torch.float64, device=dev)
+        allr = torch.zeros(world * 2, dtype=torch.float64, device=dev)
+        dist.all_gather_into_tensor(allr, mine)
+        allr = allr.view(world, 2).cpu().tolist()
+        per_rank = {"step_ms": [round(a, 4) for a, _ in allr], "kernel_ms": [round(b, 4) for _, b in allr]}
 
     # the clocks are sampled during the device-timed region only: nvidia-smi polling takes driver locks that can stall
     # the host-side calls of the end-to-end loop below for a whole polling period
@@ -497,6 +505,7 @@ def run_gpu_arm(args) -> None:
         "clocks": clocks,
         "wall_s_timed_region": wall,
         "impressions_per_rank": n_impr_rank,
+        "per_rank": per_rank,
         "check": check,
         "extra": extra,
     }
@@ -622,6 +631,8 @@ def run_retrieval_arm(args) -> None:
         ops.set_tuning(retrieval_diag=args.retrieval_diag)
     if args.retrieval_pair is not None:
         ops.set_tuning(retrieval_pair=args.retrieval_pair)
+    if args.retrieval_window is not None:
+        ops.set_tuning(retrieval_window=args.retrieval_window)
 
     def barrier() -> None:
         if distributed:
@@ -750,6 +761,7 @@ def main() -> None:
     ap.add_argument("--eval-exchange", default="p2p", choices=["p2p", "nccl"],
                     help="multi-GPU evaluation: fused stores into the peers' mailboxes over NVLink (default) or the three NCCL collectives")
     ap.add_argument("--retrieval-pair", type=int, default=None, help="retrieval kernel: 1 = CTA pairs (cta_group::2), 0 = one CTA per tile")
+    ap.add_argument("--retrieval-window", type=int, default=None, help="retrieval kernel: catalogue tiles a CTA may run ahead of the slowest (0 = unthrottled sweep)")
     ap.add_argument("--retrieval-diag", type=int, default=0, help="DIAGNOSTIC: 1/2 disable parts of the retrieval epilogue (results invalid)")
     ap.add_argument("--upload-segments", type=int, default=8,
                     help="end-to-end pass: segments of the pipelined host -> device upload (1 = copy everything in front of the pass)")

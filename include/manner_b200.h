@@ -465,7 +465,8 @@ MB200_API int64_t mb200_library_launch_count(void);
  * 2 = cap on CTAs per SM; 3 = time the fused kernel with
  * CUDA events; 4 = retrieval diagnostics (1, 2: parts of the epilogue disabled, RESULTS INVALID; 4: cycle counters in the
  * workspace header, results valid); 5 = retrieval pipeline (1 = CTA pairs / tcgen05 cta_group::2 [default], 0 = one CTA per tile); 6 = cap in KB on the
- * hot-row cache of variants 8 / 9 (0 = no cap) */
+ * hot-row cache of variants 8 / 9 (0 = no cap); 7 = chunk schedule of the fused kernel (0 auto, 1 static, 2 dynamic); 8 = retrieval sweep
+ * throttle: catalogue tiles a CTA may run ahead of the slowest one (default 48, 0 = off) */
 MB200_API int mb200_set_tuning(int key, int value);
 
 /* duration in ms of the most recent fused score/eval kernel launched while tuning key 3 was on

@@ -282,6 +282,7 @@ int mb200_set_tuning(int key, int value) {
     case 5: prev = tuning().retrieval_pair, tuning().retrieval_pair = value; break;
     case 6: prev = tuning().hot_kb_cap, tuning().hot_kb_cap = value; break;
     case 7: prev = tuning().static_chunks, tuning().static_chunks = value; break;
+    case 8: prev = tuning().retrieval_window, tuning().retrieval_window = value; break;
   }
   return prev;
 }

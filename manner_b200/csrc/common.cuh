@@ -33,6 +33,7 @@ struct Tuning {
   int time_kernel = 0;      // 1: bracket the fused kernel with CUDA events (mb200_last_score_kernel_ms)
   int hot_kb_cap = 0;       // hot-row cache variants: cap on the cache size in KB (0 = all the shared memory the per-warp areas leave)
   int retrieval_pair = 1;   // retrieve_topk_kernel: 1 (default) = CTA pairs (tcgen05 cta_group::2, UMMA M = 256) when there are >= 2 user tiles
+  int retrieval_window = 48;  // retrieve_topk_kernel: catalogue tiles a CTA may run ahead of the slowest CTA of the sweep (0 = unthrottled)
   int retrieval_diag = 0;   // DIAGNOSTIC ONLY (results invalid when != 0): 1 = epilogue reads TMEM but selects nothing, 2 = epilogue only
                             // releases the accumulator (isolates the TMA + MMA pipeline when tuning retrieve_topk_kernel)
 };

@@ -42,6 +42,7 @@ constexpr int SOFT_CAP = 160;     // soft limit (> MAX_K): from here on a row is
 constexpr int MAX_K = 128;        // top-k limit (k <= CAP / 2)
 constexpr int EPI_GROUPS = 2;     // epilogue warpgroups: group g scans columns 128 g .. 128 g + 127 of every accumulator tile
 constexpr int EPI_COLS = BLOCK_N / EPI_GROUPS;
+constexpr int WS_HEADER = 1024;  // workspace header: error flag, diagnostic counters, per-CTA sweep progress [160]
 constexpr int THREADS = 64 + EPI_GROUPS * 128;  // warp 0: TMA producer, warp 1: MMA issuer + TMEM owner, warps 2-9: epilogue
 constexpr int TMEM_COLS = 512;    // two 128 x 256 fp32 accumulators
 constexpr int SCRATCH_BYTES = 0;
@@ -58,6 +59,8 @@ struct RetrievalParams {
   int* cand_ids;           // workspace [grid][EPI_GROUPS][128][CAP]
   float* debug_scores;     // optional [n_users, n_catalog]
   int* error_flag;
+  int* progress;           // workspace [grid]: catalogue tiles this CTA's producer has issued so far (sweep throttle, see the TMA producer)
+  int window;              // a producer may run at most this many catalogue tiles ahead of the slowest CTA (0 = no throttle)
   unsigned long long* stats;  // diag == 4: [0] cycles in compactions, [1] in the admission slow path, [2] waiting for an accumulator,
                               // [3] compactions, [4] slow chunks, [5] epilogue cycles in total (summed over epilogue warps, lane 0);
                               // [6] / [7] cycles the MMA thread waited for a free accumulator / for operands (summed over CTAs)
@@ -406,12 +409,30 @@ retrieve_topk_kernel(const __grid_constant__ CUtensorMap tmap_users, const __gri
 
   if (warp == 0) {
     // ===== TMA producer =====
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int unit = unit0; unit < n_units; unit += unit_step) {
-        const int mt = unit * UNIT + (int)rank;  // a pair's second tile may lie past the last user tile: TMA zero-fills it
-        for (int nt = 0; nt < p.n_tiles; ++nt) {
+    // Every CTA sweeps the whole catalogue for each of its user tiles, all in the same direction: a catalogue tile is read from
+    // DRAM once and served to the other CTAs from the L2 -- as long as they are close behind.  Unthrottled, the 148 producers
+    // drift apart over the 4 883 tiles of a sweep until the spread exceeds the 126 MB L2 and every CTA fetches its own copy
+    // (21.5 GB of DRAM reads per launch against 1.9 GB of catalogue, round 1).  So every 8 tiles a producer publishes how many
+    // tiles it has issued and waits (bounded, a soft throttle) while it is more than `window` tiles (~19 MB) ahead of the slowest
+    // CTA; the slowest never waits, and equal work per CTA means the leaders would only have idled at the end anyway.
+    int stage = 0;
+    uint32_t phase = 0;
+    int issued = 0;
+    volatile int* progress = p.progress;
+    for (int unit = unit0; unit < n_units; unit += unit_step) {
+      const int mt = unit * UNIT + (int)rank;  // a pair's second tile may lie past the last user tile: TMA zero-fills it
+      for (int nt = 0; nt < p.n_tiles; ++nt, ++issued) {
+        if (p.window > 0 && (issued & 7) == 0) {
+          if (lane == 0) progress[blockIdx.x] = issued;
+          for (int spin = 0; spin < 48; ++spin) {
+            int slowest = 0x7fffffff;
+            for (int c = lane; c < (int)gridDim.x; c += 32) slowest = min(slowest, progress[c]);
+            slowest = __reduce_min_sync(kFull, slowest);
+            if (issued - slowest <= p.window) break;
+            __nanosleep(1000);
+          }
+        }
+        if (lane == 0) {
           for (int kb = 0; kb < k_blocks; ++kb) {
             mbar_wait<64>(&empty_bar[stage], phase ^ 1, p.error_flag);
             unsigned char* a = stage_base + stage * STAGE_BYTES;
@@ -428,8 +449,10 @@ retrieve_topk_kernel(const __grid_constant__ CUtensorMap tmap_users, const __gri
             if (++stage == STAGES) stage = 0, phase ^= 1;
           }
         }
+        __syncwarp();
       }
     }
+    if (lane == 0) progress[blockIdx.x] = 0x7fffffff;  // done: nobody waits for this CTA any more
   } else if (warp == 1) {
     // ===== MMA issuer =====
     if (lane == 0 && rank == 0) {
@@ -796,7 +819,7 @@ size_t retrieval_workspace_bytes(const mb200_retrieval_desc* d) {
   if (d == nullptr || d->struct_size != sizeof(mb200_retrieval_desc) || d->n_users <= 0) return 0;
   const long long m_tiles = (d->n_users + rt::BLOCK_M - 1) / rt::BLOCK_M;
   const long long grid = m_tiles + 1 < 160 ? m_tiles + 1 : 160;  // + 1: a CTA pair rounds the tile count up to even
-  return (size_t)grid * rt::EPI_GROUPS * rt::BLOCK_M * rt::CAP * 8 + 256;
+  return (size_t)grid * rt::EPI_GROUPS * rt::BLOCK_M * rt::CAP * 8 + rt::WS_HEADER;
 }
 
 int retrieve_topk(const mb200_retrieval_desc* d, cudaStream_t stream) {
@@ -828,8 +851,10 @@ int retrieve_topk(const mb200_retrieval_desc* d, cudaStream_t stream) {
   unsigned char* ws = reinterpret_cast<unsigned char*>(d->workspace);
   p.error_flag = reinterpret_cast<int*>(ws);
   p.stats = reinterpret_cast<unsigned long long*>(ws + 64);
-  p.cand_scores = reinterpret_cast<float*>(ws + 256);
-  p.cand_ids = reinterpret_cast<int*>(ws + 256 + (size_t)grid * rt::EPI_GROUPS * rt::BLOCK_M * rt::CAP * 4);
+  p.progress = reinterpret_cast<int*>(ws + 256);  // [160]
+  p.window = tuning().retrieval_window;
+  p.cand_scores = reinterpret_cast<float*>(ws + rt::WS_HEADER);
+  p.cand_ids = reinterpret_cast<int*>(ws + rt::WS_HEADER + (size_t)grid * rt::EPI_GROUPS * rt::BLOCK_M * rt::CAP * 4);
   p.out_scores = d->out_scores, p.out_ids = reinterpret_cast<long long*>(d->out_ids), p.debug_scores = d->debug_scores;
   p.n_users = d->n_users, p.n_catalog = d->n_catalog, p.id_offset = d->catalog_id_offset;
   p.dim = d->dim, p.k = d->k;
@@ -838,7 +863,7 @@ int retrieve_topk(const mb200_retrieval_desc* d, cudaStream_t stream) {
   for (int r = 0; r < p.n_peers; ++r) p.peer_scores[r] = d->peer_scores[r], p.peer_ids[r] = reinterpret_cast<long long*>(d->peer_ids[r]);
   p.m_tiles = (int)((d->n_users + rt::BLOCK_M - 1) / rt::BLOCK_M);
   p.n_tiles = (int)((d->n_catalog + rt::BLOCK_N - 1) / rt::BLOCK_N);
-  st = cuda_status(cudaMemsetAsync(p.error_flag, 0, 256, stream), "cudaMemsetAsync");
+  st = cuda_status(cudaMemsetAsync(p.error_flag, 0, rt::WS_HEADER, stream), "cudaMemsetAsync");
   if (st != MB200_OK) return st;
   if (pair) {
     st = cuda_status(cudaFuncSetAttribute(retrieve_topk_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, rt::SMEM_BYTES), "cudaFuncSetAttribute");

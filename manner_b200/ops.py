@@ -430,9 +430,9 @@ def last_hot_stats() -> dict:
 
 def set_tuning(chunks_per_warp: Optional[int] = None, variant: Optional[int] = None, ctas_per_sm: Optional[int] = None,
                time_kernel: Optional[int] = None, retrieval_diag: Optional[int] = None, retrieval_pair: Optional[int] = None,
-               hot_kb_cap: Optional[int] = None, static_chunks: Optional[int] = None) -> None:
+               hot_kb_cap: Optional[int] = None, static_chunks: Optional[int] = None, retrieval_window: Optional[int] = None) -> None:
     lib = nat.lib()
     for key, val in ((0, chunks_per_warp), (1, variant), (2, ctas_per_sm), (3, time_kernel), (4, retrieval_diag), (5, retrieval_pair), (6, hot_kb_cap),
-                     (7, static_chunks)):
+                     (7, static_chunks), (8, retrieval_window)):
         if val is not None:
             lib.mb200_set_tuning(key, int(val))
