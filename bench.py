@@ -402,13 +402,23 @@ def run_gpu_arm(args) -> None:
     gc.disable()  # a generation-2 collection of the interpreter (tens of ms) inside a 2 ms step is host noise, not the path
     e2e_events = []
     e2e_warm = max(args.warmup, 3)  # the end-to-end path gets its own warm-up steps (first uploads, allocator growth, sampler teardown)
+    # The public call for a split that is evaluated again and again (after every epoch): ScoreEvaluator.prepare(...) sets buffers and
+    # descriptors up once, run() = pipelined upload from the pinned host CSR (offsets first, the fused kernel starts on the first
+    # segment while the copy stream brings the rest) + pass + one pinned read-back.  --generic-e2e times upload() + evaluate() instead.
+    prepared = None
+    if not args.generic_e2e and (not distributed or args.eval_exchange == "p2p"):
+        prepared = ev.prepare(bhv, pinned, weights=kw["weights"], zscore=True, pooled_auc=kw.get("pooled_auc", False), loss=kw.get("loss"),
+                              temperature=kw.get("temperature", 0.1), step_batch=step_batch, segments=max(args.upload_segments, 1),
+                              distributed=distributed, pos_cap=pos_cap)
     for i in range(max(args.steps, 10) + e2e_warm):
         flush.fill_(rank + 1)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        # pipelined: offsets first, the fused kernel starts on the first segment while the copy stream brings the rest
-        step_bhv = ev.upload(bhv, pinned, pos_cap, pipelined=args.upload_segments > 1, segments=args.upload_segments)
-        r = ev.evaluate(step_bhv, **kw)  # includes the device -> host read of sums / AUC statistics
+        if prepared is not None:
+            r = prepared.run()  # upload + pass + device -> host read of sums / AUC statistics
+        else:
+            step_bhv = ev.upload(bhv, pinned, pos_cap, pipelined=args.upload_segments > 1, segments=args.upload_segments)
+            r = ev.evaluate(step_bhv, **kw)  # includes the device -> host read of sums / AUC statistics
         e1.record()
         torch.cuda.synchronize(dev)
         if i >= e2e_warm:
@@ -494,7 +504,8 @@ def run_gpu_arm(args) -> None:
             "value": n_impr_total / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": dev_bhv.h2d_bytes,
             "d2h_bytes_per_step": r.d2h_bytes, "ms_per_step": e2e_ms, "ms_per_step_median_rank0": e2e_median_ms, "steps": len(e2e_events),
             "ms_each_rank0": [round(x, 3) for x in e2e_events],
-            "upload": (f"pipelined: offsets, then {args.upload_segments} work-balanced segments on a copy stream overlapped with the fused kernel "
+            "api": "ScoreEvaluator.prepare(...).run()" if prepared is not None else "ScoreEvaluator.upload(...) + evaluate(...)",
+            "upload": (f"pipelined: offsets, then {args.upload_segments} segments of geometrically growing size on a copy stream overlapped with the fused kernel "
                        "(mb200_upload_begin / _finish)") if args.upload_segments > 1 else "whole set copied in front of the pass",
         },
         "gpu_launches": launches1[0] - launches0[0],
@@ -763,8 +774,9 @@ def main() -> None:
     ap.add_argument("--retrieval-pair", type=int, default=None, help="retrieval kernel: 1 = CTA pairs (cta_group::2), 0 = one CTA per tile")
     ap.add_argument("--retrieval-window", type=int, default=None, help="retrieval kernel: catalogue tiles a CTA may run ahead of the slowest (0 = unthrottled sweep)")
     ap.add_argument("--retrieval-diag", type=int, default=0, help="DIAGNOSTIC: 1/2 disable parts of the retrieval epilogue (results invalid)")
-    ap.add_argument("--upload-segments", type=int, default=8,
+    ap.add_argument("--upload-segments", type=int, default=5,
                     help="end-to-end pass: segments of the pipelined host -> device upload (1 = copy everything in front of the pass)")
+    ap.add_argument("--generic-e2e", action="store_true", help="end-to-end pass through upload() + evaluate() instead of a prepared pass")
     ap.add_argument("--variant", type=int, default=None)
     ap.add_argument("--chunks-per-warp", type=int, default=None)
     ap.add_argument("--ctas-per-sm", type=int, default=None)

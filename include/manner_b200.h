@@ -184,7 +184,8 @@ typedef struct mb200_eval_desc {
      touches a chunk (bounded: 4 s -> MB200_FLAG_UPLOAD_TIMEOUT, remaining impressions skipped).  NULL = everything is resident. */
   const uint32_t* ready;
   int32_t ready_segments; /* 1..MB200_MAX_UPLOAD_SEGMENTS when `ready` is set */
-  int32_t reserved0;
+  int32_t zero_flags;     /* != 0: the call clears *flags on the stream before it launches (a caller that reuses one flags word per
+                             pass need not queue a fill of its own) */
 } mb200_eval_desc;
 
 MB200_API int mb200_abi_version(void);
@@ -207,8 +208,8 @@ MB200_API int mb200_score_eval(const mb200_eval_desc* desc, void* stream);
  *                        before the host arrays or the descriptor go away.
  * The caller's thread never has to get past the kernel launch for the copies to be issued, so nothing deadlocks where launches
  * block (profilers that serialise kernels, CUDA_LAUNCH_BLOCKING=1).
- * Segment s ends where chunk group s of the persistent grid ends (same work measure: rows gathered + 4 per impression).  Copies
- * cover disjoint 128-byte aligned ranges.  All HOST arrays must be page-locked and stay untouched until C has run the copies.
+ * Segments grow geometrically (the first holds 1/2^(n_segments-1) of the rows gathered, each later one as much as all before it),
+ * so little is exposed in front of the kernel's first chunk.  Copies cover disjoint 128-byte aligned ranges.  All HOST arrays must be page-locked and stay untouched until C has run the copies.
  */
 typedef struct mb200_upload_desc {
   uint32_t struct_size;   /* = sizeof(mb200_upload_desc) */
@@ -472,6 +473,9 @@ MB200_API int mb200_set_tuning(int key, int value);
 /* duration in ms of the most recent fused score/eval kernel launched while tuning key 3 was on
  * (synchronises on its end event; -1 if none).  This is the kernel bench.py reports a roofline for. */
 MB200_API float mb200_last_score_kernel_ms(void);
+/* ms from `event` (a cudaEvent_t recorded with timing by the caller) to the begin of that kernel: how long the stream waited for
+ * the host to get the kernel launched (-1 if unavailable; synchronises). */
+MB200_API float mb200_last_score_kernel_begin_after(void* event);
 
 /* Hot-row cache of the most recent mb200_score_eval launch in this process (HOST int32 out[4]; synchronises the device):
  * {rows cached per module (0 = cache off for that behaviour set), sampled row reads, sampled row reads that hit the cached rows,

@@ -83,7 +83,7 @@ class EvalDesc(Structure):
         ("table_shards", (c_void_p * MAX_TABLE_SHARDS) * MAX_MODULES),
         ("ready", c_void_p),
         ("ready_segments", c_int32),
-        ("reserved0", c_int32),
+        ("zero_flags", c_int32),
     ]
 
 
@@ -233,6 +233,7 @@ SIGNATURES = {
     "mb200_library_launch_count": (c_int64, []),
     "mb200_set_tuning": (c_int, [c_int, c_int]),
     "mb200_last_score_kernel_ms": (c_float, []),
+    "mb200_last_score_kernel_begin_after": (c_float, [c_void_p]),
     "mb200_last_hot_stats": (c_int, [POINTER(c_int32)]),
 }
 

@@ -45,6 +45,7 @@ int use_device_of(const void* ptr, int* device_out) {
 // implemented in score_eval.cu / pooled_auc.cu
 float host_dcg_discount(int rank);
 float last_score_kernel_ms();
+float last_score_kernel_begin_after(cudaEvent_t since);
 int last_hot_stats(int32_t out[4]);
 size_t eval_workspace_bytes(const mb200_eval_desc* d);
 int score_eval(const mb200_eval_desc* d, cudaStream_t stream);
@@ -268,6 +269,8 @@ int64_t mb200_launch_count(void) { return g_launches.load(); }
 int64_t mb200_library_launch_count(void) { return g_library_launches.load(); }
 
 float mb200_last_score_kernel_ms(void) { return last_score_kernel_ms(); }
+
+float mb200_last_score_kernel_begin_after(void* event) { return last_score_kernel_begin_after(static_cast<cudaEvent_t>(event)); }
 
 int mb200_last_hot_stats(int32_t out[4]) { return out ? last_hot_stats(out) : MB200_ERR_INVALID_ARG; }
 

@@ -186,4 +186,9 @@ int step_loss(const float* loss, long long n_impr, int step, int kind, const int
   return cuda_status(cudaGetLastError(), "step_loss_kernel");
 }
 
+int force_load_loss_kernels() {
+  cudaFuncAttributes a;
+  return cuda_status(cudaFuncGetAttributes(&a, step_loss_kernel), "cudaFuncGetAttributes(step_loss_kernel)");
+}
+
 }  // namespace mb200

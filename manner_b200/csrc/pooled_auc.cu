@@ -670,6 +670,31 @@ int exchange_finish(const mb200_exchange_desc* d, cudaStream_t stream) {
   return cuda_status(cudaGetLastError(), "exchange_finish_kernel");
 }
 
+// Loads every kernel of this file that can be launched behind a fused kernel that is still waiting for its pipelined upload (see
+// force_load_eval_kernels in score_eval.cu), including the CUB radix-sort kernels: those are templates of the library, so they
+// are loaded by running one small sort on scratch memory.
+int force_load_auc_kernels(cudaStream_t stream) {
+  cudaFuncAttributes a;
+  int st = cuda_status(cudaFuncGetAttributes(&a, auc_build_keys_kernel), "cudaFuncGetAttributes");
+  if (st == MB200_OK) st = cuda_status(cudaFuncGetAttributes(&a, auc_rank_sum_kernel), "cudaFuncGetAttributes");
+  if (st == MB200_OK) st = cuda_status(cudaFuncGetAttributes(&a, auc_finalize_kernel), "cudaFuncGetAttributes");
+  if (st == MB200_OK) st = cuda_status(cudaFuncGetAttributes(&a, auc_stream_negatives_kernel), "cudaFuncGetAttributes");
+  if (st == MB200_OK) st = cuda_status(cudaFuncGetAttributes(&a, exchange_post_kernel), "cudaFuncGetAttributes");
+  if (st == MB200_OK) st = cuda_status(cudaFuncGetAttributes(&a, exchange_sigmoid_keys_kernel), "cudaFuncGetAttributes");
+  if (st == MB200_OK) st = cuda_status(cudaFuncGetAttributes(&a, exchange_finish_kernel), "cudaFuncGetAttributes");
+  if (st != MB200_OK) return st;
+  const long long n = 1 << 16;  // large enough for the multi-pass (onesweep) path the real sorts take
+  const size_t cub_bytes = auc_sort_workspace_bytes(n);
+  unsigned char* scratch = nullptr;
+  if ((st = cuda_status(cudaMalloc(&scratch, 2 * n * sizeof(uint32_t) + cub_bytes), "cudaMalloc(warm-up scratch)")) != MB200_OK) return st;
+  st = cuda_status(cudaMemsetAsync(scratch, 0x5a, 2 * n * sizeof(uint32_t), stream), "cudaMemsetAsync");
+  if (st == MB200_OK)
+    st = auc_sort_keys(reinterpret_cast<uint32_t*>(scratch), reinterpret_cast<uint32_t*>(scratch) + n, n, scratch + 2 * n * sizeof(uint32_t), cub_bytes, stream);
+  if (st == MB200_OK) st = cuda_status(cudaStreamSynchronize(stream), "cudaStreamSynchronize");
+  cudaFree(scratch);
+  return st;
+}
+
 // ---- read-bandwidth probe (bench.py's L2 roofline denominator) ----------------------------------------------------------
 // Every warp streams 3 KB rows (the gather's access shape: 6 x LDG.E.128 per lane and row, K rows in flight) of a buffer of
 // 2^k rows, `repeats` passes; rows of one batch are far apart like gathered rows.  With a buffer that fits the 126 MB L2 this

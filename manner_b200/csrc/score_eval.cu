@@ -1690,6 +1690,19 @@ float last_score_kernel_ms() {
   return ms;
 }
 
+// ms from a caller's event to the begin of the most recent timed fused kernel (tools/host_overhead.py: how long the GPU waited
+// for the host to get the kernel launched)
+float last_score_kernel_begin_after(cudaEvent_t since) {
+  KernelTimer* t = g_last_timer;
+  if (t == nullptr || !t->armed || since == nullptr) return -1.0f;
+  float ms = -1.0f;
+  if (cudaEventSynchronize(t->begin) != cudaSuccess || cudaEventElapsedTime(&ms, since, t->begin) != cudaSuccess) {
+    (void)cudaGetLastError();
+    return -1.0f;
+  }
+  return ms;
+}
+
 size_t eval_workspace_bytes(const mb200_eval_desc* d) {
   if (validate(d) != MB200_OK) return 0;
   LaunchPlan plan;
@@ -1817,6 +1830,10 @@ int score_eval(const mb200_eval_desc* d, cudaStream_t stream) {
     g_last_hot_dir = dir, g_last_hot_cap = plan.hot_cap;
     launches += 2;
   }
+  if (d->zero_flags && d->flags) {
+    st = cuda_status(cudaMemsetAsync(d->flags, 0, sizeof(int32_t), stream), "cudaMemsetAsync(flags)");
+    if (st != MB200_OK) return st;
+  }
   partition_kernel<<<(plan.n_chunks + 1 + 255) / 256, 256, 0, stream>>>(d->hist_offsets, d->cand_offsets, p.n_impr, plan.n_chunks,
                                                                        reinterpret_cast<int32_t*>(d->workspace));
   st = cuda_status(cudaGetLastError(), "partition_kernel");
@@ -1833,6 +1850,16 @@ int score_eval(const mb200_eval_desc* d, cudaStream_t stream) {
   if (st != MB200_OK) return st;
   note_launch(launches);
   return MB200_OK;
+}
+
+// CUDA loads kernels lazily, at their first launch, and that load can stall behind a kernel that is running and waiting for work
+// the host has yet to queue -- exactly what the fused kernel does under a pipelined upload.  Everything that is launched behind
+// it is therefore loaded ahead of time (cudaFuncGetAttributes forces the load), once per process, by mb200_upload_begin.
+int force_load_eval_kernels() {
+  cudaFuncAttributes a;
+  int st = cuda_status(cudaFuncGetAttributes(&a, reduce_partials_kernel), "cudaFuncGetAttributes(reduce_partials_kernel)");
+  if (st == MB200_OK) st = cuda_status(cudaFuncGetAttributes(&a, partition_kernel), "cudaFuncGetAttributes(partition_kernel)");
+  return st;
 }
 
 // ---- mb200_rank_metrics ---------------------------------------------------------------------------------

@@ -3,10 +3,10 @@
 // The reference moves every batch to the device before its forward pass (Lightning's transfer_batch_to_device in front of
 // cr_module.py:105 / ensemble_module.py:95); the epoch-granular path here has ONE 20 MB CSR set per pass, and copying it in
 // front of the fused kernel costs 0.4 ms of a 2.2 ms end-to-end step.  Instead the offsets go first, the persistent kernel is
-// launched at once, and the id / label arrays follow in work-balanced segments on a copy stream; after each segment a 4-byte
-// copy raises the device word `ready` to the number of leading impressions whose rows are resident.  The kernel's warps walk
-// their chunks in the same order (one chunk per segment, mb200_eval_desc.ready_segments) and wait on `ready` before they touch
-// a chunk, so the copy engine stays one segment ahead of the SMs and only the first segment is exposed.
+// launched at once, and the id / label arrays follow in segments of geometrically growing size on a copy stream; after each
+// segment a 4-byte copy raises the device word `ready` to the number of leading impressions whose rows are resident.  The
+// kernel's warps draw small chunks in impression order and wait on `ready` before they touch one, so the copy engine stays ahead
+// of the SMs and only the offsets and the small first segment are exposed.
 //
 // Copies cover disjoint 128-byte aligned element ranges, so a 32-byte sector never holds bytes of two copies: a warp that
 // reads up to the end of segment s cannot pull not-yet-written bytes of segment s + 1 into its L1.
@@ -20,6 +20,21 @@
 #include "common.cuh"
 
 namespace mb200 {
+
+int force_load_eval_kernels();               // score_eval.cu
+int force_load_loss_kernels();               // attention.cu
+int force_load_auc_kernels(cudaStream_t s);  // pooled_auc.cu
+
+// once per device and process: see force_load_eval_kernels
+static int force_load_once(int device, cudaStream_t stream) {
+  static bool loaded[64] = {false};
+  if (device < 0 || device >= 64 || loaded[device]) return MB200_OK;
+  int st = force_load_eval_kernels();
+  if (st == MB200_OK) st = force_load_loss_kernels();
+  if (st == MB200_OK) st = force_load_auc_kernels(stream);
+  if (st == MB200_OK) loaded[device] = true;
+  return st;
+}
 
 struct UploadEvents {
   cudaEvent_t reset = nullptr, offsets = nullptr;
@@ -52,13 +67,14 @@ static int validate_upload(const mb200_upload_desc* d) {
   return MB200_OK;
 }
 
-// end of segment s (1-based) in impressions: the partition_kernel rule (score_eval.cu) for chunk s * total_warps of
-// n_segments * total_warps chunks, so a chunk group of the persistent grid ends exactly where an upload segment ends
+// End of segment s (1-based) in impressions.  Segments grow geometrically -- the first holds 1/2^(S-1) of the work (rows gathered
+// + 4 per impression, the partition_kernel measure), every later one as much as all before it -- so the fused kernel waits for a
+// few hundred KB before its first chunk, and from then on each copy has the whole time the SMs spend on the data already there.
 static long long segment_end(const mb200_upload_desc* d, int s) {
   const long long n = d->n_impressions;
   if (s >= d->n_segments) return n;
   const long long total = (long long)d->h_hist_offsets[n] + d->h_cand_offsets[n] + 4 * n;
-  const long long target = total * s / d->n_segments;
+  const long long target = total >> (d->n_segments - s);
   long long lo = 0, hi = n;
   while (lo < hi) {
     const long long mid = (lo + hi) >> 1;
@@ -168,6 +184,7 @@ int upload_begin(const mb200_upload_desc* d, cudaStream_t compute) {
   if ((st = use_device_of(d->ready, &device)) != MB200_OK) return st;
   UploadEvents* ev = nullptr;
   if ((st = upload_events_for(device, &ev)) != MB200_OK) return st;
+  if ((st = force_load_once(device, compute)) != MB200_OK) return st;
   cudaStream_t cs = static_cast<cudaStream_t>(d->copy_stream);
   const long long n = d->n_impressions;
   // nothing is "ready" until this pass's copies say so; the copies start after everything already queued on the compute stream

@@ -209,14 +209,14 @@ class ScoreEvaluator:
 
     # -- inputs ----------------------------------------------------------------------------------------------
     def upload(self, bhv: Behaviours, pinned: Optional[Dict[str, object]] = None, pos_cap: Optional[int] = None,
-               step_batch: Optional[int] = None, pipelined: bool = False, segments: int = 8) -> DeviceBehaviours:
+               step_batch: Optional[int] = None, pipelined: bool = False, segments: int = 5) -> DeviceBehaviours:
         """Host CSR -> device (asynchronous on the current stream).  ``pinned`` lets a caller reuse
         page-locked staging tensors (see ``pin``); ``pos_cap`` is the multi-GPU bound of
         ``dist.agree_pos_cap`` when the caller already has it.  ``step_batch`` (the reference's eval batch size)
         additionally uploads the per-impression pad counts early fusion and the cross-entropy loss need.
 
         ``pipelined``: the copy overlaps the pass instead of preceding it (mb200_upload_begin / _finish): the offsets go first,
-        the id / label arrays follow in ``segments`` work-balanced segments on a copy stream, and the fused kernel -- launched
+        the id / label arrays follow in ``segments`` segments of geometrically growing size on a copy stream, and the fused kernel -- launched
         by the next ``launch`` / ``evaluate`` with the returned object -- starts on the first segment while the others are in
         flight.  The returned arrays must not be read by anything else before that launch.  The segment copies are queued by a
         thread of the library while this thread goes on to launch the kernel (no ordering hazard where launches block, e.g. under
@@ -251,7 +251,8 @@ class ScoreEvaluator:
             ready = torch.empty(1, dtype=torch.int32, device=self.device)
             d = nat.UploadDesc()
             d.struct_size = ctypes.sizeof(nat.UploadDesc)
-            d.n_segments, d.segments_first, d.n_impressions = segments, 0, bhv.n_impressions  # every segment by the library's thread
+            # the small early segments are queued here, the last two (three quarters of the bytes) by the library's thread
+            d.n_segments, d.segments_first, d.n_impressions = segments, max(1, segments - 2), bhv.n_impressions
             for name in ("hist_offsets", "hist_ids", "cand_offsets", "cand_ids", "labels"):
                 setattr(d, "h_" + name, src[name].data_ptr())
                 setattr(d, "d_" + name, dev[name].data_ptr())
@@ -429,6 +430,15 @@ class ScoreEvaluator:
             sums=sums_h, n_impressions=int(n_total), flags=flags_h, ks=self.ks, has_aspects=self.news_category is not None,
             auc=auc, auc_counts=counts, scores=pending.scores, per_impression=pending.per_impression, d2h_bytes=d2h, loss=loss_value,
         )
+
+    def prepare(self, bhv: Behaviours, pinned: Optional[Dict[str, object]] = None, **kwargs):
+        """A ``PreparedPass`` over a fixed behaviour set (the validation / test split evaluated after every epoch): buffers,
+        descriptors and workspaces are set up once, ``run()`` is then upload (overlapped) + pass + one pinned read-back in a
+        handful of C-ABI calls -- the host no longer keeps the stream waiting.  Keywords: weights, zscore, pooled_auc, loss,
+        temperature, step_batch, segments, distributed, group, pos_cap, want_scores (manner_b200/prepared.py)."""
+        from .prepared import PreparedPass
+
+        return PreparedPass(self, bhv, pinned, **kwargs)
 
     def evaluate(self, bhv: DeviceBehaviours, **kwargs) -> EvalResult:
         """One pass: scores (+ z-score ensemble for every row of ``weights`` [W, n_modules]) and metric
