@@ -30,7 +30,8 @@ _LOSS = {None: nat.LOSS_NONE, "ce": nat.LOSS_CE, "supcon": nat.LOSS_SUPCON}
 class PreparedPass:
     def __init__(self, ev, bhv: Behaviours, pinned: Optional[Dict[str, object]] = None, weights=None, zscore: bool = False,
                  pooled_auc: bool = False, loss: Optional[str] = None, temperature: float = 0.1, step_batch: Optional[int] = None,
-                 segments: int = 5, distributed: bool = False, group=None, pos_cap: Optional[int] = None, want_scores: bool = False) -> None:
+                 segments: int = 5, distributed: bool = False, group=None, pos_cap: Optional[int] = None, want_scores: bool = False,
+                 resident: bool = False) -> None:
         from .evaluator import EvalResult  # noqa: F401  (cycle-free import at call time)
 
         lib = nat.lib()
@@ -49,6 +50,8 @@ class PreparedPass:
             raise ValueError("empty behaviour set")
         self.pooled_auc, self.loss = bool(pooled_auc), loss
         self.distributed = bool(distributed)
+        # resident: the behaviours are copied to the device once, here, and every pass runs on them (no upload in run())
+        self.resident = bool(resident)
         if self.distributed and not (ev.exchange == "p2p" and (group is None or torch.distributed.get_backend(group) == "nccl")):
             raise ValueError("prepared multi-GPU passes use the fused exchange (ScoreEvaluator(exchange='p2p') on NCCL ranks)")
         n_mod, dev = ev.n_modules, self.dev
@@ -62,6 +65,9 @@ class PreparedPass:
             stream = torch.cuda.current_stream(dev).cuda_stream
             # ---- inputs on the device + the upload descriptor
             self.d = {k: torch.empty(v.shape, dtype=v.dtype, device=dev) for k, v in self.src.items() if isinstance(v, Tensor) and k != "marks"}
+            if self.resident:
+                for k, t in self.d.items():
+                    t.copy_(self.src[k], non_blocking=True)
             self.ready = torch.zeros(1, dtype=torch.int32, device=dev)
             up = nat.UploadDesc()
             up.struct_size = ctypes.sizeof(nat.UploadDesc)
@@ -146,7 +152,8 @@ class PreparedPass:
             if loss_kind:
                 e.loss_kind, e.loss_temperature = loss_kind, float(temperature)
                 e.cand_pad, e.loss_per_impression = self.d["cand_pad"].data_ptr(), self.loss_per.data_ptr()
-            e.ready, e.ready_segments = self.ready.data_ptr(), segments
+            if not self.resident:
+                e.ready, e.ready_segments = self.ready.data_ptr(), segments
             need = lib.mb200_eval_workspace_bytes(ctypes.byref(e))
             if need == 0:
                 e.workspace, e.workspace_bytes = None, 0
@@ -202,14 +209,19 @@ class PreparedPass:
     # ------------------------------------------------------------------------------------------------------
     def run(self):
         """Upload (overlapped) + pass + read-back.  Returns an ``EvalResult``."""
-        from .evaluator import EvalResult
+        self.launch()
+        return self.read()
 
+    def launch(self) -> None:
+        """Queues one pass on the current stream (with the pipelined upload in front unless the pass is ``resident``); no host
+        synchronisation.  ``read()`` fetches the result of the most recent launch."""
         lib, e = self.lib, self.e
-        cur = torch.cuda.current_stream(self.dev)
-        stream = cur.cuda_stream
-        nat.check(lib.mb200_upload_begin(ctypes.byref(self.up), stream), "mb200_upload_begin")
+        stream = torch.cuda.current_stream(self.dev).cuda_stream
+        if not self.resident:
+            nat.check(lib.mb200_upload_begin(ctypes.byref(self.up), stream), "mb200_upload_begin")
         nat.check(lib.mb200_score_eval(ctypes.byref(e), stream), "mb200_score_eval")
-        nat.check(lib.mb200_upload_finish(ctypes.byref(self.up)), "mb200_upload_finish")  # every copy is queued from here on
+        if not self.resident:
+            nat.check(lib.mb200_upload_finish(ctypes.byref(self.up)), "mb200_upload_finish")  # every copy is queued from here on
         if self.loss_kind:
             nat.check(lib.mb200_step_loss(self.loss_per.data_ptr(), self.n_impr, self.step_batch, self.loss_kind, self.d["cand_offsets"].data_ptr(),
                                           self.d["labels"].data_ptr(), self.loss_ptr, stream), "mb200_step_loss")
@@ -230,7 +242,13 @@ class PreparedPass:
                                            self.ws_auc.numel(), self.auc_ptr, stream), "mb200_pooled_auc")
         if self.loss_kind and self.distributed:
             torch.distributed.all_reduce(self.result[self.off_loss : self.off_loss + 2], op=torch.distributed.ReduceOp.SUM, group=self.group)
-        self.host.copy_(self.result, non_blocking=True)  # the ONE device -> host read of the pass
+
+    def read(self):
+        """The ONE device -> host read of a pass (pinned buffer), decoded into an ``EvalResult``."""
+        from .evaluator import EvalResult
+
+        cur = torch.cuda.current_stream(self.dev)
+        self.host.copy_(self.result, non_blocking=True)
         cur.synchronize()
         return self._decode(EvalResult)
 

@@ -40,6 +40,13 @@ def test_prepared_ensemble_pass_equals_evaluate(evaluator_cls, segments):
     pp = ev.prepare(bhv, segments=segments, want_scores=True, **kw)
     first = pp.run()
     _agree(first, ref)
+    # resident form: behaviours copied once at prepare(), passes queued back to back without a host read in between
+    rp = ev.prepare(bhv, resident=True, want_scores=True, **kw)
+    for _ in range(3):
+        rp.launch()
+    res = rp.read()
+    _agree(res, ref)
+    np.testing.assert_array_equal(res.sums, ref.sums)  # resident sets run the static schedule of evaluate(): bit-identical
     for _ in range(3):
         again = pp.run()
         np.testing.assert_array_equal(again.sums, first.sums)  # same chunks, same slots, same order: bit-identical
