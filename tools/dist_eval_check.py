@@ -49,6 +49,18 @@ def main() -> None:
                 ok = ok and many.auc_counts == one.auc_counts
                 if one.loss is not None:
                     ok = ok and abs(many.loss - one.loss) <= 1e-12 * abs(one.loss)
+            if exchange == "p2p":
+                # the same sharded pass as a prepared pass (pipelined upload + fused exchange, manner_b200/prepared.py), interleaved with
+                # the generic path on the same mailboxes
+                pp = ev.prepare(shard, distributed=True, pos_cap=pos_cap, step_batch=8, **kw)
+                for rep in range(3):
+                    got = pp.run()
+                    ok = ok and got.n_impressions == one.n_impressions and np.allclose(got.sums, one.sums, rtol=1e-12, atol=1e-9) and got.auc == one.auc
+                    ok = ok and got.auc_counts == one.auc_counts
+                    if one.loss is not None:
+                        ok = ok and abs(got.loss - one.loss) <= 1e-12 * abs(one.loss)
+                many = ev.evaluate(dev_shard, distributed=True, **kw)
+                ok = ok and many.auc == one.auc
             # scores in the unit interval: AUROC without the sigmoid (the rule is decided over ALL ranks' scores)
             if name == "ensemble":
                 unit = ScoreEvaluator([t * 0.02 + 0.03 for t in tables[:1]], dev, exchange=exchange)
