@@ -571,6 +571,12 @@ def extra_results(args, ev, tables, bhv, dev, flush, hbm_peak: float, l2_peak: f
            traffic=ncu_traffic(args.workload, 2, False, "bf16")[0])
     record("bf16_tables_uniform_ids", ev16, uni, dict(weights=w2, zscore=True, pooled_auc=True), 2, 2, hbm_peak, "hbm")
     del ev16, uni
+    # (b2) the ensemble epoch as the reference's EnsembleModule.on_test_epoch_end logs it: + Diversity / Personalization @5/10 of
+    # category and sentiment (ensemble_module.py:56-84,214-238) -- the full ranking instead of the positives' ranks only
+    asp = mdata.synth_aspects(n_news)
+    ev_asp = ScoreEvaluator(tables, dev, news_category=asp["category"], news_sentiment=asp["sentiment"])
+    record("ensemble_with_aspect_metrics", ev_asp, bhv, dict(weights=w2, zscore=True, pooled_auc=True), 2, tables[0].element_size(), l2_peak, "l2")
+    del ev_asp
     # (c) BASELINE.json configs[3]: CR + category + sentiment, 121 weightings re-scored from one gather
     t3 = list(tables) + [mdata.synth_table(n_news, 768, mdata.TABLE_SEEDS[2])]
     ev3 = ScoreEvaluator(t3, dev)

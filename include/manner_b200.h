@@ -206,8 +206,10 @@ MB200_API int mb200_score_eval(const mb200_eval_desc* desc, void* stream);
  *   mb200_score_eval    on S with desc.ready / desc.ready_segments = n_segments: runs while the copies are still arriving
  *   mb200_upload_finish  waits (host side) until the library thread has queued every segment and returns its status; call it
  *                        before the host arrays or the descriptor go away.
- * The caller's thread never has to get past the kernel launch for the copies to be issued, so nothing deadlocks where launches
- * block (profilers that serialise kernels, CUDA_LAUNCH_BLOCKING=1).
+ * segments_first = n_segments queues every copy on the caller's thread in front of the launch (the Python layer's default: ~2 us
+ * per copy).  With fewer, the library thread overlaps the rest with the caller's launch; plain blocking launches
+ * (CUDA_LAUNCH_BLOCKING=1) are fine with that, but a tool that serialises ALL CUDA calls behind a running kernel (ncu) can keep
+ * the thread's copies from being issued while the kernel waits for them (-> MB200_FLAG_UPLOAD_TIMEOUT after 4 s).
  * Segments grow geometrically (the first holds 1/2^(n_segments-1) of the rows gathered, each later one as much as all before it),
  * so little is exposed in front of the kernel's first chunk.  Copies cover disjoint 128-byte aligned ranges.  All HOST arrays must be page-locked and stay untouched until C has run the copies.
  */

@@ -49,7 +49,9 @@ struct EvalParams {
   float* loss_per_impr;
   float* scores;
   float* per_impr;
-  double* partials;  // [n_chunks][W][MB200_NUM_METRICS] (score_eval_kernel: one slot per chunk) or [total_warps][...] (the other kernels)
+  double* partials;  // [W][MB200_NUM_METRICS][n_partials]: one slot per chunk (score_eval_kernel) or per warp (the other kernels), slot
+                     // index innermost so that the reduction reads every (weighting, metric) row contiguously
+  int n_partials;
   const int32_t* bounds;  // [n_chunks + 1] impression boundaries of the work-balanced chunks
   int* chunk_counter;     // score_eval_kernel: next chunk to hand out (zeroed by partition_kernel); null = static round-robin
   int32_t* flags;
@@ -1010,7 +1012,7 @@ __global__ void __launch_bounds__(kThreads, MINB) score_eval_kernel(const __grid
     __syncwarp();
     for (int t = lane; t < W * MB200_NUM_METRICS; t += 32) {
       const int w = t / MB200_NUM_METRICS, k = t % MB200_NUM_METRICS;
-      p.partials[(size_t)chunk * W * MB200_NUM_METRICS + t] = k < p.acc_stride ? sm.acc[w * p.acc_stride + k] : 0.0;
+      p.partials[(size_t)t * p.n_partials + chunk] = k < p.acc_stride ? sm.acc[w * p.acc_stride + k] : 0.0;
     }
     __syncwarp();
     for (int t = lane; t < W * p.acc_stride; t += 32) sm.acc[t] = 0.0;
@@ -1269,7 +1271,7 @@ __global__ void __launch_bounds__(kStreamWarps * 32, 1) score_eval_stream_kernel
   __syncwarp();
   for (int t = lane; t < W * MB200_NUM_METRICS; t += 32) {
     const int w = t / MB200_NUM_METRICS, k = t % MB200_NUM_METRICS;
-    p.partials[(size_t)gw * W * MB200_NUM_METRICS + t] = k < p.acc_stride ? sm.acc[w * p.acc_stride + k] : 0.0;
+    p.partials[(size_t)t * p.n_partials + gw] = k < p.acc_stride ? sm.acc[w * p.acc_stride + k] : 0.0;
   }
   warp_flags = __reduce_or_sync(kFull, warp_flags);
   if (lane == 0 && warp_flags && p.flags) atomicOr(p.flags, warp_flags);
@@ -1407,7 +1409,7 @@ __global__ void __launch_bounds__(kThreads) rank_metrics_kernel(const __grid_con
     }
   }
   __syncwarp();
-  for (int t = lane; t < MB200_NUM_METRICS; t += 32) p.partials[(size_t)gw * MB200_NUM_METRICS + t] = sm.acc[t];
+  for (int t = lane; t < MB200_NUM_METRICS; t += 32) p.partials[(size_t)t * p.n_partials + gw] = sm.acc[t];
   warp_flags = __reduce_or_sync(kFull, warp_flags);
   if (lane == 0 && warp_flags && p.flags) atomicOr(p.flags, warp_flags);
 }
@@ -1444,7 +1446,8 @@ __global__ void __launch_bounds__(256) reduce_partials_kernel(const double* __re
   __shared__ double sh[256];
   const int w = blockIdx.x, k = blockIdx.y, t = threadIdx.x;
   double a = 0.0;
-  for (int g = t; g < total_warps; g += 256) a += partials[((size_t)g * W + w) * MB200_NUM_METRICS + k];
+  const double* row = partials + ((size_t)w * MB200_NUM_METRICS + k) * total_warps;  // this (weighting, metric)'s slots, contiguous
+  for (int g = t; g < total_warps; g += 256) a += row[g];
   sh[t] = a;
   __syncthreads();
   for (int s = 128; s > 0; s >>= 1) {
@@ -1796,6 +1799,7 @@ int score_eval(const mb200_eval_desc* d, cudaStream_t stream) {
   p.bounds = reinterpret_cast<int32_t*>(ws);
   p.chunk_counter = dynamic_schedule(d) ? reinterpret_cast<int*>(ws) + plan.n_chunks + 1 : nullptr;
   p.partials = reinterpret_cast<double*>(ws + plan.bounds_bytes);
+  p.n_partials = plan.n_partials;
   p.n_news = d->n_news, p.row_stride = d->row_stride;
   p.n_impr = (int)d->n_impressions, p.n_modules = d->n_modules, p.active_mask = d->active_modules_mask;
   p.vec_per_row = vec_per_row;
@@ -1908,6 +1912,7 @@ int rank_metrics(const mb200_metrics_desc* d, cudaStream_t stream) {
   p.per_impr = d->per_impression, p.flags = d->flags;
   p.bounds = reinterpret_cast<int32_t*>(d->workspace);
   p.partials = reinterpret_cast<double*>(reinterpret_cast<unsigned char*>(d->workspace) + plan.bounds_bytes);
+  p.n_partials = plan.total_warps;
   p.n_impr = (int)d->n_impressions, p.n_modules = 1, p.active_mask = 1, p.n_weightings = 1;
   p.k0 = d->k0, p.k1 = d->k1, p.cpad = plan.cpad, p.max_cand = d->max_cand, p.n_chunks = plan.n_chunks;
   p.num_categ = d->num_categ_classes, p.num_sent = d->num_sent_classes;

@@ -113,10 +113,10 @@ static int copy_segments(const mb200_upload_desc* d, int first, int last) {
   return MB200_OK;
 }
 
-// The segments that mb200_upload_begin does not queue itself are queued by ONE library thread, concurrently with the caller -- who
-// goes straight on to launch the fused kernel.  The caller's thread therefore never has to get past that launch for the copies to
-// be issued: nothing deadlocks where launches block (a profiler that serialises kernels, CUDA_LAUNCH_BLOCKING=1), which a
-// "launch first, queue the rest afterwards" order on one thread would (the kernel waits for copies the host has not issued yet).
+// The segments that mb200_upload_begin does not queue itself (segments_first < n_segments) are queued by ONE library thread,
+// concurrently with the caller -- who goes straight on to launch the fused kernel.  A blocking launch on the caller's thread
+// (CUDA_LAUNCH_BLOCKING=1) does not stop that thread; a tool that serialises every CUDA call behind a running kernel does (ncu's
+// launch-list pass starved it until the kernel's 4 s time-out), which is why the Python layer queues everything itself by default.
 struct UploadJob {
   mb200_upload_desc d;
   int first, last, device;

@@ -209,7 +209,8 @@ class ScoreEvaluator:
 
     # -- inputs ----------------------------------------------------------------------------------------------
     def upload(self, bhv: Behaviours, pinned: Optional[Dict[str, object]] = None, pos_cap: Optional[int] = None,
-               step_batch: Optional[int] = None, pipelined: bool = False, segments: int = 5) -> DeviceBehaviours:
+               step_batch: Optional[int] = None, pipelined: bool = False, segments: int = 5,
+               worker_segments: int = 0) -> DeviceBehaviours:
         """Host CSR -> device (asynchronous on the current stream).  ``pinned`` lets a caller reuse
         page-locked staging tensors (see ``pin``); ``pos_cap`` is the multi-GPU bound of
         ``dist.agree_pos_cap`` when the caller already has it.  ``step_batch`` (the reference's eval batch size)
@@ -218,15 +219,15 @@ class ScoreEvaluator:
         ``pipelined``: the copy overlaps the pass instead of preceding it (mb200_upload_begin / _finish): the offsets go first,
         the id / label arrays follow in ``segments`` segments of geometrically growing size on a copy stream, and the fused kernel -- launched
         by the next ``launch`` / ``evaluate`` with the returned object -- starts on the first segment while the others are in
-        flight.  The returned arrays must not be read by anything else before that launch.  The segment copies are queued by a
-        thread of the library while this thread goes on to launch the kernel (no ordering hazard where launches block, e.g. under
-        a profiler)."""
+        flight.  The returned arrays must not be read by anything else before that launch.  ``worker_segments`` = k lets a thread
+        of the library queue the last k segment copies while this thread goes on to launch the kernel (see prepared.py: opt-in,
+        tools that serialise CUDA calls behind a running kernel can starve those copies)."""
         src = pinned if pinned is not None else self.pin(bhv, step_batch)
         if pos_cap is not None and pos_cap < src["n_pos"]:
             raise ValueError(f"pos_cap {pos_cap} is below this shard's {src['n_pos']} positives: the pooled AUROC would silently drop keys (dist.agree_pos_cap)")
         nbytes = sum(v.numel() * v.element_size() for k, v in src.items() if isinstance(v, Tensor) and k != "marks")
         if pipelined and bhv.n_impressions >= 64 * segments and self.n_table_shards == 1:
-            return self._upload_pipelined(bhv, src, pos_cap, nbytes, int(segments))
+            return self._upload_pipelined(bhv, src, pos_cap, nbytes, int(segments), int(worker_segments))
         dev = {k: v.to(self.device, non_blocking=True) for k, v in src.items() if isinstance(v, Tensor) and k != "marks"}
         return DeviceBehaviours(
             dev["hist_offsets"], dev["hist_ids"], dev["cand_offsets"], dev["cand_ids"], dev["labels"],
@@ -234,7 +235,8 @@ class ScoreEvaluator:
             src.get("step_batch", 8), dev.get("hist_pad"), dev.get("cand_pad"),
         )
 
-    def _upload_pipelined(self, bhv: Behaviours, src: Dict[str, object], pos_cap: Optional[int], nbytes: int, segments: int) -> DeviceBehaviours:
+    def _upload_pipelined(self, bhv: Behaviours, src: Dict[str, object], pos_cap: Optional[int], nbytes: int, segments: int,
+                          worker_segments: int = 0) -> DeviceBehaviours:
         import ctypes
 
         lib = nat.lib()
@@ -251,8 +253,7 @@ class ScoreEvaluator:
             ready = torch.empty(1, dtype=torch.int32, device=self.device)
             d = nat.UploadDesc()
             d.struct_size = ctypes.sizeof(nat.UploadDesc)
-            # the small early segments are queued here, the last two (three quarters of the bytes) by the library's thread
-            d.n_segments, d.segments_first, d.n_impressions = segments, max(1, segments - 2), bhv.n_impressions
+            d.n_segments, d.segments_first, d.n_impressions = segments, max(1, segments - max(0, worker_segments)), bhv.n_impressions
             for name in ("hist_offsets", "hist_ids", "cand_offsets", "cand_ids", "labels"):
                 setattr(d, "h_" + name, src[name].data_ptr())
                 setattr(d, "d_" + name, dev[name].data_ptr())

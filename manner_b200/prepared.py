@@ -31,7 +31,7 @@ class PreparedPass:
     def __init__(self, ev, bhv: Behaviours, pinned: Optional[Dict[str, object]] = None, weights=None, zscore: bool = False,
                  pooled_auc: bool = False, loss: Optional[str] = None, temperature: float = 0.1, step_batch: Optional[int] = None,
                  segments: int = 5, distributed: bool = False, group=None, pos_cap: Optional[int] = None, want_scores: bool = False,
-                 resident: bool = False) -> None:
+                 resident: bool = False, worker_segments: int = 0) -> None:
         from .evaluator import EvalResult  # noqa: F401  (cycle-free import at call time)
 
         lib = nat.lib()
@@ -71,10 +71,11 @@ class PreparedPass:
             self.ready = torch.zeros(1, dtype=torch.int32, device=dev)
             up = nat.UploadDesc()
             up.struct_size = ctypes.sizeof(nat.UploadDesc)
-            # the small early segments are queued by this thread (a sleeping worker thread needs tens of microseconds to wake up, and the
-            # kernel would run dry behind a tiny first segment); the last two -- three quarters of the bytes, not needed before the
-            # grid is a quarter through -- by the library's thread
-            up.n_segments, up.segments_first, up.n_impressions = segments, max(1, segments - 2), self.n_impr
+            # Every segment copy is queued by this thread, in front of the kernel launch (~2 us per copy).  ``worker_segments`` = k hands
+            # the LAST k segments to the library's thread instead, which queues them while this thread is already launching the kernel
+            # (the launch reaches the GPU ~20 us earlier) -- but a tool that serialises CUDA API calls behind a running kernel (ncu)
+            # can then keep those copies from ever being issued while the kernel waits for them, so it is opt-in.
+            up.n_segments, up.segments_first, up.n_impressions = segments, max(1, segments - max(0, int(worker_segments))), self.n_impr
             for name in ("hist_offsets", "hist_ids", "cand_offsets", "cand_ids", "labels"):
                 setattr(up, "h_" + name, self.src[name].data_ptr())
                 setattr(up, "d_" + name, self.d[name].data_ptr())

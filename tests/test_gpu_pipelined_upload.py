@@ -41,7 +41,7 @@ def test_pipelined_upload_is_bit_identical(evaluator_cls, segments):
     plain = ev.evaluate(ev.upload(bhv), **kw)
     pinned = ev.pin(bhv)
     for it in range(4):  # repeated passes recycle the device buffers: the copies must wait for the previous pass
-        d = ev.upload(bhv, pinned, pipelined=True, segments=segments)
+        d = ev.upload(bhv, pinned, pipelined=True, segments=segments, worker_segments=(it % 3))  # 0, 1, 2 segments by the library's thread
         assert d.ready is not None and d.ready_segments == segments
         _same(ev.evaluate(d, **kw), plain)
 

@@ -23,6 +23,7 @@ def main() -> None:
     ap = argparse.ArgumentParser()
     ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--segments", type=int, default=8)
+    ap.add_argument("--worker-segments", type=int, default=0)
     ap.add_argument("--prepared", action="store_true", help="time ScoreEvaluator.prepare(...).run() instead of upload() + launch() + finish()")
     args = ap.parse_args()
     from manner_b200 import _native as nat
@@ -40,7 +41,7 @@ def main() -> None:
     ops.set_tuning(time_kernel=1)
     lib = nat.lib()
     rec = {k: [] for k in ("upload_us", "launch_us", "finish_us", "gpu_wait_before_kernel_ms", "kernel_ms", "e2e_ms")}
-    pp = ev.prepare(bhv, pinned, segments=args.segments, **kw) if args.prepared else None
+    pp = ev.prepare(bhv, pinned, segments=args.segments, worker_segments=args.worker_segments, **kw) if args.prepared else None
     for i in range(args.steps + 5):
         flush.fill_(1)
         torch.cuda.synchronize()
@@ -64,7 +65,7 @@ def main() -> None:
             rec["gpu_wait_before_kernel_ms"].append(float(lib.mb200_last_score_kernel_begin_after(e0.cuda_event)))
             rec["kernel_ms"].append(ops.last_score_kernel_ms())
             rec["e2e_ms"].append(e0.elapsed_time(e1))
-    print(json.dumps({k: round(statistics.median(v), 4) for k, v in rec.items()} | {"segments": args.segments, "prepared": args.prepared, "auc": res.auc}))
+    print(json.dumps({k: round(statistics.median(v), 4) for k, v in rec.items()} | {"segments": args.segments, "worker_segments": args.worker_segments, "prepared": args.prepared, "auc": res.auc}))
 
 
 if __name__ == "__main__":
