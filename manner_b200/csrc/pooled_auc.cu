@@ -494,9 +494,24 @@ __device__ bool wait_flag(const uint32_t* flag, uint32_t epoch) {
   return true;
 }
 
-__global__ void __launch_bounds__(256) exchange_post_kernel(const ExchangeParams p) {
+// One launch, two jobs that run side by side: the first kPostBlocks CTAs STORE this rank's payload and positive keys into every
+// rank's mailbox (NVLink stores, then the epoch flag); the other CTAs meanwhile prepare the sigmoid keys of this rank's sorted
+// negatives -- the rank search after the exchange then compares plain integers whichever way AUROC's sigmoid rule (known only once
+// all payloads are in) turns out.  (As two kernels back to back they cost 36 us at 2 GPUs; the stores are latency, the sigmoid is
+// fp64 arithmetic.)
+constexpr int kPostBlocks = 148;
+
+__global__ void __launch_bounds__(256) exchange_post_kernel(const ExchangeParams p, int with_sigmoid) {
+  if ((int)blockIdx.x >= kPostBlocks) {
+    if (!with_sigmoid) return;
+    const long long n_neg = p.n_rows - *p.n_pos;
+    const long long nthreads = (long long)(gridDim.x - kPostBlocks) * blockDim.x;
+    for (long long i = (long long)(blockIdx.x - kPostBlocks) * blockDim.x + threadIdx.x; i < n_neg; i += nthreads)
+      p.sorted_sig[i] = orderable_key(sigmoid_f32(key_to_float(p.sorted_neg[i])));
+    return;
+  }
   const long long n_pos = min(*p.n_pos, p.pos_capacity);
-  const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x, nthreads = (long long)gridDim.x * blockDim.x;
+  const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x, nthreads = (long long)kPostBlocks * blockDim.x;
   if (tid == 0 && p.flags) *p.flags = 0, p.flags[1] = 0;  // the exchange's own flag word (an int64 slot of the result): set by the finish kernel only
   for (int r = 0; r < p.n_ranks; ++r) {
     unsigned char* slot = slot_of_mailbox(p, r, p.my_rank);
@@ -510,7 +525,7 @@ __global__ void __launch_bounds__(256) exchange_post_kernel(const ExchangeParams
   __threadfence_system();
   __syncthreads();
   __shared__ bool last;
-  if (threadIdx.x == 0) last = atomicAdd(&own->ticket, 1u) == gridDim.x - 1;
+  if (threadIdx.x == 0) last = atomicAdd(&own->ticket, 1u) == kPostBlocks - 1;
   __syncthreads();
   if (last) {
     if (threadIdx.x == 0) own->ticket = 0, own->acc = 0;
@@ -518,15 +533,6 @@ __global__ void __launch_bounds__(256) exchange_post_kernel(const ExchangeParams
     __syncthreads();
     if ((int)threadIdx.x < p.n_ranks) st_release_sys(&reinterpret_cast<ExchangeHeader*>(slot_of_mailbox(p, threadIdx.x, p.my_rank))->flag1, p.epoch);
   }
-}
-
-// sigmoid keys of this rank's sorted negatives, computed while the peers' stores are still arriving: the rank search after the
-// exchange then compares plain integers whichever way AUROC's sigmoid rule (known only once all payloads are in) turns out
-__global__ void __launch_bounds__(256) exchange_sigmoid_keys_kernel(const uint32_t* __restrict__ sorted_neg, long long n_rows, const long long* __restrict__ n_pos,
-                                                                    uint32_t* __restrict__ sorted_sig) {
-  const long long n_neg = n_rows - *n_pos;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_neg; i += (long long)gridDim.x * blockDim.x)
-    sorted_sig[i] = orderable_key(sigmoid_f32(key_to_float(sorted_neg[i])));
 }
 
 __global__ void __launch_bounds__(256) exchange_finish_kernel(const ExchangeParams p) {
@@ -560,14 +566,46 @@ __global__ void __launch_bounds__(256) exchange_finish_kernel(const ExchangePara
   const long long n_neg = p.n_rows - my_pos;
   const bool use_sig = sig;
   const SortedKeys negs = stage_splitters<kSplitters>(use_sig ? p.sorted_sig : p.sorted_neg, n_neg, sh_split);
+  // all ranks' positives as ONE index space, so that a sweep of the grid is full whatever the number of ranks (one strided loop per
+  // rank left four fifths of the threads idle in each of R latency-bound sweeps)
   unsigned long long local = 0;
   bool overflow = false;
-  for (int r = 0; r < p.n_ranks; ++r) {
-    const unsigned char* slot = slot_of_mailbox(p, p.my_rank, r);
-    long long cnt = reinterpret_cast<const ExchangeHeader*>(slot)->n_pos;
-    if (cnt > p.pos_capacity) cnt = p.pos_capacity, overflow = true;
-    const uint32_t* keys = reinterpret_cast<const uint32_t*>(slot + p.keys_off);
-    local += use_sig ? rank_sum_span<true>(negs, sh_split, keys, cnt) : rank_sum_span<false>(negs, sh_split, keys, cnt);
+  long long first[MB200_MAX_TABLE_SHARDS + 1];
+  const uint32_t* keys_of[MB200_MAX_TABLE_SHARDS];
+  first[0] = 0;
+#pragma unroll
+  for (int r = 0; r < MB200_MAX_TABLE_SHARDS; ++r) {
+    long long cnt = 0;
+    keys_of[r] = nullptr;
+    if (r < p.n_ranks) {
+      const unsigned char* slot = slot_of_mailbox(p, p.my_rank, r);
+      cnt = reinterpret_cast<const ExchangeHeader*>(slot)->n_pos;
+      if (cnt > p.pos_capacity) cnt = p.pos_capacity, overflow = true;
+      keys_of[r] = reinterpret_cast<const uint32_t*>(slot + p.keys_off);
+    }
+    first[r + 1] = first[r] + cnt;
+  }
+  const long long total = first[MB200_MAX_TABLE_SHARDS];
+  const long long nthreads = (long long)gridDim.x * blockDim.x;
+  for (long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x; g < total; g += nthreads * kSearchIlp) {
+    uint32_t key[kSearchIlp];
+    unsigned valid = 0;
+#pragma unroll
+    for (int k = 0; k < kSearchIlp; ++k) {
+      const long long gg = g + k * nthreads;
+      key[k] = 0u;
+      if (gg < total) {
+        const uint32_t* src = keys_of[0];
+        long long base = 0;
+#pragma unroll
+        for (int r = 1; r < MB200_MAX_TABLE_SHARDS; ++r)
+          if (gg >= first[r]) src = keys_of[r], base = first[r];
+        key[k] = src[gg - base];
+        if (use_sig) key[k] = orderable_key(sigmoid_f32(key_to_float(key[k])));
+        valid |= 1u << k;
+      }
+    }
+    local += bounds_sum<kSplitters>(negs, sh_split, key, valid);
   }
   if (overflow && blockIdx.x == 0 && threadIdx.x == 0 && p.flags) atomicOr(p.flags, MB200_FLAG_POS_OVERFLOW);
 #pragma unroll
@@ -649,15 +687,11 @@ int exchange_post(const mb200_exchange_desc* d, cudaStream_t stream) {
   int st = exchange_params(d, &p);
   if (st != MB200_OK) return st;
   if ((st = use_device_of(d->out_payload, nullptr)) != MB200_OK) return st;
-  exchange_post_kernel<<<32, 256, 0, stream>>>(p);
-  if ((st = cuda_status(cudaGetLastError(), "exchange_post_kernel")) != MB200_OK) return st;
+  const int with_sigmoid = (d->n_rows > 0 && d->outside_index >= 0) ? 1 : 0;
+  const int sig_blocks = with_sigmoid ? grid_for(d->n_rows, 256 * 4, 148 * 6) : 0;
+  exchange_post_kernel<<<kPostBlocks + sig_blocks, 256, 0, stream>>>(p, with_sigmoid);
   note_launch(1);
-  if (d->n_rows > 0 && d->outside_index >= 0) {  // overlaps the flight of the stores and the wait for the slowest rank
-    exchange_sigmoid_keys_kernel<<<grid_for(d->n_rows, 256, 148 * 8), 256, 0, stream>>>(p.sorted_neg, d->n_rows, p.n_pos, p.sorted_sig);
-    note_launch(1);
-    return cuda_status(cudaGetLastError(), "exchange_sigmoid_keys_kernel");
-  }
-  return MB200_OK;
+  return cuda_status(cudaGetLastError(), "exchange_post_kernel");
 }
 
 int exchange_finish(const mb200_exchange_desc* d, cudaStream_t stream) {
@@ -680,7 +714,6 @@ int force_load_auc_kernels(cudaStream_t stream) {
   if (st == MB200_OK) st = cuda_status(cudaFuncGetAttributes(&a, auc_finalize_kernel), "cudaFuncGetAttributes");
   if (st == MB200_OK) st = cuda_status(cudaFuncGetAttributes(&a, auc_stream_negatives_kernel), "cudaFuncGetAttributes");
   if (st == MB200_OK) st = cuda_status(cudaFuncGetAttributes(&a, exchange_post_kernel), "cudaFuncGetAttributes");
-  if (st == MB200_OK) st = cuda_status(cudaFuncGetAttributes(&a, exchange_sigmoid_keys_kernel), "cudaFuncGetAttributes");
   if (st == MB200_OK) st = cuda_status(cudaFuncGetAttributes(&a, exchange_finish_kernel), "cudaFuncGetAttributes");
   if (st != MB200_OK) return st;
   const long long n = 1 << 16;  // large enough for the multi-pass (onesweep) path the real sorts take

@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Minimal target for `ncu --set full`: loads one workload, launches the fused pass a few times, exits.
 
-    python tools/ncu_target.py --case zipf|uniform|bf16|bf16_uniform|m1|m3 [--variant V] [--launches 5]
+    python tools/ncu_target.py --case zipf|uniform|bf16|bf16_uniform|m1|m3 [--aspects] [--variant V] [--launches 5]
 """
 from __future__ import annotations
 
@@ -25,11 +25,13 @@ def main() -> None:
     ap.add_argument("--case", default="zipf")
     ap.add_argument("--variant", type=int, default=-1)
     ap.add_argument("--launches", type=int, default=5)
+    ap.add_argument("--aspects", action="store_true", help="with the category / sentiment labels: Diversity / Personalization metrics, full ranking")
     args = ap.parse_args()
     dev = torch.device("cuda:0")
     n_mod, uniform, dtype = CASES[args.case]
     tables, bhv = mdata.synth_workload("small", n_modules=n_mod, uniform_ids=uniform, dtype=dtype)
-    ev = ScoreEvaluator(tables, dev)
+    asp = mdata.synth_aspects(tables[0].shape[0]) if args.aspects else None
+    ev = ScoreEvaluator(tables, dev, news_category=None if asp is None else asp["category"], news_sentiment=None if asp is None else asp["sentiment"])
     d = ev.upload(bhv)
     w = torch.tensor([[1.0, 0.4, 0.2][:n_mod]], dtype=torch.float32, device=dev)
     ops.set_tuning(variant=args.variant)
