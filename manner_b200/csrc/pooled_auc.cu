@@ -536,19 +536,22 @@ __global__ void __launch_bounds__(256) exchange_post_kernel(const ExchangeParams
 }
 
 __global__ void __launch_bounds__(256) exchange_finish_kernel(const ExchangeParams p) {
-  __shared__ bool ok, sig, last;
+  __shared__ bool last;
+  __shared__ int sh_good, sh_outside;
   __shared__ unsigned long long sh[8];
   __shared__ uint32_t sh_split[kSplitters];
-  if (threadIdx.x == 0) {
-    bool good = true, outside = false;
-    for (int r = 0; r < p.n_ranks; ++r) {
-      unsigned char* slot = slot_of_mailbox(p, p.my_rank, r);
-      good = good && wait_flag(&reinterpret_cast<ExchangeHeader*>(slot)->flag1, p.epoch);
-      if (good && p.outside_index >= 0) outside |= reinterpret_cast<const double*>(slot + p.payload_off)[p.outside_index] > 0.0;
-    }
-    ok = good, sig = outside;
+  __shared__ unsigned long long sh_stats[MB200_MAX_TABLE_SHARDS][3];
+  // one thread per rank waits for that rank's slot (a single thread walking eight system-scope polls in turn cost more than the search)
+  if (threadIdx.x == 0) sh_good = 1, sh_outside = 0;
+  __syncthreads();
+  if ((int)threadIdx.x < p.n_ranks) {
+    unsigned char* slot = slot_of_mailbox(p, p.my_rank, threadIdx.x);
+    const bool good = wait_flag(&reinterpret_cast<ExchangeHeader*>(slot)->flag1, p.epoch);
+    if (!good) atomicAnd(&sh_good, 0);
+    else if (p.outside_index >= 0 && reinterpret_cast<const double*>(slot + p.payload_off)[p.outside_index] > 0.0) atomicOr(&sh_outside, 1);
   }
   __syncthreads();
+  const bool ok = sh_good != 0, sig = sh_outside != 0;
   if (!ok) {
     if (blockIdx.x == 0 && threadIdx.x == 0 && p.flags) atomicOr(p.flags, MB200_FLAG_EXCHANGE_TIMEOUT);
     return;
@@ -622,29 +625,34 @@ __global__ void __launch_bounds__(256) exchange_finish_kernel(const ExchangePara
   }
   __syncthreads();
   if (!last) return;
-  // the last block posts this rank's three additive integers to every peer, then sums what the peers posted
+  // the last block posts this rank's three additive integers to every peer, then sums what the peers posted: one thread per peer, so
+  // the R NVLink round trips (stores + fence + flag out, flag + statistics back) run side by side
+  __shared__ unsigned long long sh_sum2;
   if (threadIdx.x == 0) {
     __threadfence();
-    const unsigned long long sum2 = atomicAdd(&own->acc, 0ull);
+    sh_sum2 = atomicAdd(&own->acc, 0ull);
     own->ticket = 0;
-    for (int r = 0; r < p.n_ranks; ++r) {
-      ExchangeHeader* h = reinterpret_cast<ExchangeHeader*>(slot_of_mailbox(p, r, p.my_rank));
-      h->sum2 = sum2, h->pos_total = my_pos, h->neg_total = n_neg;
-    }
+    sh_good = 1;
+  }
+  __syncthreads();
+  if ((int)threadIdx.x < p.n_ranks) {
+    const int r = threadIdx.x;
+    ExchangeHeader* h = reinterpret_cast<ExchangeHeader*>(slot_of_mailbox(p, r, p.my_rank));
+    h->sum2 = sh_sum2, h->pos_total = my_pos, h->neg_total = n_neg;
     __threadfence_system();
-    for (int r = 0; r < p.n_ranks; ++r) st_release_sys(&reinterpret_cast<ExchangeHeader*>(slot_of_mailbox(p, r, p.my_rank))->flag2, p.epoch);
-    unsigned long long s2 = 0;
-    long long P = 0, N = 0;
-    bool good = true;
-    for (int r = 0; r < p.n_ranks; ++r) {
-      const ExchangeHeader* h = reinterpret_cast<const ExchangeHeader*>(slot_of_mailbox(p, p.my_rank, r));
-      good = good && wait_flag(&h->flag2, p.epoch);
-      s2 += *reinterpret_cast<const volatile unsigned long long*>(&h->sum2);
-      P += *reinterpret_cast<const volatile long long*>(&h->pos_total);
-      N += *reinterpret_cast<const volatile long long*>(&h->neg_total);
-    }
-    if (!good && p.flags) atomicOr(p.flags, MB200_FLAG_EXCHANGE_TIMEOUT);
-    p.out_stats[0] = (long long)s2, p.out_stats[1] = P, p.out_stats[2] = N;
+    st_release_sys(&h->flag2, p.epoch);
+    const ExchangeHeader* in = reinterpret_cast<const ExchangeHeader*>(slot_of_mailbox(p, p.my_rank, r));
+    if (!wait_flag(&in->flag2, p.epoch)) atomicAnd(&sh_good, 0);
+    sh_stats[r][0] = *reinterpret_cast<const volatile unsigned long long*>(&in->sum2);
+    sh_stats[r][1] = (unsigned long long)*reinterpret_cast<const volatile long long*>(&in->pos_total);
+    sh_stats[r][2] = (unsigned long long)*reinterpret_cast<const volatile long long*>(&in->neg_total);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned long long s2 = 0, P = 0, N = 0;
+    for (int r = 0; r < p.n_ranks; ++r) s2 += sh_stats[r][0], P += sh_stats[r][1], N += sh_stats[r][2];
+    if (!sh_good && p.flags) atomicOr(p.flags, MB200_FLAG_EXCHANGE_TIMEOUT);
+    p.out_stats[0] = (long long)s2, p.out_stats[1] = (long long)P, p.out_stats[2] = (long long)N;
   }
 }
 

@@ -43,8 +43,8 @@ class PreparedPass:
         self.src = pinned if pinned is not None else ev.pin(bhv, step_batch)
         if (loss is not None or ev.attn_logits is not None) and "hist_pad" not in self.src:
             raise ValueError("early fusion / the losses need the step pads: pin(bhv, step_batch)")
-        if "marks" not in self.src:
-            self.src["marks"] = torch.zeros(nat.MAX_UPLOAD_SEGMENTS, dtype=torch.int32).pin_memory()
+        # page-locked scratch the upload writes its segment marks to: this pass's own (passes over one pinned set may be in flight together)
+        self.marks = torch.zeros(nat.MAX_UPLOAD_SEGMENTS, dtype=torch.int32).pin_memory()
         self.n_impr, self.n_cand = bhv.n_impressions, bhv.n_cand
         if self.n_impr < 1:
             raise ValueError("empty behaviour set")
@@ -83,7 +83,7 @@ class PreparedPass:
                 if name in self.d:
                     setattr(up, "h_" + name, self.src[name].data_ptr())
                     setattr(up, "d_" + name, self.d[name].data_ptr())
-            up.ready, up.h_marks, up.copy_stream = self.ready.data_ptr(), self.src["marks"].data_ptr(), self.copy_stream.cuda_stream
+            up.ready, up.h_marks, up.copy_stream = self.ready.data_ptr(), self.marks.data_ptr(), self.copy_stream.cuda_stream
             self.up = up
             self.h2d_bytes = sum(v.numel() * v.element_size() for k, v in self.src.items() if isinstance(v, Tensor) and k != "marks")
 
