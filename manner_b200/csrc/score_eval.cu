@@ -132,6 +132,14 @@ __device__ __forceinline__ uint4 load_row_vec(const uint4* p) {
 // torch sort semantics: NaN is the largest value; equal NaNs tie.
 __device__ __forceinline__ bool ranks_before(float a, float b) { return (a > b) || (a != a && b == b); }
 __device__ __forceinline__ bool ranks_equal(float a, float b) { return (a == b) || (a != a && b != b); }
+// The same order as one unsigned integer: key(a) > key(b) <=> ranks_before(a, b), key(a) == key(b) <=> ranks_equal(a, b).  Every NaN
+// maps to the largest key, -0 to +0's; the smallest key of a real float (-inf) is 0x007fffff, so 0 is free as "none".
+__device__ __forceinline__ unsigned rank_key(float x) {
+  if (x != x) return 0xffffffffu;
+  if (x == 0.0f) x = 0.0f;
+  const unsigned b = __float_as_uint(x);
+  return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
 
 // Sum of x_j = (bit j of mask) ? 1/log2(j+2) : 0 over j < L in the fp32 summation order of ATen's
 // CPU `sum` over a contiguous vector (SumKernel.cpp: 8-lane vectors, scalar tail first, then the
@@ -805,60 +813,53 @@ __device__ __noinline__ int rank_and_metrics(const EvalParams& p, const WarpSmem
     unsigned hit_mask = 0;
     long long gauc2 = 0;  // sum over positives of 2 * (#neg below) + (#neg equal)
 
-    if (!aspects) {
-      // positives only: lanes split the comparison partners
+    // the positives' ranks: lanes split the comparison partners (all the ranking metrics need)
 #pragma unroll 1
-      for (int b0 = 0; b0 < C; b0 += 32) {
-        const int j = b0 + lane;
-        unsigned pm = __ballot_sync(kFull, j < C && lab[j] != 0);
-        n_pos += __popc(pm);
+    for (int b0 = 0; b0 < C; b0 += 32) {
+      const int j = b0 + lane;
+      unsigned pm = __ballot_sync(kFull, j < C && lab[j] != 0);
+      n_pos += __popc(pm);
 #pragma unroll 1
-        while (pm) {
-          const int pj = b0 + __ffs(pm) - 1;
-          pm &= pm - 1;
-          const float sp = scores_w[pj];
-          int before = 0, nlt = 0, neq = 0;
-#pragma unroll 1
-          for (int k = lane; k < C; k += 32) {
-            const float sk = scores_w[k];
-            before += (ranks_before(sk, sp) || (k < pj && ranks_equal(sk, sp))) ? 1 : 0;
-            if (lab[k] == 0) nlt += (sk < sp) ? 1 : 0, neq += (sk == sp) ? 1 : 0;
-          }
-          const int rank = 1 + __reduce_add_sync(kFull, before);
-          gauc2 += 2ll * __reduce_add_sync(kFull, nlt) + __reduce_add_sync(kFull, neq);
-          min_rank = min(min_rank, rank);
-          if (rank <= 32) hit_mask |= 1u << (rank - 1);
-        }
-      }
-    } else {
-      // full ranking: lanes own candidates (needed for the identity of the top-k)
-      int my_min = 0x7fffffff, my_pos = 0;
-      unsigned my_hits = 0;
-      long long my_g2 = 0;
-#pragma unroll 1
-      for (int j = lane; j < C; j += 32) {
-        const float sj = scores_w[j];
-        const bool pos = lab[j] != 0;
+      while (pm) {
+        const int pj = b0 + __ffs(pm) - 1;
+        pm &= pm - 1;
+        const float sp = scores_w[pj];
         int before = 0, nlt = 0, neq = 0;
 #pragma unroll 1
-        for (int k = 0; k < C; ++k) {
+        for (int k = lane; k < C; k += 32) {
           const float sk = scores_w[k];
-          before += (ranks_before(sk, sj) || (k < j && ranks_equal(sk, sj))) ? 1 : 0;
-          if (pos && lab[k] == 0) nlt += (sk < sj) ? 1 : 0, neq += (sk == sj) ? 1 : 0;
+          before += (ranks_before(sk, sp) || (k < pj && ranks_equal(sk, sp))) ? 1 : 0;
+          if (lab[k] == 0) nlt += (sk < sp) ? 1 : 0, neq += (sk == sp) ? 1 : 0;
         }
-        const int rank = 1 + before;
-        if (rank <= kmax) sm.top_cat[rank - 1] = sm.ccat[j], sm.top_sent[rank - 1] = sm.csent[j];
-        if (pos) {
-          ++my_pos;
-          my_min = min(my_min, rank);
-          if (rank <= 32) my_hits |= 1u << (rank - 1);
-          my_g2 += 2ll * nlt + neq;
-        }
+        const int rank = 1 + __reduce_add_sync(kFull, before);
+        gauc2 += 2ll * __reduce_add_sync(kFull, nlt) + __reduce_add_sync(kFull, neq);
+        min_rank = min(min_rank, rank);
+        if (rank <= 32) hit_mask |= 1u << (rank - 1);
       }
-      n_pos = __reduce_add_sync(kFull, my_pos);
-      min_rank = __reduce_min_sync(kFull, my_min);
-      hit_mask = __reduce_or_sync(kFull, my_hits);
-      gauc2 = (long long)warp_sum((double)my_g2);
+    }
+    if (aspects) {
+      // Identity of the top-kmax candidates (Diversity / Personalization look at their aspect labels): kmax rounds of a warp-wide
+      // arg-max over the candidates that rank after the previous pick -- score descending, lower position first among equals, NaN
+      // above everything and equal to itself (torch.sort).  O(kmax C / 32) instead of ranking every candidate against every other
+      // (O(C^2 / 32): 27 % of the kernel's instructions with aspect metrics on, profiles/r2_ac_score_eval_aspects_ncu.json).
+      const int kk = min(kmax, C);
+      unsigned prev_key = 0xffffffffu;
+      int prev_idx = -1;
+#pragma unroll 1
+      for (int r = 0; r < kk; ++r) {
+        unsigned best_key = 0u;
+        int best_idx = 0x7fffffff;
+#pragma unroll 1
+        for (int j = lane; j < C; j += 32) {
+          const unsigned key = rank_key(scores_w[j]);
+          const bool after = key < prev_key || (key == prev_key && j > prev_idx);  // ranks strictly after the previous pick
+          if (after && (key > best_key || best_idx == 0x7fffffff)) best_key = key, best_idx = j;  // ascending j: the first of equals stays
+        }
+        const unsigned top = __reduce_max_sync(kFull, best_idx == 0x7fffffff ? 0u : best_key);
+        const int pick = __reduce_min_sync(kFull, (best_idx != 0x7fffffff && best_key == top) ? best_idx : 0x7fffffff);
+        if (lane == 0) sm.top_cat[r] = sm.ccat[pick], sm.top_sent[r] = sm.csent[pick];
+        prev_key = top, prev_idx = pick;
+      }
       __syncwarp();
     }
 
