@@ -88,3 +88,43 @@ def test_metric_object_edge_cases(metrics_mod):
     target = torch.tensor([0, 0, 1, 1, 1], device="cuda")
     out = m(preds, target, indexes=torch.tensor([7, 7, 42, 42, 42], device="cuda"))
     assert out["mrr"] == pytest.approx(0.5) and out["ndcg@5"] == pytest.approx(0.5) and out["auc"] == pytest.approx(2 / 3)
+
+
+def test_aspect_metrics_top_k_under_ties_nan_and_signed_zero(metrics_mod):
+    """The top-k whose aspect labels Diversity / Personalization look at is picked on the device by k rounds of a warp arg-max; the
+    reference takes `argsort(preds, descending=True, stable=True)[:k]` (torch.sort: NaN above everything, equal values in position
+    order, -0 == +0).  Quantised predictions (long runs of ties), NaNs, both zeros and +-inf, impressions from 1 to 300 candidates:
+    every per-impression value must equal the oracle's."""
+    g = np.random.default_rng(17)
+    sizes = np.concatenate([[1, 2, 3, 31, 32, 33, 64, 65, 300], g.integers(2, 120, 150)])
+    hsizes = g.integers(1, 50, sizes.shape[0])
+    co = np.zeros(sizes.shape[0] + 1, dtype=np.int32)
+    co[1:] = np.cumsum(sizes)
+    ho = np.zeros(sizes.shape[0] + 1, dtype=np.int32)
+    ho[1:] = np.cumsum(hsizes)
+    n, nh = int(co[-1]), int(ho[-1])
+    preds = (g.integers(-3, 4, n) / 2.0).astype(np.float32)  # 7 distinct values -> ties everywhere
+    special = g.random(n)
+    preds[special < 0.03] = np.nan
+    preds[(special >= 0.03) & (special < 0.05)] = -0.0
+    preds[(special >= 0.05) & (special < 0.06)] = np.inf
+    preds[(special >= 0.06) & (special < 0.07)] = -np.inf
+    labels = (g.random(n) < 0.1).astype(np.uint8)
+    ccat, csent = g.integers(1, 19, n).astype(np.int32), g.integers(1, 4, n).astype(np.int32)
+    hcat, hsent = g.integers(1, 19, nh).astype(np.int32), g.integers(1, 4, nh).astype(np.int32)
+    cu = lambda a: torch.from_numpy(a).cuda()
+    _, per, flags = metrics_mod.rank_metrics(cu(preds), cu(labels), cu(co), int(sizes.max()), cand_category=cu(ccat), cand_sentiment=cu(csent),
+                                             hist_offsets=cu(ho), hist_category=cu(hcat), hist_sentiment=cu(hsent), want_per_impression=True)
+    per = per.cpu().numpy()
+    assert int(flags.item()) & ~nat.FLAG_OUTSIDE_UNIT == 0
+    slots = {(nat.M_CATEG_DIV_K0, "div", "c", 5), (nat.M_CATEG_DIV_K1, "div", "c", 10), (nat.M_SENT_DIV_K0, "div", "s", 5), (nat.M_SENT_DIV_K1, "div", "s", 10),
+             (nat.M_CATEG_PERS_K0, "pers", "c", 5), (nat.M_CATEG_PERS_K1, "pers", "c", 10), (nat.M_SENT_PERS_K0, "pers", "s", 5), (nat.M_SENT_PERS_K1, "pers", "s", 10)}
+    for i in range(sizes.shape[0]):
+        p = torch.from_numpy(preds[co[i]:co[i + 1]])
+        for slot, kind, asp, k in slots:
+            ca = torch.from_numpy((ccat if asp == "c" else csent)[co[i]:co[i + 1]].astype(np.int64))
+            ha = torch.from_numpy((hcat if asp == "c" else hsent)[ho[i]:ho[i + 1]].astype(np.int64))
+            ncls = 19 if asp == "c" else 4
+            kk = min(k, int(sizes[i]))
+            want = float(mo.diversity(p, ca, ncls, kk)) if kind == "div" else float(mo.personalization(p, ca, ha, ncls, kk))
+            assert abs(per[i, slot] - want) <= 2e-6, (i, int(sizes[i]), kind, asp, k, per[i, slot], want)
