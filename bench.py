@@ -530,6 +530,7 @@ def run_gpu_arm(args) -> None:
     if distributed:
         dist.barrier()
         dist.destroy_process_group()
+        time.sleep(0.5)  # the other ranks tear NCCL down at the same moment: let whatever NCCL_DEBUG makes them say come first
     sys.stdout.flush()
     print(json.dumps(line), flush=True)  # last line of stdout, after NCCL has said whatever NCCL_DEBUG asked it to say
 
