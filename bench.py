@@ -755,10 +755,13 @@ def run_retrieval_arm(args) -> None:
                          "kernel_share_of_step": kern_ms * args.steps / total_ms if total_ms > 0 else None},
             "cpu_baseline": cpu, "clocks": clocks,
         }
-        print(json.dumps(line))
     if distributed:
         dist.barrier()
         dist.destroy_process_group()
+        time.sleep(0.5)
+    if rank == 0:
+        sys.stdout.flush()
+        print(json.dumps(line), flush=True)  # last line of stdout
 
 
 def main() -> None:
