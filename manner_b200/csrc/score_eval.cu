@@ -256,6 +256,73 @@ __device__ __noinline__ float personalization_value(const uint8_t* top, int kk, 
   return __fdiv_rn((float)mn, (float)mx);
 }
 
+// Diversity@k0, Diversity@k1, Personalization@k0, Personalization@k1 of ONE aspect in one go: the class counts of both cut-offs come
+// from a single scan of the top-k labels, and the two entropy chains (division, log, two warp reductions each) run interleaved
+// instead of back to back -- with the aspect metrics on, these dependent chains, eight calls per impression, were the largest
+// stall source after the row gathers.  Every value is computed with the operation order of diversity_value / personalization_value
+// (bit-identical results; those two stay as the single-value reference forms).
+struct AspectValues {
+  float div0, div1, pers0, pers1;
+};
+__device__ __noinline__ AspectValues aspect_values(const uint8_t* top, int kk0, int kk1, const int* hist_count, int num_classes, int lane) {
+  __builtin_assume(__isShared(top));
+  __builtin_assume(__isShared(hist_count));
+  const int kmax = max(kk0, kk1);
+  int cnt0[2], cnt1[2];
+  int mn0 = 0, mx0 = 0, mn1 = 0, mx1 = 0;
+#pragma unroll
+  for (int t = 0; t < 2; ++t) {
+    const int c = lane + 32 * t;
+    cnt0[t] = cnt1[t] = 0;
+    if (c < num_classes) {
+#pragma unroll 1
+      for (int r = 0; r < kmax; ++r) {
+        const int m = (top[r] == c) ? 1 : 0;
+        cnt0[t] += (r < kk0) ? m : 0;
+        cnt1[t] += (r < kk1) ? m : 0;
+      }
+      const int hc = hist_count[c];
+      mn0 += min(cnt0[t], hc), mx0 += max(cnt0[t], hc);
+      mn1 += min(cnt1[t], hc), mx1 += max(cnt1[t], hc);
+    }
+  }
+  float prob0[2], prob1[2], total0 = 0.f, total1 = 0.f;
+#pragma unroll
+  for (int t = 0; t < 2; ++t) {
+    prob0[t] = __fdiv_rn((float)cnt0[t], (float)num_classes);
+    prob1[t] = __fdiv_rn((float)cnt1[t], (float)num_classes);
+    total0 += prob0[t], total1 += prob1[t];
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    total0 += __shfl_xor_sync(kFull, total0, o);
+    total1 += __shfl_xor_sync(kFull, total1, o);
+  }
+  float ent0 = 0.f, ent1 = 0.f;
+#pragma unroll
+  for (int t = 0; t < 2; ++t) {
+    const int c = lane + 32 * t;
+    if (c < num_classes) {
+      const float p0 = __fdiv_rn(prob0[t], total0), p1 = __fdiv_rn(prob1[t], total1);
+      const float pc0 = fminf(fmaxf(p0, FLT_EPSILON), 1.0f - FLT_EPSILON), pc1 = fminf(fmaxf(p1, FLT_EPSILON), 1.0f - FLT_EPSILON);
+      ent0 += __fmul_rn(logf(pc0), p0);
+      ent1 += __fmul_rn(logf(pc1), p1);
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    ent0 += __shfl_xor_sync(kFull, ent0, o);
+    ent1 += __shfl_xor_sync(kFull, ent1, o);
+  }
+  const float lognc = logf((float)num_classes);
+  AspectValues v;
+  v.div0 = __fdiv_rn(-ent0, lognc), v.div1 = __fdiv_rn(-ent1, lognc);
+  mn0 = __reduce_add_sync(kFull, mn0), mx0 = __reduce_add_sync(kFull, mx0);
+  mn1 = __reduce_add_sync(kFull, mn1), mx1 = __reduce_add_sync(kFull, mx1);
+  v.pers0 = __fdiv_rn((float)mn0, (float)mx0), v.pers1 = __fdiv_rn((float)mn1, (float)mx1);
+  return v;
+}
+
 // One module of one impression: gather the history rows and mean-pool them (cr_module.py:107-123),
 // then gather the candidate rows and dot them with the pooled user vector (click_predictors.py:12).
 // The loops are branch-free on purpose: a batch always loads R rows (slots past the end re-read the
@@ -878,18 +945,18 @@ __device__ __noinline__ int rank_and_metrics(const EvalParams& p, const WarpSmem
     if (aspects) {
       const int kk0 = min(p.k0, C), kk1 = min(p.k1, C);
       if (categ_group_ok) {
-        float v;
-        v = diversity_value(sm.top_cat, kk0, p.num_categ, lane); if (lane == MB200_M_CATEG_DIV_K0) mine = v;
-        v = diversity_value(sm.top_cat, kk1, p.num_categ, lane); if (lane == MB200_M_CATEG_DIV_K1) mine = v;
-        v = personalization_value(sm.top_cat, kk0, sm.hist_cat, p.num_categ, lane); if (lane == MB200_M_CATEG_PERS_K0) mine = v;
-        v = personalization_value(sm.top_cat, kk1, sm.hist_cat, p.num_categ, lane); if (lane == MB200_M_CATEG_PERS_K1) mine = v;
+        const AspectValues v = aspect_values(sm.top_cat, kk0, kk1, sm.hist_cat, p.num_categ, lane);
+        if (lane == MB200_M_CATEG_DIV_K0) mine = v.div0;
+        if (lane == MB200_M_CATEG_DIV_K1) mine = v.div1;
+        if (lane == MB200_M_CATEG_PERS_K0) mine = v.pers0;
+        if (lane == MB200_M_CATEG_PERS_K1) mine = v.pers1;
       }
       if (sent_group_ok) {
-        float v;
-        v = diversity_value(sm.top_sent, kk0, p.num_sent, lane); if (lane == MB200_M_SENT_DIV_K0) mine = v;
-        v = diversity_value(sm.top_sent, kk1, p.num_sent, lane); if (lane == MB200_M_SENT_DIV_K1) mine = v;
-        v = personalization_value(sm.top_sent, kk0, sm.hist_sent, p.num_sent, lane); if (lane == MB200_M_SENT_PERS_K0) mine = v;
-        v = personalization_value(sm.top_sent, kk1, sm.hist_sent, p.num_sent, lane); if (lane == MB200_M_SENT_PERS_K1) mine = v;
+        const AspectValues v = aspect_values(sm.top_sent, kk0, kk1, sm.hist_sent, p.num_sent, lane);
+        if (lane == MB200_M_SENT_DIV_K0) mine = v.div0;
+        if (lane == MB200_M_SENT_DIV_K1) mine = v.div1;
+        if (lane == MB200_M_SENT_PERS_K0) mine = v.pers0;
+        if (lane == MB200_M_SENT_PERS_K1) mine = v.pers1;
       }
       __syncwarp();
     }
