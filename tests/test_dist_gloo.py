@@ -171,3 +171,20 @@ def test_two_rank_topk_exchange(tmp_path):
         np.testing.assert_array_equal(z["a2a_i"], want_i[idx])
         np.testing.assert_array_equal(z["a2a_s"], want_s[idx])
     assert sorted(sum((rt.CatalogRetriever.user_slice(37, 16, r, WORLD) for r in range(WORLD)), [])) == list(range(37))
+
+
+def test_payload_flag_bits_round_trip():
+    """The flag word travels in a packed payload as one 0 / 1 double per bit, in the order of MB200_PAYLOAD_TAIL (count, then bits
+    1, 2, 4, 8 and 64 = upload time-out); host packing, host unpacking and the decode of a reduced tail must agree."""
+    from manner_b200 import _native as nat
+
+    assert mdist.FLAG_BITS == nat.PAYLOAD_FLAG_BITS and nat.PAYLOAD_TAIL == 1 + len(mdist.FLAG_BITS)
+    for flags in (0, 1, 2 | 8, 64, 1 | 4 | 64, 1 | 2 | 4 | 8 | 64):
+        payload = mdist.pack_metric_payload(torch.zeros(2, nat.NUM_METRICS, dtype=torch.float64), torch.tensor([flags], dtype=torch.int32), 7)
+        assert payload.numel() == 2 * nat.NUM_METRICS + nat.PAYLOAD_TAIL
+        _, f, n = mdist.unpack_metric_payload(payload, torch.Size([2, nat.NUM_METRICS]))
+        assert int(f.item()) == flags and n == 7
+        tail = payload[2 * nat.NUM_METRICS + 1 :].tolist()
+        assert mdist.flags_from_payload_tail(tail) == flags
+        # after a sum over ranks an entry is "how many ranks had the bit": still decodes to the OR
+        assert mdist.flags_from_payload_tail([3.0 * v for v in tail]) == flags
