@@ -601,3 +601,17 @@ def topk_select(scores: np.ndarray, k: int, id_offset: int = 0) -> Tuple[np.ndar
     top_s[:, :kk] = np.take_along_axis(scores, order, axis=1)[:, :kk]
     top_i[:, :kk] = order[:, :kk] + id_offset
     return top_s, top_i
+
+
+def rank_key(scores: np.ndarray) -> np.ndarray:
+    """The total order the device code ranks candidates by (csrc/score_eval.cu: rank_key), restated: an unsigned key per fp32 score
+    with  key(a) > key(b)  <=>  a ranks before b in ``torch.sort(descending=True)``  and  key(a) == key(b)  <=>  they tie there
+    (every NaN above everything and equal to every other NaN, -0 == +0).  ``np.lexsort((index, -key))`` must therefore be
+    ``torch.argsort(scores, descending=True, stable=True)`` -- the order behind MRR / nDCG / Diversity / Personalization
+    (torchmetrics 0.11.4 retrieval metrics; metrics/functional.py:17,47)."""
+    x = np.asarray(scores, dtype=np.float32).copy()
+    x[x == 0.0] = 0.0  # -0 -> +0
+    b = x.view(np.uint32).astype(np.uint64)
+    key = np.where(b & 0x80000000, (~b) & 0xFFFFFFFF, b | 0x80000000)
+    key[np.isnan(x)] = 0xFFFFFFFF
+    return key.astype(np.uint64)

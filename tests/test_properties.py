@@ -86,6 +86,20 @@ def test_oracle_candidate_permutation_invariance_without_ties(c, seed):
     assert mo.pooled_auc_exact(scores[p], labels[p]) == mo.pooled_auc_exact(scores, labels)
 
 
+_SPECIAL = st.sampled_from([float("nan"), -float("nan"), 0.0, -0.0, float("inf"), -float("inf"), 1.0, -1.0, 0.5, 1e-45, -1e-45, 3.4e38])
+
+
+@settings(max_examples=200, deadline=None)
+@given(st.lists(st.one_of(_SPECIAL, st.floats(width=32, allow_nan=True, allow_infinity=True)), min_size=1, max_size=80))
+def test_rank_key_is_the_stable_descending_sort_order(values):
+    """The integer key the kernels rank by == torch's descending stable sort (NaN first, ties in position order, -0 == +0)."""
+    x = np.asarray(values, dtype=np.float32)
+    key = mo.rank_key(x).astype(np.int64)
+    mine = np.lexsort((np.arange(x.shape[0]), -key))
+    want = torch.argsort(torch.from_numpy(x), descending=True, stable=True).numpy()
+    np.testing.assert_array_equal(mine, want)
+
+
 # ---- the same properties on the CUDA path ----------------------------------------------------------------------------------
 
 
